@@ -1,0 +1,163 @@
+/* b200fft -- C ABI of the B200-native distributed R2C FFT engine (libb200fft.so).
+ *
+ * Drop-in boundary for mpiFFT4py's hot path.  The reference has no FFI of its own: its compiled
+ * boundary is the duck-typed serial-FFT function table (mpiFFT4py/serialFFT/__init__.py:1-6,
+ * pyfftw_fft.py:26-203, numpy_fft.py:25-107), the Cython helpers (mpiFFT4py/cython/maths.pyx:9-43)
+ * and mpi4py collectives called from slab.py / pencil.py / line.py.  Each entry point below names
+ * the reference interface it replaces.  Plain pointers and sizes only; every data pointer is a
+ * DEVICE pointer of the current CUDA device unless stated otherwise; `stream` is a cudaStream_t
+ * passed as void*.  All functions return 0 on success, a non-zero code otherwise
+ * (b200fft_last_error() gives the message of the calling thread's last failure).
+ */
+#ifndef B200FFT_H
+#define B200FFT_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FFT_MAXP 16 /* max ranks of one exchange (one NVSwitch box has 8 GPUs) */
+
+enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-137 datatypes() */
+enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3 };
+enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
+enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1 };
+
+enum {
+  B200FFT_OK = 0,
+  B200FFT_ERR_ARG = 1,       /* bad argument (AssertionError in the reference) */
+  B200FFT_ERR_RANKS = 2,     /* illegal rank count (IOError: slab.py:89-91, pencil.py:201-205) */
+  B200FFT_ERR_UNSUPPORTED = 3, /* length without a radix plan / too long for shared memory */
+  B200FFT_ERR_CUDA = 4,
+  B200FFT_ERR_NCCL = 5,
+  B200FFT_ERR_NOMEM = 6
+};
+
+int b200fft_version(void);
+const char* b200fft_last_error(void);
+/* 1 if complex length n has a kernel plan (n = 2^k or 3*2^k within the supported range) */
+int b200fft_supported_length(int n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Low level: one fused FFT pass.  These are what serialFFT.fft/ifft/rfft/irfft (and the copies
+ * around them) become.  Element offsets, not bytes.
+ * ------------------------------------------------------------------------------------------- */
+
+/* One side (load or store) of a pass: the transformed-axis index i (after pad/truncate mapping to
+ * the physical extent nphys) is cut into nchunk chunks of `chunk` entries, the last one taking
+ * the remainder; chunk p lives at base[p]:  base[p] + b*sb[p] + (i - p*chunk)*si[p] + j.
+ * nchunk == 1 is a plain strided array; nchunk > 1 is the per-peer block layout of an exchange --
+ * the Alltoallw subarray datatypes of slab.py:199-211 / pencil.py:218-246,971-999 and the
+ * rollaxis / transpose_Uc packs (maths.pyx:21-31, pencil.py:109-143, line.py:14-24). */
+typedef struct {
+  void* base[B200FFT_MAXP];
+  long long sb[B200FFT_MAXP];
+  long long si[B200FFT_MAXP];
+  int chunk;
+  int nchunk;
+  int nphys; /* physical extent along the FFT axis; < n means zero-pad (load) / truncate (store) */
+} b200fft_side_t;
+
+/* 2/3-rule mask folded into a load (dealias_filter maths.pyx:9-19; get_dealias_filter
+ * slab.py:191-197, pencil.py:343-349, line.py:131-136).  Zero when any band contains the index:
+ * i+i_off in [i_lo,i_hi]; b+b_off in [b_lo,b_hi]; j/jdiv+jq_off in [jq_lo,jq_hi];
+ * j%jdiv+jr_off in [jr_lo,jr_hi].  Disabled bands use lo > hi. */
+typedef struct {
+  int on;
+  int i_off, i_lo, i_hi;
+  int b_off, b_lo, b_hi;
+  int jdiv;
+  int jq_off, jq_lo, jq_hi;
+  int jr_off, jr_lo, jr_hi;
+} b200fft_mask_t;
+
+/* Batched complex FFT of length n along the strided middle axis of [B][n][J]
+ * (serialFFT fft/ifft axis 0|1: pyfftw_fft.py:26-39,115-128) with fused zero-pad
+ * (copy_to_padded slab.py:517-523), truncate + Nyquist fold (copy_from_padded slab.py:529-533,
+ * :480-482), scaling (slab.py:320,483) and mask. */
+typedef struct {
+  int precision;
+  int n;          /* transform length (logical, i.e. the padded length when padding) */
+  long long B;    /* outer batch */
+  int J;          /* inner contiguous extent */
+  int inverse;    /* 0: exp(-i..), 1: exp(+i..); normalisation only through `scale` */
+  int fold_mode;  /* store truncation: 0 none, 1 add mode -N/2 onto +N/2, 2 keep mode -N/2 only (line.py:189) */
+  double scale;
+  b200fft_side_t in, out;
+  b200fft_mask_t mask;
+} b200fft_strided_desc_t;
+
+/* Batched real<->complex FFT along contiguous rows (serialFFT rfft/irfft axis -1:
+ * pyfftw_fft.py:71-83,160-173).  Real rows: `rows` rows of n reals with pitch rpitch.  Complex
+ * side: b = row index, chunked along k.  nk = complex entries stored (R2C: truncation
+ * copy_from_padded axis 2, slab.py:535) or present (C2R: zero pad, slab.py:524-525); C2R ignores
+ * the imaginary parts of k=0 and k=n/2 like FFTW / pocketfft. */
+typedef struct {
+  int precision;
+  int n;          /* real length, even */
+  long long rows;
+  int nk;
+  double scale;
+  void* real_base;
+  long long rpitch;
+  b200fft_side_t cside;
+} b200fft_rows_desc_t;
+
+int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
+int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
+int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Communicators: replace the mpi4py communicator (comm.Alltoall / Alltoallw / Sendrecv_replace /
+ * Scatter / Send / Recv call sites listed in SURVEY.md section 2 row 7) by NCCL over NVLink.
+ * The caller distributes the 128-byte unique id (host memory) out of band (torch.distributed,
+ * MPI, a file ...) -- the role MPI_Init / comm.Split (pencil.py:192-193) play upstream.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200fft_comm* b200fft_comm_t;
+int b200fft_comm_unique_id(void* id128);
+int b200fft_comm_create(b200fft_comm_t* comm, int nranks, int rank, const void* id128);
+int b200fft_comm_destroy(b200fft_comm_t comm);
+
+/* ---------------------------------------------------------------------------------------------
+ * Distributed transform plans: slab.R2C (slab.py:49-536), pencil.R2CX / R2CY
+ * (pencil.py:145-1477) and line.R2C (line.py:41-340).  One plan per rank (SPMD); all ranks call
+ * exec collectively in the same order.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int kind;        /* B200FFT_SLAB / PENCIL_X / PENCIL_Y / LINE */
+  int precision;
+  long long N[3];  /* global real mesh (line: N[0], N[1]; N[2] ignored) */
+  int nranks;      /* comm.Get_size() */
+  int rank;        /* comm.Get_rank() */
+  int P1, P2;      /* pencil process grid (pencil.py:184-195); ignored otherwise */
+  double padsize;  /* 3/2-rule pad factor; only 1.5 has kernels */
+  int drop_nyquist;/* pencil communication='AlltoallN' layout (pencil.py:197-199,908-910) */
+  int transport;   /* B200FFT_TRANSPORT_* */
+  b200fft_comm_t comm;   /* slab / line: all ranks */
+  b200fft_comm_t comm0;  /* pencil: ranks with equal rank / P1 */
+  b200fft_comm_t comm1;  /* pencil: ranks with equal rank % P1 */
+} b200fft_plan_desc_t;
+
+typedef struct b200fft_plan* b200fft_plan_t;
+
+int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d);
+int b200fft_plan_destroy(b200fft_plan_t plan);
+/* bytes of device scratch the plan owns (the reference's work_arrays, mpibase.py:61-131) */
+size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan);
+/* fftn / fft2 (slab.py:349-485, pencil.py:634-883,1228-1477, line.py:179-260):
+ * u real_shape() [dealias 3/2: real_shape_padded()] -> fu complex_shape().  u is not modified. */
+int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream);
+/* ifftn / ifft2 (slab.py:214-346, pencil.py:386-632,1001-1226, line.py:262-340).  fu is not modified. */
+int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream);
+/* number of kernels / NCCL groups the last exec launched (for bench.py's gpu_launches) */
+int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges);
+/* device time of the exchange phases of the last exec, if timing was enabled (ms; <0 if not) */
+int b200fft_plan_set_timing(b200fft_plan_t plan, int on);
+int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_H */

@@ -1,0 +1,452 @@
+// Batched 1D FFT kernels for sm_100a with the reference's pack / pad / truncate / mask copies
+// fused into their load and store index maps.
+//
+//   strided C2C   : [B][n][J] -> [B'][n'][J]   FFT along the middle (strided) axis; replaces
+//                   serialFFT fft/ifft(axis=0|1) (pyfftw_fft.py:26-39,115-128; numpy_fft.py:25-37),
+//                   copy_to_padded/copy_from_padded (slab.py:516-536, pencil.py:351-379),
+//                   transpose_Uc / rollaxis packs (maths.pyx:21-31, pencil.py:109-143),
+//                   dealias_filter (maths.pyx:9-19) and the Alltoallw subarray datatypes
+//                   (slab.py:199-211, pencil.py:218-246,971-999).
+//   row R2C / C2R : contiguous rows; replaces rfft/irfft(axis=-1) (pyfftw_fft.py:71-83,160-173;
+//                   numpy_fft.py:39-51) plus the z pad / truncate copies and the z-chunk pack.
+//
+// Algorithm: in-place mixed-radix decimation-in-frequency in shared memory.  Stage 0 reads its
+// butterfly inputs straight from HBM into registers, the last stage writes straight from
+// registers to HBM; the digit reversal is absorbed by assigning last-stage butterflies to
+// threads in digit-reversed order so that both HBM sides stay coalesced.  One __syncthreads per
+// stage boundary.  Tensor cores are not used: the work is a butterfly network bound by HBM.
+//
+// All phase bodies are __host__ __device__ and free of CUDA builtins so that tests/emu can run
+// the identical index math on the CPU (never part of the product path).
+#pragma once
+#include "fft_radix.cuh"
+
+namespace b200fft {
+
+constexpr int MAXP = 16;  // max peers (chunks) of one exchange: 8 GPUs per box, headroom for 16
+
+// ------------------------------------------------------------------------------------------
+// compile-time radix plans
+// ------------------------------------------------------------------------------------------
+template <int I, int R0, int... Rs> struct NthRadix { static constexpr int value = NthRadix<I - 1, Rs...>::value; };
+template <int R0, int... Rs> struct NthRadix<0, R0, Rs...> { static constexpr int value = R0; };
+
+template <int I, int R0, int... Rs> struct PrefixProd { static constexpr int value = R0 * PrefixProd<I - 1, Rs...>::value; };
+template <int R0, int... Rs> struct PrefixProd<0, R0, Rs...> { static constexpr int value = 1; };
+
+template <int... Rs>
+struct Plan {
+  static constexpr int S = sizeof...(Rs);
+  static constexpr int N = (1 * ... * Rs);
+  template <int s> static constexpr int R = NthRadix<s, Rs...>::value;
+  template <int s> static constexpr int L = N / PrefixProd<s, Rs..., 1>::value;  // sub-transform length at stage s
+  template <int s> static constexpr int M = L<s> / R<s>;                         // butterfly stride at stage s
+  static constexpr int RMAX = []() { int m = 1; for (int r : {Rs...}) m = r > m ? r : m; return m; }();
+  static constexpr int RLAST = NthRadix<S - 1, Rs...>::value;
+
+  // position (in the in-place DIF array) that holds frequency k after the last stage
+  template <int s = 0> B2_HD static int pos(int k) {
+    if constexpr (s >= S) {
+      return 0;
+    } else {
+      constexpr int r = R<s>;
+      return (k % r) * M<s> + pos<s + 1>(k / r);
+    }
+  }
+};
+
+// shared-memory swizzle: element `row` of a tile whose rows are ROWB bytes; keeps every access
+// pattern of the DIF stages at the minimum number of 128-byte wavefronts (kernels).
+template <int M0, int SW>
+B2_HD int swz(int row) {
+  if constexpr (SW > 1 && (M0 % SW) == 0) return row ^ ((row / M0) & (SW - 1));
+  else return row;
+}
+
+// One DIF stage for the butterflies owned by thread `t` (of TC threads cooperating on one
+// transform).  `sm` points at this transform's element 0 (column offset included); consecutive
+// positions are RS elements apart.
+template <class real, class P, int s, int TC, int RS, int SW, bool IN_FN, bool OUT_FN, class In, class Out>
+B2_HD void fft_stage(int t, cx<real>* sm, const cx<real>* tw, int tws, In&& in, Out&& out, int fold_mode) {
+  constexpr int S = P::S;
+  constexpr int R = P::template R<s>;
+  constexpr int L = P::template L<s>;
+  constexpr int M = L / R;
+  constexpr int M0 = P::template M<0>;
+  constexpr int NB = P::N / R;
+  constexpr int ROUNDS = (NB + TC - 1) / TC;
+  using C = cx<real>;
+#pragma unroll
+  for (int rr = 0; rr < ROUNDS; ++rr) {
+    const int u = t + rr * TC;
+    if ((NB % TC) != 0 && u >= NB) break;
+    int B, q;
+    if constexpr (s == S - 1) {  // M == 1: butterflies taken in digit-reversed order
+      B = (S > 1) ? P::template pos<0>(u) : 0;
+      q = 0;
+    } else {
+      B = (u / M) * L;
+      q = u % M;
+    }
+    C v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if constexpr (IN_FN) v[r] = in(B + q + r * M);
+      else v[r] = sm[swz<M0, SW>(B + q + r * M) * RS];
+    }
+    Dft<R>::template run<1>(v);
+    if constexpr (s < S - 1) {
+      const int step = q * tws * (P::N / L);  // W_L^(q*c) = W_NTW^(q*c*(NTW/L))
+#pragma unroll
+      for (int c = 1; c < R; ++c) v[c] = cmul(v[c], tw[c * step]);
+    }
+    if constexpr (OUT_FN) {
+      if constexpr (R % 3 == 0) {  // Nyquist fold of the 3/2-rule truncation (slab.py:480-482,529-533)
+        if (fold_mode != 0 && u == 0) {
+          if (fold_mode == 1) v[R / 3] = cadd(v[R / 3], v[2 * R / 3]);
+          else v[R / 3] = v[2 * R / 3];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < R; ++c) out(u + c * NB, v[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < R; ++c) sm[swz<M0, SW>(B + q + c * M) * RS] = v[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// index maps
+// ------------------------------------------------------------------------------------------
+// One side (load or store) of a pass.  The transformed axis index i (after pad / truncate
+// mapping to the physical extent nphys) is cut into `nchunk` chunks of `chunk` entries (the
+// last one takes the remainder); chunk p lives at base[p] with its own pitches -- this is the
+// per-peer block of an exchange (send layout on stores, receive layout on loads) or, for
+// nchunk == 1, a plain strided array.  Offsets in elements:
+//     base[p] + b*sb[p] + (i - p*chunk)*si[p] + j
+struct Side {
+  void* base[MAXP];
+  long long sb[MAXP];
+  long long si[MAXP];
+  int chunk;
+  int nchunk;
+  int nphys;
+};
+
+// 2/3-rule mask folded into a load (maths.pyx:9-19; masks slab.py:191-197, pencil.py:343-349,
+// line.py:131-136).  An element is zeroed when any enabled band contains its index:
+//   i + i_off in [i_lo, i_hi] ; b + b_off in [b_lo, b_hi] ;
+//   (j / jdiv) + jq_off in [jq_lo, jq_hi] ; (j % jdiv) + jr_off in [jr_lo, jr_hi]
+struct Mask {
+  int on;
+  int i_off, i_lo, i_hi;
+  int b_off, b_lo, b_hi;
+  int jdiv;
+  int jq_off, jq_lo, jq_hi;
+  int jr_off, jr_lo, jr_hi;
+};
+
+B2_HD int chunk_of(int i, int chunk, int nchunk) {
+  int p = i / chunk;
+  return p < nchunk ? p : nchunk - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// strided C2C pass
+// ------------------------------------------------------------------------------------------
+template <class real>
+struct StridedParams {
+  Side in, out;
+  long long B;
+  int J;
+  int n;
+  int inverse;
+  int fold_mode;  // 0 none, 1 add (slab/pencil/line P>1), 2 replace (line P==1, line.py:189)
+  real scale;
+  Mask mask;
+  const cx<real>* tw;
+  int tws;  // table length / n
+};
+
+template <class real, class P>
+struct StridedCfg {
+  static constexpr int CB = (int)sizeof(cx<real>);
+  static constexpr int ROWB = (P::N * 128 <= 48 * 1024) ? 128 : (P::N * 64 <= 100 * 1024) ? 64 : 32;
+  static constexpr int T0 = ROWB / CB;
+  static constexpr int NBMIN = P::N / P::RMAX;
+  static constexpr int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+  static constexpr int TC_ = pow2floor(NBMIN) < (256 / T0) ? pow2floor(NBMIN) : (256 / T0);
+  static constexpr int TC = TC_ < 1 ? 1 : TC_;
+  static constexpr int T = (T0 * TC >= 128) ? T0 : (128 / TC);
+  static constexpr int NT = T * TC;
+  static constexpr int SW = (T * CB >= 128) ? 1 : 128 / (T * CB);
+  static constexpr int SMEM = (P::S > 1) ? P::N * T * CB : 0;
+  static constexpr int NPHASE = P::S;
+};
+
+template <class real, class P>
+struct StridedK {
+  using Cfg = StridedCfg<real, P>;
+  using C = cx<real>;
+  using Params = StridedParams<real>;
+  static constexpr int NPHASE = Cfg::NPHASE;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+
+  // 1D grid: consecutive blocks walk the column tiles of one batch entry (adjacent 64-byte
+  // segments of the same rows -> neighbouring CTAs share DRAM pages and L2 sectors).
+  B2_HD static unsigned long long blocks(const Params& p) {
+    return (unsigned long long)((p.J + Cfg::T - 1) / Cfg::T) * (unsigned long long)p.B;
+  }
+  B2_HD static void decode(const Params& p, unsigned blk, int& bx, int& by) {
+    const unsigned nt = (unsigned)((p.J + Cfg::T - 1) / Cfg::T);
+    by = (int)(blk / nt);
+    bx = (int)(blk - (unsigned)by * nt);
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int by) {
+    constexpr int T = Cfg::T;
+    const int c = tid % T;
+    const int t = tid / T;
+    const int j = bx * T + c;
+    const long long b = by;
+    const bool live = j < p.J;
+    C* sm = reinterpret_cast<C*>(smraw) + c;
+    const int n = P::N;
+
+    bool colzero = !live;
+    if (p.mask.on && live) {
+      const Mask& m = p.mask;
+      const int bb = (int)b + m.b_off, jq = j / m.jdiv + m.jq_off, jr = j % m.jdiv + m.jr_off;
+      if ((bb >= m.b_lo && bb <= m.b_hi) || (jq >= m.jq_lo && jq <= m.jq_hi) || (jr >= m.jr_lo && jr <= m.jr_hi))
+        colzero = true;
+    }
+
+    auto in = [&](int i) -> C {
+      if (colzero) return C{0, 0};
+      int ip = i;
+      if (p.in.nphys < n) {  // zero-pad on load: copy_to_padded (slab.py:517-523)
+        const int h = p.in.nphys / 2;
+        if (i < h) ip = i;
+        else if (i >= n - h) ip = i - (n - p.in.nphys);
+        else return C{0, 0};
+      }
+      if (p.mask.on) {
+        const int ii = ip + p.mask.i_off;
+        if (ii >= p.mask.i_lo && ii <= p.mask.i_hi) return C{0, 0};
+      }
+      const int pc = (p.in.nchunk > 1) ? chunk_of(ip, p.in.chunk, p.in.nchunk) : 0;
+      const C* ptr = reinterpret_cast<const C*>(p.in.base[pc]) + b * p.in.sb[pc] +
+                     (long long)(ip - pc * p.in.chunk) * p.in.si[pc] + j;
+      C v = *ptr;
+      return p.inverse ? cswap(v) : v;
+    };
+    auto out = [&](int k, C v) {
+      if (!live) return;
+      int kp = k;
+      if (p.out.nphys < n) {  // truncate on store: copy_from_padded (slab.py:529-533)
+        const int h = p.out.nphys / 2;
+        if (k <= h) kp = k;
+        else if (k > n - h) kp = k - (n - p.out.nphys);
+        else return;
+      }
+      const int pc = (p.out.nchunk > 1) ? chunk_of(kp, p.out.chunk, p.out.nchunk) : 0;
+      C* ptr = reinterpret_cast<C*>(p.out.base[pc]) + b * p.out.sb[pc] +
+               (long long)(kp - pc * p.out.chunk) * p.out.si[pc] + j;
+      if (p.inverse) v = cswap(v);
+      *ptr = cscale(v, p.scale);
+    };
+    fft_stage<real, P, s, Cfg::TC, T, Cfg::SW, (s == 0), (s == P::S - 1)>(t, sm, p.tw, p.tws, in, out, p.fold_mode);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// contiguous-row R2C / C2R passes (half-length complex FFT + split / merge step)
+// ------------------------------------------------------------------------------------------
+template <class real>
+struct RowParams {
+  Side cside;          // complex side: out for R2C, in for C2R; chunked along k, b = row
+  const void* rin;     // R2C: real input rows
+  void* rout;          // C2R: real output rows
+  long long rpitch;    // real row pitch (elements)
+  long long rows;
+  int n;               // real length (= 2*P::N)
+  int nk;              // number of complex entries kept (R2C, truncation) / present (C2R, zero pad)
+  real scale;
+  const cx<real>* tw;  // table of W_NTW^j
+  int tws;             // NTW / n
+};
+
+template <class real, class P>
+struct RowCfg {
+  static constexpr int CB = (int)sizeof(cx<real>);
+  static constexpr int H = P::N;
+  static constexpr int NBMIN = P::N / P::RMAX;
+  static constexpr int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
+  static constexpr int TC_ = pow2floor(NBMIN) < 256 ? pow2floor(NBMIN) : 256;
+  static constexpr int TC = TC_ < 1 ? 1 : TC_;
+  static constexpr int RPC_T = (256 / TC) < 1 ? 1 : (256 / TC);                      // rows per CTA by threads
+  static constexpr int RPC_S = (64 * 1024) / (H * CB) < 1 ? 1 : (64 * 1024) / (H * CB);  // by shared memory
+  static constexpr int RPC = RPC_T < RPC_S ? RPC_T : RPC_S;
+  static constexpr int NT = TC * RPC;
+  static constexpr int SW = 128 / CB;
+  static constexpr int SMEM = RPC * H * CB;
+  static constexpr int NPHASE = P::S + 1;
+};
+
+template <class real, class P>
+struct R2CK {  // forward: real rows -> complex rows
+  using Cfg = RowCfg<real, P>;
+  using C = cx<real>;
+  using Params = RowParams<real>;
+  static constexpr int NPHASE = Cfg::NPHASE;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+  B2_HD static unsigned long long blocks(const Params& p) {
+    return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
+  }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int H = Cfg::H, TC = Cfg::TC;
+    constexpr int M0 = P::template M<0>;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.rows;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * H;
+    if constexpr (s < P::S) {
+      const C* src = reinterpret_cast<const C*>(reinterpret_cast<const real*>(p.rin) + row * p.rpitch);
+      auto in = [&](int i) -> C { return live ? src[i] : C{0, 0}; };  // z[i] = x[2i] + i*x[2i+1]
+      auto out = [](int, C) {};
+      // every stage writes shared memory (the split step needs all of F)
+      fft_stage<real, P, s, TC, 1, Cfg::SW, (s == 0), false>(t, sm, p.tw, 2 * p.tws, in, out, 0);
+    } else {
+      // split step: X[k] = E[k] + W_n^k O[k],  X[H-k] = conj(E[k] - W_n^k O[k])
+      if (!live) return;
+      const Side& o = p.cside;
+      auto store = [&](int k, C v) {
+        if (k >= p.nk) return;
+        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+        C* ptr = reinterpret_cast<C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk);
+        *ptr = cscale(v, p.scale);
+      };
+      constexpr int NK = H / 2 + 1;
+      constexpr int ROUNDS = (NK + TC - 1) / TC;
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int k = t + rr * TC;
+        if (k >= NK) break;
+        if (k == 0) {
+          C f = sm[swz<M0, Cfg::SW>(0)];
+          store(0, C{f.x + f.y, 0});
+          store(H, C{f.x - f.y, 0});
+        } else {
+          const C a = sm[swz<M0, Cfg::SW>(P::template pos<0>(k))];
+          const C bq = sm[swz<M0, Cfg::SW>(P::template pos<0>(H - k))];
+          const C e = C{(real)0.5 * (a.x + bq.x), (real)0.5 * (a.y - bq.y)};   // (a + conj b)/2
+          const C d = C{(real)0.5 * (a.x - bq.x), (real)0.5 * (a.y + bq.y)};   // (a - conj b)/2
+          const C o2 = mul_mi(d);                                              // O = -i (a - conj b)/2
+          const C wo = cmul(p.tw[k * p.tws], o2);
+          store(k, cadd(e, wo));
+          if (k != H - k) store(H - k, cconj(csub(e, wo)));
+        }
+      }
+    }
+  }
+};
+
+template <class real, class P>
+struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's scale carries 1/n)
+  using Cfg = RowCfg<real, P>;
+  using C = cx<real>;
+  using Params = RowParams<real>;
+  static constexpr int NPHASE = Cfg::NPHASE;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+  B2_HD static unsigned long long blocks(const Params& p) {
+    return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
+  }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int H = Cfg::H, TC = Cfg::TC;
+    constexpr int M0 = P::template M<0>;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.rows;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * H;
+    if constexpr (s == 0) {
+      // merge step: G[k] = (X[k] + conj X[H-k]) + i W_n^-k (X[k] - conj X[H-k]); stored swapped
+      const Side& o = p.cside;
+      auto load = [&](int k) -> C {
+        if (!live || k >= p.nk) return C{0, 0};  // zero pad in z: copy_to_padded axis 2 (slab.py:524-525)
+        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+        return *(reinterpret_cast<const C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk));
+      };
+      constexpr int NK = H / 2 + 1;
+      constexpr int ROUNDS = (NK + TC - 1) / TC;
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int k = t + rr * TC;
+        if (k >= NK) break;
+        if (k == 0) {
+          const real x0 = load(0).x, xh = load(H).x;  // imaginary parts of DC / Nyquist ignored (C2R)
+          sm[swz<M0, Cfg::SW>(0)] = cswap(C{x0 + xh, x0 - xh});
+        } else {
+          const C a = load(k), bq = load(H - k);
+          const C e = C{a.x + bq.x, a.y - bq.y};            // a + conj b
+          const C d = C{a.x - bq.x, a.y + bq.y};            // a - conj b
+          const C o2 = cmul(cconj(p.tw[k * p.tws]), d);    // W_n^-k (a - conj b)
+          const C io = mul_pi(o2);
+          sm[swz<M0, Cfg::SW>(k)] = cswap(cadd(e, io));
+          if (k != H - k) sm[swz<M0, Cfg::SW>(H - k)] = cswap(cadd(cconj(e), mul_pi(cconj(o2))));
+        }
+      }
+    } else {
+      constexpr int st = s - 1;
+      real* dst = reinterpret_cast<real*>(p.rout) + row * p.rpitch;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int m, C v) {
+        if (!live) return;
+        // z = swap(FFT(swap G)) ; x[2m] = Re z, x[2m+1] = Im z
+        C z = C{v.y * p.scale, v.x * p.scale};
+        *reinterpret_cast<C*>(dst + 2 * (long long)m) = z;
+      };
+      fft_stage<real, P, st, TC, 1, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, 0);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// device entry + host launcher
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+template <class K, int s>
+__device__ __forceinline__ void run_phases(const typename K::Params& p, void* sm, int bx, int by) {
+  K::template phase<s>(p, sm, (int)threadIdx.x, bx, by);
+  if constexpr (s + 1 < K::NPHASE) {
+    __syncthreads();
+    run_phases<K, s + 1>(p, sm, bx, by);
+  }
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::NT) fft_kernel(const __grid_constant__ typename K::Params p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  int bx, by;
+  K::decode(p, blockIdx.x, bx, by);
+  run_phases<K, 0>(p, smraw, bx, by);
+}
+#endif
+
+}  // namespace b200fft

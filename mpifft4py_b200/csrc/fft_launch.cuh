@@ -1,0 +1,29 @@
+// Kernel launcher shared by the per-precision translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "fft_kernels.cuh"
+#include "fft_plans.h"
+
+namespace b200fft {
+
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+template <class K>
+int launch_k(const typename K::Params& p, cudaStream_t st) {
+  if (K::SMEM > SMEM_LIMIT) return -1;
+  static bool configured = false;
+  if (!configured) {
+    if (K::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(fft_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+      if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+  }
+  unsigned long long nblk = K::blocks(p);
+  if (nblk == 0) return 0;
+  if (nblk > 2147483647ull) return -2;
+  fft_kernel<K><<<(unsigned)nblk, K::NT, K::SMEM, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b200fft

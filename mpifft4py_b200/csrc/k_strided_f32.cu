@@ -1,0 +1,6 @@
+// strided FFT kernels, float precision (sm_100a)
+#define REAL float
+#define SUFFIX f32
+#define B2_CAT_(a, b) a##b
+#define B2_CAT(a, b) B2_CAT_(a, b)
+#include "k_strided.inc"
