@@ -18,6 +18,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define B200FFT_API __attribute__((visibility("default")))
+#else
+#define B200FFT_API
+#endif
+
 #define B200FFT_MAXP 16 /* max ranks of one exchange (one NVSwitch box has 8 GPUs) */
 
 enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-137 datatypes() */
@@ -35,10 +41,10 @@ enum {
   B200FFT_ERR_NOMEM = 6
 };
 
-int b200fft_version(void);
-const char* b200fft_last_error(void);
+B200FFT_API int b200fft_version(void);
+B200FFT_API const char* b200fft_last_error(void);
 /* 1 if complex length n has a kernel plan (n = 2^k or 3*2^k within the supported range) */
-int b200fft_supported_length(int n);
+B200FFT_API int b200fft_supported_length(int n);
 
 /* ---------------------------------------------------------------------------------------------
  * Low level: one fused FFT pass.  These are what serialFFT.fft/ifft/rfft/irfft (and the copies
@@ -105,9 +111,9 @@ typedef struct {
   b200fft_side_t cside;
 } b200fft_rows_desc_t;
 
-int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
-int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
-int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
+B200FFT_API int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
+B200FFT_API int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
+B200FFT_API int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Communicators: replace the mpi4py communicator (comm.Alltoall / Alltoallw / Sendrecv_replace /
@@ -116,9 +122,9 @@ int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
  * MPI, a file ...) -- the role MPI_Init / comm.Split (pencil.py:192-193) play upstream.
  * ------------------------------------------------------------------------------------------- */
 typedef struct b200fft_comm* b200fft_comm_t;
-int b200fft_comm_unique_id(void* id128);
-int b200fft_comm_create(b200fft_comm_t* comm, int nranks, int rank, const void* id128);
-int b200fft_comm_destroy(b200fft_comm_t comm);
+B200FFT_API int b200fft_comm_unique_id(void* id128);
+B200FFT_API int b200fft_comm_create(b200fft_comm_t* comm, int nranks, int rank, const void* id128);
+B200FFT_API int b200fft_comm_destroy(b200fft_comm_t comm);
 
 /* ---------------------------------------------------------------------------------------------
  * Distributed transform plans: slab.R2C (slab.py:49-536), pencil.R2CX / R2CY
@@ -142,20 +148,20 @@ typedef struct {
 
 typedef struct b200fft_plan* b200fft_plan_t;
 
-int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d);
-int b200fft_plan_destroy(b200fft_plan_t plan);
+B200FFT_API int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d);
+B200FFT_API int b200fft_plan_destroy(b200fft_plan_t plan);
 /* bytes of device scratch the plan owns (the reference's work_arrays, mpibase.py:61-131) */
-size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan);
+B200FFT_API size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan);
 /* fftn / fft2 (slab.py:349-485, pencil.py:634-883,1228-1477, line.py:179-260):
  * u real_shape() [dealias 3/2: real_shape_padded()] -> fu complex_shape().  u is not modified. */
-int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream);
+B200FFT_API int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream);
 /* ifftn / ifft2 (slab.py:214-346, pencil.py:386-632,1001-1226, line.py:262-340).  fu is not modified. */
-int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream);
+B200FFT_API int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream);
 /* number of kernels / NCCL groups the last exec launched (for bench.py's gpu_launches) */
-int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges);
+B200FFT_API int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges);
 /* device time of the exchange phases of the last exec, if timing was enabled (ms; <0 if not) */
-int b200fft_plan_set_timing(b200fft_plan_t plan, int on);
-int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms);
+B200FFT_API int b200fft_plan_set_timing(b200fft_plan_t plan, int on);
+B200FFT_API int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,521 @@
+// libb200fft.so -- C ABI (include/b200fft.h): fused FFT passes, NCCL communicators and the
+// distributed slab / pencil / line R2C plans that replace mpiFFT4py's hot path.
+//
+// A plan is a short program of steps (row R2C/C2R pass, strided C2C pass, exchange) over five
+// buffers: the caller's input and output and up to three device work buffers owned by the plan
+// (the reference's work_arrays, mpibase.py:61-131).  Every copy the reference does between its
+// FFT calls (pack, transpose, pad, truncate, mask, scale) is part of a pass's index map; the MPI
+// collectives become one NCCL send/recv group per exchange, with each rank's own block written
+// straight into the receive buffer by the producing FFT pass.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "desc_convert.h"
+#include "fft_dispatch.h"
+#include "fft_plans.h"
+#include "plan_program.h"
+
+using namespace b200fft;
+
+namespace b200fft {
+bool plan_exists(int n) {
+  switch (n) {
+#define X(nn, ...) case nn:
+    B200FFT_PLANS(X)
+#undef X
+    return true;
+    default:
+      return false;
+  }
+}
+}  // namespace b200fft
+
+namespace {
+
+#define g_err (b200fft::plan_err())
+using b200fft::fail;
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(B200FFT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ---- twiddle tables (device), one per (device, length, precision) ------------------------------
+std::mutex g_tw_mu;
+std::map<std::tuple<int, int, int>, void*> g_tw;
+
+template <class real>
+int get_tw(int len, const cx<real>** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  auto key = std::make_tuple(dev, len, (int)sizeof(real));
+  auto it = g_tw.find(key);
+  if (it == g_tw.end()) {
+    std::vector<cx<real>> h = make_twiddles<real>(len);
+    void* d = nullptr;
+    e = cudaMalloc(&d, h.size() * sizeof(cx<real>));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
+    e = cudaMemcpy(d, h.data(), h.size() * sizeof(cx<real>), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(twiddles)");
+    it = g_tw.emplace(key, d).first;
+  }
+  *out = reinterpret_cast<const cx<real>*>(it->second);
+  return 0;
+}
+
+int map_launch_rc(int rc, const char* what, int n) {
+  if (rc == 0) return 0;
+  if (rc == -1) return fail(B200FFT_ERR_UNSUPPORTED, "%s: no kernel plan for length %d (supported: 2^k, 3*2^k that fit shared memory)", what, n);
+  if (rc == -2) return fail(B200FFT_ERR_ARG, "%s: grid too large", what);
+  return cuda_fail((cudaError_t)rc, what);
+}
+
+int exec_strided(const b200fft_strided_desc_t& d, cudaStream_t st) {
+  if (const char* e = check_strided(d)) return fail(B200FFT_ERR_ARG, "strided pass: %s", e);
+  if (d.B == 0 || d.J == 0) return 0;
+  if (d.precision == B200FFT_DOUBLE) {
+    const cx<double>* tw;
+    if (int rc = get_tw<double>(d.n, &tw)) return rc;
+    return map_launch_rc(launch_strided_f64(d.n, convert_strided<double>(d, tw, 1), st), "strided pass", d.n);
+  }
+  const cx<float>* tw;
+  if (int rc = get_tw<float>(d.n, &tw)) return rc;
+  return map_launch_rc(launch_strided_f32(d.n, convert_strided<float>(d, tw, 1), st), "strided pass", d.n);
+}
+
+int exec_rows(const b200fft_rows_desc_t& d, bool fwd, cudaStream_t st) {
+  if (const char* e = check_rows(d)) return fail(B200FFT_ERR_ARG, "row pass: %s", e);
+  if (d.rows == 0) return 0;
+  const int h = d.n / 2;
+  int rc;
+  if (d.precision == B200FFT_DOUBLE) {
+    const cx<double>* tw;
+    if (int r = get_tw<double>(d.n, &tw)) return r;
+    auto p = convert_rows<double>(d, tw, 1, fwd);
+    rc = fwd ? launch_r2c_f64(h, p, st) : launch_c2r_f64(h, p, st);
+  } else {
+    const cx<float>* tw;
+    if (int r = get_tw<float>(d.n, &tw)) return r;
+    auto p = convert_rows<float>(d, tw, 1, fwd);
+    rc = fwd ? launch_r2c_f32(h, p, st) : launch_c2r_f32(h, p, st);
+  }
+  return map_launch_rc(rc, fwd ? "R2C pass" : "C2R pass", d.n);
+}
+
+// ---- NCCL through dlopen: the library loads (and does P == 1 work) without NCCL ---------------
+struct NcclApi {
+  void* h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(B200FFT_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define L(sym)                                                                         \
+  g_nccl.sym = reinterpret_cast<decltype(g_nccl.sym)>(dlsym(h, "nccl" #sym));          \
+  if (!g_nccl.sym) return fail(B200FFT_ERR_NCCL, "libnccl lacks nccl" #sym);
+  L(GetUniqueId) L(CommInitRank) L(CommDestroy) L(GroupStart) L(GroupEnd) L(Send) L(Recv) L(GetErrorString)
+#undef L
+  g_nccl.h = h;
+  return 0;
+}
+
+int nccl_fail(ncclResult_t r, const char* what) {
+  return fail(B200FFT_ERR_NCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+}
+
+}  // namespace
+
+struct b200fft_comm {
+  ncclComm_t comm;
+  int nranks;
+  int rank;
+};
+
+struct b200fft_plan {
+  b200fft_plan_desc_t d;
+  Program prog[2][3];  // [forward=0 / inverse=1][dealias]
+  void* ws[3] = {nullptr, nullptr, nullptr};
+  size_t wbytes[3] = {0, 0, 0};
+  int last_kernels = 0, last_exch = 0;
+  int timing = 0;
+  cudaEvent_t ev[2 * 16];
+  int nev = 0;
+  bool ev_made = false;
+  float last_fft_ms = -1.f, last_exch_ms = -1.f;
+  std::vector<std::pair<int, int>> ev_marks;  // (event index start, is_exchange)
+};
+
+namespace {
+
+bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int validate_desc(const b200fft_plan_desc_t& d) {
+  if (d.precision != B200FFT_SINGLE && d.precision != B200FFT_DOUBLE) return fail(B200FFT_ERR_ARG, "precision must be single or double");
+  if (d.nranks < 1 || d.rank < 0 || d.rank >= d.nranks) return fail(B200FFT_ERR_ARG, "bad rank / nranks");
+  const int dims = d.kind == B200FFT_LINE ? 2 : 3;
+  for (int i = 0; i < dims; ++i)
+    if (d.N[i] < 4 || d.N[i] % 2) return fail(B200FFT_ERR_ARG, "N[%d]=%lld: mesh sizes must be even and >= 4", i, d.N[i]);
+  const int P = d.nranks;
+  if (d.kind == B200FFT_SLAB) {
+    if (!is_pow2(P) || P > d.N[0])  // slab.py:89-91
+      return fail(B200FFT_ERR_RANKS, "Number of cpus must be a power of two <= N[0]");
+    if (d.N[0] % P || d.N[1] % P) return fail(B200FFT_ERR_ARG, "N[0], N[1] must be divisible by the number of ranks");
+    if (P > B200FFT_MAXP) return fail(B200FFT_ERR_RANKS, "at most %d ranks", B200FFT_MAXP);
+  } else if (d.kind == B200FFT_LINE) {
+    if (d.N[0] % P || d.N[1] % (2 * P)) return fail(B200FFT_ERR_ARG, "N[0], N[1]/2 must be divisible by the number of ranks");
+    if (P > B200FFT_MAXP) return fail(B200FFT_ERR_RANKS, "at most %d ranks", B200FFT_MAXP);
+  } else if (d.kind == B200FFT_PENCIL_X || d.kind == B200FFT_PENCIL_Y) {
+    if (P < 2) return fail(B200FFT_ERR_ARG, "pencil decomposition needs more than one rank");  // pencil.py:176
+    if (P % 2) return fail(B200FFT_ERR_RANKS, "Number of cpus must be even");                    // pencil.py:201-202
+    if (d.P1 < 1 || d.P2 < 1 || d.P1 * d.P2 != P) return fail(B200FFT_ERR_ARG, "P1*P2 must equal the number of ranks");
+    if ((d.P1 % 2) || (d.P2 % 2))  // pencil.py:204-205
+      return fail(B200FFT_ERR_RANKS, "Number of cpus in each direction must be even power of 2");
+    if (d.P1 > B200FFT_MAXP || d.P2 > B200FFT_MAXP) return fail(B200FFT_ERR_RANKS, "at most %d ranks per direction", B200FFT_MAXP);
+    for (int i = 0; i < 3; ++i)
+      if (d.N[i] % d.P1 || d.N[i] % d.P2) return fail(B200FFT_ERR_ARG, "N must be divisible by P1 and P2");
+    const int zparts = d.kind == B200FFT_PENCIL_X ? d.P2 : d.P1;
+    if ((d.N[2] / 2) % zparts) return fail(B200FFT_ERR_ARG, "N[2]/2 must be divisible by the z process count");
+  } else {
+    return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
+  }
+  if (P > 1) {
+    if (d.kind == B200FFT_SLAB || d.kind == B200FFT_LINE) {
+      if (!d.comm) return fail(B200FFT_ERR_ARG, "multi-rank plan needs a communicator");
+      if (d.comm->nranks != P || d.comm->rank != d.rank) return fail(B200FFT_ERR_ARG, "communicator does not match nranks / rank");
+    } else {
+      if (!d.comm0 || !d.comm1) return fail(B200FFT_ERR_ARG, "pencil plan needs comm0 and comm1");
+      if (d.comm0->nranks != d.P1 || d.comm0->rank != d.rank % d.P1) return fail(B200FFT_ERR_ARG, "comm0 must hold the P1 ranks with equal rank / P1");
+      if (d.comm1->nranks != d.P2 || d.comm1->rank != d.rank / d.P1) return fail(B200FFT_ERR_ARG, "comm1 must hold the P2 ranks with equal rank %% P1");
+    }
+  }
+  return 0;
+}
+
+// lengths used by a program must have kernels
+int check_lengths(const Program& pg) {
+  for (const Step& s : pg.steps) {
+    if (s.type == ST_STRIDED && !plan_exists(s.n))
+      return fail(B200FFT_ERR_UNSUPPORTED, "no kernel plan for complex length %d", s.n);
+    if ((s.type == ST_R2C || s.type == ST_C2R) && (s.n % 2 || !plan_exists(s.n / 2)))
+      return fail(B200FFT_ERR_UNSUPPORTED, "no kernel plan for real length %d", s.n);
+  }
+  return 0;
+}
+
+int ensure_program(b200fft_plan* pl, int inverse, int dealias) {
+  Program& pg = pl->prog[inverse][dealias];
+  if (pg.built) {
+    if (pg.error) return fail(pg.error, "%s", pg.errmsg.c_str());
+    return 0;
+  }
+  pg.built = true;
+  if (dealias == B200FFT_DEALIAS_3_2) {
+    const int dims = pl->d.kind == B200FFT_LINE ? 2 : 3;
+    bool ok = std::fabs(pl->d.padsize - 1.5) < 1e-12;
+    for (int i = 0; i < dims; ++i) ok = ok && (pl->d.N[i] % 2 == 0);
+    if (!ok) {
+      pg.error = fail(B200FFT_ERR_UNSUPPORTED, "3/2-rule kernels exist for padsize == 1.5 only (got %g)", pl->d.padsize);
+      pg.errmsg = g_err;
+      return pg.error;
+    }
+  }
+  int rc = build_program(pl->d, inverse, dealias, pg);
+  if (!rc) rc = check_lengths(pg);
+  if (rc) {
+    pg.error = rc;
+    pg.errmsg = g_err;
+    pg.steps.clear();
+    return rc;
+  }
+  // grow the work buffers
+  const size_t csz = pl->d.precision == B200FFT_DOUBLE ? 16 : 8;
+  for (int w = 0; w < 3; ++w) {
+    const size_t need = (size_t)pg.need[BUF_W0 + w] * csz;
+    if (need > pl->wbytes[w]) {
+      if (pl->ws[w]) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+        cudaFree(pl->ws[w]);
+        pl->ws[w] = nullptr;
+        pl->wbytes[w] = 0;
+      }
+      cudaError_t e = cudaMalloc(&pl->ws[w], need);
+      if (e != cudaSuccess) {
+        pg.built = false;
+        return fail(B200FFT_ERR_NOMEM, "cudaMalloc(%zu bytes of work space): %s", need, cudaGetErrorString(e));
+      }
+      pl->wbytes[w] = need;
+    }
+  }
+  return 0;
+}
+
+void* resolve(const b200fft_plan* pl, const Ref& r, const void* in, void* out, size_t esz) {
+  char* base;
+  switch (r.buf) {
+    case BUF_IN: base = (char*)const_cast<void*>(in); break;
+    case BUF_OUT: base = (char*)out; break;
+    default: base = (char*)pl->ws[r.buf - BUF_W0]; break;
+  }
+  return base + (size_t)r.off * esz;
+}
+
+void fill_side(const b200fft_plan* pl, const SideT& s, b200fft_side_t& o, const void* in, void* out, size_t csz) {
+  std::memset(&o, 0, sizeof(o));
+  for (int q = 0; q < s.nchunk; ++q) {
+    o.base[q] = resolve(pl, s.base[q], in, out, csz);
+    o.sb[q] = s.sb[q];
+    o.si[q] = s.si[q];
+  }
+  o.chunk = s.chunk;
+  o.nchunk = s.nchunk;
+  o.nphys = s.nphys;
+}
+
+int run_exchange(b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz, cudaStream_t st) {
+  b200fft_comm_t c = s.comm == 0 ? pl->d.comm : (s.comm == 1 ? pl->d.comm0 : pl->d.comm1);
+  if (!c) return fail(B200FFT_ERR_ARG, "exchange without communicator");
+  ncclResult_t r = g_nccl.GroupStart();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+  for (int q = 0; q < s.npeers; ++q) {
+    if (q == s.me) continue;  // own block was written in place by the producing pass
+    r = g_nccl.Send(resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, ncclChar, q, c->comm, st);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclSend");
+    r = g_nccl.Recv(resolve(pl, s.recv[q], in, out, csz), (size_t)s.rcnt[q] * csz, ncclChar, q, c->comm, st);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclRecv");
+  }
+  r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+  return 0;
+}
+
+int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void* out, cudaStream_t st) {
+  if (dealias < 0 || dealias > 2) return fail(B200FFT_ERR_ARG, "dealias must be None, '3/2-rule' or '2/3-rule'");
+  if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;  // forward 2/3 == plain (slab.py:389)
+  if (!in || !out) return fail(B200FFT_ERR_ARG, "null data pointer");
+  if (int rc = ensure_program(pl, inverse, dealias)) return rc;
+  const Program& pg = pl->prog[inverse][dealias];
+  const size_t csz = pl->d.precision == B200FFT_DOUBLE ? 16 : 8;
+  const size_t rsz = csz / 2;
+  pl->last_kernels = 0;
+  pl->last_exch = 0;
+  pl->ev_marks.clear();
+  int evi = 0;
+  if (pl->timing && !pl->ev_made) {
+    for (int i = 0; i < 32; ++i) cudaEventCreate(&pl->ev[i]);
+    pl->ev_made = true;
+  }
+  for (const Step& s : pg.steps) {
+    if (pl->timing && evi + 2 <= 32) cudaEventRecord(pl->ev[evi], st);
+    int rc = 0;
+    if (s.type == ST_STRIDED) {
+      b200fft_strided_desc_t d;
+      std::memset(&d, 0, sizeof(d));
+      d.precision = pl->d.precision;
+      d.n = s.n;
+      d.B = s.B;
+      d.J = s.J;
+      d.inverse = s.inverse;
+      d.fold_mode = s.fold;
+      d.scale = s.scale;
+      fill_side(pl, s.in, d.in, in, out, csz);
+      fill_side(pl, s.out, d.out, in, out, csz);
+      d.mask = s.mask;
+      rc = exec_strided(d, st);
+      pl->last_kernels++;
+    } else if (s.type == ST_R2C || s.type == ST_C2R) {
+      b200fft_rows_desc_t d;
+      std::memset(&d, 0, sizeof(d));
+      d.precision = pl->d.precision;
+      d.n = s.n;
+      d.rows = s.rows;
+      d.nk = s.nk;
+      d.scale = s.scale;
+      d.real_base = resolve(pl, s.real, in, out, rsz);
+      d.rpitch = s.rpitch;
+      fill_side(pl, s.cside, d.cside, in, out, csz);
+      rc = exec_rows(d, s.type == ST_R2C, st);
+      pl->last_kernels++;
+    } else {
+      rc = run_exchange(pl, s, in, out, csz, st);
+      pl->last_exch++;
+    }
+    if (rc) return rc;
+    if (pl->timing && evi + 2 <= 32) {
+      cudaEventRecord(pl->ev[evi + 1], st);
+      pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
+      evi += 2;
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+int b200fft_version(void) { return 100; }
+
+const char* b200fft_last_error(void) { return g_err.c_str(); }
+
+int b200fft_supported_length(int n) { return plan_exists(n) ? 1 : 0; }
+
+int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream) {
+  if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
+  return exec_strided(*d, (cudaStream_t)stream);
+}
+
+int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream) {
+  if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
+  return exec_rows(*d, true, (cudaStream_t)stream);
+}
+
+int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream) {
+  if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
+  return exec_rows(*d, false, (cudaStream_t)stream);
+}
+
+int b200fft_comm_unique_id(void* id128) {
+  if (!id128) return fail(B200FFT_ERR_ARG, "null id buffer");
+  if (int rc = load_nccl()) return rc;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "unique id is 128 bytes");
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+
+int b200fft_comm_create(b200fft_comm_t* comm, int nranks, int rank, const void* id128) {
+  if (!comm || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(B200FFT_ERR_ARG, "bad communicator arguments");
+  if (int rc = load_nccl()) return rc;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t c;
+  ncclResult_t r = g_nccl.CommInitRank(&c, nranks, id, rank);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitRank");
+  b200fft_comm* out = new b200fft_comm;
+  out->comm = c;
+  out->nranks = nranks;
+  out->rank = rank;
+  *comm = out;
+  return 0;
+}
+
+int b200fft_comm_destroy(b200fft_comm_t comm) {
+  if (!comm) return 0;
+  if (g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
+  delete comm;
+  return 0;
+}
+
+int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
+  if (!plan || !d) return fail(B200FFT_ERR_ARG, "null argument");
+  if (int rc = validate_desc(*d)) return rc;
+  if (d->transport != B200FFT_TRANSPORT_NCCL) return fail(B200FFT_ERR_UNSUPPORTED, "only the NCCL transport is built");
+  if (d->nranks > 1)
+    if (int rc = load_nccl()) return rc;
+  b200fft_plan* pl = new b200fft_plan;
+  pl->d = *d;
+  if (pl->d.kind == B200FFT_LINE) pl->d.N[2] = 0;
+  // the plain programs are validated eagerly so that unsupported sizes fail at construction
+  Program probe;
+  int rc = build_program(pl->d, 0, B200FFT_DEALIAS_NONE, probe);
+  if (!rc) rc = check_lengths(probe);
+  if (rc) {
+    delete pl;
+    return rc;
+  }
+  *plan = pl;
+  return 0;
+}
+
+int b200fft_plan_destroy(b200fft_plan_t plan) {
+  if (!plan) return 0;
+  cudaDeviceSynchronize();
+  for (int w = 0; w < 3; ++w)
+    if (plan->ws[w]) cudaFree(plan->ws[w]);
+  if (plan->ev_made)
+    for (int i = 0; i < 32; ++i) cudaEventDestroy(plan->ev[i]);
+  delete plan;
+  return 0;
+}
+
+size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan) {
+  if (!plan) return 0;
+  return plan->wbytes[0] + plan->wbytes[1] + plan->wbytes[2];
+}
+
+int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream) {
+  if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
+  return run_program(plan, 0, dealias, u, fu, (cudaStream_t)stream);
+}
+
+int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream) {
+  if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
+  return run_program(plan, 1, dealias, fu, u, (cudaStream_t)stream);
+}
+
+int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges) {
+  if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
+  if (kernels) *kernels = plan->last_kernels;
+  if (exchanges) *exchanges = plan->last_exch;
+  return 0;
+}
+
+int b200fft_plan_set_timing(b200fft_plan_t plan, int on) {
+  if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
+  plan->timing = on ? 1 : 0;
+  return 0;
+}
+
+int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms) {
+  if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
+  float f = -1.f, x = -1.f;
+  if (plan->timing && !plan->ev_marks.empty()) {
+    f = 0.f;
+    x = 0.f;
+    for (auto& m : plan->ev_marks) {
+      cudaEventSynchronize(plan->ev[m.first + 1]);
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, plan->ev[m.first], plan->ev[m.first + 1]) == cudaSuccess) (m.second ? x : f) += ms;
+    }
+  }
+  if (fft_ms) *fft_ms = f;
+  if (exchange_ms) *exchange_ms = x;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,565 @@
+// Plan programs: the step lists (row pass / strided pass / exchange) of the distributed slab,
+// pencil and line transforms.  Host-only and CUDA-free so that libb200fft.so and the CPU emulator
+// (tests/emu) build the very same programs.
+#pragma once
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+
+namespace b200fft {
+constexpr int PMAXP = B200FFT_MAXP;
+
+inline std::string& plan_err() {
+  static thread_local std::string e;
+  return e;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  plan_err() = buf;
+  return code;
+}
+}  // namespace b200fft
+
+namespace b200fft {
+// ================================================================================================
+// plan programs
+// ================================================================================================
+enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_W0 = 2, BUF_W1 = 3, BUF_W2 = 4, NBUF = 5 };
+
+struct Ref {
+  int buf = BUF_IN;
+  long long off = 0;
+};
+
+struct SideT {
+  Ref base[PMAXP];
+  long long sb[PMAXP] = {0};
+  long long si[PMAXP] = {0};
+  int chunk = 1, nchunk = 1, nphys = 1;
+};
+
+enum StepType { ST_STRIDED, ST_R2C, ST_C2R, ST_EXCH };
+
+struct Step {
+  StepType type = ST_STRIDED;
+  // strided
+  int n = 0;
+  long long B = 1;
+  int J = 1;
+  int inverse = 0, fold = 0;
+  double scale = 1.0;
+  SideT in, out;
+  b200fft_mask_t mask;
+  // rows
+  long long rows = 0;
+  int nk = 0;
+  Ref real;
+  long long rpitch = 0;
+  SideT cside;
+  // exchange
+  int comm = 0;  // 0: world, 1: comm0, 2: comm1
+  int npeers = 0, me = 0;
+  Ref send[PMAXP], recv[PMAXP];
+  long long scnt[PMAXP] = {0}, rcnt[PMAXP] = {0};
+};
+
+struct Program {
+  std::vector<Step> steps;
+  long long need[NBUF] = {0, 0, 0, 0, 0};  // complex elements needed in W0..W2
+  bool built = false;
+  int error = 0;
+  std::string errmsg;
+};
+
+inline b200fft_mask_t mask_off() {
+  b200fft_mask_t m;
+  std::memset(&m, 0, sizeof(m));
+  m.jdiv = 1;
+  m.i_lo = m.b_lo = m.jq_lo = m.jr_lo = 1;
+  m.i_hi = m.b_hi = m.jq_hi = m.jr_hi = 0;
+  return m;
+}
+
+// band of indices zeroed by the 2/3-rule along an axis of (unpadded) size N:
+// keep iff |k| < kmax, kmax = 2/3*(N//2+1)  (slab.py:191-197)
+inline void band(long long N, bool half, int& lo, int& hi) {
+  const double kmax = 2. / 3. * (double)(N / 2 + 1);
+  const int l = (int)std::ceil(kmax);
+  lo = l;
+  hi = half ? 0x3fffffff : (int)N - l;
+}
+
+inline SideT nat(int buf, long long off, long long sb, long long si, int nphys) {
+  SideT s;
+  s.base[0].buf = buf;
+  s.base[0].off = off;
+  s.sb[0] = sb;
+  s.si[0] = si;
+  s.chunk = nphys;
+  s.nchunk = 1;
+  s.nphys = nphys;
+  return s;
+}
+
+struct Builder {
+  Program& pg;
+  explicit Builder(Program& p) : pg(p) {}
+  void use(int buf, long long end) {
+    if (buf >= BUF_W0 && end > pg.need[buf]) pg.need[buf] = end;
+  }
+  Step& strided(int n, long long B, long long J, int inverse, const SideT& in, const SideT& out, int fold = 0,
+                double scale = 1.0) {
+    Step s;
+    s.type = ST_STRIDED;
+    s.n = n;
+    s.B = B;
+    s.J = (int)J;
+    s.inverse = inverse;
+    s.fold = fold;
+    s.scale = scale;
+    s.in = in;
+    s.out = out;
+    s.mask = mask_off();
+    pg.steps.push_back(s);
+    return pg.steps.back();
+  }
+  Step& rows(bool fwd, long long rows, int n, int nk, int realbuf, const SideT& cside, double scale = 1.0) {
+    Step s;
+    s.type = fwd ? ST_R2C : ST_C2R;
+    s.rows = rows;
+    s.n = n;
+    s.nk = nk;
+    s.real.buf = realbuf;
+    s.real.off = 0;
+    s.rpitch = n;
+    s.cside = cside;
+    s.scale = scale;
+    s.mask = mask_off();
+    pg.steps.push_back(s);
+    return pg.steps.back();
+  }
+  Step& exch(int comm, int npeers, int me) {
+    Step s;
+    s.type = ST_EXCH;
+    s.comm = comm;
+    s.npeers = npeers;
+    s.me = me;
+    s.mask = mask_off();
+    pg.steps.push_back(s);
+    return pg.steps.back();
+  }
+};
+
+inline int ipad(double p, long long x) { return (int)(p * (double)x); }
+
+// Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
+inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
+  Builder b(pg);
+  const bool padded = dealias == B200FFT_DEALIAS_3_2;
+  const bool masked = inverse && dealias == B200FFT_DEALIAS_2_3;
+  const double p = padded ? d.padsize : 1.0;
+  const int P = d.nranks, me = d.rank;
+  const long long N0 = d.N[0], N1 = d.N[1], N2 = d.N[2];
+
+  if (d.kind == B200FFT_SLAB) {
+    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = N2 / 2 + 1;
+    const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
+    if (padded && P > 1 && P > N0 / 2)  // slab.py:311,446
+      return fail(B200FFT_ERR_ARG, "Number of processors cannot be larger than N[0]//2 for 3/2-rule");
+    const double p3 = p * p * p;
+    const long long blk = (long long)pNp0 * Np1 * Nf;
+    if (!inverse) {
+      if (P == 1) {
+        if (!padded) {  // slab.py:366-370
+          b.rows(true, N0 * N1, (int)N2, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
+          b.strided((int)N1, N0, Nf, 0, nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1));
+          b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
+        } else {  // slab.py:371-387
+          b.rows(true, (long long)pN0 * pN1, pN2, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
+          b.use(BUF_W0, (long long)pN0 * pN1 * Nf);
+          b.strided(pN1, pN0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), nat(BUF_W1, 0, N1 * Nf, Nf, (int)N1), 1);
+          b.use(BUF_W1, (long long)pN0 * N1 * Nf);
+          b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), 1, 1.0 / p3);
+        }
+      } else {  // slab.py:389-483
+        const int recvbuf = padded ? BUF_W2 : BUF_OUT;
+        b.rows(true, (long long)pNp0 * pN1, pN2, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
+        b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
+        SideT o;
+        o.chunk = (int)Np1;
+        o.nchunk = P;
+        o.nphys = (int)N1;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
+          o.base[q].off = q * blk;
+          o.sb[q] = Np1 * Nf;
+          o.si[q] = Nf;
+        }
+        b.strided(pN1, pNp0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), o, padded ? 1 : 0);
+        b.use(BUF_W1, P * blk);
+        b.use(recvbuf, P * blk);
+        Step& x = b.exch(0, P, me);
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W1; x.send[q].off = q * blk; x.scnt[q] = blk;
+          x.recv[q].buf = recvbuf; x.recv[q].off = q * blk; x.rcnt[q] = blk;
+        }
+        b.strided(pN0, 1, Np1 * Nf, 0, nat(recvbuf, 0, 0, Np1 * Nf, pN0), nat(BUF_OUT, 0, 0, Np1 * Nf, (int)N0),
+                  padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+      }
+    } else {
+      const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+      if (P == 1) {  // slab.py:247-268
+        Step& sx = b.strided(pN0, 1, N1 * Nf, 1, nat(BUF_IN, 0, 0, N1 * Nf, (int)N0), nat(BUF_W0, 0, 0, N1 * Nf, pN0));
+        b.use(BUF_W0, (long long)pN0 * N1 * Nf);
+        if (masked) {
+          sx.mask.on = 1;
+          sx.mask.jdiv = (int)Nf;
+          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        }
+        if (!padded) {
+          b.strided((int)N1, N0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1));
+          b.rows(false, N0 * N1, (int)N2, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), scale);
+        } else {
+          b.strided(pN1, pN0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W1, 0, pN1 * Nf, Nf, pN1));
+          b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
+          b.rows(false, (long long)pN0 * pN1, pN2, (int)Nf, BUF_OUT, nat(BUF_W1, 0, Nf, 1, (int)Nf), scale);
+        }
+      } else {  // slab.py:270-345
+        SideT o;
+        o.chunk = pNp0;
+        o.nchunk = P;
+        o.nphys = pN0;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+          o.base[q].off = q * blk;
+          o.sb[q] = 0;
+          o.si[q] = Np1 * Nf;
+        }
+        Step& sx = b.strided(pN0, 1, Np1 * Nf, 1, nat(BUF_IN, 0, 0, Np1 * Nf, (int)N0), o);
+        if (masked) {
+          sx.mask.on = 1;
+          sx.mask.jdiv = (int)Nf;
+          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+          sx.mask.jq_off = (int)(me * Np1);
+          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        }
+        b.use(BUF_W0, P * blk);
+        b.use(BUF_W1, P * blk);
+        Step& x = b.exch(0, P, me);
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = q * blk; x.scnt[q] = blk;
+          x.recv[q].buf = BUF_W1; x.recv[q].off = q * blk; x.rcnt[q] = blk;
+        }
+        SideT g;
+        g.chunk = (int)Np1;
+        g.nchunk = P;
+        g.nphys = (int)N1;
+        for (int q = 0; q < P; ++q) {
+          g.base[q].buf = BUF_W1;
+          g.base[q].off = q * blk;
+          g.sb[q] = Np1 * Nf;
+          g.si[q] = Nf;
+        }
+        b.strided(pN1, pNp0, Nf, 1, g, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1));
+        b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
+        b.rows(false, (long long)pNp0 * pN1, pN2, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), scale);
+      }
+    }
+    return 0;
+  }
+
+  if (d.kind == B200FFT_PENCIL_X || d.kind == B200FFT_PENCIL_Y) {
+    const bool alignX = d.kind == B200FFT_PENCIL_X;
+    const int P1 = d.P1, P2 = d.P2;
+    const int c0 = me % P1, c1 = me / P1;
+    const long long Nf = N2 / 2 + 1;
+    const long long a = N0 / P1, bq = N1 / P2;      // real block: (a, bq, N2)
+    const int pa = ipad(p, a), pbq = ipad(p, bq);
+    const int pN0 = ipad(p, N0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
+    const int zparts = alignX ? P2 : P1, zme = alignX ? c1 : c0;
+    const long long C = Nf / zparts;
+    long long zc[PMAXP], zoff[PMAXP + 1];
+    zoff[0] = 0;
+    for (int q = 0; q < zparts; ++q) {
+      zc[q] = C + ((q == zparts - 1 && !d.drop_nyquist) ? Nf % zparts : 0);
+      zoff[q + 1] = zoff[q] + zc[q];
+    }
+    const long long kzl = zc[zme];
+    const int nk = (int)zoff[zparts];  // Nf, or Nf-1 for the AlltoallN layout
+    const double p3 = p * p * p;
+    const long long rowsz = (long long)pa * pbq;  // z rows per rank
+    
+    const double iscale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+
+    // z pass stores / loads: kz cut into zparts chunks, one per peer of the z communicator
+    auto zside = [&](int selfbuf, long long selfoff, int otherbuf, bool recv_layout) {
+      SideT s;
+      s.chunk = (int)C;
+      s.nchunk = zparts;
+      s.nphys = nk;
+      for (int q = 0; q < zparts; ++q) {
+        if (recv_layout) {  // blocks from q: [rowsz][zc[q]] at rowsz*zoff[q]
+          s.base[q].buf = otherbuf;
+          s.base[q].off = rowsz * zoff[q];
+        } else {
+          s.base[q].buf = (q == zme) ? selfbuf : otherbuf;
+          s.base[q].off = (q == zme) ? selfoff : rowsz * zoff[q];
+        }
+        s.sb[q] = zc[q];
+        s.si[q] = 1;
+      }
+      return s;
+    };
+
+    if (alignX) {
+      const long long y1 = N1 / P1;
+      const long long blk2 = (long long)pa * y1 * kzl;     // comm0 exchange block
+      const long long blk1 = rowsz * kzl;                  // comm1 block [pa][pbq][kzl]
+      if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
+        const int recv2 = padded ? BUF_W2 : BUF_OUT;
+        b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
+        b.use(BUF_W0, rowsz * nk);
+        b.use(BUF_W1, P2 * blk1);
+        Step& x1 = b.exch(2, P2, c1);
+        for (int q = 0; q < P2; ++q) {
+          x1.send[q].buf = BUF_W0; x1.send[q].off = rowsz * zoff[q]; x1.scnt[q] = rowsz * zc[q];
+          x1.recv[q].buf = BUF_W1; x1.recv[q].off = q * blk1; x1.rcnt[q] = blk1;
+        }
+        SideT g;  // gather y from the P2 peers
+        g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+        for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk1; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
+        SideT o;  // split y over the P1 peers
+        o.chunk = (int)y1; o.nchunk = P1; o.nphys = (int)N1;
+        for (int q = 0; q < P1; ++q) {
+          o.base[q].buf = (q == c0) ? recv2 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = y1 * kzl; o.si[q] = kzl;
+        }
+        b.strided(pN1, pa, kzl, 0, g, o, padded ? 1 : 0);
+        b.use(BUF_W0, P1 * blk2);
+        b.use(recv2, P1 * blk2);
+        Step& x2 = b.exch(1, P1, c0);
+        for (int q = 0; q < P1; ++q) {
+          x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
+          x2.recv[q].buf = recv2; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+        }
+        b.strided(pN0, 1, y1 * kzl, 0, nat(recv2, 0, 0, y1 * kzl, pN0), nat(BUF_OUT, 0, 0, y1 * kzl, (int)N0),
+                  padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+      } else {  // pencil.py:1082-1105 (+ padded :1196-1223)
+        SideT o;
+        o.chunk = pa; o.nchunk = P1; o.nphys = pN0;
+        for (int q = 0; q < P1; ++q) {
+          o.base[q].buf = (q == c0) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = 0; o.si[q] = y1 * kzl;
+        }
+        Step& sx = b.strided(pN0, 1, y1 * kzl, 1, nat(BUF_IN, 0, 0, y1 * kzl, (int)N0), o);
+        if (masked) {
+          sx.mask.on = 1;
+          sx.mask.jdiv = (int)kzl;
+          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+          sx.mask.jq_off = (int)(c0 * y1);
+          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+          sx.mask.jr_off = (int)(c1 * C);
+        }
+        b.use(BUF_W0, P1 * blk2);
+        b.use(BUF_W1, P1 * blk2);
+        Step& x2 = b.exch(1, P1, c0);
+        for (int q = 0; q < P1; ++q) {
+          x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
+          x2.recv[q].buf = BUF_W1; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+        }
+        SideT g;
+        g.chunk = (int)y1; g.nchunk = P1; g.nphys = (int)N1;
+        for (int q = 0; q < P1; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk2; g.sb[q] = y1 * kzl; g.si[q] = kzl; }
+        SideT o2;
+        o2.chunk = pbq; o2.nchunk = P2; o2.nphys = pN1;
+        for (int q = 0; q < P2; ++q) {
+          o2.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0;
+          o2.base[q].off = (q == c1) ? rowsz * zoff[c1] : q * blk1;
+          o2.sb[q] = pbq * kzl; o2.si[q] = kzl;
+        }
+        b.strided(pN1, pa, kzl, 1, g, o2);
+        b.use(BUF_W0, P2 * blk1);
+        b.use(BUF_W2, rowsz * nk);
+        Step& x1 = b.exch(2, P2, c1);
+        for (int q = 0; q < P2; ++q) {
+          x1.send[q].buf = BUF_W0; x1.send[q].off = q * blk1; x1.scnt[q] = blk1;
+          x1.recv[q].buf = BUF_W2; x1.recv[q].off = rowsz * zoff[q]; x1.rcnt[q] = rowsz * zc[q];
+        }
+        b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
+      }
+    } else {  // alignment Y
+      const long long x2l = N0 / P2;                        // final local x extent
+      const long long blk = x2l * pbq * kzl;                // comm1 exchange block
+      const long long blk1 = rowsz * kzl;                   // comm0 block [pa][pbq][kzl]
+      if (!inverse) {  // pencil.py:730-754 (+ padded :853-881)
+        b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
+        b.use(BUF_W0, rowsz * nk);
+        b.use(BUF_W1, P1 * blk1);
+        Step& xa = b.exch(1, P1, c0);
+        for (int q = 0; q < P1; ++q) {
+          xa.send[q].buf = BUF_W0; xa.send[q].off = rowsz * zoff[q]; xa.scnt[q] = rowsz * zc[q];
+          xa.recv[q].buf = BUF_W1; xa.recv[q].off = q * blk1; xa.rcnt[q] = blk1;
+        }
+        SideT o;
+        o.chunk = (int)x2l; o.nchunk = P2; o.nphys = (int)N0;
+        for (int q = 0; q < P2; ++q) {
+          o.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = 0; o.si[q] = pbq * kzl;
+        }
+        b.strided(pN0, 1, pbq * kzl, 0, nat(BUF_W1, 0, 0, pbq * kzl, pN0), o, padded ? 1 : 0);
+        b.use(BUF_W0, P2 * blk);
+        b.use(BUF_W2, P2 * blk);
+        Step& xb = b.exch(2, P2, c1);
+        for (int q = 0; q < P2; ++q) {
+          xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
+          xb.recv[q].buf = BUF_W2; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+        }
+        SideT g;
+        g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+        for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W2; g.base[q].off = q * blk; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
+        b.strided(pN1, x2l, kzl, 0, g, nat(BUF_OUT, 0, N1 * kzl, kzl, (int)N1), padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+      } else {  // pencil.py:483-507 (+ padded :597-629)
+        SideT o;
+        o.chunk = pbq; o.nchunk = P2; o.nphys = pN1;
+        for (int q = 0; q < P2; ++q) {
+          o.base[q].buf = (q == c1) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = pbq * kzl; o.si[q] = kzl;
+        }
+        Step& sy = b.strided(pN1, x2l, kzl, 1, nat(BUF_IN, 0, N1 * kzl, kzl, (int)N1), o);
+        if (masked) {
+          sy.mask.on = 1;
+          sy.mask.jdiv = 0x3fffffff;
+          band(N0, false, sy.mask.b_lo, sy.mask.b_hi);
+          sy.mask.b_off = (int)(c1 * x2l);
+          band(N1, false, sy.mask.i_lo, sy.mask.i_hi);
+          band(N2, true, sy.mask.jr_lo, sy.mask.jr_hi);
+          sy.mask.jr_off = (int)(c0 * C);
+        }
+        b.use(BUF_W0, P2 * blk);
+        b.use(BUF_W1, P2 * blk);
+        Step& xb = b.exch(2, P2, c1);
+        for (int q = 0; q < P2; ++q) {
+          xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
+          xb.recv[q].buf = BUF_W1; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+        }
+        SideT o2;
+        o2.chunk = pa; o2.nchunk = P1; o2.nphys = pN0;
+        for (int q = 0; q < P1; ++q) {
+          o2.base[q].buf = (q == c0) ? BUF_W2 : BUF_W0;
+          o2.base[q].off = (q == c0) ? rowsz * zoff[c0] : q * blk1;
+          o2.sb[q] = 0; o2.si[q] = pbq * kzl;
+        }
+        b.strided(pN0, 1, pbq * kzl, 1, nat(BUF_W1, 0, 0, pbq * kzl, (int)N0), o2);
+        b.use(BUF_W0, P1 * blk1);
+        b.use(BUF_W2, rowsz * nk);
+        Step& xa = b.exch(1, P1, c0);
+        for (int q = 0; q < P1; ++q) {
+          xa.send[q].buf = BUF_W0; xa.send[q].off = q * blk1; xa.scnt[q] = blk1;
+          xa.recv[q].buf = BUF_W2; xa.recv[q].off = rowsz * zoff[q]; xa.rcnt[q] = rowsz * zc[q];
+        }
+        b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
+      }
+    }
+    return 0;
+  }
+
+  if (d.kind == B200FFT_LINE) {
+    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = N1 / 2 + 1;
+    const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1);
+    const long long kc = Np1 / 2;
+    long long kcl[PMAXP], koff[PMAXP + 1];
+    koff[0] = 0;
+    for (int q = 0; q < P; ++q) {
+      kcl[q] = kc + (q == P - 1 ? 1 : 0);
+      koff[q + 1] = koff[q] + kcl[q];
+    }
+    const long long Npf = (P == 1) ? Nf : kcl[me];
+    const double p2 = p * p;
+    const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
+    if (!inverse) {
+      if (P == 1) {  // line.py:182-191
+        if (!padded) {
+          b.rows(true, N0, (int)N1, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
+          b.strided((int)N0, 1, Nf, 0, nat(BUF_OUT, 0, 0, Nf, (int)N0), nat(BUF_OUT, 0, 0, Nf, (int)N0));
+        } else {
+          b.rows(true, pN0, pN1, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
+          b.use(BUF_W0, (long long)pN0 * Nf);
+          b.strided(pN0, 1, Nf, 0, nat(BUF_W0, 0, 0, Nf, pN0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 2, 1.0 / p2);
+        }
+      } else {  // line.py:193-258
+        const int recvbuf = padded ? BUF_W1 : BUF_OUT;
+        SideT o;
+        o.chunk = (int)kc; o.nchunk = P; o.nphys = (int)Nf;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? recvbuf : BUF_W0;
+          o.base[q].off = (q == me) ? (long long)me * pNp0 * Npf : (long long)pNp0 * koff[q];
+          o.sb[q] = kcl[q]; o.si[q] = 1;
+        }
+        b.rows(true, pNp0, pN1, (int)Nf, BUF_IN, o);
+        b.use(BUF_W0, (long long)pNp0 * Nf);
+        b.use(recvbuf, (long long)pN0 * Npf);
+        Step& x = b.exch(0, P, me);
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = (long long)pNp0 * koff[q]; x.scnt[q] = (long long)pNp0 * kcl[q];
+          x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf; x.rcnt[q] = (long long)pNp0 * Npf;
+        }
+        b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
+                  padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
+      }
+    } else {
+      if (P == 1) {  // line.py:274-283
+        Step& sx = b.strided(pN0, 1, Nf, 1, nat(BUF_IN, 0, 0, Nf, (int)N0), nat(BUF_W0, 0, 0, Nf, pN0));
+        b.use(BUF_W0, (long long)pN0 * Nf);
+        if (masked) {
+          sx.mask.on = 1;
+          sx.mask.jdiv = 0x3fffffff;
+          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+          band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        }
+        b.rows(false, pN0, pN1, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), iscale);
+      } else {  // line.py:285-338
+        const long long blk = (long long)pNp0 * Npf;
+        SideT o;
+        o.chunk = pNp0; o.nchunk = P; o.nphys = pN0;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+          o.base[q].off = (q == me) ? (long long)pNp0 * koff[me] : q * blk;
+          o.sb[q] = 0; o.si[q] = Npf;
+        }
+        Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
+        if (masked) {
+          sx.mask.on = 1;
+          sx.mask.jdiv = 0x3fffffff;
+          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+          band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
+          sx.mask.jr_off = (int)(me * kc);
+        }
+        b.use(BUF_W0, P * blk);
+        b.use(BUF_W1, (long long)pNp0 * Nf);
+        Step& x = b.exch(0, P, me);
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = q * blk; x.scnt[q] = blk;
+          x.recv[q].buf = BUF_W1; x.recv[q].off = (long long)pNp0 * koff[q]; x.rcnt[q] = (long long)pNp0 * kcl[q];
+        }
+        SideT g;
+        g.chunk = (int)kc; g.nchunk = P; g.nphys = (int)Nf;
+        for (int q = 0; q < P; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = (long long)pNp0 * koff[q]; g.sb[q] = kcl[q]; g.si[q] = 1; }
+        b.rows(false, pNp0, pN1, (int)Nf, BUF_OUT, g, iscale);
+      }
+    }
+    return 0;
+  }
+  return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
+}
+
+
+}  // namespace b200fft

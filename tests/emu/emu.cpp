@@ -11,6 +11,7 @@
 
 #include "../../mpifft4py_b200/csrc/desc_convert.h"
 #include "../../mpifft4py_b200/csrc/fft_plans.h"
+#include "../../mpifft4py_b200/csrc/plan_program.h"
 
 using namespace b200fft;
 
@@ -84,6 +85,73 @@ int emu_exec_c2r(const b200fft_rows_desc_t* d) {
   if (const char* e = check_rows(*d)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
   return d->precision == B200FFT_DOUBLE ? rows<double, false>(*d) : rows<float, false>(*d);
 }
+// Run one distributed transform for ALL ranks in lockstep: the same plan programs as
+// libb200fft.so (plan_program.h), kernels emulated on the CPU, exchanges done by memcpy.
+int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void** ins, void** outs) {
+  const int P = d0->nranks;
+  if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;
+  const size_t csz = d0->precision == B200FFT_DOUBLE ? 16 : 8;
+  std::vector<Program> pg((size_t)P);
+  std::vector<std::vector<unsigned char>> ws((size_t)P * 3);
+  for (int r = 0; r < P; ++r) {
+    b200fft_plan_desc_t d = *d0;
+    d.rank = r;
+    if (int rc = build_program(d, inverse, dealias, pg[r])) {
+      std::fprintf(stderr, "emu plan: %s\n", plan_err().c_str());
+      return rc;
+    }
+    for (int w = 0; w < 3; ++w) ws[(size_t)r * 3 + w].assign((size_t)pg[r].need[BUF_W0 + w] * csz + 64, 0xff);  // NaN poison
+  }
+  auto resolve = [&](int r, const Ref& ref, size_t esz) -> void* {
+    char* base;
+    if (ref.buf == BUF_IN) base = (char*)ins[r];
+    else if (ref.buf == BUF_OUT) base = (char*)outs[r];
+    else base = (char*)ws[(size_t)r * 3 + (ref.buf - BUF_W0)].data();
+    return base + (size_t)ref.off * esz;
+  };
+  auto side = [&](int r, const SideT& s) {
+    b200fft_side_t o;
+    std::memset(&o, 0, sizeof(o));
+    for (int q = 0; q < s.nchunk; ++q) { o.base[q] = resolve(r, s.base[q], csz); o.sb[q] = s.sb[q]; o.si[q] = s.si[q]; }
+    o.chunk = s.chunk; o.nchunk = s.nchunk; o.nphys = s.nphys;
+    return o;
+  };
+  const size_t nsteps = pg[0].steps.size();
+  for (int r = 1; r < P; ++r) if (pg[r].steps.size() != nsteps) return 90;
+  for (size_t si = 0; si < nsteps; ++si) {
+    for (int r = 0; r < P; ++r) {
+      const Step& s = pg[r].steps[si];
+      int rc = 0;
+      if (s.type == ST_STRIDED) {
+        b200fft_strided_desc_t d;
+        std::memset(&d, 0, sizeof(d));
+        d.precision = d0->precision; d.n = s.n; d.B = s.B; d.J = s.J; d.inverse = s.inverse;
+        d.fold_mode = s.fold; d.scale = s.scale; d.in = side(r, s.in); d.out = side(r, s.out); d.mask = s.mask;
+        rc = emu_exec_strided(&d);
+      } else if (s.type == ST_R2C || s.type == ST_C2R) {
+        b200fft_rows_desc_t d;
+        std::memset(&d, 0, sizeof(d));
+        d.precision = d0->precision; d.n = s.n; d.rows = s.rows; d.nk = s.nk; d.scale = s.scale;
+        d.real_base = resolve(r, s.real, csz / 2); d.rpitch = s.rpitch; d.cside = side(r, s.cside);
+        rc = s.type == ST_R2C ? emu_exec_r2c(&d) : emu_exec_c2r(&d);
+      } else {
+        for (int q = 0; q < s.npeers; ++q) {
+          if (q == s.me) continue;
+          int w;  // world rank of peer q of this communicator (pencil.py:192-195)
+          if (s.comm == 0) w = q;
+          else if (s.comm == 1) w = (r / d0->P1) * d0->P1 + q;
+          else w = q * d0->P1 + (r % d0->P1);
+          const Step& t = pg[w].steps[si];
+          if (t.type != ST_EXCH || t.rcnt[s.me] != s.scnt[q]) return 91;
+          std::memcpy(resolve(w, t.recv[s.me], csz), resolve(r, s.send[q], csz), (size_t)s.scnt[q] * csz);
+        }
+      }
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
 // kernel launch geometry, for DESIGN.md / tests
 int emu_strided_config(int precision, int n, int* T, int* TC, int* smem) {
   switch (n) {

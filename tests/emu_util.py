@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "emu.cpp")
 LIB = os.path.join(HERE, "emu", "libb200fft_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "mpifft4py_b200", "csrc", f) for f in
-                ("fft_kernels.cuh", "fft_radix.cuh", "fft_plans.h", "desc_convert.h")] + \
+                ("fft_kernels.cuh", "fft_radix.cuh", "fft_plans.h", "desc_convert.h", "plan_program.h")] + \
        [os.path.join(ROOT, "include", "b200fft.h")]
 
 _lib = None

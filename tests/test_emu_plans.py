@@ -1,0 +1,161 @@
+"""The distributed plan programs of libb200fft.so (csrc/plan_program.h), executed for ALL ranks in
+lockstep by the CPU emulator (kernels emulated, exchanges by memcpy), against the oracle.
+
+This pins every step list -- index maps, peer offsets, uneven Nyquist chunks, masks, scales --
+without a GPU; tests/test_gpu_*.py then run the same programs on the device over NCCL."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import emu_util
+import oracle
+from mpifft4py_b200 import _cdefs as D
+
+TOL = {"double": 5e-14, "single": 5e-6}
+
+
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0):
+    d = D.PlanDesc()
+    d.kind = kind
+    d.precision = D.DOUBLE if prec == "double" else D.SINGLE
+    for i, n in enumerate(N):
+        d.N[i] = n
+    d.nranks = P
+    d.rank = 0
+    d.P1, d.P2 = P1, P2
+    d.padsize = 1.5
+    d.drop_nyquist = drop
+    d.transport = 0
+    return d
+
+
+def run_plan(d, inverse, dealias, ins, out_shapes, out_dtype):
+    lib = emu_util.load()
+    P = d.nranks
+    ins = [np.ascontiguousarray(a) for a in ins]
+    outs = [np.full(s, np.nan, dtype=out_dtype) for s in out_shapes]
+    ip = (C.c_void_p * P)(*[a.ctypes.data for a in ins])
+    op = (C.c_void_p * P)(*[a.ctypes.data for a in outs])
+    rc = lib.emu_plan_run(C.byref(d), inverse, dealias, ip, op)
+    assert rc == 0, rc
+    return outs
+
+
+def _check(got, ref, tol):
+    for r, (g, e) in enumerate(zip(got, ref)):
+        assert g.shape == e.shape, (r, g.shape, e.shape)
+        assert np.isfinite(g).all(), "rank %d: unwritten output" % r
+        assert oracle.rel_l2(g, e) <= tol, (r, oracle.rel_l2(g, e))
+
+
+def _rand_c(rng, shape, ct):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(ct)
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("P", [1, 2, 4])
+@pytest.mark.parametrize("N", [(8, 16, 32), (16, 16, 16), (32, 8, 8)])
+def test_slab(N, P, prec):
+    if P > N[0] // 2 or N[1] % P:
+        pytest.skip("illegal decomposition")
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(sum(N) + P)
+    d = _desc(D.SLAB, N, P, prec)
+    tol = TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    ref = oracle.slab.fftn(u, N, P, precision=prec)
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
+    _check(got, ref, tol)
+    # inverse of an arbitrary complex spectrum (non-Hermitian content included), plain and 2/3
+    fu = [_rand_c(rng, g.complex_shape(), ct) for _ in range(P)]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule")):
+        ref = oracle.slab.ifftn(fu, N, P, dealias=name, precision=prec)
+        got = run_plan(d, 1, mode, fu, [g.real_shape()] * P, rt)
+        _check(got, ref, tol)
+    # 3/2-rule both ways on generic inputs
+    ref = oracle.slab.ifftn(fu, N, P, dealias="3/2-rule", precision=prec)
+    got = run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, rt)
+    _check(got, ref, tol)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    ref = oracle.slab.fftn(up, N, P, dealias="3/2-rule", precision=prec)
+    got = run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()] * P, ct)
+    _check(got, ref, tol)
+
+
+@pytest.mark.parametrize("comm", ["Alltoallw", "AlltoallN"])
+@pytest.mark.parametrize("P,P1", [(4, None), (8, None), (8, 2), (16, 4)])
+@pytest.mark.parametrize("alignment", ["X", "Y"])
+@pytest.mark.parametrize("N", [(8, 16, 32), (16, 16, 16)])
+def test_pencil(N, alignment, P, P1, comm):
+    prec = "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.pencil.Geometry(N, P, alignment, P1, comm)
+    zparts = g.P2 if alignment == "X" else g.P1
+    if (N[2] // 2) % zparts or any(n % g.P1 or n % g.P2 for n in N):
+        pytest.skip("illegal decomposition")
+    rng = np.random.default_rng(sum(N) + P + (P1 or 0))
+    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"))
+    kw = dict(alignment=alignment, P1=P1, communication=comm, precision=prec)
+    tol = TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.pencil.fftn(u, N, P, **kw), tol)
+    fu = [_rand_c(rng, s, ct) for s in cshape]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.pencil.ifftn(fu, N, P, dealias=name, **kw), tol)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), oracle.pencil.fftn(up, N, P, dealias="3/2-rule", **kw), tol)
+
+
+def test_pencil_single_precision():
+    N, P, prec = (8, 16, 32), 4, "single"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.pencil.Geometry(N, P, "X", None, "Alltoall")
+    rng = np.random.default_rng(0)
+    d = _desc(D.PENCIL_X, N, P, prec, g.P1, g.P2)
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    ref = oracle.pencil.fftn(u, N, P, alignment="X", precision=prec)
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct)
+    _check(got, ref, TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, got, [g.real_shape()] * P, rt), u, TOL[prec])
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+@pytest.mark.parametrize("N", [(16, 32), (64, 32)])
+def test_line(N, P, prec):
+    if N[1] % (2 * P) or N[0] % P:
+        pytest.skip("illegal decomposition")
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.line.Geometry(N, P)
+    rng = np.random.default_rng(sum(N) + P)
+    d = _desc(D.LINE, N, P, prec)
+    tol = TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct)
+    _check(got, oracle.line.fft2(u, N, P, precision=prec), tol)  # reference pack trick: exact here
+    fu = [_rand_c(rng, s, ct) for s in cshape]
+    modes = [(D.DEALIAS_NONE, None), (D.DEALIAS_3_2, "3/2-rule"), (D.DEALIAS_2_3, "2/3-rule")]
+    for mode, name in modes:
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.line.ifft2(fu, N, P, dealias=name, precision=prec), tol)
+    # 3/2 forward on a reference-test-style input (tests/test_FFT.py:112-156): both semantics agree
+    C0 = np.fft.rfft2(A.astype(np.float64)).astype(ct)
+    C0[-N[0] // 2] = 0
+    c0 = [np.ascontiguousarray(C0[g.complex_local_slice(r)]) for r in range(P)]
+    ap = oracle.line.ifft2(c0, N, P, dealias="3/2-rule", precision=prec)
+    ref = oracle.line.fft2(ap, N, P, dealias="3/2-rule", precision=prec)
+    _check(run_plan(d, 0, D.DEALIAS_3_2, ap, cshape, ct), ref, 4 * tol)
+    # generic padded input: the engine implements plain truncation of the Nyquist column (exact=True)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    ref = oracle.line.fft2(up, N, P, dealias="3/2-rule", precision=prec, exact=(P > 1))
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), ref, tol)
