@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- R2C fftn+ifftn round trip (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port), host cores
+
+A step is one fftn + one ifftn of the workload (default: slab.R2C 1024^3 double -- the north-star
+configuration; it fits one GPU).  `value` is GFLOP/s by the 5*M*log2(M) convention (M = global
+real points) with device-resident arrays; `e2e` is the same through the numpy API with pinned host
+buffers, H2D and D2H inside the timed region.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, N, precision, dealias, kwargs)
+    "slab1024_f64": ("slab", (1024, 1024, 1024), "double", None, {}),
+    "slab1024_f64_32": ("slab", (1024, 1024, 1024), "double", "3/2-rule", {}),
+    "slab512_f64": ("slab", (512, 512, 512), "double", None, {}),
+    "slab256_f32": ("slab", (256, 256, 256), "single", None, {}),
+    "pencilX512_f64": ("pencil", (512, 512, 512), "double", None, dict(alignment="X", P1=2, communication="Alltoallw")),
+    "pencilX1024_f64": ("pencil", (1024, 1024, 1024), "double", None, dict(alignment="X", P1=None, communication="Alltoallw")),
+    "pencilY2048_f32": ("pencil", (2048, 2048, 2048), "single", None, dict(alignment="Y", P1=None, communication="Alltoallw")),
+    "line8192_f32": ("line", (8192, 8192), "single", None, {}),
+}
+METRIC = "R2C fftn+ifftn round-trip GFLOP/s (5*M*log2(M) per transform)"
+UNIT = "GFLOP/s"
+
+
+def flops_roundtrip(shape):
+    M = float(np.prod([float(s) for s in shape]))
+    return 2.0 * 5.0 * M * math.log2(M)
+
+
+def describe(name, P):
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    return {"workload": "%s.R2C N=%s %s fftn+ifftn round trip, dealias=%s" % (kind, "x".join(map(str, N)), prec, dealias),
+            "name": name, "N": list(N), "precision": prec, "dealias": dealias,
+            "decomposition": ("%s P=%d" % (kind, P)) + ("".join(" %s=%s" % kv for kv in sorted(kw.items()))),
+            "l2": "operands >> 126 MB L2 (no flush needed)" if np.prod(N) * 4 > 1 << 30 else "L2 flushed between steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": (float(np.median(sm)) if sm else None), "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port of slab/pencil/line + pocketfft)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(name, budget_s=20.0):
+    """Pick a bounded sample of the workload: same class / precision / dealias, smaller mesh."""
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    if kind == "line":
+        n = 4096
+        return (n, n)
+    n = 256
+    return (n, n, n)
+
+
+def cpu_roundtrip(kind, N, prec, dealias, workers):
+    import oracle
+    oracle.common.set_workers(workers)
+    rt, ct = oracle.common.dtypes(prec)
+    rng = np.random.default_rng(1234)
+    if kind == "line":
+        g = oracle.line.Geometry(N, 1)
+        shape = g.real_shape_padded() if dealias == "3/2-rule" else g.real_shape()
+        u = [rng.random(shape).astype(rt)]
+        t0 = time.perf_counter()
+        fu = oracle.line.fft2(u, N, 1, dealias=dealias, precision=prec)
+        oracle.line.ifft2(fu, N, 1, dealias=dealias, precision=prec)
+        return time.perf_counter() - t0, shape
+    g = oracle.slab.Geometry(N, 1)
+    shape = g.real_shape_padded() if dealias == "3/2-rule" else g.real_shape()
+    u = [rng.random(shape).astype(rt)]
+    t0 = time.perf_counter()
+    fu = oracle.slab.fftn(u, N, 1, dealias=dealias, precision=prec)
+    oracle.slab.ifftn(fu, N, 1, dealias=dealias, precision=prec)
+    return time.perf_counter() - t0, shape
+
+
+def cpu_baseline(name, reps=1):
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    Ns = cpu_sample(name)
+    cpu_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)  # warm-up (imports, plans)
+    # grow the sample while it stays within ~10-30 s of work
+    best = None
+    t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
+    if kind != "line" and t < 4.0 and Ns[0] < N[0]:
+        Ns = tuple(2 * n for n in Ns)
+        t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
+    best = t
+    for _ in range(reps - 1):
+        t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
+        best = min(best, t)
+    return {"value": flops_roundtrip(shape) / best / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d), %s %s "
+                      "round trip, %.2f s" % (kind, cores, "x".join(map(str, Ns)), prec, best),
+            "seconds": best, "N": list(Ns)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    Ns = cpu_sample(name)
+    cpu_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)
+    t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
+    budget = 150.0
+    if kind != "line" and t * 8 * (args.steps + args.warmup) < budget and Ns[0] < N[0]:
+        Ns = tuple(2 * n for n in Ns)
+    for _ in range(args.warmup):
+        cpu_roundtrip(kind, Ns, prec, dealias, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = flops_roundtrip(shape) / dt / 1e9
+    cfg = describe(name, 1)
+    sample = ("oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d) on a bounded sample "
+              "%s %s of the %s workload" % (kind, cores, "x".join(map(str, Ns)), prec, "x".join(map(str, N))))
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def make_transform(m, comm, name):
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    Nn = np.array(N, dtype=int)
+    L = np.array([2 * np.pi] * len(N))
+    if kind == "slab":
+        return m.Slab_R2C(Nn, L, comm, prec)
+    if kind == "pencil":
+        return m.Pencil_R2C(Nn, L, comm, prec, **kw)
+    return m.Line_R2C(Nn, L, comm, prec)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mpifft4py_b200 as m
+    from mpifft4py_b200.comm import SelfComm, world
+
+    P = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if P > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = world()
+    else:
+        comm = SelfComm()
+    name = args.workload
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    F = make_transform(m, comm, name)
+    fwd, inv = (F.fft2, F.ifft2) if kind == "line" else (F.fftn, F.ifftn)
+    rshape = tuple(int(s) for s in (F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()))
+    cshape = tuple(int(s) for s in F.complex_shape())
+    rdt = torch.float64 if prec == "double" else torch.float32
+    cdt = torch.complex128 if prec == "double" else torch.complex64
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    u = torch.rand(rshape, dtype=rdt, device="cuda", generator=g)
+    fu = torch.empty(cshape, dtype=cdt, device="cuda")
+    u2 = torch.empty_like(u)
+    gshape = tuple(int(1.5 * n) if dealias == "3/2-rule" else n for n in N)
+    flops = flops_roundtrip(gshape)
+    small = np.prod(N) * 4 <= 1 << 30
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if small else None
+
+    def barrier():
+        if P > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        fwd(u, fu, dealias)
+        inv(fu, u2, dealias)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st = torch.cuda.current_stream()
+    times = []
+    barrier()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(args.steps):
+            step()
+        e1.record(st)
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            step()
+            e1.record(st)
+            barrier()
+            total_ms += e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if P > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tms.item()) / args.steps
+    value = flops / (ms_per_step * 1e-3) / 1e9
+    k1, x1 = F.last_launches()
+    err = (torch.linalg.vector_norm(u2 - u) / torch.linalg.vector_norm(u)).item()
+
+    # ---- roofline: per-pass device times from events on the launching stream --------------------
+    F.set_timing(True)
+    acc = {}
+    reps = 3
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        fwd(u, fu, dealias)
+        torch.cuda.synchronize()
+        for i, s in enumerate(F.last_steps()):
+            acc.setdefault(("fwd", i, s[0], s[3]), [0.0, s[2]])[0] += s[1]
+        if flush is not None:
+            flush.fill_(1)
+        inv(fu, u2, dealias)
+        torch.cuda.synchronize()
+        for i, s in enumerate(F.last_steps()):
+            acc.setdefault(("inv", i, s[0], s[3]), [0.0, s[2]])[0] += s[1]
+    F.set_timing(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    passes = []
+    for (d, i, ty, ln), (ms, by) in sorted(acc.items()):
+        ms /= reps
+        passes.append({"dir": d, "step": i, "type": ty, "len": ln, "ms": round(ms, 4), "bytes": by,
+                       "GBps": round(by / (ms * 1e-3) / 1e9, 1) if ms > 0 else None})
+    ffts = [p for p in passes if p["type"] != "exchange"]
+    dom = max(ffts, key=lambda p: p["ms"])
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(name, {}).get("%s_%s_%d" % (dom["dir"], dom["type"], dom["len"]))
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": "%s %s n=%d (step %d)" % (dom["dir"], dom["type"], dom["len"], dom["step"]),
+                "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(dom["GBps"] / hbm_peak, 4),
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": dom["bytes"], "ms": dom["ms"],
+                "passes": passes,
+                "sum_fft_ms": round(sum(p["ms"] for p in ffts), 4),
+                "sum_exchange_ms": round(sum(p["ms"] for p in passes if p["type"] == "exchange"), 4)}
+    xs = [p for p in passes if p["type"] == "exchange" and p["ms"] > 0]
+    if xs:
+        roofline["nvlink"] = {"achieved_GBps_per_direction": round(sum(p["bytes"] for p in xs) / sum(p["ms"] for p in xs) / 1e6, 1),
+                              "peak": 770.0, "unit": "GB/s", "peak_source": "measured peer copy (B200_PROFILING.md)"}
+
+    # ---- e2e: numpy API, pinned host buffers, H2D + D2H inside the timed region -------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            del u2
+            torch.cuda.empty_cache()
+            rnp, cnp = (np.float64, np.complex128) if prec == "double" else (np.float32, np.complex64)
+            hu = m.empty(rshape, dtype=rnp)
+            hf = m.empty(cshape, dtype=cnp)
+            hu[...] = np.random.default_rng(1234 + rank).random(rshape[-1], dtype=np.float64).astype(rnp)  # broadcast rows
+            nst = max(1, min(args.steps, args.e2e_steps))
+            fwd(hu, hf, dealias)
+            inv(hf, hu, dealias)  # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nst):
+                fwd(hu, hf, dealias)   # H2D(u) + transform + D2H(fu)
+                inv(hf, hu, dealias)   # H2D(fu) + transform + D2H(u)
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / nst], dtype=torch.float64, device="cuda")
+            if P > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            nb = hu.nbytes + hf.nbytes
+            e2e = {"value": flops / float(dt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb),
+                   "d2h_bytes_per_step": int(nb), "ms_per_step": float(dt.item()) * 1e3, "steps": nst,
+                   "api": "numpy arrays in pinned host memory through %s.fftn/ifftn" % type(F).__name__}
+        except Exception as e:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+
+    cpu = None
+    if rank == 0 and P == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(name)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+
+    if P > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": describe(name, P),
+               "roundtrip_rel_l2": err, "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
+               "kernels_per_transform": int(k1), "nccl_groups_per_transform": int(x1),
+               "roofline": roofline, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
+               "workspace_bytes": F.workspace_bytes()}
+        print(json.dumps(out))
+    if P > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="slab1024_f64", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world_size:
+        if world_size == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

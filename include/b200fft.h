@@ -111,6 +111,12 @@ typedef struct {
   b200fft_side_t cside;
 } b200fft_rows_desc_t;
 
+/* Stream-ordered copy with cudaMemcpyDefault (either side may be host memory; pinned host memory
+ * is copied by DMA without staging).  Used by the Python layer when callers pass numpy arrays,
+ * which is how every reference caller passes data (host arrays, slab.py:214,349). */
+B200FFT_API int b200fft_copy(void* dst, const void* src, size_t bytes, void* stream);
+B200FFT_API int b200fft_stream_sync(void* stream);
+
 B200FFT_API int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
@@ -162,6 +168,10 @@ B200FFT_API int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, in
 /* device time of the exchange phases of the last exec, if timing was enabled (ms; <0 if not) */
 B200FFT_API int b200fft_plan_set_timing(b200fft_plan_t plan, int on);
 B200FFT_API int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms);
+/* per-step record of the last exec (timing on): type 0 strided C2C, 1 R2C, 2 C2R, 3 exchange; device
+ * time in ms; algorithmic bytes = operand read once + result written once (SURVEY.md section 8d;
+ * for an exchange: bytes sent to other ranks); transform length n.  Returns the step count in *n. */
+B200FFT_API int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len);
 
 #ifdef __cplusplus
 }

@@ -172,6 +172,8 @@ struct b200fft_plan {
   bool ev_made = false;
   float last_fft_ms = -1.f, last_exch_ms = -1.f;
   std::vector<std::pair<int, int>> ev_marks;  // (event index start, is_exchange)
+  std::vector<int> st_type, st_len;
+  std::vector<double> st_bytes;
 };
 
 namespace {
@@ -329,6 +331,9 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   pl->last_kernels = 0;
   pl->last_exch = 0;
   pl->ev_marks.clear();
+  pl->st_type.clear();
+  pl->st_len.clear();
+  pl->st_bytes.clear();
   int evi = 0;
   if (pl->timing && !pl->ev_made) {
     for (int i = 0; i < 32; ++i) cudaEventCreate(&pl->ev[i]);
@@ -370,6 +375,15 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       pl->last_exch++;
     }
     if (rc) return rc;
+    {  // algorithmic bytes of the step: operand read once, result written once
+      double bytes = 0;
+      if (s.type == ST_STRIDED) bytes = (double)s.B * s.J * ((double)s.in.nphys + (double)s.out.nphys) * (double)csz;
+      else if (s.type == ST_R2C || s.type == ST_C2R) bytes = (double)s.rows * ((double)s.n * rsz + (double)s.nk * csz);
+      else for (int q = 0; q < s.npeers; ++q) if (q != s.me) bytes += (double)s.scnt[q] * csz;
+      pl->st_type.push_back((int)s.type);
+      pl->st_len.push_back(s.type == ST_EXCH ? s.npeers : s.n);
+      pl->st_bytes.push_back(bytes);
+    }
     if (pl->timing && evi + 2 <= 32) {
       cudaEventRecord(pl->ev[evi + 1], st);
       pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
@@ -391,6 +405,20 @@ int b200fft_version(void) { return 100; }
 const char* b200fft_last_error(void) { return g_err.c_str(); }
 
 int b200fft_supported_length(int n) { return plan_exists(n) ? 1 : 0; }
+
+int b200fft_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  if (!dst || !src) return fail(B200FFT_ERR_ARG, "null pointer in copy");
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
+  return 0;
+}
+
+int b200fft_stream_sync(void* stream) {
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  return 0;
+}
 
 int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream) {
   if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
@@ -515,6 +543,27 @@ int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchan
   }
   if (fft_ms) *fft_ms = f;
   if (exchange_ms) *exchange_ms = x;
+  return 0;
+}
+
+int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len) {
+  if (!plan || !n) return fail(B200FFT_ERR_ARG, "null argument");
+  const int cnt = (int)plan->st_type.size();
+  *n = cnt;
+  for (int i = 0; i < cnt && i < max; ++i) {
+    if (type) type[i] = plan->st_type[i];
+    if (bytes) bytes[i] = plan->st_bytes[i];
+    if (len) len[i] = plan->st_len[i];
+    if (ms) {
+      ms[i] = -1.f;
+      if (plan->timing && i < (int)plan->ev_marks.size()) {
+        const int e0 = plan->ev_marks[i].first;
+        cudaEventSynchronize(plan->ev[e0 + 1]);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, plan->ev[e0], plan->ev[e0 + 1]) == cudaSuccess) ms[i] = t;
+      }
+    }
+  }
   return 0;
 }
 

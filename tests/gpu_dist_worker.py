@@ -1,0 +1,166 @@
+"""Multi-GPU worker (one process per GPU, NCCL): every class / alignment / dealias mode against the
+oracle on seeded inputs, plus the reference's golden vectors.  Launched by torch.distributed.run
+from tests/test_gpu_multi.py (or directly under gpurun --gpus N)."""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mpifft4py_b200 as m  # noqa: E402
+import oracle  # noqa: E402
+from mpifft4py_b200.comm import world  # noqa: E402
+
+TOL = {"double": 1e-12, "single": 1e-5}
+L3 = np.array([2 * np.pi] * 3)
+
+
+def rand_c(rng, shape, ct):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(ct)
+
+
+def check(name, got, ref, tol, rank):
+    err = oracle.rel_l2(got, ref)
+    if not (err <= tol) or got.shape != ref.shape:
+        raise SystemExit("rank %d: %s: rel L2 %.3e > %.1e (shapes %r %r)" % (rank, name, err, tol, got.shape, ref.shape))
+
+
+def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None):
+    P, r = comm.Get_size(), comm.Get_rank()
+    rt, ct = oracle.common.dtypes(prec)
+    tol = TOL[prec]
+    rng = np.random.default_rng(99)  # same stream on every rank: global arrays are identical
+    if kind == "slab":
+        F = m.Slab_R2C(np.array(N), L3, comm, prec, communication=communication or "Alltoallw")
+        g = oracle.slab.Geometry(N, P)
+        cshape = [g.complex_shape()] * P
+        fwd = lambda u, d=None: oracle.slab.fftn(u, N, P, dealias=d, precision=prec)
+        inv = lambda f, d=None: oracle.slab.ifftn(f, N, P, dealias=d, precision=prec)
+    else:
+        F = m.Pencil_R2C(np.array(N), L3, comm, prec, P1=P1, communication=communication, alignment=alignment)
+        g = oracle.pencil.Geometry(N, P, alignment, P1, communication)
+        cshape = [g.complex_shape(q) for q in range(P)]
+        kw = dict(alignment=alignment, P1=P1, communication=communication, precision=prec)
+        fwd = lambda u, d=None: oracle.pencil.fftn(u, N, P, dealias=d, **kw)
+        inv = lambda f, d=None: oracle.pencil.ifftn(f, N, P, dealias=d, **kw)
+    tag = "%s %s %s %s P=%d" % (kind, alignment, communication, prec, P)
+    assert tuple(int(s) for s in F.complex_shape()) == tuple(cshape[r])
+    A = rng.random(N).astype(rt)
+    u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
+    c = F.fftn(u[r], np.zeros(cshape[r], dtype=ct))
+    check(tag + " fftn", c, fwd(u)[r], tol, r)
+    a = F.ifftn(c, np.zeros(F.real_shape(), dtype=rt))
+    check(tag + " roundtrip", a, u[r], tol, r)
+    fu = [rand_c(rng, s, ct) for s in cshape]
+    for d in (None, "2/3-rule", "3/2-rule"):
+        shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
+        got = F.ifftn(fu[r], np.zeros(shp, dtype=rt), dealias=d)
+        check(tag + " ifftn %s" % d, got, inv(fu, d)[r], tol, r)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    got = F.fftn(up[r], np.zeros(cshape[r], dtype=ct), dealias="3/2-rule")
+    check(tag + " fftn 3/2", got, fwd(up, "3/2-rule")[r], tol, r)
+    # CUDA tensors in place of numpy arrays
+    tu = torch.from_numpy(u[r]).cuda()
+    tf = torch.zeros(tuple(int(s) for s in cshape[r]), dtype=torch.complex128 if prec == "double" else torch.complex64,
+                     device="cuda")
+    F.fftn(tu, tf)
+    check(tag + " fftn tensors", tf.cpu().numpy(), c, 1e-15, r)
+
+
+def run_line(comm, N, prec):
+    P, r = comm.Get_size(), comm.Get_rank()
+    rt, ct = oracle.common.dtypes(prec)
+    tol = TOL[prec]
+    rng = np.random.default_rng(17)
+    F = m.Line_R2C(np.array(N), L3[:2], comm, prec)
+    g = oracle.line.Geometry(N, P)
+    cshape = [g.complex_shape(q) for q in range(P)]
+    A = rng.random(N).astype(rt)
+    u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
+    c = F.fft2(u[r], np.zeros(cshape[r], dtype=ct))
+    check("line fft2", c, oracle.line.fft2(u, N, P, precision=prec)[r], tol, r)
+    check("line roundtrip", F.ifft2(c, np.zeros(F.real_shape(), dtype=rt)), u[r], tol, r)
+    fu = [rand_c(rng, s, ct) for s in cshape]
+    for d in (None, "2/3-rule", "3/2-rule"):
+        shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
+        got = F.ifft2(fu[r], np.zeros(shp, dtype=rt), dealias=d)
+        check("line ifft2 %s" % d, got, oracle.line.ifft2(fu, N, P, dealias=d, precision=prec)[r], tol, r)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    got = F.fft2(up[r], np.zeros(cshape[r], dtype=ct), dealias="3/2-rule")
+    check("line fft2 3/2", got, oracle.line.fft2(up, N, P, dealias="3/2-rule", precision=prec, exact=True)[r], tol, r)
+
+
+def run_golden(comm):
+    P, r = comm.Get_size(), comm.Get_rank()
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
+        z = np.load(path)
+        meta = json.loads(str(z["meta"]))
+        if meta["P"] != P:
+            continue
+        prec = meta["precision"]
+        tol = TOL[prec]
+        N = meta["N"]
+        if meta["kind"] == "slab":
+            F = m.Slab_R2C(np.array(N), L3, comm, prec, communication=meta["communication"])
+            fwd, inv = F.fftn, F.ifftn
+        elif meta["kind"] == "pencil":
+            F = m.Pencil_R2C(np.array(N), L3, comm, prec, P1=meta["P1"], communication=meta["communication"],
+                             alignment=meta["alignment"])
+            fwd, inv = F.fftn, F.ifftn
+        else:
+            F = m.Line_R2C(np.array(N), L3[:2], comm, prec)
+            fwd, inv = F.fft2, F.ifft2
+        info = meta["ranks"][r]
+        rs = tuple(slice(*s) for s in info["real_local_slice"])
+        rps = tuple(slice(*s) for s in info["real_local_slice_padded"])
+        cs = tuple(slice(*s) for s in info["complex_local_slice"])
+        A, Cg = z["A"], z["C"]
+        name = os.path.basename(path)
+        c = fwd(np.ascontiguousarray(A[rs]), np.zeros(Cg[cs].shape, dtype=Cg.dtype))
+        check(name + " C", c, Cg[cs], tol, r)
+        check(name + " A2", inv(np.ascontiguousarray(Cg[cs]), np.zeros(A[rs].shape, dtype=A.dtype)), z["A2"][rs], tol, r)
+        Cin = Cg.copy()
+        if meta["kind"] == "line":
+            Cin[-N[0] // 2] = 0
+        Ap = z["Ap"]
+        check(name + " Ap", inv(np.ascontiguousarray(Cin[cs]), np.zeros(Ap[rps].shape, dtype=Ap.dtype), dealias="3/2-rule"),
+              Ap[rps], tol, r)
+        check(name + " Cp", fwd(np.ascontiguousarray(Ap[rps]), np.zeros(Cg[cs].shape, dtype=Cg.dtype), dealias="3/2-rule"),
+              z["Cp"][cs], 10 * tol, r)
+        if meta["has23"]:
+            check(name + " A23", inv(np.ascontiguousarray(Cg[cs]), np.zeros(A[rs].shape, dtype=A.dtype), dealias="2/3-rule"),
+                  z["A23"][rs], tol, r)
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = world()
+    P = comm.Get_size()
+    N = (32, 64, 128)
+    for prec in ("double", "single"):
+        run_3d(comm, "slab", N, prec)
+        run_line(comm, (64, 128), prec)
+    run_3d(comm, "slab", N, "double", communication="Alltoall")
+    if P >= 4:
+        grids = [None] + ([2] if P == 8 else [])
+        for al in "XY":
+            for P1 in grids:
+                for cm in ("Alltoall", "Alltoallw", "AlltoallN"):
+                    run_3d(comm, "pencil", N, "double", al, P1, cm)
+            run_3d(comm, "pencil", N, "single", al, None, "Alltoall")
+    run_golden(comm)
+    comm.barrier()
+    dist.destroy_process_group()
+    print("GPU_WORKER_OK", comm.Get_rank() if False else local)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,7 +1,11 @@
-"""CPU emulation of the CUDA FFT kernels (same phase bodies, g++-compiled) against numpy.fft.
+"""The fused FFT passes against numpy.fft, on two backends:
 
-Covers every radix plan in both precisions plus each fused index map.  The emulator is test
-infrastructure; the GPU parity tests (-m gpu) run the real kernels through the C-ABI."""
+  emu : the CPU emulator (same phase bodies, g++-compiled, tests/emu) -- runs in `-m "not gpu"`;
+  gpu : the real sm_100a kernels through the C ABI (b200fft_exec_strided / _r2c / _c2r) -- `-m gpu`.
+        Test arrays live in page-locked host memory, which the device addresses directly (UVA), so
+        the very same descriptors are used on both backends.
+
+Covers every radix plan in both precisions plus each fused index map."""
 import ctypes as C
 
 import numpy as np
@@ -9,6 +13,53 @@ import pytest
 
 import emu_util
 from mpifft4py_b200 import _cdefs as D
+
+
+class _Emu(object):
+    name = "emu"
+
+    def arr(self, a):
+        return np.ascontiguousarray(a)
+
+    def zeros(self, shape, dtype):
+        return np.zeros(shape, dtype=dtype)
+
+    def call(self, fn, desc):
+        return getattr(emu_util.load(), "emu_" + fn)(C.byref(desc))
+
+
+class _Gpu(object):
+    name = "gpu"
+
+    def __init__(self):
+        from mpifft4py_b200 import _lib, mpibase
+        import torch
+        assert torch.cuda.is_available()
+        torch.cuda.init()
+        self.L = _lib.lib()
+        self.check = _lib.check
+        self.mpibase = mpibase
+
+    def arr(self, a):
+        out = self.mpibase.empty(a.shape, dtype=a.dtype)  # pinned: device-addressable
+        out[...] = a
+        return out
+
+    def zeros(self, shape, dtype):
+        return self.mpibase.zeros(shape, dtype=dtype)
+
+    def call(self, fn, desc):
+        rc = getattr(self.L, "b200fft_" + fn)(C.byref(desc), None)
+        if rc == 0:
+            self.check(self.L.b200fft_stream_sync(None))
+        else:
+            print(self.L.b200fft_last_error())
+        return rc
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)], scope="module")
+def be(request):
+    return _Emu() if request.param == "emu" else _Gpu()
 
 LENS2 = [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
 LENS3 = [3, 6, 12, 24, 48, 96, 192, 384, 768, 1536, 3072, 6144, 12288]
@@ -26,9 +77,8 @@ def _cplx(rng, shape, ct):
     return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(ct)
 
 
-def run_strided(x, n, out, inverse=0, scale=1.0, in_side=None, out_side=None, fold=0, mask=None,
+def run_strided(be, x, n, out, inverse=0, scale=1.0, in_side=None, out_side=None, fold=0, mask=None,
                 B=None, J=None, prec=None):
-    lib = emu_util.load()
     d = D.StridedDesc()
     ref = x if x is not None else out
     if prec is None:
@@ -44,112 +94,112 @@ def run_strided(x, n, out, inverse=0, scale=1.0, in_side=None, out_side=None, fo
     d.out = out_side if out_side is not None else D.plain_side(_ptr(out), out.shape[1] * out.shape[2],
                                                                out.shape[2], n)
     d.mask = mask if mask is not None else D.no_mask()
-    rc = lib.emu_exec_strided(C.byref(d))
+    rc = be.call("exec_strided", d)
     assert rc == 0, rc
     return out
 
 
 @pytest.mark.parametrize("prec", ["d", "s"])
 @pytest.mark.parametrize("n", LENS2 + LENS3)
-def test_strided_c2c_all_plans(n, prec):
+def test_strided_c2c_all_plans(be, n, prec):
     ct = np.complex128 if prec == "d" else np.complex64
     tol = 2e-15 * max(1, np.log2(n)) if prec == "d" else 6e-7 * max(1, np.log2(n))
     rng = np.random.default_rng(n)
     J = 5 if n > 512 else 19  # not a multiple of the tile width: exercises dead lanes
     B = 1 if n > 512 else 2
-    x = _cplx(rng, (B, n, J), ct)
-    out = np.zeros_like(x)
-    run_strided(x, n, out)
+    x = be.arr(_cplx(rng, (B, n, J), ct))
+    out = be.zeros(x.shape, x.dtype)
+    run_strided(be, x, n, out)
     assert _rel(out, np.fft.fft(x.astype(np.complex128), axis=1)) < tol
     if n <= 2048:
-        out2 = np.zeros_like(x)
-        run_strided(out, n, out2, inverse=1, scale=1.0 / n)
+        out2 = be.zeros(x.shape, x.dtype)
+        run_strided(be, out, n, out2, inverse=1, scale=1.0 / n)
         assert _rel(out2, x) < 2 * tol
 
 
 @pytest.mark.parametrize("n", [8, 64, 1024, 12, 96, 1536])
-def test_strided_in_place(n):
+def test_strided_in_place(be, n):
     rng = np.random.default_rng(1)
-    x = _cplx(rng, (3, n, 7), np.complex128)
+    x = be.arr(_cplx(rng, (3, n, 7), np.complex128))
     ref = np.fft.fft(x, axis=1)
-    run_strided(x, n, x)
+    run_strided(be, x, n, x)
     assert _rel(x, ref) < 1e-14
 
 
 @pytest.mark.parametrize("N", [8, 32, 64, 256, 1024])
-def test_pad_on_load_and_truncate_fold_on_store(N):
+def test_pad_on_load_and_truncate_fold_on_store(be, N):
     """copy_to_padded + ifft and fft + copy_from_padded (slab.py:516-533) in one pass each."""
     rng = np.random.default_rng(N)
     n = 3 * N // 2
     B, J = 2, 6
-    fu = _cplx(rng, (B, N, J), np.complex128)
+    fu = be.arr(_cplx(rng, (B, N, J), np.complex128))
     # inverse with zero padding and the reference's padsize scaling
-    up = np.zeros((B, n, J), dtype=np.complex128)
-    run_strided(fu, n, up, inverse=1, scale=1.5 / n,
+    up = be.zeros((B, n, J), np.complex128)
+    run_strided(be, fu, n, up, inverse=1, scale=1.5 / n,
                 in_side=D.plain_side(_ptr(fu), N * J, J, N))
     fp = np.zeros((B, n, J), dtype=np.complex128)
     fp[:, :N // 2] = fu[:, :N // 2]
     fp[:, -(N // 2):] = fu[:, N // 2:]
     assert _rel(up, np.fft.ifft(fp * 1.5, axis=1)) < 1e-14
     # forward with truncation + Nyquist fold
-    x = _cplx(rng, (B, n, J), np.complex128)
+    x = be.arr(_cplx(rng, (B, n, J), np.complex128))
     X = np.fft.fft(x, axis=1)
     ref = np.zeros((B, N, J), dtype=np.complex128)
     ref[:, :N // 2 + 1] = X[:, :N // 2 + 1]
     ref[:, N // 2:] += X[:, -(N // 2):]
-    got = np.zeros_like(ref)
-    run_strided(x, n, got, scale=1 / 1.5, fold=1, out_side=D.plain_side(_ptr(got), N * J, J, N))
+    got = be.zeros(ref.shape, ref.dtype)
+    run_strided(be, x, n, got, scale=1 / 1.5, fold=1, out_side=D.plain_side(_ptr(got), N * J, J, N))
     assert _rel(got, ref / 1.5) < 1e-14
     # line.py:189 variant (P == 1): mode -N/2 only, no fold
     ref2 = np.ascontiguousarray(X[:, np.r_[0:N // 2, n - N // 2:n]])
-    got2 = np.zeros_like(ref2)
-    run_strided(x, n, got2, fold=2, out_side=D.plain_side(_ptr(got2), N * J, J, N))
+    got2 = be.zeros(ref2.shape, ref2.dtype)
+    run_strided(be, x, n, got2, fold=2, out_side=D.plain_side(_ptr(got2), N * J, J, N))
     assert _rel(got2, ref2) < 1e-14
 
 
 @pytest.mark.parametrize("P,n", [(2, 16), (4, 64), (8, 1024), (4, 96)])
-def test_peer_chunk_store_and_gather_load(P, n):
+def test_peer_chunk_store_and_gather_load(be, P, n):
     """Store into the per-peer send layout (U_mpi of slab.py:394-403 / subarraysB :206-209), gather
     from the receive layout on load (transpose_Uc, maths.pyx:21-31)."""
     rng = np.random.default_rng(P * n)
     B, J = 3, 5
     c = n // P
-    x = _cplx(rng, (B, n, J), np.complex128)
+    x = be.arr(_cplx(rng, (B, n, J), np.complex128))
     X = np.fft.fft(x, axis=1)
-    blocks = [np.zeros((B, c, J), dtype=np.complex128) for _ in range(P)]
+    blocks = [be.zeros((B, c, J), np.complex128) for _ in range(P)]
     side = D.chunked_side([_ptr(b) for b in blocks], [c * J] * P, [J] * P, c, n)
-    run_strided(x, n, None, out_side=side)
+    run_strided(be, x, n, None, out_side=side)
     for p in range(P):
         assert _rel(blocks[p], X[:, p * c:(p + 1) * c]) < 1e-14
     # gather: the same blocks as the receive side of the next pass
-    y = np.zeros_like(x)
-    run_strided(None, n, y, inverse=1, scale=1.0 / n, in_side=side, B=B, J=J)
+    y = be.zeros(x.shape, x.dtype)
+    run_strided(be, None, n, y, inverse=1, scale=1.0 / n, in_side=side, B=B, J=J)
     assert _rel(y, x) < 1e-14
 
 
-def test_uneven_last_chunk_with_padding():
+def test_uneven_last_chunk_with_padding(be):
     """Padded + chunked together: slab 3/2 inverse y pass gathers N1 = P*Np1 physical rows from P
     peers and pads to 1.5*N1 (slab.py:332-338)."""
     rng = np.random.default_rng(5)
     P, N, J, B = 4, 32, 3, 2
     n = 48
     c = N // P
-    blocks = [_cplx(rng, (B, c, J), np.complex128) for _ in range(P)]
+    blocks = [be.arr(_cplx(rng, (B, c, J), np.complex128)) for _ in range(P)]
     full = np.concatenate(blocks, axis=1)
     fp = np.zeros((B, n, J), dtype=np.complex128)
     fp[:, :N // 2] = full[:, :N // 2]
     fp[:, -(N // 2):] = full[:, N // 2:]
     side = D.chunked_side([_ptr(b) for b in blocks], [c * J] * P, [J] * P, c, N)
-    out = np.zeros((B, n, J), dtype=np.complex128)
-    run_strided(None, n, out, inverse=1, scale=1.0 / n, in_side=side, B=B, J=J)
+    out = be.zeros((B, n, J), np.complex128)
+    run_strided(be, None, n, out, inverse=1, scale=1.0 / n, in_side=side, B=B, J=J)
     assert _rel(out, np.fft.ifft(fp, axis=1)) < 1e-14
 
 
-def test_mask_bands():
+def test_mask_bands(be):
     """2/3-rule mask (slab.py:191-197) folded into the load of the first inverse pass."""
     rng = np.random.default_rng(9)
     N0, N1, Nf = 16, 8, 9  # pass over axis 0 of (N0, N1*Nf): i = kx, j = (ky, kz)
-    fu = _cplx(rng, (1, N0, N1 * Nf), np.complex128)
+    fu = be.arr(_cplx(rng, (1, N0, N1 * Nf), np.complex128))
     kx = np.fft.fftfreq(N0, 1. / N0)
     ky = np.fft.fftfreq(N1, 1. / N1)
     kz = np.fft.rfftfreq(16, 1. / 16)
@@ -164,13 +214,12 @@ def test_mask_bands():
     m.jdiv = Nf
     m.jq_off, m.jq_lo, m.jq_hi = 0, lo[1], N1 - lo[1]
     m.jr_off, m.jr_lo, m.jr_hi = 0, lo[2], 1 << 30
-    out = np.zeros_like(fu)
-    run_strided(fu, N0, out, inverse=1, scale=1.0 / N0, mask=m)
+    out = be.zeros(fu.shape, fu.dtype)
+    run_strided(be, fu, N0, out, inverse=1, scale=1.0 / N0, mask=m)
     assert _rel(out, ref) < 1e-14
 
 
-def run_rows(fn, real, cplx_side, n, rows, nk, prec, scale=1.0):
-    lib = emu_util.load()
+def run_rows(be, fn, real, cplx_side, n, rows, nk, prec, scale=1.0):
     d = D.RowsDesc()
     d.precision = prec
     d.n = n
@@ -180,52 +229,52 @@ def run_rows(fn, real, cplx_side, n, rows, nk, prec, scale=1.0):
     d.real_base = _ptr(real)
     d.rpitch = real.shape[1]
     d.cside = cplx_side
-    rc = getattr(lib, fn)(C.byref(d))
+    rc = be.call(fn, d)
     assert rc == 0
 
 
 @pytest.mark.parametrize("prec", ["d", "s"])
 @pytest.mark.parametrize("h", [2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 256, 384, 512, 768, 1024,
                                1536, 2048, 8192, 12288])
-def test_rows_r2c_c2r(h, prec):
+def test_rows_r2c_c2r(be, h, prec):
     n = 2 * h
     rt, ct = (np.float64, np.complex128) if prec == "d" else (np.float32, np.complex64)
     pr = D.DOUBLE if prec == "d" else D.SINGLE
     tol = 3e-15 * max(1, np.log2(n)) if prec == "d" else 8e-7 * max(1, np.log2(n))
     rng = np.random.default_rng(h)
     rows = 3 if h > 512 else 11
-    x = rng.standard_normal((rows, n)).astype(rt)
-    X = np.zeros((rows, h + 1), dtype=ct)
-    run_rows("emu_exec_r2c", x, D.plain_side(_ptr(X), h + 1, 1, h + 1), n, rows, h + 1, pr)
+    x = be.arr(rng.standard_normal((rows, n)).astype(rt))
+    X = be.zeros((rows, h + 1), ct)
+    run_rows(be, "exec_r2c", x, D.plain_side(_ptr(X), h + 1, 1, h + 1), n, rows, h + 1, pr)
     ref = np.fft.rfft(x.astype(np.float64), axis=1)
     assert _rel(X, ref) < tol
     # C2R of an arbitrary (non-Hermitian-clean) spectrum: imag of DC / Nyquist must be ignored
-    Y = _cplx(rng, (rows, h + 1), ct)
-    y = np.zeros((rows, n), dtype=rt)
-    run_rows("emu_exec_c2r", y, D.plain_side(_ptr(Y), h + 1, 1, h + 1), n, rows, h + 1, pr, scale=1.0 / n)
+    Y = be.arr(_cplx(rng, (rows, h + 1), ct))
+    y = be.zeros((rows, n), rt)
+    run_rows(be, "exec_c2r", y, D.plain_side(_ptr(Y), h + 1, 1, h + 1), n, rows, h + 1, pr, scale=1.0 / n)
     assert _rel(y, np.fft.irfft(Y.astype(np.complex128), n=n, axis=1)) < 2 * tol
 
 
 @pytest.mark.parametrize("N", [8, 32, 256])
-def test_rows_truncate_and_zero_pad(N):
+def test_rows_truncate_and_zero_pad(be, N):
     """3/2-rule z pass: R2C on 1.5N keeps Nf modes (slab.py:535); C2R pads Nf modes to 1.5N/2+1."""
     n = 3 * N // 2
     Nf = N // 2 + 1
     rng = np.random.default_rng(N)
     rows = 5
-    x = rng.standard_normal((rows, n))
-    X = np.zeros((rows, Nf), dtype=np.complex128)
-    run_rows("emu_exec_r2c", x, D.plain_side(_ptr(X), Nf, 1, Nf), n, rows, Nf, D.DOUBLE)
+    x = be.arr(rng.standard_normal((rows, n)))
+    X = be.zeros((rows, Nf), np.complex128)
+    run_rows(be, "exec_r2c", x, D.plain_side(_ptr(X), Nf, 1, Nf), n, rows, Nf, D.DOUBLE)
     assert _rel(X, np.fft.rfft(x, axis=1)[:, :Nf]) < 1e-14
-    Y = _cplx(rng, (rows, Nf), np.complex128)
-    y = np.zeros((rows, n))
-    run_rows("emu_exec_c2r", y, D.plain_side(_ptr(Y), Nf, 1, Nf), n, rows, Nf, D.DOUBLE, scale=1.0 / n)
+    Y = be.arr(_cplx(rng, (rows, Nf), np.complex128))
+    y = be.zeros((rows, n), np.float64)
+    run_rows(be, "exec_c2r", y, D.plain_side(_ptr(Y), Nf, 1, Nf), n, rows, Nf, D.DOUBLE, scale=1.0 / n)
     Yp = np.zeros((rows, n // 2 + 1), dtype=np.complex128)
     Yp[:, :Nf] = Y
     assert _rel(y, np.fft.irfft(Yp, n=n, axis=1)) < 1e-14
 
 
-def test_rows_uneven_kz_chunks():
+def test_rows_uneven_kz_chunks(be):
     """pencil z pass: kz split over P2 peers, the last one carrying the Nyquist plane
     (pencil.py:80-90 _distribution; subarrays2B :240-244)."""
     rng = np.random.default_rng(3)
@@ -233,13 +282,13 @@ def test_rows_uneven_kz_chunks():
     Nf = n // 2 + 1
     c = (n // 2) // P2
     lens = [c] * (P2 - 1) + [c + 1]
-    x = rng.standard_normal((rows, n))
-    blocks = [np.zeros((rows, l), dtype=np.complex128) for l in lens]
+    x = be.arr(rng.standard_normal((rows, n)))
+    blocks = [be.zeros((rows, l), np.complex128) for l in lens]
     side = D.chunked_side([_ptr(b) for b in blocks], lens, [1] * P2, c, Nf)
-    run_rows("emu_exec_r2c", x, side, n, rows, Nf, D.DOUBLE)
+    run_rows(be, "exec_r2c", x, side, n, rows, Nf, D.DOUBLE)
     X = np.fft.rfft(x, axis=1)
     for p in range(P2):
         assert _rel(blocks[p], X[:, p * c:p * c + lens[p]]) < 1e-14
-    y = np.zeros_like(x)
-    run_rows("emu_exec_c2r", y, side, n, rows, Nf, D.DOUBLE, scale=1.0 / n)
+    y = be.zeros(x.shape, x.dtype)
+    run_rows(be, "exec_c2r", y, side, n, rows, Nf, D.DOUBLE, scale=1.0 / n)
     assert _rel(y, x) < 1e-14
