@@ -56,7 +56,8 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None):
     c = F.fftn(u[r], np.zeros(cshape[r], dtype=ct))
     check(tag + " fftn", c, fwd(u)[r], tol, r)
     a = F.ifftn(c, np.zeros(F.real_shape(), dtype=rt))
-    check(tag + " roundtrip", a, u[r], tol, r)
+    # 'AlltoallN' drops the Nyquist plane (pencil.py:909-910), so its round trip is the oracle's, not u
+    check(tag + " roundtrip", a, inv(fwd(u))[r] if communication == "AlltoallN" else u[r], tol, r)
     fu = [rand_c(rng, s, ct) for s in cshape]
     for d in (None, "2/3-rule", "3/2-rule"):
         shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
