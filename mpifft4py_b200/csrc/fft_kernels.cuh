@@ -63,6 +63,19 @@ B2_HD int swz(int row) {
   else return row;
 }
 
+// Twiddles of one butterfly: w[c] = W^c for c = 1..R-1 from ONE table load (W = tw[step]) and a
+// product tree of depth <= log2(R) (w[c] = w[c/2] * w[c - c/2]).  A per-element table gather
+// costs up to 32 L1 wavefronts per warp instruction and saturated the LSU pipe (profiles/r01a);
+// the multiplies ride on the idle FP pipe.  Rounding: <= 4 products, ~5e-16 (double) per twiddle.
+template <int R, class real>
+B2_HD void twiddle_powers(cx<real>* w, const cx<real>* tw, int step) {
+  if constexpr (R > 1) {
+    w[1] = tw[step];
+#pragma unroll
+    for (int c = 2; c < R; ++c) w[c] = cmul(w[c / 2], w[c - c / 2]);
+  }
+}
+
 // One DIF stage for the butterflies owned by thread `t` (of TC threads cooperating on one
 // transform).  `sm` points at this transform's element 0 (column offset included); consecutive
 // positions are RS elements apart.
@@ -96,15 +109,17 @@ B2_HD void fft_stage(int t, cx<real>* sm, const cx<real>* tw, int tws, In&& in, 
     }
     Dft<R>::template run<1>(v);
     if constexpr (s < S - 1) {
-      const int step = q * tws * (P::N / L);  // W_L^(q*c) = W_NTW^(q*c*(NTW/L))
+      C w[R];
+      twiddle_powers<R>(w, tw, q * tws * (P::N / L));  // W_L^q = W_NTW^(q*(NTW/L))
 #pragma unroll
-      for (int c = 1; c < R; ++c) v[c] = cmul(v[c], tw[c * step]);
+      for (int c = 1; c < R; ++c) v[c] = cmul(v[c], w[c]);
     }
     if constexpr (OUT_FN) {
       if constexpr (R % 3 == 0) {  // Nyquist fold of the 3/2-rule truncation (slab.py:480-482,529-533)
-        if (fold_mode != 0 && u == 0) {
-          if (fold_mode == 1) v[R / 3] = cadd(v[R / 3], v[2 * R / 3]);
-          else v[R / 3] = v[2 * R / 3];
+        if (fold_mode != 0 && u == 0) {  // slots R/3 and 2R/3 hold frequencies n/3 and 2n/3 (= -n/3)
+          if (fold_mode == 1) v[R / 3] = v[2 * R / 3] = cadd(v[R / 3], v[2 * R / 3]);
+          else if (fold_mode == 2) v[R / 3] = v[2 * R / 3];
+          else v[2 * R / 3] = v[R / 3];
         }
       }
 #pragma unroll
@@ -152,6 +167,38 @@ B2_HD int chunk_of(int i, int chunk, int nchunk) {
   return p < nchunk ? p : nchunk - 1;
 }
 
+typedef unsigned long long addr_t;
+
+// byte address of element (b, physical row r, column j) of a side
+template <int CB>
+B2_HD addr_t side_addr(const Side& sd, long long b, int r, long long j) {
+  const int pc = (sd.nchunk > 1) ? chunk_of(r, sd.chunk, sd.nchunk) : 0;
+  return (addr_t)sd.base[pc] + (addr_t)((b * sd.sb[pc] + (long long)(r - pc * sd.chunk) * sd.si[pc] + j) * CB);
+}
+
+// 16 / 8-byte asynchronous global -> shared copy (LDGSTS): no registers hold the data, so a CTA
+// keeps its whole tile in flight; src_bytes == 0 zero-fills (pad rows, masked entries, dead lanes).
+template <int BYTES>
+B2_HD void async_copy(void* dst_smem, addr_t src, bool valid) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  const int nb = valid ? BYTES : 0;
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+#else
+  unsigned char* d = reinterpret_cast<unsigned char*>(dst_smem);
+  const unsigned char* g = reinterpret_cast<const unsigned char*>(src);
+  for (int i = 0; i < BYTES; ++i) d[i] = valid ? g[i] : (unsigned char)0;
+#endif
+}
+B2_HD void async_copy_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // strided C2C pass
 // ------------------------------------------------------------------------------------------
@@ -169,11 +216,25 @@ struct StridedParams {
   int tws;  // table length / n
 };
 
-template <class real, class P>
+// Tile geometry.  A CTA owns T adjacent columns (ROWB = T*sizeof(complex) contiguous bytes per
+// row) of one batch entry, all n rows: n*ROWB bytes of shared memory plus an n-entry row-address
+// table.  ROWB is the widest of 128 / 64 / 32 / 16 bytes that still leaves room for 3 (128 B) or
+// 2 resident CTAs per SM -- while one CTA computes, the asynchronous loads of the others are in
+// flight, which is what keeps HBM busy.
+template <class real, class P, int MB = 0, int RB = 0>
 struct StridedCfg {
   static constexpr int CB = (int)sizeof(cx<real>);
-  static constexpr int ROWB = (P::N * 128 <= 48 * 1024) ? 128 : (P::N * 64 <= 100 * 1024) ? 64 : 32;
-  static constexpr int T0 = ROWB / CB;
+  static constexpr int LIM = 227 * 1024;
+  static constexpr bool fits(int rowb, int k, bool tab) { return k * (P::N * rowb + (tab ? P::N * 8 : 0) + 1024) <= LIM; }
+  static constexpr int ROWB = RB > 0                    ? RB
+                              : (P::N * 128 <= 32 * 1024) ? 128
+                              : fits(128, 3, true)      ? 128
+                              : fits(64, 2, true)       ? 64
+                              : fits(32, 2, true)       ? 32
+                              : fits(32, 1, false)      ? 32
+                                                        : 16;
+  static constexpr bool TAB = fits(ROWB, 1, true);
+  static constexpr int T0 = ROWB / CB < 1 ? 1 : ROWB / CB;
   static constexpr int NBMIN = P::N / P::RMAX;
   static constexpr int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
   static constexpr int TC_ = pow2floor(NBMIN) < (256 / T0) ? pow2floor(NBMIN) : (256 / T0);
@@ -181,21 +242,25 @@ struct StridedCfg {
   static constexpr int T = (T0 * TC >= 128) ? T0 : (128 / TC);
   static constexpr int NT = T * TC;
   static constexpr int SW = (T * CB >= 128) ? 1 : 128 / (T * CB);
-  static constexpr int SMEM = (P::S > 1) ? P::N * T * CB : 0;
-  static constexpr int NPHASE = P::S;
+  static constexpr int TILE = P::N * T * CB;
+  static constexpr int SMEM = TILE + (TAB ? P::N * 8 : 0);
+  static constexpr int NPHASE = P::S + 3;
+  static constexpr int MINB_ = LIM / (SMEM + 1024);
+  static constexpr int MINB = MB > 0 ? MB : (MINB_ < 1 ? 1 : (MINB_ > 3 ? 3 : MINB_));
 };
 
-template <class real, class P>
+template <class real, class P, int MB = 0, int RB = 0>
 struct StridedK {
-  using Cfg = StridedCfg<real, P>;
+  using Cfg = StridedCfg<real, P, MB, RB>;
   using C = cx<real>;
   using Params = StridedParams<real>;
   static constexpr int NPHASE = Cfg::NPHASE;
   static constexpr int NT = Cfg::NT;
   static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int MINB = Cfg::MINB;
 
-  // 1D grid: consecutive blocks walk the column tiles of one batch entry (adjacent 64-byte
-  // segments of the same rows -> neighbouring CTAs share DRAM pages and L2 sectors).
+  // 1D grid: consecutive blocks walk the column tiles of one batch entry (adjacent ROWB-byte
+  // segments of the same rows -> neighbouring CTAs share DRAM pages and L2 lines).
   B2_HD static unsigned long long blocks(const Params& p) {
     return (unsigned long long)((p.J + Cfg::T - 1) / Cfg::T) * (unsigned long long)p.B;
   }
@@ -205,60 +270,93 @@ struct StridedK {
     bx = (int)(blk - (unsigned)by * nt);
   }
 
+  // address of load row i (logical index of the transform input) for column j0; 0 = zero fill:
+  // copy_to_padded (slab.py:517-523) and the kx / ky band of the 2/3-rule mask
+  B2_HD static addr_t in_row(const Params& p, long long b, int i, int j0) {
+    constexpr int n = P::N;
+    int ip = i;
+    if (p.in.nphys < n) {
+      const int h = p.in.nphys / 2;
+      if (i >= h) {
+        if (i < n - h) return 0;
+        ip = i - (n - p.in.nphys);
+      }
+    }
+    if (p.mask.on) {
+      const int ii = ip + p.mask.i_off;
+      if (ii >= p.mask.i_lo && ii <= p.mask.i_hi) return 0;
+    }
+    return side_addr<Cfg::CB>(p.in, b, ip, j0);
+  }
+  // address of store row for output frequency k; 0 = dropped: copy_from_padded (slab.py:529-533).
+  // The inverse transform is the forward one with the output index reversed (k -> -k mod n).
+  B2_HD static addr_t out_row(const Params& p, long long b, int k, int j0) {
+    constexpr int n = P::N;
+    int kp = p.inverse ? (k == 0 ? 0 : n - k) : k;
+    if (p.out.nphys < n) {
+      const int h = p.out.nphys / 2;
+      if (kp > h) {
+        if (kp <= n - h) return 0;
+        kp -= n - p.out.nphys;
+      }
+    }
+    return side_addr<Cfg::CB>(p.out, b, kp, j0);
+  }
+
   template <int s>
   B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int by) {
-    constexpr int T = Cfg::T;
+    constexpr int T = Cfg::T, n = P::N, CB = Cfg::CB;
+    constexpr int M0 = P::template M<0>;
     const int c = tid % T;
     const int t = tid / T;
-    const int j = bx * T + c;
+    const int j0 = bx * T;
     const long long b = by;
-    const bool live = j < p.J;
-    C* sm = reinterpret_cast<C*>(smraw) + c;
-    const int n = P::N;
+    const bool live = j0 + c < p.J;
+    addr_t* tab = reinterpret_cast<addr_t*>(reinterpret_cast<unsigned char*>(smraw) + Cfg::TILE);
 
-    bool colzero = !live;
-    if (p.mask.on && live) {
-      const Mask& m = p.mask;
-      const int bb = (int)b + m.b_off, jq = j / m.jdiv + m.jq_off, jr = j % m.jdiv + m.jr_off;
-      if ((bb >= m.b_lo && bb <= m.b_hi) || (jq >= m.jq_lo && jq <= m.jq_hi) || (jr >= m.jr_lo && jr <= m.jr_hi))
-        colzero = true;
+    if constexpr (s == 0) {  // load-row address table
+      if constexpr (Cfg::TAB)
+        for (int i = tid; i < n; i += Cfg::NT) tab[i] = in_row(p, b, i, j0);
+    } else if constexpr (s == 1) {  // whole tile global -> shared, asynchronously
+      bool colzero = !live;
+      if (p.mask.on && live) {
+        const Mask& m = p.mask;
+        const int j = j0 + c;
+        const int bb = (int)b + m.b_off, jq = j / m.jdiv + m.jq_off, jr = j % m.jdiv + m.jr_off;
+        if ((bb >= m.b_lo && bb <= m.b_hi) || (jq >= m.jq_lo && jq <= m.jq_hi) || (jr >= m.jr_lo && jr <= m.jr_hi))
+          colzero = true;
+      }
+      C* sm = reinterpret_cast<C*>(smraw) + c;
+      const addr_t fallback = (addr_t)p.tw;  // any valid address: never dereferenced when size == 0
+#pragma unroll 4
+      for (int i = t; i < n; i += Cfg::TC) {
+        addr_t a;
+        if constexpr (Cfg::TAB) a = tab[i];
+        else a = in_row(p, b, i, j0);
+        const bool ok = (a != 0) && !colzero;
+        async_copy<CB>(sm + swz<M0, Cfg::SW>(i) * T, ok ? a + (addr_t)c * CB : fallback, ok);
+      }
+    } else if constexpr (s == 2) {  // store-row address table (overlaps the loads in flight)
+      if constexpr (Cfg::TAB)
+        for (int k = tid; k < n; k += Cfg::NT) tab[k] = out_row(p, b, k, j0);
+      async_copy_wait();
+    } else {
+      constexpr int st = s - 3;
+      C* sm = reinterpret_cast<C*>(smraw) + c;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int k, C v) {
+        if (!live) return;
+        addr_t a;
+        if constexpr (Cfg::TAB) a = tab[k];
+        else a = out_row(p, b, k, j0);
+        if (a == 0) return;
+        if (p.scale != (real)1) v = cscale(v, p.scale);
+        *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
+      };
+      // reversed output index: the slot that survives a "keep -N/2" truncation is the other one
+      const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
+      fft_stage<real, P, st, Cfg::TC, T, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, p.tws, in, out, fold);
     }
-
-    auto in = [&](int i) -> C {
-      if (colzero) return C{0, 0};
-      int ip = i;
-      if (p.in.nphys < n) {  // zero-pad on load: copy_to_padded (slab.py:517-523)
-        const int h = p.in.nphys / 2;
-        if (i < h) ip = i;
-        else if (i >= n - h) ip = i - (n - p.in.nphys);
-        else return C{0, 0};
-      }
-      if (p.mask.on) {
-        const int ii = ip + p.mask.i_off;
-        if (ii >= p.mask.i_lo && ii <= p.mask.i_hi) return C{0, 0};
-      }
-      const int pc = (p.in.nchunk > 1) ? chunk_of(ip, p.in.chunk, p.in.nchunk) : 0;
-      const C* ptr = reinterpret_cast<const C*>(p.in.base[pc]) + b * p.in.sb[pc] +
-                     (long long)(ip - pc * p.in.chunk) * p.in.si[pc] + j;
-      C v = *ptr;
-      return p.inverse ? cswap(v) : v;
-    };
-    auto out = [&](int k, C v) {
-      if (!live) return;
-      int kp = k;
-      if (p.out.nphys < n) {  // truncate on store: copy_from_padded (slab.py:529-533)
-        const int h = p.out.nphys / 2;
-        if (k <= h) kp = k;
-        else if (k > n - h) kp = k - (n - p.out.nphys);
-        else return;
-      }
-      const int pc = (p.out.nchunk > 1) ? chunk_of(kp, p.out.chunk, p.out.nchunk) : 0;
-      C* ptr = reinterpret_cast<C*>(p.out.base[pc]) + b * p.out.sb[pc] +
-               (long long)(kp - pc * p.out.chunk) * p.out.si[pc] + j;
-      if (p.inverse) v = cswap(v);
-      *ptr = cscale(v, p.scale);
-    };
-    fft_stage<real, P, s, Cfg::TC, T, Cfg::SW, (s == 0), (s == P::S - 1)>(t, sm, p.tw, p.tws, in, out, p.fold_mode);
   }
 };
 
@@ -304,6 +402,7 @@ struct R2CK {  // forward: real rows -> complex rows
   static constexpr int NPHASE = Cfg::NPHASE;
   static constexpr int NT = Cfg::NT;
   static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int MINB = 1;
   B2_HD static unsigned long long blocks(const Params& p) {
     return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
   }
@@ -366,9 +465,11 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
   using Cfg = RowCfg<real, P>;
   using C = cx<real>;
   using Params = RowParams<real>;
-  static constexpr int NPHASE = Cfg::NPHASE;
+  static constexpr int SROW = Cfg::H + 16 / Cfg::CB;  // H slots (swizzled) + one for X[H], 16-byte aligned rows
+  static constexpr int NPHASE = P::S + 2;
   static constexpr int NT = Cfg::NT;
-  static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int SMEM = Cfg::RPC * SROW * Cfg::CB;
+  static constexpr int MINB = 1;
   B2_HD static unsigned long long blocks(const Params& p) {
     return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
   }
@@ -379,20 +480,30 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
 
   template <int s>
   B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
-    constexpr int H = Cfg::H, TC = Cfg::TC;
+    constexpr int H = Cfg::H, TC = Cfg::TC, CB = Cfg::CB;
     constexpr int M0 = P::template M<0>;
     const int rl = tid / TC, t = tid % TC;
     const long long row = (long long)bx * Cfg::RPC + rl;
     const bool live = row < p.rows;
-    C* sm = reinterpret_cast<C*>(smraw) + rl * H;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * SROW;
     if constexpr (s == 0) {
-      // merge step: G[k] = (X[k] + conj X[H-k]) + i W_n^-k (X[k] - conj X[H-k]); stored swapped
+      // spectrum row -> shared, asynchronously; entries k >= nk are the z zero pad
+      // (copy_to_padded axis 2, slab.py:524-525); chunks are the receive blocks of an exchange
       const Side& o = p.cside;
-      auto load = [&](int k) -> C {
-        if (!live || k >= p.nk) return C{0, 0};  // zero pad in z: copy_to_padded axis 2 (slab.py:524-525)
-        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
-        return *(reinterpret_cast<const C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk));
-      };
+      const addr_t fallback = (addr_t)p.tw;
+#pragma unroll 4
+      for (int k = t; k <= H; k += TC) {
+        const bool ok = live && k < p.nk;
+        addr_t a = fallback;
+        if (ok) {
+          const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+          a = (addr_t)o.base[pc] + (addr_t)((row * o.sb[pc] + (k - pc * o.chunk)) * CB);
+        }
+        async_copy<CB>(sm + (k < H ? swz<M0, Cfg::SW>(k) : H), a, ok);
+      }
+      async_copy_wait();
+    } else if constexpr (s == 1) {
+      // merge step, in place: G[k] = (X[k] + conj X[H-k]) + i W_n^-k (X[k] - conj X[H-k]); stored swapped
       constexpr int NK = H / 2 + 1;
       constexpr int ROUNDS = (NK + TC - 1) / TC;
 #pragma unroll
@@ -400,10 +511,10 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
         const int k = t + rr * TC;
         if (k >= NK) break;
         if (k == 0) {
-          const real x0 = load(0).x, xh = load(H).x;  // imaginary parts of DC / Nyquist ignored (C2R)
+          const real x0 = sm[swz<M0, Cfg::SW>(0)].x, xh = sm[H].x;  // imaginary parts of DC / Nyquist ignored (C2R)
           sm[swz<M0, Cfg::SW>(0)] = cswap(C{x0 + xh, x0 - xh});
         } else {
-          const C a = load(k), bq = load(H - k);
+          const C a = sm[swz<M0, Cfg::SW>(k)], bq = sm[swz<M0, Cfg::SW>(H - k)];
           const C e = C{a.x + bq.x, a.y - bq.y};            // a + conj b
           const C d = C{a.x - bq.x, a.y + bq.y};            // a - conj b
           const C o2 = cmul(cconj(p.tw[k * p.tws]), d);    // W_n^-k (a - conj b)
@@ -413,7 +524,7 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
         }
       }
     } else {
-      constexpr int st = s - 1;
+      constexpr int st = s - 2;
       real* dst = reinterpret_cast<real*>(p.rout) + row * p.rpitch;
       auto in = [](int) -> C { return C{0, 0}; };
       auto out = [&](int m, C v) {
@@ -441,7 +552,7 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, void* sm
 }
 
 template <class K>
-__global__ void __launch_bounds__(K::NT) fft_kernel(const __grid_constant__ typename K::Params p) {
+__global__ void __launch_bounds__(K::NT, K::MINB) fft_kernel(const __grid_constant__ typename K::Params p) {
   extern __shared__ __align__(128) unsigned char smraw[];
   int bx, by;
   K::decode(p, blockIdx.x, bx, by);
