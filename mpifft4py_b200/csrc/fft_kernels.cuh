@@ -257,6 +257,8 @@ struct StridedK {
   static constexpr int NPHASE = Cfg::NPHASE;
   static constexpr int NT = Cfg::NT;
   static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int SMEM1 = Cfg::SMEM;
+  static constexpr bool PIPE = false;
   static constexpr int MINB = Cfg::MINB;
 
   // 1D grid: consecutive blocks walk the column tiles of one batch entry (adjacent ROWB-byte
@@ -377,32 +379,64 @@ struct RowParams {
   int tws;             // NTW / n
 };
 
+// Threads per row TC and rows per CTA.  TC is the largest lane count (a multiple of a warp where
+// the row is long enough) that keeps >= 85% of the butterfly slots of every stage busy; the CTA
+// takes as many rows as fit a ~32 KB buffer (<= 256 threads).  Row kernels are persistent and
+// double-buffered: while a CTA transforms one group of rows, the asynchronous loads of its next
+// group are in flight, so every resident CTA always has a buffer's worth of HBM reads outstanding.
 template <class real, class P>
 struct RowCfg {
   static constexpr int CB = (int)sizeof(cx<real>);
   static constexpr int H = P::N;
-  static constexpr int NBMIN = P::N / P::RMAX;
-  static constexpr int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
-  static constexpr int TC_ = pow2floor(NBMIN) < 256 ? pow2floor(NBMIN) : 256;
-  static constexpr int TC = TC_ < 1 ? 1 : TC_;
-  static constexpr int RPC_T = (256 / TC) < 1 ? 1 : (256 / TC);                      // rows per CTA by threads
-  static constexpr int RPC_S = (64 * 1024) / (H * CB) < 1 ? 1 : (64 * 1024) / (H * CB);  // by shared memory
-  static constexpr int RPC = RPC_T < RPC_S ? RPC_T : RPC_S;
+  static constexpr int SROW = H + 16 / CB;  // H slots (swizzled) + one for X[H] (C2R), rows stay 16-byte aligned
+  template <int s = 0>
+  static constexpr long long slots(int tc) {  // sum over stages of rounds * radix
+    if constexpr (s >= P::S) {
+      return 0;
+    } else {
+      constexpr int R = P::template R<s>;
+      return (long long)(((H / R) + tc - 1) / tc) * R + slots<s + 1>(tc);
+    }
+  }
+  static constexpr bool good(int tc) {  // S*H useful element slots out of tc * slots(tc)
+    return tc >= 1 && tc <= 256 && (tc == 1 || tc * 4 <= H) && 100LL * P::S * H >= 85LL * tc * slots(tc);
+  }
+  static constexpr int pick() {
+    constexpr int cand[] = {256, 192, 128, 96, 64, 48, 32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
+    for (int c : cand)
+      if (good(c)) return c;
+    return 1;
+  }
+  static constexpr int TC = pick();
+  static constexpr int RPC_T = (256 / TC) < 1 ? 1 : (256 / TC);                          // rows per CTA by threads
+  static constexpr int RPC_S = (32 * 1024) / (SROW * CB) < 1 ? 1 : (32 * 1024) / (SROW * CB);  // by shared memory
+  static constexpr int RPC_ = RPC_T < RPC_S ? RPC_T : RPC_S;
+  static constexpr int RPC = (RPC_ * TC >= 32) ? ((RPC_ * TC) / 32 * 32) / TC : RPC_;  // whole warps
   static constexpr int NT = TC * RPC;
   static constexpr int SW = 128 / CB;
-  static constexpr int SMEM = RPC * H * CB;
-  static constexpr int NPHASE = P::S + 1;
+  static constexpr int SMEM1 = RPC * SROW * CB;
+  static constexpr bool PIPE = 2 * SMEM1 + 1024 <= 227 * 1024;
+  static constexpr int SMEM = PIPE ? 2 * SMEM1 : SMEM1;
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB_CAP = P::RMAX >= 12 ? 3 : 4;  // radix-12/16 butterflies spill under the 4-CTA register budget
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > MINB_CAP ? MINB_CAP : MINB_);
 };
 
 template <class real, class P>
 struct R2CK {  // forward: real rows -> complex rows
+  // Stage 0 loads its butterfly inputs straight from HBM into registers (coalesced 16-byte loads,
+  // all issued before the first use): staging the row through shared memory first, as C2R does,
+  // measured 20% slower here because the kernel is bound by LSU wavefronts, not by load latency.
   using Cfg = RowCfg<real, P>;
   using C = cx<real>;
   using Params = RowParams<real>;
-  static constexpr int NPHASE = Cfg::NPHASE;
+  static constexpr int NPHASE = P::S + 1;
   static constexpr int NT = Cfg::NT;
-  static constexpr int SMEM = Cfg::SMEM;
-  static constexpr int MINB = 1;
+  static constexpr int SMEM = Cfg::SMEM1;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = false;
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > Cfg::MINB_CAP ? Cfg::MINB_CAP : MINB_);
   B2_HD static unsigned long long blocks(const Params& p) {
     return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
   }
@@ -418,7 +452,7 @@ struct R2CK {  // forward: real rows -> complex rows
     const int rl = tid / TC, t = tid % TC;
     const long long row = (long long)bx * Cfg::RPC + rl;
     const bool live = row < p.rows;
-    C* sm = reinterpret_cast<C*>(smraw) + rl * H;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
     if constexpr (s < P::S) {
       const C* src = reinterpret_cast<const C*>(reinterpret_cast<const real*>(p.rin) + row * p.rpitch);
       auto in = [&](int i) -> C { return live ? src[i] : C{0, 0}; };  // z[i] = x[2i] + i*x[2i+1]
@@ -430,10 +464,10 @@ struct R2CK {  // forward: real rows -> complex rows
       if (!live) return;
       const Side& o = p.cside;
       auto store = [&](int k, C v) {
-        if (k >= p.nk) return;
+        if (k >= p.nk) return;  // z truncation of the 3/2-rule: copy_from_padded axis 2 (slab.py:535)
         const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
         C* ptr = reinterpret_cast<C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk);
-        *ptr = cscale(v, p.scale);
+        *ptr = (p.scale != (real)1) ? cscale(v, p.scale) : v;
       };
       constexpr int NK = H / 2 + 1;
       constexpr int ROUNDS = (NK + TC - 1) / TC;
@@ -465,11 +499,12 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
   using Cfg = RowCfg<real, P>;
   using C = cx<real>;
   using Params = RowParams<real>;
-  static constexpr int SROW = Cfg::H + 16 / Cfg::CB;  // H slots (swizzled) + one for X[H], 16-byte aligned rows
   static constexpr int NPHASE = P::S + 2;
   static constexpr int NT = Cfg::NT;
-  static constexpr int SMEM = Cfg::RPC * SROW * Cfg::CB;
-  static constexpr int MINB = 1;
+  static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = Cfg::PIPE;
+  static constexpr int MINB = Cfg::MINB;
   B2_HD static unsigned long long blocks(const Params& p) {
     return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
   }
@@ -485,23 +520,21 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
     const int rl = tid / TC, t = tid % TC;
     const long long row = (long long)bx * Cfg::RPC + rl;
     const bool live = row < p.rows;
-    C* sm = reinterpret_cast<C*>(smraw) + rl * SROW;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
     if constexpr (s == 0) {
       // spectrum row -> shared, asynchronously; entries k >= nk are the z zero pad
       // (copy_to_padded axis 2, slab.py:524-525); chunks are the receive blocks of an exchange
       const Side& o = p.cside;
-      const addr_t fallback = (addr_t)p.tw;
 #pragma unroll 4
       for (int k = t; k <= H; k += TC) {
         const bool ok = live && k < p.nk;
-        addr_t a = fallback;
+        addr_t a = (addr_t)p.tw;
         if (ok) {
           const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
           a = (addr_t)o.base[pc] + (addr_t)((row * o.sb[pc] + (k - pc * o.chunk)) * CB);
         }
         async_copy<CB>(sm + (k < H ? swz<M0, Cfg::SW>(k) : H), a, ok);
       }
-      async_copy_wait();
     } else if constexpr (s == 1) {
       // merge step, in place: G[k] = (X[k] + conj X[H-k]) + i W_n^-k (X[k] - conj X[H-k]); stored swapped
       constexpr int NK = H / 2 + 1;
@@ -545,6 +578,7 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
 template <class K, int s>
 __device__ __forceinline__ void run_phases(const typename K::Params& p, void* sm, int bx, int by) {
   K::template phase<s>(p, sm, (int)threadIdx.x, bx, by);
+  if constexpr (s == 0) async_copy_wait();  // phase 0 of the row kernels only issues its loads
   if constexpr (s + 1 < K::NPHASE) {
     __syncthreads();
     run_phases<K, s + 1>(p, sm, bx, by);
@@ -554,9 +588,36 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, void* sm
 template <class K>
 __global__ void __launch_bounds__(K::NT, K::MINB) fft_kernel(const __grid_constant__ typename K::Params p) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  int bx, by;
-  K::decode(p, blockIdx.x, bx, by);
-  run_phases<K, 0>(p, smraw, bx, by);
+  if constexpr (K::PIPE) {
+    // persistent, double-buffered: phase 0 (asynchronous loads) of the CTA's next work item is
+    // issued before the current item's compute phases; launched with one CTA per resident slot
+    const unsigned nblk = (unsigned)K::blocks(p);
+    unsigned g = blockIdx.x;
+    int buf = 0, bx, by;
+    if (g < nblk) {
+      K::decode(p, g, bx, by);
+      K::template phase<0>(p, smraw, (int)threadIdx.x, bx, by);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (; g < nblk; g += gridDim.x) {
+      const unsigned gn = g + gridDim.x;
+      if (gn < nblk) {
+        K::decode(p, gn, bx, by);
+        K::template phase<0>(p, smraw + (buf ^ 1) * K::SMEM1, (int)threadIdx.x, bx, by);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      __syncthreads();
+      K::decode(p, g, bx, by);
+      run_phases<K, 1>(p, smraw + buf * K::SMEM1, bx, by);
+      __syncthreads();  // every read of this buffer is done before the next iteration refills it
+      buf ^= 1;
+    }
+  } else {
+    int bx, by;
+    K::decode(p, blockIdx.x, bx, by);
+    run_phases<K, 0>(p, smraw, bx, by);
+  }
 }
 #endif
 

@@ -11,8 +11,14 @@
   X(192, 16, 12) X(384, 4, 8, 12) X(768, 8, 8, 12) X(1536, 16, 8, 12)           \
   X(3072, 16, 16, 12) X(6144, 8, 8, 8, 12) X(12288, 16, 8, 8, 12)
 
+// Precision-specific defaults of the strided pass: X(n, min CTAs per SM (0 = auto), tile row bytes
+// (0 = auto), radices...).  Double-precision radix-16 butterflies need > 85 registers per thread,
+// which costs the third resident CTA per SM; 4 stages of radix <= 8 measured faster.
+#define B200FFT_STRIDED_F64_PLANS(X) X(1024, 0, 0, 4, 4, 8, 8)
+#define B200FFT_STRIDED_F32_PLANS(X)
+
 // alternative plans for A/B timing: X(n, variant, min CTAs per SM (0 = auto), tile row bytes (0 = auto), radices...)
 #define B200FFT_ALT_PLANS(X)                                                              \
-  X(1024, 1, 2, 0, 16, 8, 8) X(1024, 2, 0, 0, 8, 8, 4, 4) X(1024, 3, 0, 0, 4, 4, 8, 8)    \
+  X(1024, 1, 2, 0, 16, 8, 8) X(1024, 2, 0, 0, 8, 8, 4, 4) X(1024, 3, 0, 0, 16, 8, 8)      \
   X(1024, 4, 0, 0, 8, 4, 4, 8) X(1024, 5, 1, 128, 4, 4, 8, 8) X(1024, 6, 3, 32, 4, 4, 8, 8) \
   X(1024, 7, 1, 128, 16, 8, 8) X(1536, 1, 0, 0, 4, 4, 8, 12) X(1536, 2, 0, 0, 8, 8, 2, 12)
