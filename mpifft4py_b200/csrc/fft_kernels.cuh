@@ -109,10 +109,22 @@ B2_HD void fft_stage(int t, cx<real>* sm, const cx<real>* tw, int tws, In&& in, 
     }
     Dft<R>::template run<1>(v);
     if constexpr (s < S - 1) {
-      C w[R];
-      twiddle_powers<R>(w, tw, q * tws * (P::N / L));  // W_L^q = W_NTW^(q*(NTW/L))
+      if constexpr (R >= 16 && sizeof(real) == 8) {
+        // double-precision radix 16: 16 values + 16 twiddles would need > 128 registers; run the
+        // powers as a chain (2 live twiddles) so that three CTAs stay resident per SM
+        const C w1 = tw[q * tws * (P::N / L)];
+        C wc = w1;
 #pragma unroll
-      for (int c = 1; c < R; ++c) v[c] = cmul(v[c], w[c]);
+        for (int c = 1; c < R; ++c) {
+          v[c] = cmul(v[c], wc);
+          if (c + 1 < R) wc = cmul(wc, w1);
+        }
+      } else {
+        C w[R];
+        twiddle_powers<R>(w, tw, q * tws * (P::N / L));  // W_L^q = W_NTW^(q*(NTW/L))
+#pragma unroll
+        for (int c = 1; c < R; ++c) v[c] = cmul(v[c], w[c]);
+      }
     }
     if constexpr (OUT_FN) {
       if constexpr (R % 3 == 0) {  // Nyquist fold of the 3/2-rule truncation (slab.py:480-482,529-533)
@@ -418,7 +430,8 @@ struct RowCfg {
   static constexpr bool PIPE = 2 * SMEM1 + 1024 <= 227 * 1024;
   static constexpr int SMEM = PIPE ? 2 * SMEM1 : SMEM1;
   static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
-  static constexpr int MINB_CAP = P::RMAX >= 12 ? 3 : 4;  // radix-12/16 butterflies spill under the 4-CTA register budget
+  // register budget: double-precision radix-16 butterflies need ~128 registers, radix-12 ~96
+  static constexpr int MINB_CAP = (P::RMAX >= 16 && CB == 16) ? 2 : (P::RMAX >= 12 ? 3 : 4);
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > MINB_CAP ? MINB_CAP : MINB_);
 };
 

@@ -11,14 +11,20 @@
   X(192, 16, 12) X(384, 4, 8, 12) X(768, 8, 8, 12) X(1536, 16, 8, 12)           \
   X(3072, 16, 16, 12) X(6144, 8, 8, 8, 12) X(12288, 16, 8, 8, 12)
 
-// Precision-specific defaults of the strided pass: X(n, min CTAs per SM (0 = auto), tile row bytes
-// (0 = auto), radices...).  Double-precision radix-16 butterflies need > 85 registers per thread,
-// which costs the third resident CTA per SM; 4 stages of radix <= 8 measured faster.
-#define B200FFT_STRIDED_F64_PLANS(X) X(1024, 0, 0, 4, 4, 8, 8)
+// Row (R2C / C2R) kernels: same radix plans.  (Taking the factor 3 in the first stage removes the
+// shared-memory bank conflicts of the 12-long runs in the middle stage but measured 3-5% slower
+// for n = 1536 double -- the radix-12 twiddle tree costs more FP64 than the conflicts cost LSU.)
+#define B200FFT_ROW_PLANS(X) B200FFT_PLANS(X)
+
+// Precision-specific overrides of the strided pass: X(n, min CTAs per SM (0 = auto), tile row bytes
+// (0 = auto), radices...).  None at present: with chained twiddle powers the double-precision
+// (16, 8, 8) plan fits the 80-register budget of three CTAs per SM and measured 10% faster than
+// four stages of radix <= 8 (fewer shared-memory round trips; the pass is LSU-bound).
+#define B200FFT_STRIDED_F64_PLANS(X)
 #define B200FFT_STRIDED_F32_PLANS(X)
 
 // alternative plans for A/B timing: X(n, variant, min CTAs per SM (0 = auto), tile row bytes (0 = auto), radices...)
 #define B200FFT_ALT_PLANS(X)                                                              \
-  X(1024, 1, 2, 0, 16, 8, 8) X(1024, 2, 0, 0, 8, 8, 4, 4) X(1024, 3, 0, 0, 16, 8, 8)      \
+  X(1024, 1, 2, 0, 16, 8, 8) X(1024, 2, 0, 0, 8, 8, 4, 4) X(1024, 3, 0, 0, 4, 4, 8, 8)    \
   X(1024, 4, 0, 0, 8, 4, 4, 8) X(1024, 5, 1, 128, 4, 4, 8, 8) X(1024, 6, 3, 32, 4, 4, 8, 8) \
   X(1024, 7, 1, 128, 16, 8, 8) X(1536, 1, 0, 0, 4, 4, 8, 12) X(1536, 2, 0, 0, 8, 8, 2, 12)

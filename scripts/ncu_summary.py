@@ -2,6 +2,7 @@
 """Summarise an .ncu-rep (ncu --set full capture) into a small CSV for profiles/.
 
     python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_xxx.csv
+    python scripts/ncu_summary.py gpurun_out/ncu_raw_xxx.csv profiles/r01_xxx.csv   (raw page exported on the box)
 """
 import csv
 import subprocess
@@ -39,7 +40,10 @@ METRICS = [
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box with `ncu -i x.ncu-rep --page raw --csv`
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}

@@ -65,7 +65,7 @@ static int rows(const b200fft_rows_desc_t& d) {
   case n:                                                             \
     if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);        \
     else return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);
-    B200FFT_PLANS(X)
+    B200FFT_ROW_PLANS(X)
 #undef X
     default:
       return -1;
