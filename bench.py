@@ -106,59 +106,134 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port of slab/pencil/line + pocketfft)
+# reference arm: the reference's own CPU implementation of the path on this box's host cores.
+#   kind "reference": the UNMODIFIED mpiFFT4py (pip-installed into baseline/_ref)
+#       driven through its public API by oracle/refshim -- its MPI ranks run as threads of this
+#       process (fake mpi4py, memcpy collectives) with its numpy.fft backend; pyfftw / mpi4py /
+#       mpirun do not exist in this image.
+#   kind "port": oracle/ (numpy restatement, pocketfft through scipy.fft workers=cores) when the
+#       install is absent.
+# Both are test infrastructure: nothing here is on the product path.
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(name, budget_s=20.0):
-    """Pick a bounded sample of the workload: same class / precision / dealias, smaller mesh."""
+def cpu_sample(name):
+    """Bounded sample of the workload: same class / precision / dealias, smaller mesh."""
     kind, N, prec, dealias, kw = WORKLOADS[name]
     if kind == "line":
-        n = 4096
-        return (n, n)
-    n = 256
-    return (n, n, n)
+        return (4096, 4096)
+    return (256, 256, 256)
 
 
-def cpu_roundtrip(kind, N, prec, dealias, workers):
+def _pow2_floor(x):
+    p = 1
+    while 2 * p <= x:
+        p *= 2
+    return p
+
+
+def _load_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    import load_reference
+    if not load_reference.reference_available():
+        return None
+    try:
+        load_reference.load()
+    except Exception:  # noqa: BLE001
+        return None
+    return load_reference
+
+
+def reference_roundtrip(lr, kind, N, prec, dealias, kw, P, reps):
+    """min over `reps` of (max over ranks of) one fftn+ifftn of the unmodified reference."""
+    from mpi4py import MPI  # the refshim's in-process stand-in
+
+    def body():
+        Nn = np.array(N, dtype=int)
+        L = np.array([2 * np.pi] * len(N))
+        comm = MPI.COMM_WORLD
+        if kind == "slab":
+            from mpiFFT4py.slab import R2C
+            F = R2C(Nn, L, comm, prec)
+        elif kind == "pencil":
+            from mpiFFT4py.pencil import R2C
+            F = R2C(Nn, L, comm, prec, **kw)
+        else:
+            from mpiFFT4py.line import R2C
+            F = R2C(Nn, L, comm, prec)
+        fwd, inv = (F.fft2, F.ifft2) if kind == "line" else (F.fftn, F.ifftn)
+        rshape = F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()
+        u = np.random.default_rng(1234 + comm.Get_rank()).random(rshape).astype(F.float)
+        fu = np.zeros(F.complex_shape(), dtype=F.complex)
+        u2 = np.zeros_like(u)
+        fwd(u, fu, dealias)
+        inv(fu, u2, dealias)  # warm-up: work arrays, subarray types
+        best = None
+        for _ in range(reps):
+            comm.barrier()
+            t0 = time.perf_counter()
+            fwd(u, fu, dealias)
+            inv(fu, u2, dealias)
+            comm.barrier()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best
+
+    return max(lr.run_ranks(P, body))
+
+
+def port_roundtrip(kind, N, prec, dealias, workers):
     import oracle
     oracle.common.set_workers(workers)
     rt, ct = oracle.common.dtypes(prec)
     rng = np.random.default_rng(1234)
-    if kind == "line":
-        g = oracle.line.Geometry(N, 1)
-        shape = g.real_shape_padded() if dealias == "3/2-rule" else g.real_shape()
-        u = [rng.random(shape).astype(rt)]
-        t0 = time.perf_counter()
-        fu = oracle.line.fft2(u, N, 1, dealias=dealias, precision=prec)
-        oracle.line.ifft2(fu, N, 1, dealias=dealias, precision=prec)
-        return time.perf_counter() - t0, shape
-    g = oracle.slab.Geometry(N, 1)
+    mod = oracle.line if kind == "line" else oracle.slab
+    g = mod.Geometry(N, 1)
     shape = g.real_shape_padded() if dealias == "3/2-rule" else g.real_shape()
     u = [rng.random(shape).astype(rt)]
+    fwd, inv = (mod.fft2, mod.ifft2) if kind == "line" else (mod.fftn, mod.ifftn)
     t0 = time.perf_counter()
-    fu = oracle.slab.fftn(u, N, 1, dealias=dealias, precision=prec)
-    oracle.slab.ifftn(fu, N, 1, dealias=dealias, precision=prec)
-    return time.perf_counter() - t0, shape
+    fu = fwd(u, N, 1, dealias=dealias, precision=prec)
+    inv(fu, N, 1, dealias=dealias, precision=prec)
+    return time.perf_counter() - t0
 
 
-def cpu_baseline(name, reps=1):
+def cpu_time(name, Ns, reps):
+    """(seconds per round trip, descriptor) of the CPU reference on mesh Ns."""
     kind, N, prec, dealias, kw = WORKLOADS[name]
     cores = os.cpu_count() or 1
+    lr = _load_reference()
+    if lr is not None and kind in ("slab", "line"):
+        P = min(_pow2_floor(cores), 32, Ns[0] // 2)
+        t = reference_roundtrip(lr, kind, Ns, prec, dealias, kw, P, reps)
+        return t, {"kind": "reference", "cores": P,
+                   "how": "unmodified mpiFFT4py %s.R2C (baseline/_ref) under oracle/refshim: %d ranks as threads, "
+                          "numpy.fft backend, memcpy collectives" % (kind, P)}
+    if lr is not None and kind == "pencil":
+        P = 8 if cores >= 8 else 4
+        t = reference_roundtrip(lr, kind, Ns, prec, dealias, kw, P, reps)
+        return t, {"kind": "reference", "cores": P,
+                   "how": "unmodified mpiFFT4py pencil.R2C (baseline/_ref) under oracle/refshim: %d ranks as threads, "
+                          "numpy.fft backend, memcpy collectives" % P}
+    port_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)  # warm-up
+    t = min(port_roundtrip(kind, Ns, prec, dealias, cores) for _ in range(reps))
+    return t, {"kind": "port", "cores": cores,
+               "how": "oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d)" % (kind, cores)}
+
+
+def global_real_shape(Ns, dealias):
+    return tuple(int(1.5 * n) for n in Ns) if dealias == "3/2-rule" else tuple(Ns)
+
+
+def cpu_baseline(name):
+    """About 10-30 s of host work on a bounded sample of the workload."""
+    kind, N, prec, dealias, kw = WORKLOADS[name]
     Ns = cpu_sample(name)
-    cpu_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)  # warm-up (imports, plans)
-    # grow the sample while it stays within ~10-30 s of work
-    best = None
-    t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
-    if kind != "line" and t < 4.0 and Ns[0] < N[0]:
+    t, d = cpu_time(name, Ns, 1)
+    if kind != "line" and t < 1.5 and Ns[0] < N[0]:
         Ns = tuple(2 * n for n in Ns)
-        t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
-    best = t
-    for _ in range(reps - 1):
-        t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
-        best = min(best, t)
-    return {"value": flops_roundtrip(shape) / best / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d), %s %s "
-                      "round trip, %.2f s" % (kind, cores, "x".join(map(str, Ns)), prec, best),
-            "seconds": best, "N": list(Ns)}
+        t, d = cpu_time(name, Ns, 2)
+    return {"value": flops_roundtrip(global_real_shape(Ns, dealias)) / t / 1e9, "unit": UNIT, "cores": d["cores"],
+            "kind": d["kind"], "sample": "%s; %s %s round trip (dealias=%s), %.2f s" % (d["how"], "x".join(map(str, Ns)), prec, dealias, t),
+            "seconds": t, "N": list(Ns), "host_cores": os.cpu_count()}
 
 
 def run_reference(args):
@@ -167,27 +242,25 @@ def run_reference(args):
         return 0
     name = args.workload
     kind, N, prec, dealias, kw = WORKLOADS[name]
-    cores = os.cpu_count() or 1
     Ns = cpu_sample(name)
-    cpu_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)
-    t, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
-    budget = 150.0
-    if kind != "line" and t * 8 * (args.steps + args.warmup) < budget and Ns[0] < N[0]:
+    t, d = cpu_time(name, Ns, 1)
+    if kind != "line" and t * 8 * (args.steps + args.warmup) < 150.0 and Ns[0] < N[0]:
         Ns = tuple(2 * n for n in Ns)
     for _ in range(args.warmup):
-        cpu_roundtrip(kind, Ns, prec, dealias, cores)
+        cpu_time(name, Ns, 1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, shape = cpu_roundtrip(kind, Ns, prec, dealias, cores)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = flops_roundtrip(shape) / dt / 1e9
+    ts = [cpu_time(name, Ns, 1)[0] for _ in range(args.steps)]
+    wall = (time.perf_counter() - t0) / args.steps
+    dt = float(np.mean(ts))
+    val = flops_roundtrip(global_real_shape(Ns, dealias)) / dt / 1e9
     cfg = describe(name, 1)
-    sample = ("oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d) on a bounded sample "
-              "%s %s of the %s workload" % (kind, cores, "x".join(map(str, Ns)), prec, "x".join(map(str, N))))
+    sample = "%s on a bounded sample %s %s of the %s workload (setup %.2f s per step excluded)" % (
+        d["how"], "x".join(map(str, Ns)), prec, "x".join(map(str, N)), wall - dt)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": cfg,
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": d["cores"], "kind": d["kind"], "sample": sample,
+                            "host_cores": os.cpu_count()},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
     return 0
@@ -321,7 +394,7 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(name, {}).get("%s_%s_%d" % (dom["dir"], dom["type"], dom["len"]))
+        traffic = tj.get(name, {}).get("%s_%d_%s_%d" % (dom["dir"], dom["step"], dom["type"], dom["len"])) if P == 1 else None
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": "%s %s n=%d (step %d)" % (dom["dir"], dom["type"], dom["len"], dom["step"]),

@@ -24,10 +24,18 @@ import numpy as np
 REFERENCE_ROOT = os.environ.get("MPIFFT4PY_REFERENCE", "/root/reference")
 SCRATCH = os.environ.get("MPIFFT4PY_REF_SCRATCH", "/tmp/mpifft4py_ref_build")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# `pip install --no-deps --target baseline/_ref <copy of /root/reference>`: the
+# unmodified reference with its Cython extension already built.  Git-ignored, but it travels to
+# the GPU box, where it is what bench.py's reference arm times.
+INSTALLED = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "baseline", "_ref")
+
+
+def installed_available():
+    return os.path.isfile(os.path.join(INSTALLED, "mpiFFT4py", "slab.py"))
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mpiFFT4py"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mpiFFT4py")) or installed_available()
 
 
 def _apply_compat_patches():
@@ -120,6 +128,19 @@ def load():
     _apply_compat_patches()
     if _HERE not in sys.path:
         sys.path.insert(0, _HERE)  # fake mpi4py
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "mpiFFT4py")):
+        # GPU box: only the prebuilt install exists
+        if INSTALLED not in sys.path:
+            sys.path.insert(1, INSTALLED)
+        try:
+            importlib.import_module("mpiFFT4py.cython.maths")
+            how = "cython (baseline/_ref)"
+        except Exception:  # noqa: BLE001
+            _inject_maths_standin()
+            how = "standin (baseline/_ref)"
+        _loaded = importlib.import_module("mpiFFT4py")
+        _loaded._refshim_maths = how
+        return _loaded
     root = _build_scratch_copy()
     with open(os.path.join(root, ".built")) as f:
         how = f.read()
