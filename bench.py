@@ -363,19 +363,26 @@ def run_ours(args):
     F.set_timing(True)
     acc = {}
     reps = 3
-    for _ in range(reps):
+
+    def record(direction, rep):
+        # the chunks of a pipelined pass share a pass id: add their times and bytes
+        for s in F.last_steps():
+            a = acc.setdefault((direction, s[4], s[0], s[3]), [0.0, 0.0])
+            a[0] += s[1]
+            if rep == 0:
+                a[1] += s[2]
+
+    for rep in range(reps):
         if flush is not None:
             flush.fill_(1)
         fwd(u, fu, dealias)
         torch.cuda.synchronize()
-        for i, s in enumerate(F.last_steps()):
-            acc.setdefault(("fwd", i, s[0], s[3]), [0.0, s[2]])[0] += s[1]
+        record("fwd", rep)
         if flush is not None:
             flush.fill_(1)
         inv(fu, u2, dealias)
         torch.cuda.synchronize()
-        for i, s in enumerate(F.last_steps()):
-            acc.setdefault(("inv", i, s[0], s[3]), [0.0, s[2]])[0] += s[1]
+        record("inv", rep)
     F.set_timing(False)
     peaks = {}
     try:
@@ -446,10 +453,14 @@ def run_ours(args):
 
     if P > 1:
         dist.barrier()
+    cfg = describe(name, P)
+    if P > 1:
+        cfg["exchange"] = {"transport": getattr(F, "transport_used", "nccl"),
+                           "pipelined_chunks": sum(1 for s in F.last_steps() if s[0] == "exchange") // max(1, int(x1) and len({s[4] for s in F.last_steps() if s[0] == "exchange"}))}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": describe(name, P),
+               "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": cfg,
                "roundtrip_rel_l2": err, "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
                "kernels_per_transform": int(k1), "nccl_groups_per_transform": int(x1),
                "roofline": roofline, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,

@@ -150,6 +150,9 @@ typedef struct {
   b200fft_comm_t comm;   /* slab / line: all ranks */
   b200fft_comm_t comm0;  /* pencil: ranks with equal rank / P1 */
   b200fft_comm_t comm1;  /* pencil: ranks with equal rank % P1 */
+  int chunks;      /* pipeline depth of the exchange (the MPI collectives of slab.py:281-332,406-471
+                      cut into `chunks` pieces, each overlapped with the FFT passes of the next
+                      piece on a second stream); 0 = automatic, 1 = no overlap */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;
@@ -163,6 +166,15 @@ B200FFT_API size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan);
 B200FFT_API int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream);
 /* ifftn / ifft2 (slab.py:214-346, pencil.py:386-632,1001-1226, line.py:262-340).  fu is not modified. */
 B200FFT_API int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream);
+/* Copy-engine transport (transport = B200FFT_TRANSPORT_P2P, slab plans): the all-to-all becomes
+ * cudaMemcpyAsync pushes into the peers' receive buffers over NVLink (DMA engines, no SMs), ordered
+ * by 32-bit sequence flags and stream memory operations, so that it overlaps the FFT passes of the
+ * next chunk without competing for SMs.  After plan_create every rank calls _p2p_handles (fills
+ * 256 bytes: CUDA IPC handles of its three work buffers and its flag words), the host exchanges
+ * them (allgather, rank order) and every rank calls _p2p_connect with the nranks*256 bytes.
+ * Replaces the same collectives as the NCCL path (slab.py:281-332,406-471). */
+B200FFT_API int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256);
+B200FFT_API int b200fft_plan_p2p_connect(b200fft_plan_t plan, const void* all_handles);
 /* number of kernels / NCCL groups the last exec launched (for bench.py's gpu_launches) */
 B200FFT_API int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges);
 /* device time of the exchange phases of the last exec, if timing was enabled (ms; <0 if not) */
@@ -170,8 +182,10 @@ B200FFT_API int b200fft_plan_set_timing(b200fft_plan_t plan, int on);
 B200FFT_API int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchange_ms);
 /* per-step record of the last exec (timing on): type 0 strided C2C, 1 R2C, 2 C2R, 3 exchange; device
  * time in ms; algorithmic bytes = operand read once + result written once (SURVEY.md section 8d;
- * for an exchange: bytes sent to other ranks); transform length n.  Returns the step count in *n. */
-B200FFT_API int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len);
+ * for an exchange: bytes sent to other ranks); transform length n; pass = index of the logical pass
+ * the step belongs to (the chunks of a pipelined pass share it).  Returns the step count in *n. */
+B200FFT_API int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len,
+                                        int* pass);
 
 #ifdef __cplusplus
 }

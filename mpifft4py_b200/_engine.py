@@ -5,6 +5,7 @@ Callers may pass numpy arrays (what every reference caller does -- they are stag
 device buffers owned by the object) or CUDA ``torch.Tensor``s (used in place, zero copy).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -56,11 +57,43 @@ class Transform(object):
         d.padsize = float(self.padsize)
         d.drop_nyquist = int(drop_nyquist)
         d.transport = D.TRANSPORT_NCCL
-        d.comm = _comm.nccl_handle(comm) if comm is not None else None
-        d.comm0 = _comm.nccl_handle(comm0) if comm0 is not None else None
-        d.comm1 = _comm.nccl_handle(comm1) if comm1 is not None else None
-        h = C.c_void_p()
-        _lib.check(_lib.lib().b200fft_plan_create(C.byref(h), C.byref(d)))
+        d.chunks = int(getattr(self, "exchange_chunks", 0) or os.environ.get("B200FFT_CHUNKS", "0"))
+        # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
+        # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
+        # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree
+        # to use if any of them cannot map its peers' buffers (no IPC / no peer access).
+        choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT", "p2p")).lower()
+        assert choice in ("p2p", "nccl"), "transport must be 'p2p' or 'nccl'"
+        h = None
+        if kind == D.SLAB and int(nranks) > 1 and choice == "p2p":
+            d.transport = D.TRANSPORT_P2P
+            d.comm = None
+            h = C.c_void_p()
+            L = _lib.lib()
+            mine = C.create_string_buffer(256)
+            ok = L.b200fft_plan_create(C.byref(h), C.byref(d)) == 0 and L.b200fft_plan_p2p_handles(h, mine) == 0
+            err = "" if ok else L.b200fft_last_error().decode("utf-8", "replace")
+            replies = comm.allgather((ok, mine.raw, err))
+            if all(r[0] for r in replies):
+                ok = L.b200fft_plan_p2p_connect(h, b"".join(r[1] for r in replies)) == 0
+                err = "" if ok else L.b200fft_last_error().decode("utf-8", "replace")
+            else:
+                ok = False
+                err = next(r[2] for r in replies if not r[0]) or err
+            if not all(comm.allgather(ok)):
+                import warnings
+                warnings.warn("mpifft4py_b200: copy-engine transport unavailable (%s); using NCCL send/recv" % err)
+                if h:
+                    L.b200fft_plan_destroy(h)
+                h = None
+        if h is None:
+            d.transport = D.TRANSPORT_NCCL
+            d.comm = _comm.nccl_handle(comm) if comm is not None else None
+            d.comm0 = _comm.nccl_handle(comm0) if comm0 is not None else None
+            d.comm1 = _comm.nccl_handle(comm1) if comm1 is not None else None
+            h = C.c_void_p()
+            _lib.check(_lib.lib().b200fft_plan_create(C.byref(h), C.byref(d)))
+        self.transport_used = "p2p" if d.transport == D.TRANSPORT_P2P else "nccl"
         self._plan = h
         self._plan_desc = d
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -142,13 +175,16 @@ class Transform(object):
         return f.value, x.value
 
     def last_steps(self):
-        """[(type, ms, algorithmic_bytes, length)] of the last transform; type in
-        {'c2c', 'r2c', 'c2r', 'exchange'}; ms < 0 unless set_timing(True)."""
+        """[(type, ms, algorithmic_bytes, length, pass)] of the last transform; type in
+        {'c2c', 'r2c', 'c2r', 'exchange'}; ms < 0 unless set_timing(True); the chunks of a
+        pipelined pass share `pass`."""
+        M = 64
         n = C.c_int()
-        ty = (C.c_int * 16)()
-        ms = (C.c_float * 16)()
-        by = (C.c_double * 16)()
-        ln = (C.c_int * 16)()
-        _lib.check(_lib.lib().b200fft_plan_last_steps(self._plan, 16, C.byref(n), ty, ms, by, ln))
+        ty = (C.c_int * M)()
+        ms = (C.c_float * M)()
+        by = (C.c_double * M)()
+        ln = (C.c_int * M)()
+        ps = (C.c_int * M)()
+        _lib.check(_lib.lib().b200fft_plan_last_steps(self._plan, M, C.byref(n), ty, ms, by, ln, ps))
         names = ["c2c", "r2c", "c2r", "exchange"]
-        return [(names[ty[i]], float(ms[i]), float(by[i]), int(ln[i])) for i in range(min(n.value, 16))]
+        return [(names[ty[i]], float(ms[i]), float(by[i]), int(ln[i]), int(ps[i])) for i in range(min(n.value, M))]

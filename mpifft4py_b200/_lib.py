@@ -18,6 +18,7 @@ SYMBOLS = [
     "b200fft_plan_create", "b200fft_plan_destroy", "b200fft_plan_workspace_bytes",
     "b200fft_exec_forward", "b200fft_exec_inverse", "b200fft_plan_last_launches",
     "b200fft_plan_set_timing", "b200fft_plan_last_phase_ms", "b200fft_plan_last_steps",
+    "b200fft_plan_p2p_handles", "b200fft_plan_p2p_connect",
 ]
 
 
@@ -53,9 +54,12 @@ def lib():
     L.b200fft_exec_inverse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.b200fft_plan_last_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.b200fft_plan_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.b200fft_plan_p2p_handles.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200fft_plan_p2p_connect.argtypes = [C.c_void_p, C.c_void_p]
     L.b200fft_plan_last_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.b200fft_plan_last_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                          C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+                                          C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int)]
     for name in SYMBOLS:
         getattr(L, name)
     _lib = L

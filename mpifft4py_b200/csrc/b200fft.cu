@@ -7,10 +7,12 @@
 // FFT calls (pack, transpose, pad, truncate, mask, scale) is part of a pass's index map; the MPI
 // collectives become one NCCL send/recv group per exchange, with each rank's own block written
 // straight into the receive buffer by the producing FFT pass.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -152,7 +154,34 @@ int nccl_fail(ncclResult_t r, const char* what) {
   return fail(B200FFT_ERR_NCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
 }
 
+// ---- driver API stream memory operations (copy-engine transport), through dlopen -----------------
+struct CuApi {
+  void* h = nullptr;
+  CUresult (*WaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*WriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+};
+CuApi g_cu;
+std::mutex g_cu_mu;
+
+int load_cuda_driver() {
+  std::lock_guard<std::mutex> lk(g_cu_mu);
+  if (g_cu.h) return 0;
+  void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(B200FFT_ERR_CUDA, "cannot dlopen libcuda.so.1: %s", dlerror());
+  auto sym = [&](const char* a, const char* b) {
+    void* f = dlsym(h, a);
+    return f ? f : dlsym(h, b);
+  };
+  g_cu.WaitValue32 = reinterpret_cast<decltype(g_cu.WaitValue32)>(sym("cuStreamWaitValue32_v2", "cuStreamWaitValue32"));
+  g_cu.WriteValue32 = reinterpret_cast<decltype(g_cu.WriteValue32)>(sym("cuStreamWriteValue32_v2", "cuStreamWriteValue32"));
+  if (!g_cu.WaitValue32 || !g_cu.WriteValue32) return fail(B200FFT_ERR_CUDA, "libcuda lacks cuStreamWaitValue32 / cuStreamWriteValue32");
+  g_cu.h = h;
+  return 0;
+}
+
 }  // namespace
+
+constexpr int P2P_STAGE = 512;  // staging words for flag values (ring)
 
 struct b200fft_comm {
   ncclComm_t comm;
@@ -167,12 +196,29 @@ struct b200fft_plan {
   size_t wbytes[3] = {0, 0, 0};
   int last_kernels = 0, last_exch = 0;
   int timing = 0;
-  cudaEvent_t ev[2 * 16];
+  // copy-engine (P2P) transport: peers' work buffers and flag words mapped through CUDA IPC.
+  // Blocks are pushed into the peer's receive buffer by cudaMemcpyAsync (DMA over NVLink, no SMs);
+  // arrival and buffer-reuse credits are 32-bit sequence numbers written / awaited by stream
+  // memory operations, so nothing blocks the host and no kernel spins.
+  struct {
+    bool connected = false;
+    void* flags = nullptr;                   // uint32 arrived[MAXP] then credit[MAXP]
+    void* peer_ws[B200FFT_MAXP][3] = {};
+    void* peer_flags[B200FFT_MAXP] = {};
+    cudaStream_t wait_stream = nullptr;
+    std::vector<cudaEvent_t> send_ev;
+    unsigned stage_slot = 0;                 // next staging word (flag values travel by 4-byte DMA)
+    unsigned seq = 0;                        // exchange steps executed so far (identical on all ranks)
+    unsigned calls = 0;                      // transforms with exchanges executed so far
+  } p2p;
+  cudaStream_t comm_stream = nullptr;   // exchanges of pipelined programs run here
+  std::vector<cudaEvent_t> sched_ev;    // ordering events between the two streams
+  cudaEvent_t ev[2 * 64];
   int nev = 0;
   bool ev_made = false;
   float last_fft_ms = -1.f, last_exch_ms = -1.f;
   std::vector<std::pair<int, int>> ev_marks;  // (event index start, is_exchange)
-  std::vector<int> st_type, st_len;
+  std::vector<int> st_type, st_len, st_pass;
   std::vector<double> st_bytes;
 };
 
@@ -210,7 +256,9 @@ int validate_desc(const b200fft_plan_desc_t& d) {
     return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
   }
   if (P > 1) {
-    if (d.kind == B200FFT_SLAB || d.kind == B200FFT_LINE) {
+    if (d.transport == B200FFT_TRANSPORT_P2P) {
+      // no communicator: peers are reached through IPC-mapped buffers (b200fft_plan_p2p_connect)
+    } else if (d.kind == B200FFT_SLAB || d.kind == B200FFT_LINE) {
       if (!d.comm) return fail(B200FFT_ERR_ARG, "multi-rank plan needs a communicator");
       if (d.comm->nranks != P || d.comm->rank != d.rank) return fail(B200FFT_ERR_ARG, "communicator does not match nranks / rank");
     } else {
@@ -263,6 +311,7 @@ int ensure_program(b200fft_plan* pl, int inverse, int dealias) {
   for (int w = 0; w < 3; ++w) {
     const size_t need = (size_t)pg.need[BUF_W0 + w] * csz;
     if (need > pl->wbytes[w]) {
+      if (pl->p2p.connected) return fail(B200FFT_ERR_NOMEM, "P2P plans size their buffers at connect time (need %zu > %zu)", need, pl->wbytes[w]);
       if (pl->ws[w]) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
@@ -320,6 +369,67 @@ int run_exchange(b200fft_plan* pl, const Step& s, const void* in, void* out, siz
   return 0;
 }
 
+int cu_fail(CUresult r, const char* what) { return fail(B200FFT_ERR_CUDA, "%s: CUresult %d", what, (int)r); }
+
+// Publish `value` in a peer's flag word, ordered after everything queued on `st` so far: a stream
+// memory operation writes it into a local staging word and a 4-byte DMA copy carries it across
+// NVLink (stream order = the data copies before it have completed).
+int post_flag(b200fft_plan* pl, cudaStream_t st, void* peer_word, unsigned value) {
+  auto& pp = pl->p2p;
+  unsigned* stage = reinterpret_cast<unsigned*>(pp.flags) + 2 * B200FFT_MAXP + (pp.stage_slot++ % P2P_STAGE);
+  if (CUresult r = g_cu.WriteValue32((CUstream)st, (CUdeviceptr)stage, value, CU_STREAM_WRITE_VALUE_DEFAULT))
+    return cu_fail(r, "cuStreamWriteValue32");
+  cudaError_t e = cudaMemcpyAsync(peer_word, stage, sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(flag)");
+  return 0;
+}
+
+// Copy-engine exchange of one step: push every peer's block, publish the sequence number, then
+// (on the wait stream) wait for every peer's block to land here and record the step's event.
+int run_exchange_p2p(b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz, cudaStream_t s1) {
+  auto& pp = pl->p2p;
+  if (!pp.connected) return fail(B200FFT_ERR_ARG, "P2P plan used before b200fft_plan_p2p_connect");
+  const unsigned seq = ++pp.seq;
+  unsigned* fl = reinterpret_cast<unsigned*>(pp.flags);
+  if (s.first_exch && pp.calls > 0)  // peers must have finished reading what the previous transform sent them
+    for (int q = 0; q < s.npeers; ++q)
+      if (q != s.me)
+        if (CUresult r = g_cu.WaitValue32((CUstream)s1, (CUdeviceptr)(fl + B200FFT_MAXP + q), pp.calls, CU_STREAM_WAIT_VALUE_GEQ))
+          return cu_fail(r, "cuStreamWaitValue32(credit)");
+  for (int k = 1; k < s.npeers; ++k) {  // staggered peer order: no two ranks target the same GPU at once
+    const int q = (s.me + k) % s.npeers;
+    char* dst = (char*)pp.peer_ws[q][s.rpeer[q].buf - BUF_W0] + (size_t)s.rpeer[q].off * csz;
+    cudaError_t e = cudaMemcpyAsync(dst, resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, cudaMemcpyDeviceToDevice, s1);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(peer)");
+  }
+  for (int q = 0; q < s.npeers; ++q)
+    if (q != s.me)
+      if (int rc = post_flag(pl, s1, (unsigned*)pp.peer_flags[q] + s.me, seq)) return rc;
+  return 0;
+}
+
+// wait-stream half of a P2P exchange step: own sends done + all peers' blocks arrived -> rec_ev
+int finish_exchange_p2p(b200fft_plan* pl, const Step& s, cudaStream_t s1, int idx) {
+  auto& pp = pl->p2p;
+  while ((int)pp.send_ev.size() <= idx) {
+    cudaEvent_t e;
+    if (cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) return cuda_fail(rc, "cudaEventCreate");
+    pp.send_ev.push_back(e);
+  }
+  cudaEventRecord(pp.send_ev[(size_t)idx], s1);
+  cudaStreamWaitEvent(pp.wait_stream, pp.send_ev[(size_t)idx], 0);
+  unsigned* fl = reinterpret_cast<unsigned*>(pp.flags);
+  for (int q = 0; q < s.npeers; ++q)
+    if (q != s.me)
+      if (CUresult r = g_cu.WaitValue32((CUstream)pp.wait_stream, (CUdeviceptr)(fl + q), pp.seq, CU_STREAM_WAIT_VALUE_GEQ))
+        return cu_fail(r, "cuStreamWaitValue32(arrived)");
+  if (s.rec_ev >= 0) {
+    cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], pp.wait_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+  }
+  return 0;
+}
+
 int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void* out, cudaStream_t st) {
   if (dealias < 0 || dealias > 2) return fail(B200FFT_ERR_ARG, "dealias must be None, '3/2-rule' or '2/3-rule'");
   if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;  // forward 2/3 == plain (slab.py:389)
@@ -333,14 +443,41 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   pl->ev_marks.clear();
   pl->st_type.clear();
   pl->st_len.clear();
+  pl->st_pass.clear();
   pl->st_bytes.clear();
   int evi = 0;
   if (pl->timing && !pl->ev_made) {
-    for (int i = 0; i < 32; ++i) cudaEventCreate(&pl->ev[i]);
+    for (int i = 0; i < 128; ++i) cudaEventCreate(&pl->ev[i]);
     pl->ev_made = true;
   }
+  // scheduling resources of pipelined programs: a high-priority communication stream (its few
+  // NCCL CTAs must win SM slots against the FFT grids) and one event per cross-stream edge
+  if (pg.nevents > 0) {
+    if (!pl->comm_stream) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      cudaError_t e = cudaStreamCreateWithPriority(&pl->comm_stream, cudaStreamNonBlocking, hi);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
+    }
+    while ((int)pl->sched_ev.size() < pg.nevents) {
+      cudaEvent_t e;
+      cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (rc != cudaSuccess) return cuda_fail(rc, "cudaEventCreate");
+      pl->sched_ev.push_back(e);
+    }
+  }
+  bool use_p2p = false;
+  for (const Step& s : pg.steps) use_p2p = use_p2p || (s.type == ST_EXCH);
+  use_p2p = use_p2p && pl->d.transport == B200FFT_TRANSPORT_P2P;
+  int nexch = 0;
+  cudaStream_t caller = st;
   for (const Step& s : pg.steps) {
-    if (pl->timing && evi + 2 <= 32) cudaEventRecord(pl->ev[evi], st);
+    st = (s.stream == 1 && pl->comm_stream) ? pl->comm_stream : caller;
+    if (s.wait_ev >= 0) {
+      cudaError_t e = cudaStreamWaitEvent(st, pl->sched_ev[(size_t)s.wait_ev], 0);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    }
+    if (pl->timing && evi + 2 <= 128) cudaEventRecord(pl->ev[evi], st);
     int rc = 0;
     if (s.type == ST_STRIDED) {
       b200fft_strided_desc_t d;
@@ -370,6 +507,9 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       fill_side(pl, s.cside, d.cside, in, out, csz);
       rc = exec_rows(d, s.type == ST_R2C, st);
       pl->last_kernels++;
+    } else if (use_p2p) {
+      rc = run_exchange_p2p(pl, s, in, out, csz, st);
+      pl->last_exch++;
     } else {
       rc = run_exchange(pl, s, in, out, csz, st);
       pl->last_exch++;
@@ -382,14 +522,27 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       else for (int q = 0; q < s.npeers; ++q) if (q != s.me) bytes += (double)s.scnt[q] * csz;
       pl->st_type.push_back((int)s.type);
       pl->st_len.push_back(s.type == ST_EXCH ? s.npeers : s.n);
+      pl->st_pass.push_back(s.pass);
       pl->st_bytes.push_back(bytes);
     }
-    if (pl->timing && evi + 2 <= 32) {
+    if (pl->timing && evi + 2 <= 128) {
       cudaEventRecord(pl->ev[evi + 1], st);
       pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
       evi += 2;
     }
+    if (s.type == ST_EXCH && use_p2p) {
+      if (int rc2 = finish_exchange_p2p(pl, s, st, nexch++)) return rc2;
+    } else if (s.rec_ev >= 0) {
+      cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+    }
+    if (use_p2p && s.last_reader) {  // hand the receive buffers back to the peers
+      for (int q = 0; q < pl->d.nranks; ++q)
+        if (q != pl->d.rank)
+          if (int rc2 = post_flag(pl, st, (unsigned*)pl->p2p.peer_flags[q] + B200FFT_MAXP + pl->d.rank, pl->p2p.calls + 1)) return rc2;
+    }
   }
+  if (use_p2p) pl->p2p.calls++;
   return 0;
 }
 
@@ -472,9 +625,14 @@ int b200fft_comm_destroy(b200fft_comm_t comm) {
 int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
   if (!plan || !d) return fail(B200FFT_ERR_ARG, "null argument");
   if (int rc = validate_desc(*d)) return rc;
-  if (d->transport != B200FFT_TRANSPORT_NCCL) return fail(B200FFT_ERR_UNSUPPORTED, "only the NCCL transport is built");
-  if (d->nranks > 1)
+  if (d->transport != B200FFT_TRANSPORT_NCCL && d->transport != B200FFT_TRANSPORT_P2P)
+    return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
+  if (d->transport == B200FFT_TRANSPORT_P2P && d->nranks > 1 && d->kind != B200FFT_SLAB)
+    return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) transport is built for slab plans; use NCCL for pencil / line");
+  if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_NCCL)
     if (int rc = load_nccl()) return rc;
+  if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_P2P)
+    if (int rc = load_cuda_driver()) return rc;
   b200fft_plan* pl = new b200fft_plan;
   pl->d = *d;
   if (pl->d.kind == B200FFT_LINE) pl->d.N[2] = 0;
@@ -496,7 +654,20 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
   for (int w = 0; w < 3; ++w)
     if (plan->ws[w]) cudaFree(plan->ws[w]);
   if (plan->ev_made)
-    for (int i = 0; i < 32; ++i) cudaEventDestroy(plan->ev[i]);
+    for (int i = 0; i < 128; ++i) cudaEventDestroy(plan->ev[i]);
+  for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
+  if (plan->p2p.connected) {
+    for (int q = 0; q < plan->d.nranks; ++q) {
+      if (q == plan->d.rank) continue;
+      for (int w = 0; w < 3; ++w)
+        if (plan->p2p.peer_ws[q][w]) cudaIpcCloseMemHandle(plan->p2p.peer_ws[q][w]);
+      if (plan->p2p.peer_flags[q]) cudaIpcCloseMemHandle(plan->p2p.peer_flags[q]);
+    }
+  }
+  if (plan->p2p.flags) cudaFree(plan->p2p.flags);
+  if (plan->p2p.wait_stream) cudaStreamDestroy(plan->p2p.wait_stream);
+  if (plan->comm_stream) cudaStreamDestroy(plan->comm_stream);
   delete plan;
   return 0;
 }
@@ -514,6 +685,57 @@ int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int deali
 int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int dealias, void* stream) {
   if (!plan) return fail(B200FFT_ERR_ARG, "null plan");
   return run_program(plan, 1, dealias, fu, u, (cudaStream_t)stream);
+}
+
+int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256) {
+  if (!plan || !handles256) return fail(B200FFT_ERR_ARG, "null argument");
+  if (plan->d.transport != B200FFT_TRANSPORT_P2P || plan->d.nranks < 2) return fail(B200FFT_ERR_ARG, "not a multi-rank P2P plan");
+  // size the work buffers for every program now: their addresses are what the peers map
+  size_t need[3] = {256, 256, 256};
+  const size_t csz = plan->d.precision == B200FFT_DOUBLE ? 16 : 8;
+  for (int inv = 0; inv < 2; ++inv)
+    for (int de = 0; de < 3; ++de) {
+      if (de == B200FFT_DEALIAS_3_2 && std::fabs(plan->d.padsize - 1.5) > 1e-12) continue;
+      Program pg;
+      if (build_program(plan->d, inv, de, pg) || check_lengths(pg)) continue;
+      for (int w = 0; w < 3; ++w) need[w] = std::max(need[w], (size_t)pg.need[BUF_W0 + w] * csz);
+    }
+  for (int w = 0; w < 3; ++w) {
+    if (plan->ws[w]) cudaFree(plan->ws[w]);
+    cudaError_t e = cudaMalloc(&plan->ws[w], need[w]);
+    if (e != cudaSuccess) return fail(B200FFT_ERR_NOMEM, "cudaMalloc(%zu bytes of work space): %s", need[w], cudaGetErrorString(e));
+    plan->wbytes[w] = need[w];
+  }
+  cudaError_t e = cudaMalloc(&plan->p2p.flags, (2 * B200FFT_MAXP + P2P_STAGE) * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(plan->p2p.flags, 0, (2 * B200FFT_MAXP + P2P_STAGE) * sizeof(unsigned));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(flags)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");
+  cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(handles256);
+  for (int w = 0; w < 3; ++w)
+    if ((e = cudaIpcGetMemHandle(&h[w], plan->ws[w])) != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+  if ((e = cudaIpcGetMemHandle(&h[3], plan->p2p.flags)) != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle(flags)");
+  return 0;
+}
+
+int b200fft_plan_p2p_connect(b200fft_plan_t plan, const void* all_handles) {
+  if (!plan || !all_handles) return fail(B200FFT_ERR_ARG, "null argument");
+  if (!plan->p2p.flags) return fail(B200FFT_ERR_ARG, "call b200fft_plan_p2p_handles first");
+  const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int q = 0; q < plan->d.nranks; ++q) {
+    if (q == plan->d.rank) continue;
+    for (int w = 0; w < 3; ++w) {
+      cudaError_t e = cudaIpcOpenMemHandle(&plan->p2p.peer_ws[q][w], h[4 * q + w], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (is NVLink / P2P available between the GPUs?)");
+    }
+    cudaError_t e = cudaIpcOpenMemHandle(&plan->p2p.peer_flags[q], h[4 * q + 3], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle(flags)");
+  }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaError_t e = cudaStreamCreateWithPriority(&plan->p2p.wait_stream, cudaStreamNonBlocking, hi);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
+  plan->p2p.connected = true;
+  return 0;
 }
 
 int b200fft_plan_last_launches(b200fft_plan_t plan, int* kernels, int* exchanges) {
@@ -546,7 +768,7 @@ int b200fft_plan_last_phase_ms(b200fft_plan_t plan, float* fft_ms, float* exchan
   return 0;
 }
 
-int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len) {
+int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, float* ms, double* bytes, int* len, int* pass) {
   if (!plan || !n) return fail(B200FFT_ERR_ARG, "null argument");
   const int cnt = (int)plan->st_type.size();
   *n = cnt;
@@ -554,6 +776,7 @@ int b200fft_plan_last_steps(b200fft_plan_t plan, int max, int* n, int* type, flo
     if (type) type[i] = plan->st_type[i];
     if (bytes) bytes[i] = plan->st_bytes[i];
     if (len) len[i] = plan->st_len[i];
+    if (pass) pass[i] = plan->st_pass[i];
     if (ms) {
       ms[i] = -1.f;
       if (plan->timing && i < (int)plan->ev_marks.size()) {

@@ -15,7 +15,7 @@ from mpifft4py_b200 import _cdefs as D
 TOL = {"double": 5e-14, "single": 5e-6}
 
 
-def _desc(kind, N, P, prec, P1=1, P2=1, drop=0):
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0):
     d = D.PlanDesc()
     d.kind = kind
     d.precision = D.DOUBLE if prec == "double" else D.SINGLE
@@ -27,6 +27,7 @@ def _desc(kind, N, P, prec, P1=1, P2=1, drop=0):
     d.padsize = 1.5
     d.drop_nyquist = drop
     d.transport = 0
+    d.chunks = chunks
     return d
 
 
@@ -53,16 +54,21 @@ def _rand_c(rng, shape, ct):
     return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(ct)
 
 
+@pytest.mark.parametrize("chunks", [0, 2, 4])
 @pytest.mark.parametrize("prec", ["double", "single"])
 @pytest.mark.parametrize("P", [1, 2, 4])
 @pytest.mark.parametrize("N", [(8, 16, 32), (16, 16, 16), (32, 8, 8)])
-def test_slab(N, P, prec):
+def test_slab(N, P, prec, chunks):
+    """chunks > 1: the exchange is cut into pieces pipelined against the FFT passes (two streams on
+    the device; the emulator runs the same step list in program order)."""
     if P > N[0] // 2 or N[1] % P:
         pytest.skip("illegal decomposition")
+    if chunks and (P == 1 or prec == "single"):
+        pytest.skip("chunking only changes multi-rank programs; one precision is enough")
     rt, ct = oracle.common.dtypes(prec)
     g = oracle.slab.Geometry(N, P)
     rng = np.random.default_rng(sum(N) + P)
-    d = _desc(D.SLAB, N, P, prec)
+    d = _desc(D.SLAB, N, P, prec, chunks=chunks)
     tol = TOL[prec]
     A = rng.random(N).astype(rt)
     u = [A[g.real_local_slice(r)] for r in range(P)]
