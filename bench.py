@@ -455,8 +455,9 @@ def run_ours(args):
         dist.barrier()
     cfg = describe(name, P)
     if P > 1:
+        ex = [s for s in F.last_steps() if s[0] == "exchange"]
         cfg["exchange"] = {"transport": getattr(F, "transport_used", "nccl"),
-                           "pipelined_chunks": sum(1 for s in F.last_steps() if s[0] == "exchange") // max(1, int(x1) and len({s[4] for s in F.last_steps() if s[0] == "exchange"}))}
+                           "pipelined_chunks": len(ex) // max(1, len({s[4] for s in ex}))}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

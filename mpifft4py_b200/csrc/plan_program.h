@@ -179,19 +179,24 @@ inline int ipad(double p, long long x) { return (int)(p * (double)x); }
 
 // Pipeline depth of a chunked exchange: the local extent `ext` is cut into C equal chunks; chunk c's
 // exchange runs on the communication stream while the FFT passes of chunk c+1 run.  Auto: the
-// largest C in {8, 4, 2} that divides ext and keeps every per-peer message >= 4 MB (below that
-// launch latency, not NVLink bandwidth, sets the exchange time and chunking only adds launches).
-// max_auto: NCCL exchanges run as kernels that compete with the FFT grids for SMs -- measured at
-// 1024^3 on 4 GPUs: 10.6 ms (1 chunk), 10.0 (2), 11.1 (4), 11.7 (8) -- so NCCL plans stop at 2;
-// the copy-engine (P2P) transport does not touch the SMs and takes deeper pipelines.
-inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, int max_auto) {
+// largest C in {8, 4, 2} that divides ext and keeps every per-peer message above a floor.
+//  * NCCL exchanges are kernels that compete with the FFT grids for SMs -- measured at 1024^3 double
+//    on 4 GPUs: 10.6 ms (1 chunk), 10.0 (2), 11.1 (4), 11.7 (8) -- so NCCL plans stop at 2 chunks
+//    (floor 4 MB: below that launch latency, not NVLink bandwidth, sets the exchange time).
+//  * Copy-engine (P2P) exchanges leave the SMs alone but pay ~25 us per queued copy + flag
+//    (2 GPUs, 8 chunks: +0.19 ms over 1 chunk; 8 GPUs, 8 chunks of 16.8 MB x 7 peers: 2.58 ms
+//    against 1.07 ms of pure transfer).  A 48 MB floor keeps that overhead under ~30% of the
+//    transfer time: 8 chunks at P = 2 and 4, 2 chunks at P = 8 for 1024^3 double.
+inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, bool p2p) {
   if (requested > 0) {
     int c = requested;
     while (c > 1 && ext % c) --c;
     return c < 1 ? 1 : c;
   }
+  const int max_auto = p2p ? 8 : 2;
+  const long long floor_bytes = p2p ? (48ll << 20) : (4ll << 20);
   for (int c : {8, 4, 2})
-    if (c <= max_auto && ext % c == 0 && peer_msg_bytes / c >= (4ll << 20)) return c;
+    if (c <= max_auto && ext % c == 0 && peer_msg_bytes / c >= floor_bytes) return c;
   return 1;
 }
 
@@ -229,7 +234,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
       } else {  // slab.py:389-483
         // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
         const int recvbuf = (padded || p2p) ? BUF_W2 : BUF_OUT;
-        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p ? 8 : 2);
+        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p);
         const long long xc = pNp0 / C;
         b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
         b.use(BUF_W1, P * blk);
@@ -321,7 +326,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         // padded planes are larger than the send blocks: give its output a buffer of its own then
         const int ybuf = BUF_W2;
         b.use(ybuf, (long long)pNp0 * pN1 * Nf);
-        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p ? 8 : 2);
+        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p);
         const long long xc = pNp0 / C;
         std::vector<int> xev((size_t)C);
         for (int c = 0; c < C; ++c) {  // all exchanges are queued first: they only depend on the x pass

@@ -152,6 +152,48 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
   return 0;
 }
 
+// Copy-engine transport invariants of every program of a plan: rank r pushes its block for peer q to
+// rpeer[q]; that must be exactly where q's own program expects the block from r (recv[r]), with equal
+// counts, inside q's buffer; exactly one first_exch and one last_reader per program with exchanges;
+// all ranks agree on the number of exchange steps (the sequence numbers advance in lockstep).
+int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* nexch_out) {
+  const int P = d0->nranks;
+  std::vector<Program> pg((size_t)P);
+  for (int r = 0; r < P; ++r) {
+    b200fft_plan_desc_t d = *d0;
+    d.rank = r;
+    if (int rc = build_program(d, inverse, dealias, pg[r])) return rc;
+  }
+  const size_t nsteps = pg[0].steps.size();
+  int nexch = 0;
+  for (int r = 0; r < P; ++r) {
+    if (pg[r].steps.size() != nsteps) return 100;
+    int first = 0, last = 0, ex = 0;
+    for (size_t si = 0; si < nsteps; ++si) {
+      const Step& s = pg[r].steps[si];
+      last += s.last_reader;
+      if (s.type != ST_EXCH) continue;
+      ++ex;
+      first += s.first_exch;
+      if (s.comm != 0) return 101;  // only world exchanges (slab) are built for this transport
+      for (int q = 0; q < s.npeers; ++q) {
+        if (q == s.me) continue;
+        const Step& t = pg[q].steps[si];
+        if (t.type != ST_EXCH) return 102;
+        if (s.rpeer[q].buf != t.recv[s.me].buf || s.rpeer[q].off != t.recv[s.me].off) return 103;
+        if (s.scnt[q] != t.rcnt[s.me]) return 104;
+        if (s.rpeer[q].buf < BUF_W0) return 105;  // peers may only write plan-owned buffers
+        if (s.rpeer[q].off + s.scnt[q] > pg[q].need[s.rpeer[q].buf]) return 106;
+      }
+    }
+    if (ex > 0 && (first != 1 || last != 1)) return 107;
+    if (r == 0) nexch = ex;
+    else if (ex != nexch) return 108;
+  }
+  if (nexch_out) *nexch_out = nexch;
+  return 0;
+}
+
 // kernel launch geometry, for DESIGN.md / tests
 int emu_strided_config(int precision, int n, int* T, int* TC, int* smem) {
   switch (n) {

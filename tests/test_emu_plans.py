@@ -165,3 +165,48 @@ def test_line(N, P, prec):
     up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
     ref = oracle.line.fft2(up, N, P, dealias="3/2-rule", precision=prec, exact=(P > 1))
     _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), ref, tol)
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 2, 4])
+@pytest.mark.parametrize("P", [2, 4, 8])
+@pytest.mark.parametrize("N", [(32, 32, 32), (64, 32, 16), (1024, 1024, 1024)])
+def test_slab_p2p_program_invariants(N, P, chunks):
+    """Copy-engine transport: every rank's push target is exactly the peer's receive slot, peers only
+    write plan-owned buffers, one credit wait / one credit return per transform, equal step counts."""
+    lib = emu_util.load()
+    d = _desc(D.SLAB, N, P, "double", chunks=chunks)
+    d.transport = D.TRANSPORT_P2P
+    for inverse in (0, 1):
+        for dealias in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+            if dealias == D.DEALIAS_3_2 and P > N[0] // 2:
+                continue
+            n = C.c_int()
+            rc = lib.emu_check_p2p(C.byref(d), inverse, dealias, C.byref(n))
+            assert rc == 0, (rc, inverse, dealias)
+            if chunks:
+                assert n.value == min(chunks, max(1, n.value))
+    # the automatic depth follows the measured cost model: 1024^3 double -> 8 chunks at P = 2, 4; 2 at P = 8
+    if N[0] == 1024 and chunks == 0:
+        n = C.c_int()
+        assert lib.emu_check_p2p(C.byref(d), 0, D.DEALIAS_NONE, C.byref(n)) == 0
+        assert n.value == {2: 8, 4: 8, 8: 2}[P]
+
+
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_slab_p2p_layout_runs_in_emulator(chunks):
+    """The P2P programs receive into a plan buffer instead of the caller's output: same results."""
+    N, P, prec = (16, 16, 16), 4, "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(3)
+    d = _desc(D.SLAB, N, P, prec, chunks=chunks)
+    d.transport = D.TRANSPORT_P2P
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    ref = oracle.slab.fftn(u, N, P, precision=prec)
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
+    _check(got, ref, TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, got, [g.real_shape()] * P, rt), u, TOL[prec])
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()] * P, ct),
+           oracle.slab.fftn(up, N, P, dealias="3/2-rule", precision=prec), TOL[prec])
