@@ -35,6 +35,7 @@ WORKLOADS = {
     "pencilX1024_f64": ("pencil", (1024, 1024, 1024), "double", None, dict(alignment="X", P1=None, communication="Alltoallw")),
     "pencilY2048_f32": ("pencil", (2048, 2048, 2048), "single", None, dict(alignment="Y", P1=None, communication="Alltoallw")),
     "line8192_f32": ("line", (8192, 8192), "single", None, {}),
+    "line16384_f32": ("line", (16384, 16384), "single", None, {}),
 }
 METRIC = "R2C fftn+ifftn round-trip GFLOP/s (5*M*log2(M) per transform)"
 UNIT = "GFLOP/s"

@@ -244,7 +244,8 @@ struct StridedCfg {
                               : fits(64, 2, true)       ? 64
                               : fits(32, 2, true)       ? 32
                               : fits(32, 1, false)      ? 32
-                                                        : 16;
+                              : fits(16, 1, false)      ? 16
+                                                        : 8;  // one single-precision column (n = 16384)
   static constexpr bool TAB = fits(ROWB, 1, true);
   static constexpr int T0 = ROWB / CB < 1 ? 1 : ROWB / CB;
   static constexpr int NBMIN = P::N / P::RMAX;

@@ -6,7 +6,7 @@
 #define B200FFT_PLANS(X)                                                        \
   X(2, 2) X(4, 4) X(8, 8) X(16, 16) X(32, 4, 8) X(64, 8, 8) X(128, 16, 8)       \
   X(256, 16, 16) X(512, 8, 8, 8) X(1024, 16, 8, 8) X(2048, 16, 16, 8)           \
-  X(4096, 16, 16, 16) X(8192, 16, 8, 8, 8)                                      \
+  X(4096, 16, 16, 16) X(8192, 16, 8, 8, 8) X(16384, 16, 16, 8, 8)               \
   X(3, 3) X(6, 6) X(12, 12) X(24, 2, 12) X(48, 4, 12) X(96, 8, 12)              \
   X(192, 16, 12) X(384, 4, 8, 12) X(768, 8, 8, 12) X(1536, 16, 8, 12)           \
   X(3072, 16, 16, 12) X(6144, 8, 8, 8, 12) X(12288, 16, 8, 8, 12)

@@ -117,6 +117,20 @@ def test_strided_c2c_all_plans(be, n, prec):
         assert _rel(out2, x) < 2 * tol
 
 
+def test_strided_c2c_16384_single(be):
+    """line.R2C 16384^2 float32 (BASELINE.json config 5a): the x pass is one 16384-point column per
+    CTA (128 KB of shared memory, no address table)."""
+    n = 16384
+    rng = np.random.default_rng(n)
+    x = be.arr(_cplx(rng, (1, n, 3), np.complex64))
+    out = be.zeros(x.shape, x.dtype)
+    run_strided(be, x, n, out)
+    assert _rel(out, np.fft.fft(x.astype(np.complex128), axis=1)) < 6e-7 * 14
+    back = be.zeros(x.shape, x.dtype)
+    run_strided(be, out, n, back, inverse=1, scale=1.0 / n)
+    assert _rel(back, x) < 2e-6 * 14
+
+
 @pytest.mark.parametrize("n", [8, 64, 1024, 12, 96, 1536])
 def test_strided_in_place(be, n):
     rng = np.random.default_rng(1)
