@@ -139,6 +139,19 @@ def run_golden(comm):
                   z["A23"][rs], tol, r)
 
 
+def run_known_answer(comm):
+    """Taylor-Green kinetic energy of the reference's demo (demo/spectral_dns_solver.py:103-105) with the
+    slab transforms distributed over all ranks, CUDA tensors end to end."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import spectral_dns_solver as sds
+    N = np.array([32, 32, 32], dtype=int)
+    F = m.Slab_R2C(N, L3, comm, "double")
+    k = sds.solve(F, torch, lambda a: torch.from_numpy(a).cuda(), N)
+    k = comm.reduce(k)
+    if comm.Get_rank() == 0 and round(k - sds.KNOWN_ANSWER, 7) != 0:
+        raise SystemExit("Taylor-Green known answer: got %.12f, expected %.12f" % (k, sds.KNOWN_ANSWER))
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -158,6 +171,7 @@ def main():
                     run_3d(comm, "pencil", N, "double", al, P1, cm)
             run_3d(comm, "pencil", N, "single", al, None, "Alltoall")
     run_golden(comm)
+    run_known_answer(comm)
     comm.barrier()
     dist.destroy_process_group()
     print("GPU_WORKER_OK", comm.Get_rank() if False else local)
