@@ -27,7 +27,8 @@ extern "C" {
 #define B200FFT_MAXP 16 /* max ranks of one exchange (one NVSwitch box has 8 GPUs) */
 
 enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-137 datatypes() */
-enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3 };
+enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3,
+       B200FFT_SLAB_C2C = 4 /* slab.C2C, slab.py:538-825: u and fu are both complex */ };
 enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
 enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1 };
 

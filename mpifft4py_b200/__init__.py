@@ -5,6 +5,7 @@ Same names as ``mpiFFT4py/__init__.py:1-8``: ``Slab_R2C``, ``Pencil_R2C``, ``Lin
 running as hand-written sm_100a kernels behind the C ABI in ``include/b200fft.h``.
 """
 from .slab import R2C as Slab_R2C
+from .slab import C2C as Slab_C2C
 from .pencil import R2C as Pencil_R2C
 from .line import R2C as Line_R2C
 from .mpibase import work_arrays, datatypes, empty, zeros

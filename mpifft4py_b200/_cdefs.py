@@ -3,7 +3,7 @@ import ctypes as C
 
 MAXP = 16
 SINGLE, DOUBLE = 0, 1
-SLAB, PENCIL_X, PENCIL_Y, LINE = 0, 1, 2, 3
+SLAB, PENCIL_X, PENCIL_Y, LINE, SLAB_C2C = 0, 1, 2, 3, 4
 DEALIAS_NONE, DEALIAS_3_2, DEALIAS_2_3 = 0, 1, 2
 TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1
 

@@ -65,7 +65,7 @@ class Transform(object):
         choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT", "p2p")).lower()
         assert choice in ("p2p", "nccl"), "transport must be 'p2p' or 'nccl'"
         h = None
-        if kind == D.SLAB and int(nranks) > 1 and choice == "p2p":
+        if kind in (D.SLAB, D.SLAB_C2C) and int(nranks) > 1 and choice == "p2p":
             d.transport = D.TRANSPORT_P2P
             d.comm = None
             h = C.c_void_p()

@@ -87,14 +87,17 @@ int map_launch_rc(int rc, const char* what, int n) {
 int exec_strided(const b200fft_strided_desc_t& d, cudaStream_t st) {
   if (const char* e = check_strided(d)) return fail(B200FFT_ERR_ARG, "strided pass: %s", e);
   if (d.B == 0 || d.J == 0) return 0;
+  const bool rows = contiguous_rows(d);  // J == 1, unit stride: threads walk along the row instead
   if (d.precision == B200FFT_DOUBLE) {
     const cx<double>* tw;
     if (int rc = get_tw<double>(d.n, &tw)) return rc;
-    return map_launch_rc(launch_strided_f64(d.n, convert_strided<double>(d, tw, 1), st), "strided pass", d.n);
+    auto p = convert_strided<double>(d, tw, 1);
+    return map_launch_rc(rows ? launch_rowc2c_f64(d.n, p, st) : launch_strided_f64(d.n, p, st), "strided pass", d.n);
   }
   const cx<float>* tw;
   if (int rc = get_tw<float>(d.n, &tw)) return rc;
-  return map_launch_rc(launch_strided_f32(d.n, convert_strided<float>(d, tw, 1), st), "strided pass", d.n);
+  auto p = convert_strided<float>(d, tw, 1);
+  return map_launch_rc(rows ? launch_rowc2c_f32(d.n, p, st) : launch_strided_f32(d.n, p, st), "strided pass", d.n);
 }
 
 int exec_rows(const b200fft_rows_desc_t& d, bool fwd, cudaStream_t st) {
@@ -233,7 +236,7 @@ int validate_desc(const b200fft_plan_desc_t& d) {
   for (int i = 0; i < dims; ++i)
     if (d.N[i] < 4 || d.N[i] % 2) return fail(B200FFT_ERR_ARG, "N[%d]=%lld: mesh sizes must be even and >= 4", i, d.N[i]);
   const int P = d.nranks;
-  if (d.kind == B200FFT_SLAB) {
+  if (d.kind == B200FFT_SLAB || d.kind == B200FFT_SLAB_C2C) {
     if (!is_pow2(P) || P > d.N[0])  // slab.py:89-91
       return fail(B200FFT_ERR_RANKS, "Number of cpus must be a power of two <= N[0]");
     if (d.N[0] % P || d.N[1] % P) return fail(B200FFT_ERR_ARG, "N[0], N[1] must be divisible by the number of ranks");
@@ -258,7 +261,7 @@ int validate_desc(const b200fft_plan_desc_t& d) {
   if (P > 1) {
     if (d.transport == B200FFT_TRANSPORT_P2P) {
       // no communicator: peers are reached through IPC-mapped buffers (b200fft_plan_p2p_connect)
-    } else if (d.kind == B200FFT_SLAB || d.kind == B200FFT_LINE) {
+    } else if (d.kind == B200FFT_SLAB || d.kind == B200FFT_SLAB_C2C || d.kind == B200FFT_LINE) {
       if (!d.comm) return fail(B200FFT_ERR_ARG, "multi-rank plan needs a communicator");
       if (d.comm->nranks != P || d.comm->rank != d.rank) return fail(B200FFT_ERR_ARG, "communicator does not match nranks / rank");
     } else {
@@ -627,7 +630,7 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
   if (int rc = validate_desc(*d)) return rc;
   if (d->transport != B200FFT_TRANSPORT_NCCL && d->transport != B200FFT_TRANSPORT_P2P)
     return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
-  if (d->transport == B200FFT_TRANSPORT_P2P && d->nranks > 1 && d->kind != B200FFT_SLAB)
+  if (d->transport == B200FFT_TRANSPORT_P2P && d->nranks > 1 && d->kind != B200FFT_SLAB && d->kind != B200FFT_SLAB_C2C)
     return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) transport is built for slab plans; use NCCL for pencil / line");
   if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_NCCL)
     if (int rc = load_nccl()) return rc;

@@ -115,6 +115,11 @@ inline const char* check_strided(const b200fft_strided_desc_t& d) {
   return nullptr;
 }
 
+// a strided pass whose "columns" are single elements of contiguous rows: served by the row C2C kernel
+inline bool contiguous_rows(const b200fft_strided_desc_t& d) {
+  return d.J == 1 && d.in.nchunk == 1 && d.out.nchunk == 1 && d.in.si[0] == 1 && d.out.si[0] == 1 && !d.mask.on;
+}
+
 inline const char* check_rows(const b200fft_rows_desc_t& d) {
   if (d.precision != B200FFT_SINGLE && d.precision != B200FFT_DOUBLE) return "bad precision";
   if (d.n < 4 || d.n % 2 || d.rows < 0) return "bad sizes";

@@ -7,6 +7,8 @@ namespace b200fft {
 // return cudaError_t as int; -1 when the length has no plan / does not fit shared memory
 int launch_strided_f64(int n, const StridedParams<double>& p, cudaStream_t st);
 int launch_strided_f32(int n, const StridedParams<float>& p, cudaStream_t st);
+int launch_rowc2c_f64(int n, const StridedParams<double>& p, cudaStream_t st);
+int launch_rowc2c_f32(int n, const StridedParams<float>& p, cudaStream_t st);
 int launch_r2c_f64(int h, const RowParams<double>& p, cudaStream_t st);
 int launch_r2c_f32(int h, const RowParams<float>& p, cudaStream_t st);
 int launch_c2r_f64(int h, const RowParams<double>& p, cudaStream_t st);

@@ -586,6 +586,62 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
 };
 
 // ------------------------------------------------------------------------------------------
+// contiguous-row C2C pass (the z pass of slab.C2C, slab.py:538-825): the strided pass's index maps
+// (zero pad on load, truncate / fold on store, reversed output index for the inverse, scale) on
+// rows that are contiguous in memory (J == 1, unit element stride).  Threads walk along the row, so
+// HBM accesses are coalesced; geometry and pipelining are those of the C2R kernel.
+// ------------------------------------------------------------------------------------------
+template <class real, class P>
+struct RowC2CK {
+  using Cfg = RowCfg<real, P>;
+  using SK = StridedK<real, P>;
+  using C = cx<real>;
+  using Params = StridedParams<real>;
+  static constexpr int NPHASE = P::S + 1;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = Cfg::PIPE;
+  static constexpr int MINB = Cfg::MINB;
+  B2_HD static unsigned long long blocks(const Params& p) {
+    return (unsigned long long)((p.B + Cfg::RPC - 1) / Cfg::RPC);
+  }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int n = P::N, TC = Cfg::TC, CB = Cfg::CB;
+    constexpr int M0 = P::template M<0>;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.B;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
+    if constexpr (s == 0) {
+#pragma unroll 4
+      for (int i = t; i < n; i += TC) {
+        const addr_t a = live ? SK::in_row(p, row, i, 0) : 0;
+        async_copy<CB>(sm + swz<M0, Cfg::SW>(i), a ? a : (addr_t)p.tw, a != 0);
+      }
+    } else {
+      constexpr int st = s - 1;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int k, C v) {
+        if (!live) return;
+        const addr_t a = SK::out_row(p, row, k, 0);
+        if (a == 0) return;
+        if (p.scale != (real)1) v = cscale(v, p.scale);
+        *reinterpret_cast<C*>(a) = v;
+      };
+      const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
+      fft_stage<real, P, st, TC, 1, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, p.tws, in, out, fold);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // device entry + host launcher
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)

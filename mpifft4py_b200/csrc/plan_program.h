@@ -209,8 +209,12 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
   const int P = d.nranks, me = d.rank;
   const long long N0 = d.N[0], N1 = d.N[1], N2 = d.N[2];
 
-  if (d.kind == B200FFT_SLAB) {
-    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = N2 / 2 + 1;
+  if (d.kind == B200FFT_SLAB || d.kind == B200FFT_SLAB_C2C) {
+    // slab.C2C (slab.py:538-825) reuses every R2C shape with Nf = N[2] (slab.py:565-567); its z pass is
+    // a contiguous-row C2C, its truncations fold in y and z at P > 1 (copy_from_padded, :816-823) and
+    // keep mode -N/2 in x (:796-797) and everywhere at P == 1 (the `ks` gather, :735-738)
+    const bool c2c = d.kind == B200FFT_SLAB_C2C;
+    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = c2c ? N2 : N2 / 2 + 1;
     const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
     if (padded && P > 1 && P > N0 / 2)  // slab.py:311,446
       return fail(B200FFT_ERR_ARG, "Number of processors cannot be larger than N[0]//2 for 3/2-rule");
@@ -218,18 +222,37 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
     const long long blk = (long long)pNp0 * Np1 * Nf;
     const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
     const bool p2p = d.transport == B200FFT_TRANSPORT_P2P && P > 1;  // peers write into plan-owned buffers only
+    const int yfold = !padded ? 0 : (c2c && P == 1) ? 2 : 1;
+    const int xfold = !padded ? 0 : c2c ? 2 : 1;
+    const int zfold = !padded ? 0 : (P == 1) ? 2 : 1;
+    // z pass over `rows` rows starting at row `row0` of the caller's array; the spectrum side is
+    // [rows][Nf] at `coff` of buffer `cbuf`
+    auto zfwd = [&](long long rows, long long row0, int cbuf, long long coff) -> Step& {
+      if (c2c)
+        return b.strided(pN2, rows, 1, 0, nat(BUF_IN, row0 * pN2, pN2, 1, pN2), nat(cbuf, coff, Nf, 1, (int)Nf), zfold);
+      Step& z = b.rows(true, rows, pN2, (int)Nf, BUF_IN, nat(cbuf, coff, Nf, 1, (int)Nf));
+      z.real.off = row0 * pN2;
+      return z;
+    };
+    auto zinv = [&](long long rows, long long row0, int cbuf, long long coff, double scale) -> Step& {
+      if (c2c)
+        return b.strided(pN2, rows, 1, 1, nat(cbuf, coff, Nf, 1, (int)Nf), nat(BUF_OUT, row0 * pN2, pN2, 1, pN2), 0, scale);
+      Step& z = b.rows(false, rows, pN2, (int)Nf, BUF_OUT, nat(cbuf, coff, Nf, 1, (int)Nf), scale);
+      z.real.off = row0 * pN2;
+      return z;
+    };
     if (!inverse) {
       if (P == 1) {
         if (!padded) {  // slab.py:366-370
-          b.rows(true, N0 * N1, (int)N2, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
+          zfwd(N0 * N1, 0, BUF_OUT, 0);
           b.strided((int)N1, N0, Nf, 0, nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1));
           b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
         } else {  // slab.py:371-387
-          b.rows(true, (long long)pN0 * pN1, pN2, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
+          zfwd((long long)pN0 * pN1, 0, BUF_W0, 0);
           b.use(BUF_W0, (long long)pN0 * pN1 * Nf);
-          b.strided(pN1, pN0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), nat(BUF_W1, 0, N1 * Nf, Nf, (int)N1), 1);
+          b.strided(pN1, pN0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), nat(BUF_W1, 0, N1 * Nf, Nf, (int)N1), yfold);
           b.use(BUF_W1, (long long)pN0 * N1 * Nf);
-          b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), 1, 1.0 / p3);
+          b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
         }
       } else {  // slab.py:389-483
         // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
@@ -242,8 +265,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int c = 0; c < C; ++c) {
           const long long x0 = c * xc;
           b.fixed = 0;
-          Step& z = b.rows(true, xc * pN1, pN2, (int)Nf, BUF_IN, nat(BUF_W0, x0 * pN1 * Nf, Nf, 1, (int)Nf));
-          z.real.off = x0 * pN1 * pN2;
+          zfwd(xc * pN1, x0 * pN1, BUF_W0, x0 * pN1 * Nf);
           SideT o;
           o.chunk = (int)Np1;
           o.nchunk = P;
@@ -255,7 +277,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
             o.si[q] = Nf;
           }
           b.fixed = 1;
-          Step& y = b.strided(pN1, xc, Nf, 0, nat(BUF_W0, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, padded ? 1 : 0);
+          Step& y = b.strided(pN1, xc, Nf, 0, nat(BUF_W0, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
           y.rec_ev = pg.nevents++;
           b.fixed = 2;
           Step& x = b.exch(0, P, me);
@@ -272,7 +294,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         const int last_ev = pg.nevents - 1;  // exchanges run in order on one stream
         b.fixed = 3;
         Step& fx = b.strided(pN0, 1, Np1 * Nf, 0, nat(recvbuf, 0, 0, Np1 * Nf, pN0), nat(BUF_OUT, 0, 0, Np1 * Nf, (int)N0),
-                             padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+                             xfold, padded ? 1.0 / p3 : 1.0);
         fx.wait_ev = last_ev;
         fx.last_reader = 1;
       }
@@ -286,15 +308,15 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           sx.mask.jdiv = (int)Nf;
           band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
           band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
-          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+          band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
         }
         if (!padded) {
           b.strided((int)N1, N0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1));
-          b.rows(false, N0 * N1, (int)N2, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), scale);
+          zinv(N0 * N1, 0, BUF_W0, 0, scale);
         } else {
           b.strided(pN1, pN0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W1, 0, pN1 * Nf, Nf, pN1));
           b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
-          b.rows(false, (long long)pN0 * pN1, pN2, (int)Nf, BUF_OUT, nat(BUF_W1, 0, Nf, 1, (int)Nf), scale);
+          zinv((long long)pN0 * pN1, 0, BUF_W1, 0, scale);
         }
       } else {  // slab.py:270-345
         // x pass, then per chunk of local x planes: exchange (communication stream) -> y and z
@@ -316,7 +338,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
           band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
           sx.mask.jq_off = (int)(me * Np1);
-          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+          band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
         }
         sx.rec_ev = pg.nevents++;
         const int x_ev = sx.rec_ev;
@@ -360,8 +382,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           Step& y = b.strided(pN1, xc, Nf, 1, g, nat(ybuf, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
           y.wait_ev = xev[(size_t)c];
           b.fixed = 3;
-          Step& z = b.rows(false, xc * pN1, pN2, (int)Nf, BUF_OUT, nat(ybuf, x0 * pN1 * Nf, Nf, 1, (int)Nf), scale);
-          z.real.off = x0 * pN1 * pN2;
+          Step& z = zinv(xc * pN1, x0 * pN1, ybuf, x0 * pN1 * Nf, scale);
           // credits go back after the last z pass, not the last y pass: W2 (this program's y output)
           // is the forward program's receive buffer, which the peers fill as soon as they hold credits
           z.last_reader = (c == C - 1);

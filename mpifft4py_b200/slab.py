@@ -23,6 +23,8 @@ class R2C(Transform):
     meaningless on a GPU).
     """
 
+    _plan_kind = D.SLAB
+
     def __init__(self, N, L, comm, precision,
                  communication="Alltoallw",
                  padsize=1.5,
@@ -48,7 +50,7 @@ class R2C(Transform):
         if not self.num_processes in [2**i for i in range(int(np.log2(N[0]))+1)]:
             raise IOError("Number of cpus must be in ",
                           [2**i for i in range(int(np.log2(N[0]))+1)])
-        self._create_plan(D.SLAB, N, self.num_processes, self.rank, comm=comm)
+        self._create_plan(self._plan_kind, N, self.num_processes, self.rank, comm=comm)
 
     def real_shape(self):
         """The local shape of the real data"""
@@ -213,4 +215,89 @@ class R2C(Transform):
             fu[:, N[1]//2:] += fp[:, -N[1]//2:, :(N[2]//2+1)]
         elif axis == 2:
             fu[:] = fp[:, :, :(N[2]//2+1)]
+        return fu
+
+
+class C2C(R2C):
+    """3D complex-to-complex FFT, slab decomposition: drop-in for ``mpiFFT4py.slab.C2C``
+    (``slab.py:538-825``).  Reuses every R2C shape with ``Nf = N[2]`` (``:565-567``); both arrays are
+    complex.  Same fused passes as R2C with a contiguous-row C2C kernel along z.
+
+    3/2-rule semantics follow the reference: on several ranks the truncation folds the two Nyquist
+    modes in y and z (``copy_from_padded``, ``:816-823``) and keeps mode -N/2 in x (``:796-797``); on
+    one rank it keeps mode -N/2 in all three directions (the ``ks`` gather, ``:735-738``).
+    ``dealias='2/3-rule'`` raises a broadcast ``ValueError`` upstream (the mask is inherited from
+    R2C with an rfft-sized z extent); here it applies the intended mask over the full kz range.
+    """
+
+    _plan_kind = D.SLAB_C2C
+
+    def __init__(self, N, L, comm, precision,
+                 communication="Alltoall",
+                 padsize=1.5,
+                 threads=1,
+                 planner_effort=defaultdict(lambda: "FFTW_MEASURE")):
+        R2C.__init__(self, N, L, comm, precision, communication=communication, padsize=padsize,
+                     threads=threads, planner_effort=planner_effort)
+        self.Nf = N[2]
+        self.Nfp = int(self.padsize*self.N[2])
+        # Rename since there's no real space (slab.py:569-575)
+        self.original_shape_padded = self.real_shape_padded
+        self.original_shape = self.real_shape
+        self.transformed_shape = self.complex_shape
+        self.original_local_slice = self.real_local_slice
+        self.transformed_local_slice = self.complex_local_slice
+        self.ks = (fftfreq(N[2])*N[2]).astype(int)
+
+    def global_shape(self, padsize=1.):
+        """Global size of problem in transformed space"""
+        return (int(padsize*self.N[0]), int(padsize*self.N[1]), int(padsize*self.N[2]))
+
+    def transformed_local_wavenumbers(self):
+        return (fftfreq(self.N[0], 1./self.N[0]),
+                fftfreq(self.N[1], 1./self.N[1])[self.transformed_local_slice()[1]],
+                fftfreq(self.N[2], 1./self.N[2]))
+
+    def get_dealias_filter(self):
+        kx, ky, kz = self.transformed_local_wavenumbers()
+        K = np.meshgrid(kx, ky, kz, indexing='ij', sparse=True)
+        kmax = 2./3.*(self.N//2+1)
+        return np.array((abs(K[0]) < kmax[0])*(abs(K[1]) < kmax[1])*(abs(K[2]) < kmax[2]), dtype=np.uint8)
+
+    def ifftn(self, fu, u, dealias=None):
+        """``slab.py:587-698``: fu of transformed_shape() -> u of original_shape() [3/2-rule:
+        original_shape_padded()], both complex.  fu is not modified."""
+        assert dealias in ('3/2-rule', '2/3-rule', 'None', None)
+        ushape = self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
+        return self._run(1, fu, u, dealias, self.complex_shape(), self.complex, ushape, self.complex)
+
+    def fftn(self, u, fu, dealias=None):
+        """``slab.py:700-800``."""
+        assert dealias in ('3/2-rule', '2/3-rule', 'None', None)
+        ushape = self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
+        return self._run(0, u, fu, dealias, ushape, self.complex, self.complex_shape(), self.complex)
+
+    @staticmethod
+    def copy_to_padded(fu, fp, N, axis=0):
+        """Host helper kept for API parity (``slab.py:802-813``)."""
+        if axis == 0:
+            fp[:N[0]//2] = fu[:N[0]//2]
+            fp[-N[0]//2:] = fu[N[0]//2:]
+        elif axis == 1:
+            fp[:, :N[1]//2] = fu[:, :N[1]//2]
+            fp[:, -N[1]//2:] = fu[:, N[1]//2:]
+        elif axis == 2:
+            fp[:, :, :N[2]//2] = fu[:, :, :N[2]//2]
+            fp[:, :, -N[2]//2:] = fu[:, :, N[2]//2:]
+        return fp
+
+    @staticmethod
+    def copy_from_padded(fp, fu, N, axis=0):
+        """Host helper kept for API parity (``slab.py:815-825``)."""
+        if axis == 1:
+            fu.fill(0)
+            fu[:, :N[1]//2+1, :N[2]//2+1] = fp[:, :N[1]//2+1, :N[2]//2+1]
+            fu[:, :N[1]//2+1, N[2]//2:] += fp[:, :N[1]//2+1, -N[2]//2:]
+            fu[:, N[1]//2:, :N[2]//2+1] += fp[:, -N[1]//2:, :N[2]//2+1]
+            fu[:, N[1]//2:, N[2]//2:] += fp[:, -N[1]//2:, -N[2]//2:]
         return fu

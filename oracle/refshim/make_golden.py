@@ -173,6 +173,54 @@ def line(N, P, precision):
     return out
 
 
+def slab_c2c(N, P, precision):
+    """slab.C2C (slab.py:538-825): tests/golden_c2c/*.npz.  A: seeded complex input; C = fftn(A);
+    A2 = ifftn(C); Ap = ifftn(C, '3/2-rule'); Cp = fftn(Ap, '3/2-rule').  (Its '2/3-rule' raises.)"""
+    from mpi4py import MPI
+    N = np.array(N, dtype=int)
+    L = np.array([2 * np.pi] * 3)
+    ct = np.complex64 if precision == "single" else np.complex128
+    rng = np.random.default_rng(SEED)
+    A = (rng.random(tuple(N)) + 1j * rng.random(tuple(N))).astype(ct)
+
+    def body():
+        from mpiFFT4py.slab import C2C
+        FFT = C2C(N, L, MPI.COMM_WORLD, precision)
+        info = dict(rank=int(FFT.rank), real_shape=_shape(FFT.original_shape()),
+                    complex_shape=_shape(FFT.transformed_shape()),
+                    real_shape_padded=_shape(FFT.original_shape_padded()),
+                    real_local_slice=_sl(FFT.original_local_slice()),
+                    real_local_slice_padded=_sl(FFT.original_local_slice(padsize=1.5)),
+                    complex_local_slice=_sl(FFT.transformed_local_slice()),
+                    global_shape=_shape(FFT.global_shape()), global_shape_padded=_shape(FFT.global_shape(1.5)))
+        a = np.zeros(FFT.original_shape(), dtype=FFT.complex)
+        a[:] = A[FFT.original_local_slice()]
+        c = FFT.fftn(a, np.zeros(FFT.transformed_shape(), dtype=FFT.complex)).copy()
+        a2 = FFT.ifftn(c.copy(), np.zeros(FFT.original_shape(), dtype=FFT.complex)).copy()
+        ap = FFT.ifftn(c.copy(), np.zeros(FFT.original_shape_padded(), dtype=FFT.complex), dealias="3/2-rule").copy()
+        cp = FFT.fftn(ap.copy(), np.zeros(FFT.transformed_shape(), dtype=FFT.complex), dealias="3/2-rule").copy()
+        return info, c, a2, ap, cp
+
+    res = load_reference.run_ranks(P, body)
+    C = np.zeros(tuple(N), dtype=ct)
+    Cp = np.zeros_like(C)
+    A2 = np.zeros_like(C)
+    Ap = np.zeros(tuple(int(1.5 * n) for n in N), dtype=ct)
+    metas = []
+    for info, c, a2, ap, cp in res:
+        cs = tuple(slice(*s) for s in info["complex_local_slice"])
+        rs = tuple(slice(*s) for s in info["real_local_slice"])
+        rps = tuple(slice(*s) for s in info["real_local_slice_padded"])
+        C[cs] = c
+        Cp[cs] = cp
+        A2[rs] = a2
+        Ap[rps] = ap
+        metas.append(info)
+    meta = dict(kind="slabc2c", N=_shape(N), P=P, precision=precision, seed=SEED, ranks=metas,
+                reference_version="1.1.2", maths=load_reference.load()._refshim_maths)
+    return dict(A=A, C=C, A2=A2, Ap=Ap, Cp=Cp, meta=np.array(json.dumps(meta)))
+
+
 CONFIGS = []
 N3 = (8, 16, 32)
 for P, comm, prec in [(1, "Alltoallw", "double"), (2, "Alltoall", "double"), (4, "Alltoallw", "double"),
@@ -198,6 +246,12 @@ def main():
     for name, args in LINES:
         d = line(*args)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print("wrote", name)
+    out_c2c = os.path.join(os.path.dirname(OUT), "golden_c2c")
+    os.makedirs(out_c2c, exist_ok=True)
+    for P, prec in [(1, "double"), (2, "double"), (4, "double"), (2, "single")]:
+        name = "c2c_P%d_%s" % (P, prec[0])
+        np.savez_compressed(os.path.join(out_c2c, name + ".npz"), **slab_c2c(N3, P, prec))
         print("wrote", name)
 
 

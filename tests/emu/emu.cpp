@@ -46,6 +46,17 @@ static const cx<real>* table(int len) {
 template <class real>
 static int strided(const b200fft_strided_desc_t& d) {
   auto p = convert_strided<real>(d, table<real>(d.n), 1);
+  if (contiguous_rows(d)) {
+    switch (d.n) {
+#define X(n, ...) \
+  case n:         \
+    return emulate<RowC2CK<real, Plan<__VA_ARGS__>>>(p);
+      B200FFT_PLANS(X)
+#undef X
+      default:
+        return -1;
+    }
+  }
   switch (d.n) {
 #define X(n, ...) \
   case n:         \

@@ -139,6 +139,29 @@ def run_golden(comm):
                   z["A23"][rs], tol, r)
 
 
+def run_c2c(comm, N, prec):
+    """slab.C2C (slab.py:538-825) on all ranks against the oracle, every dealias mode."""
+    P, r = comm.Get_size(), comm.Get_rank()
+    rt, ct = oracle.common.dtypes(prec)
+    tol = TOL[prec]
+    rng = np.random.default_rng(41)
+    F = m.Slab_C2C(np.array(N), L3, comm, prec)
+    g = oracle.slab.GeometryC2C(N, P)
+    A = rand_c(rng, N, ct)
+    u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
+    c = F.fftn(u[r], np.zeros(g.complex_shape(), dtype=ct))
+    check("c2c fftn", c, oracle.slab.c2c_fftn(u, N, P, precision=prec)[r], tol, r)
+    check("c2c roundtrip", F.ifftn(c, np.zeros(g.real_shape(), dtype=ct)), u[r], tol, r)
+    fu = [rand_c(rng, g.complex_shape(), ct) for _ in range(P)]
+    for d in (None, "2/3-rule", "3/2-rule"):
+        shp = g.real_shape_padded() if d == "3/2-rule" else g.real_shape()
+        got = F.ifftn(fu[r], np.zeros(shp, dtype=ct), dealias=d)
+        check("c2c ifftn %s" % d, got, oracle.slab.c2c_ifftn(fu, N, P, dealias=d, precision=prec)[r], tol, r)
+    up = [rand_c(rng, g.real_shape_padded(), ct) for _ in range(P)]
+    got = F.fftn(up[r], np.zeros(g.complex_shape(), dtype=ct), dealias="3/2-rule")
+    check("c2c fftn 3/2", got, oracle.slab.c2c_fftn(up, N, P, dealias="3/2-rule", precision=prec)[r], tol, r)
+
+
 def run_known_answer(comm):
     """Taylor-Green kinetic energy of the reference's demo (demo/spectral_dns_solver.py:103-105) with the
     slab transforms distributed over all ranks, CUDA tensors end to end."""
@@ -163,6 +186,8 @@ def main():
         run_3d(comm, "slab", N, prec)
         run_line(comm, (64, 128), prec)
     run_3d(comm, "slab", N, "double", communication="Alltoall")
+    run_c2c(comm, N, "double")
+    run_c2c(comm, (32, 32, 32), "single")
     if P >= 4:
         grids = [None] + ([2] if P == 8 else [])
         for al in "XY":

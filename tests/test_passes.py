@@ -306,3 +306,48 @@ def test_rows_uneven_kz_chunks(be):
     y = be.zeros(x.shape, x.dtype)
     run_rows(be, "exec_c2r", y, side, n, rows, Nf, D.DOUBLE, scale=1.0 / n)
     assert _rel(y, x) < 1e-14
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+@pytest.mark.parametrize("n", [4, 8, 64, 512, 1024, 2048, 6, 12, 96, 768, 1536])
+def test_rows_c2c(be, n, prec):
+    """Contiguous-row C2C (J == 1, unit stride): the z pass of slab.C2C; forward and inverse."""
+    ct = np.complex128 if prec == "d" else np.complex64
+    tol = 2e-15 * max(1, np.log2(n)) if prec == "d" else 6e-7 * max(1, np.log2(n))
+    rng = np.random.default_rng(n)
+    rows = 5 if n > 256 else 37
+    x = be.arr(_cplx(rng, (rows, n, 1), ct))
+    out = be.zeros(x.shape, x.dtype)
+    run_strided(be, x, n, out)
+    assert _rel(out, np.fft.fft(x.astype(np.complex128), axis=1)) < tol
+    back = be.zeros(x.shape, x.dtype)
+    run_strided(be, out, n, back, inverse=1, scale=1.0 / n)
+    assert _rel(back, x) < 2 * tol
+
+
+@pytest.mark.parametrize("N", [8, 64, 1024])
+def test_rows_c2c_pad_truncate_fold(be, N):
+    """3/2-rule along a contiguous axis (slab.C2C z pass, slab.py:803-825): zero pad on load for the
+    inverse, truncation with fold (P > 1) or keeping mode -N/2 (P == 1, the `ks` gather) on store."""
+    rng = np.random.default_rng(N)
+    n = 3 * N // 2
+    rows = 6
+    fu = be.arr(_cplx(rng, (rows, N, 1), np.complex128))
+    up = be.zeros((rows, n, 1), np.complex128)
+    run_strided(be, fu, n, up, inverse=1, scale=1.5 / n, in_side=D.plain_side(_ptr(fu), N, 1, N))
+    fp = np.zeros((rows, n, 1), dtype=np.complex128)
+    fp[:, :N // 2] = fu[:, :N // 2]
+    fp[:, -(N // 2):] = fu[:, N // 2:]
+    assert _rel(up, np.fft.ifft(fp * 1.5, axis=1)) < 1e-14
+    x = be.arr(_cplx(rng, (rows, n, 1), np.complex128))
+    X = np.fft.fft(x, axis=1)
+    ref = np.zeros((rows, N, 1), dtype=np.complex128)
+    ref[:, :N // 2 + 1] = X[:, :N // 2 + 1]
+    ref[:, N // 2:] += X[:, -(N // 2):]
+    got = be.zeros(ref.shape, ref.dtype)
+    run_strided(be, x, n, got, fold=1, out_side=D.plain_side(_ptr(got), N, 1, N))
+    assert _rel(got, ref) < 1e-14
+    ref2 = np.ascontiguousarray(X[:, np.r_[0:N // 2, n - N // 2:n]])
+    got2 = be.zeros(ref2.shape, ref2.dtype)
+    run_strided(be, x, n, got2, fold=2, out_side=D.plain_side(_ptr(got2), N, 1, N))
+    assert _rel(got2, ref2) < 1e-14
