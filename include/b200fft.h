@@ -30,7 +30,8 @@ enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-
 enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3,
        B200FFT_SLAB_C2C = 4 /* slab.C2C, slab.py:538-825: u and fu are both complex */ };
 enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
-enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1 };
+enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1,
+       B200FFT_TRANSPORT_STORE = 2 /* fused: the producing FFT pass stores into the peers' buffers */ };
 
 enum {
   B200FFT_OK = 0,
@@ -173,7 +174,14 @@ B200FFT_API int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* 
  * next chunk without competing for SMs.  After plan_create every rank calls _p2p_handles (fills
  * 256 bytes: CUDA IPC handles of its three work buffers and its flag words), the host exchanges
  * them (allgather, rank order) and every rank calls _p2p_connect with the nranks*256 bytes.
- * Replaces the same collectives as the NCCL path (slab.py:281-332,406-471). */
+ * Replaces the same collectives as the NCCL path (slab.py:281-332,406-471).
+ *
+ * Fused transport (transport = B200FFT_TRANSPORT_STORE, slab plans; same handshake): no copy step at
+ * all -- the FFT pass that produces the exchanged data (forward: the y pass, inverse: the x pass)
+ * stores every peer's block straight into that peer's receive buffer through the IPC mapping
+ * (st.global over NVLink / NVSwitch), tile by tile as the butterflies finish, so the transfer
+ * overlaps the math inside ONE kernel; an exchange step only publishes / awaits the sequence flags.
+ * The send buffer, its HBM write + read and the per-copy launch cost of the other transports vanish. */
 B200FFT_API int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256);
 B200FFT_API int b200fft_plan_p2p_connect(b200fft_plan_t plan, const void* all_handles);
 /* number of kernels / NCCL groups the last exec launched (for bench.py's gpu_launches) */

@@ -5,7 +5,7 @@ MAXP = 16
 SINGLE, DOUBLE = 0, 1
 SLAB, PENCIL_X, PENCIL_Y, LINE, SLAB_C2C = 0, 1, 2, 3, 4
 DEALIAS_NONE, DEALIAS_3_2, DEALIAS_2_3 = 0, 1, 2
-TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1
+TRANSPORT_NCCL, TRANSPORT_P2P, TRANSPORT_STORE = 0, 1, 2
 
 ERR_ARG, ERR_RANKS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = 1, 2, 3, 4, 5, 6
 

@@ -62,11 +62,14 @@ class Transform(object):
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree
         # to use if any of them cannot map its peers' buffers (no IPC / no peer access).
+        # "store" is the fused transport: same peer mappings, but the y (forward) / x (inverse) FFT
+        # pass stores each peer's block straight into that peer's receive buffer over NVLink, so no
+        # copy step, send buffer or per-copy launch cost remains (include/b200fft.h).
         choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT", "p2p")).lower()
-        assert choice in ("p2p", "nccl"), "transport must be 'p2p' or 'nccl'"
+        assert choice in ("p2p", "nccl", "store"), "transport must be 'p2p', 'store' or 'nccl'"
         h = None
-        if kind in (D.SLAB, D.SLAB_C2C) and int(nranks) > 1 and choice == "p2p":
-            d.transport = D.TRANSPORT_P2P
+        if kind in (D.SLAB, D.SLAB_C2C) and int(nranks) > 1 and choice in ("p2p", "store"):
+            d.transport = D.TRANSPORT_P2P if choice == "p2p" else D.TRANSPORT_STORE
             d.comm = None
             h = C.c_void_p()
             L = _lib.lib()
@@ -93,7 +96,7 @@ class Transform(object):
             d.comm1 = _comm.nccl_handle(comm1) if comm1 is not None else None
             h = C.c_void_p()
             _lib.check(_lib.lib().b200fft_plan_create(C.byref(h), C.byref(d)))
-        self.transport_used = "p2p" if d.transport == D.TRANSPORT_P2P else "nccl"
+        self.transport_used = {D.TRANSPORT_P2P: "p2p", D.TRANSPORT_STORE: "store"}.get(d.transport, "nccl")
         self._plan = h
         self._plan_desc = d
         self.device = torch.device("cuda", torch.cuda.current_device())

@@ -259,7 +259,7 @@ int validate_desc(const b200fft_plan_desc_t& d) {
     return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
   }
   if (P > 1) {
-    if (d.transport == B200FFT_TRANSPORT_P2P) {
+    if (d.transport == B200FFT_TRANSPORT_P2P || d.transport == B200FFT_TRANSPORT_STORE) {
       // no communicator: peers are reached through IPC-mapped buffers (b200fft_plan_p2p_connect)
     } else if (d.kind == B200FFT_SLAB || d.kind == B200FFT_SLAB_C2C || d.kind == B200FFT_LINE) {
       if (!d.comm) return fail(B200FFT_ERR_ARG, "multi-rank plan needs a communicator");
@@ -338,7 +338,9 @@ void* resolve(const b200fft_plan* pl, const Ref& r, const void* in, void* out, s
   switch (r.buf) {
     case BUF_IN: base = (char*)const_cast<void*>(in); break;
     case BUF_OUT: base = (char*)out; break;
-    default: base = (char*)pl->ws[r.buf - BUF_W0]; break;
+    default:  // r.peer >= 0: that rank's work buffer through its IPC mapping (fused transport)
+      base = (char*)((r.peer >= 0 && r.peer != pl->d.rank) ? pl->p2p.peer_ws[r.peer][r.buf - BUF_W0] : pl->ws[r.buf - BUF_W0]);
+      break;
   }
   return base + (size_t)r.off * esz;
 }
@@ -387,19 +389,29 @@ int post_flag(b200fft_plan* pl, cudaStream_t st, void* peer_word, unsigned value
   return 0;
 }
 
+// Block `st` until every peer has handed this rank's blocks of the previous transform back (its last
+// reader of received data has run): only then may this rank write into the peers' buffers again.
+int wait_credits(b200fft_plan* pl, cudaStream_t st) {
+  auto& pp = pl->p2p;
+  if (pp.calls == 0) return 0;
+  unsigned* fl = reinterpret_cast<unsigned*>(pp.flags);
+  for (int q = 0; q < pl->d.nranks; ++q)
+    if (q != pl->d.rank)
+      if (CUresult r = g_cu.WaitValue32((CUstream)st, (CUdeviceptr)(fl + B200FFT_MAXP + q), pp.calls, CU_STREAM_WAIT_VALUE_GEQ))
+        return cu_fail(r, "cuStreamWaitValue32(credit)");
+  return 0;
+}
+
 // Copy-engine exchange of one step: push every peer's block, publish the sequence number, then
 // (on the wait stream) wait for every peer's block to land here and record the step's event.
 int run_exchange_p2p(b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz, cudaStream_t s1) {
   auto& pp = pl->p2p;
   if (!pp.connected) return fail(B200FFT_ERR_ARG, "P2P plan used before b200fft_plan_p2p_connect");
   const unsigned seq = ++pp.seq;
-  unsigned* fl = reinterpret_cast<unsigned*>(pp.flags);
-  if (s.first_exch && pp.calls > 0)  // peers must have finished reading what the previous transform sent them
-    for (int q = 0; q < s.npeers; ++q)
-      if (q != s.me)
-        if (CUresult r = g_cu.WaitValue32((CUstream)s1, (CUdeviceptr)(fl + B200FFT_MAXP + q), pp.calls, CU_STREAM_WAIT_VALUE_GEQ))
-          return cu_fail(r, "cuStreamWaitValue32(credit)");
-  for (int k = 1; k < s.npeers; ++k) {  // staggered peer order: no two ranks target the same GPU at once
+  if (s.first_exch && !s.fused)  // peers must have finished reading what the previous transform sent them
+    if (int rc = wait_credits(pl, s1)) return rc;
+  // fused transport: the FFT pass this step waited for has stored the blocks already
+  for (int k = 1; k < s.npeers && !s.fused; ++k) {  // staggered peer order: no two ranks target the same GPU at once
     const int q = (s.me + k) % s.npeers;
     char* dst = (char*)pp.peer_ws[q][s.rpeer[q].buf - BUF_W0] + (size_t)s.rpeer[q].off * csz;
     cudaError_t e = cudaMemcpyAsync(dst, resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, cudaMemcpyDeviceToDevice, s1);
@@ -471,7 +483,8 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   }
   bool use_p2p = false;
   for (const Step& s : pg.steps) use_p2p = use_p2p || (s.type == ST_EXCH);
-  use_p2p = use_p2p && pl->d.transport == B200FFT_TRANSPORT_P2P;
+  use_p2p = use_p2p && (pl->d.transport == B200FFT_TRANSPORT_P2P || pl->d.transport == B200FFT_TRANSPORT_STORE);
+  if (use_p2p && !pl->p2p.connected) return fail(B200FFT_ERR_ARG, "P2P plan used before b200fft_plan_p2p_connect");
   int nexch = 0;
   cudaStream_t caller = st;
   for (const Step& s : pg.steps) {
@@ -480,6 +493,8 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       cudaError_t e = cudaStreamWaitEvent(st, pl->sched_ev[(size_t)s.wait_ev], 0);
       if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
     }
+    if (use_p2p && s.wait_credits)  // this pass stores into the peers' receive buffers
+      if (int rc = wait_credits(pl, st)) return rc;
     if (pl->timing && evi + 2 <= 128) cudaEventRecord(pl->ev[evi], st);
     int rc = 0;
     if (s.type == ST_STRIDED) {
@@ -628,13 +643,14 @@ int b200fft_comm_destroy(b200fft_comm_t comm) {
 int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
   if (!plan || !d) return fail(B200FFT_ERR_ARG, "null argument");
   if (int rc = validate_desc(*d)) return rc;
-  if (d->transport != B200FFT_TRANSPORT_NCCL && d->transport != B200FFT_TRANSPORT_P2P)
+  const bool peer_mapped = d->transport == B200FFT_TRANSPORT_P2P || d->transport == B200FFT_TRANSPORT_STORE;
+  if (d->transport != B200FFT_TRANSPORT_NCCL && !peer_mapped)
     return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
-  if (d->transport == B200FFT_TRANSPORT_P2P && d->nranks > 1 && d->kind != B200FFT_SLAB && d->kind != B200FFT_SLAB_C2C)
-    return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) transport is built for slab plans; use NCCL for pencil / line");
+  if (peer_mapped && d->nranks > 1 && d->kind != B200FFT_SLAB && d->kind != B200FFT_SLAB_C2C)
+    return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) and fused (STORE) transports are built for slab plans; use NCCL for pencil / line");
   if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_NCCL)
     if (int rc = load_nccl()) return rc;
-  if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_P2P)
+  if (d->nranks > 1 && peer_mapped)
     if (int rc = load_cuda_driver()) return rc;
   b200fft_plan* pl = new b200fft_plan;
   pl->d = *d;
@@ -692,7 +708,8 @@ int b200fft_exec_inverse(b200fft_plan_t plan, const void* fu, void* u, int deali
 
 int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256) {
   if (!plan || !handles256) return fail(B200FFT_ERR_ARG, "null argument");
-  if (plan->d.transport != B200FFT_TRANSPORT_P2P || plan->d.nranks < 2) return fail(B200FFT_ERR_ARG, "not a multi-rank P2P plan");
+  if ((plan->d.transport != B200FFT_TRANSPORT_P2P && plan->d.transport != B200FFT_TRANSPORT_STORE) || plan->d.nranks < 2)
+    return fail(B200FFT_ERR_ARG, "not a multi-rank P2P plan");
   // size the work buffers for every program now: their addresses are what the peers map
   size_t need[3] = {256, 256, 256};
   const size_t csz = plan->d.precision == B200FFT_DOUBLE ? 16 : 8;

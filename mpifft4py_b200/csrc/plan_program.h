@@ -38,6 +38,7 @@ enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_W0 = 2, BUF_W1 = 3, BUF_W2 = 4, NBUF = 5
 struct Ref {
   int buf = BUF_IN;
   long long off = 0;
+  int peer = -1;  // >= 0: the buffer of that rank (fused transport: stores land in the peer's memory)
 };
 
 struct SideT {
@@ -80,6 +81,11 @@ struct Step {
   // and whether a pass is the last reader of received data (returns the credits)
   Ref rpeer[PMAXP];
   int first_exch = 0, last_reader = 0;
+  // fused (peer-store) transport: the producing FFT pass has already stored the blocks into the
+  // peers' receive buffers, so the exchange step moves no data and only publishes / awaits the
+  // sequence flags (`fused`); the first pass of a program that stores into peer memory must hold the
+  // peers' credits first (`wait_credits`)
+  int fused = 0, wait_credits = 0;
 };
 
 struct Program {
@@ -187,7 +193,8 @@ inline int ipad(double p, long long x) { return (int)(p * (double)x); }
 //    (2 GPUs, 8 chunks: +0.19 ms over 1 chunk; 8 GPUs, 8 chunks of 16.8 MB x 7 peers: 2.58 ms
 //    against 1.07 ms of pure transfer).  A 48 MB floor keeps that overhead under ~30% of the
 //    transfer time: 8 chunks at P = 2 and 4, 2 chunks at P = 8 for 1024^3 double.
-inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, bool p2p) {
+inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, bool p2p, bool store = false) {
+  if (store && requested <= 0) return 1;  // the producing pass is the transfer: nothing to pipeline by default
   if (requested > 0) {
     int c = requested;
     while (c > 1 && ext % c) --c;
@@ -221,7 +228,10 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
     const double p3 = p * p * p;
     const long long blk = (long long)pNp0 * Np1 * Nf;
     const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
-    const bool p2p = d.transport == B200FFT_TRANSPORT_P2P && P > 1;  // peers write into plan-owned buffers only
+    // fused transport: the y (forward) / x (inverse) pass stores each peer's block into that peer's
+    // receive buffer -- exactly where the copy-engine transport's DMA would put it (`rpeer`)
+    const bool store = d.transport == B200FFT_TRANSPORT_STORE && P > 1;
+    const bool p2p = (d.transport == B200FFT_TRANSPORT_P2P || store) && P > 1;  // peers write into plan-owned buffers only
     const int yfold = !padded ? 0 : (c2c && P == 1) ? 2 : 1;
     const int xfold = !padded ? 0 : c2c ? 2 : 1;
     const int zfold = !padded ? 0 : (P == 1) ? 2 : 1;
@@ -257,10 +267,10 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
       } else {  // slab.py:389-483
         // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
         const int recvbuf = (padded || p2p) ? BUF_W2 : BUF_OUT;
-        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p);
+        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p, store);
         const long long xc = pNp0 / C;
         b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
-        b.use(BUF_W1, P * blk);
+        if (!store) b.use(BUF_W1, P * blk);  // send buffer
         b.use(recvbuf, P * blk);
         for (int c = 0; c < C; ++c) {
           const long long x0 = c * xc;
@@ -273,11 +283,17 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           for (int q = 0; q < P; ++q) {
             o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
             o.base[q].off = q * blk + x0 * Np1 * Nf;
+            if (store && q != me) {  // block `me` of peer q's receive buffer
+              o.base[q].buf = recvbuf;
+              o.base[q].off = me * blk + x0 * Np1 * Nf;
+              o.base[q].peer = q;
+            }
             o.sb[q] = Np1 * Nf;
             o.si[q] = Nf;
           }
           b.fixed = 1;
           Step& y = b.strided(pN1, xc, Nf, 0, nat(BUF_W0, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
+          y.wait_credits = store && c == 0;
           y.rec_ev = pg.nevents++;
           b.fixed = 2;
           Step& x = b.exch(0, P, me);
@@ -285,6 +301,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           x.wait_ev = y.rec_ev;
           x.rec_ev = pg.nevents++;
           x.first_exch = (c == 0);
+          x.fused = store;
           for (int q = 0; q < P; ++q) {
             x.send[q].buf = BUF_W1; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
             x.recv[q].buf = recvbuf; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;
@@ -328,10 +345,16 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P; ++q) {
           o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
           o.base[q].off = q * blk;
+          if (store && q != me) {  // block `me` of peer q's receive buffer
+            o.base[q].buf = BUF_W1;
+            o.base[q].off = me * blk;
+            o.base[q].peer = q;
+          }
           o.sb[q] = 0;
           o.si[q] = Np1 * Nf;
         }
         Step& sx = b.strided(pN0, 1, Np1 * Nf, 1, nat(BUF_IN, 0, 0, Np1 * Nf, (int)N0), o);
+        sx.wait_credits = store;
         if (masked) {
           sx.mask.on = 1;
           sx.mask.jdiv = (int)Nf;
@@ -342,13 +365,14 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         }
         sx.rec_ev = pg.nevents++;
         const int x_ev = sx.rec_ev;
-        b.use(BUF_W0, P * blk);
+        if (!store) b.use(BUF_W0, P * blk);  // send buffer
         b.use(BUF_W1, P * blk);
         // the y pass of chunk c writes W0 rows that the sends of later chunks still read when the
         // padded planes are larger than the send blocks: give its output a buffer of its own then
         const int ybuf = BUF_W2;
         b.use(ybuf, (long long)pNp0 * pN1 * Nf);
-        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p);
+        // (fused transport: the x pass has moved everything, one flag step covers all planes)
+        const int C = store ? 1 : pick_chunks(d.chunks, pNp0, blk * csz, p2p);
         const long long xc = pNp0 / C;
         std::vector<int> xev((size_t)C);
         for (int c = 0; c < C; ++c) {  // all exchanges are queued first: they only depend on the x pass
@@ -360,6 +384,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           x.rec_ev = pg.nevents++;
           xev[(size_t)c] = x.rec_ev;
           x.first_exch = (c == 0);
+          x.fused = store;
           for (int q = 0; q < P; ++q) {
             x.send[q].buf = BUF_W0; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
             x.recv[q].buf = BUF_W1; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;

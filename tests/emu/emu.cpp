@@ -117,7 +117,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
     char* base;
     if (ref.buf == BUF_IN) base = (char*)ins[r];
     else if (ref.buf == BUF_OUT) base = (char*)outs[r];
-    else base = (char*)ws[(size_t)r * 3 + (ref.buf - BUF_W0)].data();
+    else base = (char*)ws[(size_t)(ref.peer >= 0 ? ref.peer : r) * 3 + (ref.buf - BUF_W0)].data();  // peer: fused transport
     return base + (size_t)ref.off * esz;
   };
   auto side = [&](int r, const SideT& s) {
@@ -154,6 +154,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
           else w = q * d0->P1 + (r % d0->P1);
           const Step& t = pg[w].steps[si];
           if (t.type != ST_EXCH || t.rcnt[s.me] != s.scnt[q]) return 91;
+          if (s.fused) continue;  // the producing pass stored straight into the peer's buffer
           std::memcpy(resolve(w, t.recv[s.me], csz), resolve(r, s.send[q], csz), (size_t)s.scnt[q] * csz);
         }
       }
@@ -179,11 +180,38 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
   int nexch = 0;
   for (int r = 0; r < P; ++r) {
     if (pg[r].steps.size() != nsteps) return 100;
-    int first = 0, last = 0, ex = 0;
+    int first = 0, last = 0, ex = 0, credits = 0, peer_stores = 0;
     for (size_t si = 0; si < nsteps; ++si) {
       const Step& s = pg[r].steps[si];
       last += s.last_reader;
-      if (s.type != ST_EXCH) continue;
+      if (s.type != ST_EXCH) {
+        // fused transport: a pass may store into peer q's buffer only where q's exchange step expects
+        // this rank's block, and only after the credits were awaited
+        credits += s.wait_credits;
+        const SideT& o = s.type == ST_STRIDED ? s.out : s.cside;
+        const SideT& in = s.in;
+        for (int q = 0; q < in.nchunk && s.type == ST_STRIDED; ++q)
+          if (in.base[q].peer >= 0) return 110;  // no remote loads
+        for (int q = 0; q < o.nchunk; ++q) {
+          if (o.base[q].peer < 0) continue;
+          if (d0->transport != B200FFT_TRANSPORT_STORE || s.type != ST_STRIDED || o.base[q].peer != q || q == r) return 111;
+          if (!credits) return 112;
+          ++peer_stores;
+          // the next exchange step of this program is the one that announces these stores
+          size_t sx = si + 1;
+          while (sx < nsteps && pg[r].steps[sx].type != ST_EXCH) ++sx;
+          if (sx == nsteps) return 113;
+          const Step& x = pg[r].steps[sx];
+          const Step& t = pg[q].steps[sx];
+          if (!x.fused || t.type != ST_EXCH || !t.fused) return 114;
+          // chunk q of the store side covers rows [q*chunk, ...) with pitch si and batch pitch sb: it must be the
+          // block peer q receives from r
+          if (o.base[q].buf != t.recv[r].buf || o.base[q].off != t.recv[r].off) return 115;
+          if (o.base[q].buf < BUF_W0 || t.recv[r].off + t.rcnt[r] > pg[q].need[t.recv[r].buf]) return 116;
+        }
+        continue;
+      }
+      if ((d0->transport == B200FFT_TRANSPORT_STORE) != (s.fused != 0)) return 117;
       ++ex;
       first += s.first_exch;
       if (s.comm != 0) return 101;  // only world exchanges (slab) are built for this transport
@@ -198,6 +226,8 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
       }
     }
     if (ex > 0 && (first != 1 || last != 1)) return 107;
+    if (d0->transport == B200FFT_TRANSPORT_STORE && ex > 0 && (credits != 1 || peer_stores == 0)) return 118;
+    if (d0->transport != B200FFT_TRANSPORT_STORE && (credits || peer_stores)) return 119;
     if (r == 0) nexch = ex;
     else if (ex != nexch) return 108;
   }

@@ -31,13 +31,15 @@ def check(name, got, ref, tol, rank):
         raise SystemExit("rank %d: %s: rel L2 %.3e > %.1e (shapes %r %r)" % (rank, name, err, tol, got.shape, ref.shape))
 
 
-def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None):
+def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None):
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
     rng = np.random.default_rng(99)  # same stream on every rank: global arrays are identical
     if kind == "slab":
         F = m.Slab_R2C(np.array(N), L3, comm, prec, communication=communication or "Alltoallw")
+        if transport:
+            F.transport = transport  # read when the device plan is created (first transform)
         g = oracle.slab.Geometry(N, P)
         cshape = [g.complex_shape()] * P
         fwd = lambda u, d=None: oracle.slab.fftn(u, N, P, dealias=d, precision=prec)
@@ -49,7 +51,7 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None):
         kw = dict(alignment=alignment, P1=P1, communication=communication, precision=prec)
         fwd = lambda u, d=None: oracle.pencil.fftn(u, N, P, dealias=d, **kw)
         inv = lambda f, d=None: oracle.pencil.ifftn(f, N, P, dealias=d, **kw)
-    tag = "%s %s %s %s P=%d" % (kind, alignment, communication, prec, P)
+    tag = "%s %s %s %s %s P=%d" % (kind, alignment, communication, transport, prec, P)
     assert tuple(int(s) for s in F.complex_shape()) == tuple(cshape[r])
     A = rng.random(N).astype(rt)
     u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
@@ -72,6 +74,15 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None):
                      device="cuda")
     F.fftn(tu, tf)
     check(tag + " fftn tensors", tf.cpu().numpy(), c, 1e-15, r)
+    if transport:
+        assert F.transport_used == transport, (F.transport_used, transport)
+        # back-to-back transforms without host synchronisation: the credit / sequence flags alone keep
+        # the peers out of buffers that are still being read
+        ta = torch.empty_like(tu)
+        for _ in range(6):
+            F.fftn(tu, tf)
+            F.ifftn(tf, ta)
+        check(tag + " 6 round trips", ta.cpu().numpy(), u[r], tol, r)
 
 
 def run_line(comm, N, prec):
@@ -139,13 +150,15 @@ def run_golden(comm):
                   z["A23"][rs], tol, r)
 
 
-def run_c2c(comm, N, prec):
+def run_c2c(comm, N, prec, transport=None):
     """slab.C2C (slab.py:538-825) on all ranks against the oracle, every dealias mode."""
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
     rng = np.random.default_rng(41)
     F = m.Slab_C2C(np.array(N), L3, comm, prec)
+    if transport:
+        F.transport = transport
     g = oracle.slab.GeometryC2C(N, P)
     A = rand_c(rng, N, ct)
     u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
@@ -182,6 +195,16 @@ def main():
     comm = world()
     P = comm.Get_size()
     N = (32, 64, 128)
+    if len(sys.argv) > 1 and sys.argv[1] == "--transport":
+        # one slab transport only (tests/test_zz_gpu_transports.py): "store" = fused peer stores, "nccl"
+        for prec in ("double", "single"):
+            run_3d(comm, "slab", N, prec, transport=sys.argv[2])
+        run_3d(comm, "slab", (64, 64, 64), "double", transport=sys.argv[2])
+        run_c2c(comm, N, "double", transport=sys.argv[2])
+        comm.barrier()
+        dist.destroy_process_group()
+        print("GPU_WORKER_OK", local)
+        return
     for prec in ("double", "single"):
         run_3d(comm, "slab", N, prec)
         run_line(comm, (64, 128), prec)

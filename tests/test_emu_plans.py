@@ -210,3 +210,61 @@ def test_slab_p2p_layout_runs_in_emulator(chunks):
     up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
     _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()] * P, ct),
            oracle.slab.fftn(up, N, P, dealias="3/2-rule", precision=prec), TOL[prec])
+
+
+@pytest.mark.parametrize("chunks", [0, 1, 2, 4])
+@pytest.mark.parametrize("P", [2, 4, 8])
+@pytest.mark.parametrize("N", [(32, 32, 32), (64, 32, 16), (1024, 1024, 1024)])
+def test_slab_fused_store_program_invariants(N, P, chunks):
+    """Fused transport: the y (forward) / x (inverse) pass stores block `me` of every peer's receive
+    buffer exactly where that peer's program expects it, inside the peer's plan-owned buffer, after
+    one credit wait; exchange steps move no data; no pass loads from a peer."""
+    lib = emu_util.load()
+    d = _desc(D.SLAB, N, P, "double", chunks=chunks)
+    d.transport = D.TRANSPORT_STORE
+    for inverse in (0, 1):
+        for dealias in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+            if dealias == D.DEALIAS_3_2 and P > N[0] // 2:
+                continue
+            n = C.c_int()
+            rc = lib.emu_check_p2p(C.byref(d), inverse, dealias, C.byref(n))
+            assert rc == 0, (rc, inverse, dealias)
+            # one flag step per forward chunk (default: one); the inverse x pass moves everything at once
+            assert n.value == 1 if inverse else 1 <= n.value <= max(1, chunks)  # (a divisor of the local planes)
+
+
+@pytest.mark.parametrize("kind", ["r2c", "c2c"])
+@pytest.mark.parametrize("chunks", [0, 2])
+@pytest.mark.parametrize("P", [2, 4])
+def test_slab_fused_store_runs_in_emulator(P, chunks, kind):
+    """Peer stores land in the other ranks' buffers (the emulator resolves `peer` references to that
+    rank's work space, as the IPC mapping does on the device): same results as the oracle, every mode."""
+    N, prec = (16, 16, 16), "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(7 + P)
+    c2c = kind == "c2c"
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks)
+    d.transport = D.TRANSPORT_STORE
+    if c2c:
+        cs = (N[0], N[1] // P, N[2])
+        A = _rand_c(rng, N, ct)
+        fwd = lambda u, **k: oracle.slab.c2c_fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.c2c_ifftn(fu, N, P, precision=prec, **k)
+        padded = [_rand_c(rng, g.real_shape_padded(), ct) for _ in range(P)]
+        it = ct
+    else:
+        cs = g.complex_shape()
+        A = rng.random(N).astype(rt)
+        fwd = lambda u, **k: oracle.slab.fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.ifftn(fu, N, P, precision=prec, **k)
+        padded = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+        it = rt
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, [cs] * P, ct)
+    _check(got, fwd(u), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, got, [g.real_shape()] * P, it), u, TOL[prec])
+    fu = [_rand_c(rng, cs, ct) for _ in range(P)]
+    _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()] * P, it), inv(fu, dealias="2/3-rule"), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, it), inv(fu, dealias="3/2-rule"), TOL[prec])
+    _check(run_plan(d, 0, D.DEALIAS_3_2, padded, [cs] * P, ct), fwd(padded, dealias="3/2-rule"), TOL[prec])
