@@ -47,6 +47,11 @@ B200FFT_API int b200fft_version(void);
 B200FFT_API const char* b200fft_last_error(void);
 /* 1 if complex length n has a kernel plan (n = 2^k or 3*2^k within the supported range) */
 B200FFT_API int b200fft_supported_length(int n);
+/* Tuning switch for A/B measurements (same as the B200FFT_VARIANT environment variable): selects an
+ * alternative kernel or radix plan where one is compiled; 0 = the defaults.  Returns the old value.
+ * 20: strided passes with rows >= 1 MB apart run on 2-CTA clusters (128-byte rows split over
+ * distributed shared memory); 21: all strided passes that have a cluster plan do. */
+B200FFT_API int b200fft_set_variant(int v);
 
 /* ---------------------------------------------------------------------------------------------
  * Low level: one fused FFT pass.  These are what serialFFT.fft/ifft/rfft/irfft (and the copies

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -40,6 +41,15 @@ bool plan_exists(int n) {
     default:
       return false;
   }
+}
+static int g_variant = -1;
+int kernel_variant() {
+  if (g_variant < 0) {
+    const char* e = std::getenv("B200FFT_VARIANT");
+    g_variant = e ? std::atoi(e) : 0;
+    if (g_variant < 0) g_variant = 0;
+  }
+  return g_variant;
 }
 }  // namespace b200fft
 
@@ -576,6 +586,12 @@ int b200fft_version(void) { return 100; }
 const char* b200fft_last_error(void) { return g_err.c_str(); }
 
 int b200fft_supported_length(int n) { return plan_exists(n) ? 1 : 0; }
+
+int b200fft_set_variant(int v) {
+  const int old = b200fft::kernel_variant();
+  b200fft::g_variant = v < 0 ? 0 : v;
+  return old;
+}
 
 int b200fft_copy(void* dst, const void* src, size_t bytes, void* stream) {
   if (bytes == 0) return 0;

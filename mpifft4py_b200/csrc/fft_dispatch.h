@@ -15,4 +15,6 @@ int launch_c2r_f64(int h, const RowParams<double>& p, cudaStream_t st);
 int launch_c2r_f32(int h, const RowParams<float>& p, cudaStream_t st);
 // does the last stage of the plan for complex length n hold the factor 3 (fold-capable)?
 bool plan_exists(int n);
+// tuning switch (B200FFT_VARIANT environment variable, b200fft_set_variant): 0 = default kernels
+int kernel_variant();
 }  // namespace b200fft

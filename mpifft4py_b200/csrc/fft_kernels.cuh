@@ -287,8 +287,11 @@ struct StridedK {
 
   // address of load row i (logical index of the transform input) for column j0; 0 = zero fill:
   // copy_to_padded (slab.py:517-523) and the kx / ky band of the 2/3-rule mask
-  B2_HD static addr_t in_row(const Params& p, long long b, int i, int j0) {
-    constexpr int n = P::N;
+  B2_HD static addr_t in_row(const Params& p, long long b, int i, int j0) { return in_row_n<P::N>(p, b, i, j0); }
+  B2_HD static addr_t out_row(const Params& p, long long b, int k, int j0) { return out_row_n<P::N>(p, b, k, j0); }
+  // (n: length of the whole transform -- the cluster kernel runs half-length plans on each CTA)
+  template <int n>
+  B2_HD static addr_t in_row_n(const Params& p, long long b, int i, int j0) {
     int ip = i;
     if (p.in.nphys < n) {
       const int h = p.in.nphys / 2;
@@ -305,8 +308,8 @@ struct StridedK {
   }
   // address of store row for output frequency k; 0 = dropped: copy_from_padded (slab.py:529-533).
   // The inverse transform is the forward one with the output index reversed (k -> -k mod n).
-  B2_HD static addr_t out_row(const Params& p, long long b, int k, int j0) {
-    constexpr int n = P::N;
+  template <int n>
+  B2_HD static addr_t out_row_n(const Params& p, long long b, int k, int j0) {
     int kp = p.inverse ? (k == 0 ? 0 : n - k) : k;
     if (p.out.nphys < n) {
       const int h = p.out.nphys / 2;
@@ -371,6 +374,105 @@ struct StridedK {
       // reversed output index: the slot that survives a "keep -N/2" truncation is the other one
       const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
       fft_stage<real, P, st, Cfg::TC, T, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, p.tws, in, out, fold);
+    }
+  }
+};
+
+
+// ------------------------------------------------------------------------------------------
+// strided C2C pass on a 2-CTA cluster ("far" strides: the x pass of a slab)
+// ------------------------------------------------------------------------------------------
+// When rows of the transformed axis are >= 1 MB apart every row segment of a tile lies in its own
+// 2 MB page and the pass is bound by address translations per byte: 128-byte row
+// segments halve them, but a whole n x 128 B column tile leaves room for one CTA per SM only.
+// Here a column tile of n = 2H rows x 128 bytes is split over the two CTAs of a cluster BY ROWS:
+// CTA r loads rows [rH, (r+1)H) (H x 128 B, the footprint of today's 64-byte tiles, so the same
+// number of CTAs stay resident), the pair runs the first radix-2 DIF stage across distributed shared
+// memory,
+//     s[i] = a[i] + a[i+H]            -> CTA 0 (even output frequencies 2k')
+//     d[i] = (a[i] - a[i+H]) W_n^i    -> CTA 1 (odd output frequencies 2k'+1)
+// and each CTA finishes with an independent H-point transform of its half and stores H rows of 128
+// bytes.  Every (i, column) pair of the cross stage is read and rewritten by exactly one thread
+// (CTA r takes i in [rH/2, (r+1)H/2)), so it needs no barrier between its loads and stores: one
+// cluster barrier before it (both tiles have landed) and one after it (all remote writes are done).
+// Pad / truncate / fold / mask / inverse index maps are those of StridedK, evaluated for the full
+// length n; the two folded modes +-N/2 are even frequencies and stay in one butterfly of CTA 0.
+template <class real, class PS>
+struct ClusterStridedK {
+  using SK = StridedK<real, PS, 0, 128>;
+  using Cfg = typename SK::Cfg;
+  using C = cx<real>;
+  using Params = StridedParams<real>;
+  static constexpr int H = PS::N, N = 2 * PS::N;
+  static constexpr int CLUSTER = 2;
+  static constexpr int NPHASE = PS::S + 4;
+  static constexpr int SYNC_BEFORE = 3;  // cluster-wide barriers before and after this phase
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int MINB = Cfg::MINB;
+  static_assert(Cfg::TAB, "cluster tiles keep their row-address table in shared memory");
+  static_assert(Cfg::SW == 1, "128-byte rows need no swizzle");
+
+  B2_HD static unsigned long long blocks(const Params& p) { return 2ull * SK::blocks(p); }
+  B2_HD static void decode(const Params& p, unsigned blk, int& bx, int& by) { SK::decode(p, blk / 2, bx, by); }
+
+  // `sm`: this CTA's tile, `peer`: the other CTA's tile (distributed shared memory), `rank`: 0 / 1
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, void* peerraw, int tid, int rank, int bx, int by) {
+    constexpr int T = Cfg::T, CB = Cfg::CB, TC = Cfg::TC;
+    const int c = tid % T;
+    const int t = tid / T;
+    const int j0 = bx * T;
+    const long long b = by;
+    const bool live = j0 + c < p.J;
+    addr_t* tab = reinterpret_cast<addr_t*>(reinterpret_cast<unsigned char*>(smraw) + Cfg::TILE);
+
+    if constexpr (s == 0) {  // load-row addresses of this CTA's half
+      for (int i = tid; i < H; i += NT) tab[i] = SK::template in_row_n<N>(p, b, rank * H + i, j0);
+    } else if constexpr (s == 1) {  // H rows x 128 bytes, global -> shared, asynchronously
+      bool colzero = !live;
+      if (p.mask.on && live) {
+        const Mask& m = p.mask;
+        const int j = j0 + c;
+        const int bb = (int)b + m.b_off, jq = j / m.jdiv + m.jq_off, jr = j % m.jdiv + m.jr_off;
+        if ((bb >= m.b_lo && bb <= m.b_hi) || (jq >= m.jq_lo && jq <= m.jq_hi) || (jr >= m.jr_lo && jr <= m.jr_hi))
+          colzero = true;
+      }
+      C* sm = reinterpret_cast<C*>(smraw) + c;
+      const addr_t fallback = (addr_t)p.tw;
+#pragma unroll 4
+      for (int i = t; i < H; i += TC) {
+        const addr_t a = tab[i];
+        const bool ok = (a != 0) && !colzero;
+        async_copy<CB>(sm + i * T, ok ? a + (addr_t)c * CB : fallback, ok);
+      }
+    } else if constexpr (s == 2) {  // store-row addresses: CTA `rank` owns output frequencies 2k' + rank
+      for (int k = tid; k < H; k += NT) tab[k] = SK::template out_row_n<N>(p, b, 2 * k + rank, j0);
+      async_copy_wait();
+    } else if constexpr (s == 3) {  // radix-2 stage across the pair
+      C* own = reinterpret_cast<C*>(smraw) + c;
+      C* oth = reinterpret_cast<C*>(peerraw) + c;
+      C* lo = rank == 0 ? own : oth;  // rows i      (CTA 0's tile)
+      C* hi = rank == 0 ? oth : own;  // rows i + H  (CTA 1's tile)
+#pragma unroll 4
+      for (int i = rank * (H / 2) + t; i < (rank + 1) * (H / 2); i += TC) {
+        const C a = lo[i * T], bq = hi[i * T];
+        lo[i * T] = cadd(a, bq);
+        hi[i * T] = cmul(csub(a, bq), p.tw[i * p.tws]);
+      }
+    } else {
+      constexpr int st = s - 4;
+      C* sm = reinterpret_cast<C*>(smraw) + c;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int k, C v) {
+        if (!live) return;
+        const addr_t a = tab[k];
+        if (a == 0) return;
+        if (p.scale != (real)1) v = cscale(v, p.scale);
+        *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
+      };
+      const int fold = rank != 0 ? 0 : (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
+      fft_stage<real, PS, st, TC, T, 1, false, (st == PS::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, fold);
     }
   }
 };
@@ -688,6 +790,38 @@ __global__ void __launch_bounds__(K::NT, K::MINB) fft_kernel(const __grid_consta
     K::decode(p, blockIdx.x, bx, by);
     run_phases<K, 0>(p, smraw, bx, by);
   }
+}
+
+// Cluster kernel: the two CTAs of a cluster share one column tile (ClusterStridedK).  Cluster-wide
+// barriers (which also order distributed-shared-memory accesses) surround the cross stage; every
+// thread of both CTAs reaches every barrier (no early exits), and no CTA touches its partner's
+// shared memory after the second one, so either may retire first.
+template <class K, int s>
+__device__ __forceinline__ void run_cluster_phases(const typename K::Params& p, void* sm, void* peer, int rank, int bx, int by) {
+  K::template phase<s>(p, sm, peer, (int)threadIdx.x, rank, bx, by);
+  if constexpr (s + 1 < K::NPHASE) {
+    if constexpr (s + 1 == K::SYNC_BEFORE || s == K::SYNC_BEFORE) {
+      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    } else {
+      __syncthreads();
+    }
+    run_cluster_phases<K, s + 1>(p, sm, peer, rank, bx, by);
+  }
+}
+
+template <class K>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K::NT, K::MINB)
+    fft_cluster_kernel(const __grid_constant__ typename K::Params p) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  // generic address of the partner CTA's copy of smraw (distributed shared memory window)
+  void* peer;
+  asm volatile("mapa.u64 %0, %1, %2;\n" : "=l"(peer) : "l"(smraw), "r"(rank ^ 1u));
+  int bx, by;
+  K::decode(p, blockIdx.x, bx, by);
+  run_cluster_phases<K, 0>(p, smraw, peer, (int)rank, bx, by);
 }
 #endif
 

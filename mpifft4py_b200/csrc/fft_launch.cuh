@@ -36,4 +36,24 @@ int launch_k(const typename K::Params& p, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// 2-CTA cluster kernels (ClusterStridedK): the cluster shape is a compile-time attribute of the kernel,
+// the grid holds two CTAs per column tile
+template <class K>
+int launch_cluster_k(const typename K::Params& p, cudaStream_t st) {
+  if (K::SMEM > SMEM_LIMIT) return -1;
+  static bool configured = false;
+  if (!configured) {
+    if (K::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(fft_cluster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+      if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+  }
+  const unsigned long long nblk = K::blocks(p);
+  if (nblk == 0) return 0;
+  if (nblk > 2147483647ull) return -2;
+  fft_cluster_kernel<K><<<(unsigned)nblk, K::NT, K::SMEM, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace b200fft

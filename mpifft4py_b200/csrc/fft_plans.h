@@ -28,3 +28,8 @@
   X(1024, 1, 2, 0, 16, 8, 8) X(1024, 2, 0, 0, 8, 8, 4, 4) X(1024, 3, 0, 0, 4, 4, 8, 8)    \
   X(1024, 4, 0, 0, 8, 4, 4, 8) X(1024, 5, 1, 128, 4, 4, 8, 8) X(1024, 6, 3, 32, 4, 4, 8, 8) \
   X(1024, 7, 1, 128, 16, 8, 8) X(1536, 1, 0, 0, 4, 4, 8, 12) X(1536, 2, 0, 0, 8, 8, 2, 12)
+
+// 2-CTA cluster plans of the strided pass for far strides (ClusterStridedK): X(n, radices of the n/2-point
+// sub-transform each CTA runs after the cross stage).  The factor 3 stays in the last stage (fold).
+#define B200FFT_CLUSTER_PLANS(X) \
+  X(1024, 8, 8, 8) X(1536, 8, 8, 12) X(2048, 16, 8, 8) X(3072, 16, 8, 12)

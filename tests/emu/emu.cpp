@@ -35,6 +35,35 @@ static int emulate(const typename K::Params& p) {
   return 0;
 }
 
+// 2-CTA cluster kernels: both CTAs of a cluster are stepped through phase s (each seeing the other's
+// shared memory as `peer`) before either starts phase s+1 -- at least as strict as the cluster barriers
+// around the cross stage and the CTA barriers elsewhere.
+template <class K, int s>
+static void emu_cluster_phases(const typename K::Params& p, std::vector<unsigned char>* sm, int bx, int by) {
+  for (int rank = 0; rank < 2; ++rank)
+    for (int tid = 0; tid < K::NT; ++tid) K::template phase<s>(p, sm[rank].data(), sm[rank ^ 1].data(), tid, rank, bx, by);
+  if constexpr (s + 1 < K::NPHASE) emu_cluster_phases<K, s + 1>(p, sm, bx, by);
+}
+
+template <class K>
+static int emulate_cluster(const typename K::Params& p) {
+  const unsigned long long nblk = K::blocks(p);
+  std::vector<unsigned char> sm[2];
+  for (auto& v : sm) v.resize((size_t)K::SMEM + 256);
+  for (unsigned long long b = 0; b < nblk; b += 2) {
+    int bx, by, bx1, by1;
+    K::decode(p, (unsigned)b, bx, by);
+    K::decode(p, (unsigned)b + 1, bx1, by1);
+    if (bx != bx1 || by != by1) return 95;  // both CTAs of a cluster work on the same tile
+    for (auto& v : sm)
+      for (auto& c : v) c = 0x7f;
+    emu_cluster_phases<K, 0>(p, sm, bx, by);
+  }
+  return 0;
+}
+
+static int g_emu_variant = 0;
+
 template <class real>
 static const cx<real>* table(int len) {
   static std::map<int, std::vector<cx<real>>> cache;
@@ -56,6 +85,12 @@ static int strided(const b200fft_strided_desc_t& d) {
       default:
         return -1;
     }
+  }
+  if (g_emu_variant == 21) {
+#define X(nn, ...) \
+  if (d.n == nn) return emulate_cluster<ClusterStridedK<real, Plan<__VA_ARGS__>>>(p);
+    B200FFT_CLUSTER_PLANS(X)
+#undef X
   }
   switch (d.n) {
 #define X(n, ...) \
@@ -84,6 +119,11 @@ static int rows(const b200fft_rows_desc_t& d) {
 }
 
 extern "C" {
+int emu_set_variant(int v) {  // 21: lengths with a cluster plan run the 2-CTA cluster kernel
+  const int old = g_emu_variant;
+  g_emu_variant = v;
+  return old;
+}
 int emu_exec_strided(const b200fft_strided_desc_t* d) {
   if (const char* e = check_strided(*d)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
   return d->precision == B200FFT_DOUBLE ? strided<double>(*d) : strided<float>(*d);

@@ -1,0 +1,63 @@
+"""GPU worker for kernel variants that are not the default (run in a subprocess with a timeout by
+tests/test_zz_gpu_experimental.py, so that a fault cannot take the main test process down).
+
+    python tests/gpu_variant_worker.py cluster    # 2-CTA cluster strided pass (variant 21 / 20)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import torch  # noqa: E402
+
+import cluster_checks as cc  # noqa: E402
+import oracle  # noqa: E402
+import test_passes as tp  # noqa: E402
+
+
+def cluster():
+    import mpifft4py_b200 as m
+    from mpifft4py_b200.comm import SelfComm
+    be = tp._Gpu()
+    be.L.b200fft_set_variant(21)  # every strided pass whose length has a cluster plan
+    cc.run_all(be)
+    # whole transforms whose x pass is a cluster launch (1024 plain, 1536 with the 3/2-rule), against the oracle
+    N = (1024, 16, 16)
+    F = m.Slab_R2C(np.array(N), np.array([2 * np.pi] * 3), SelfComm(), "double")
+    A = np.random.default_rng(3).random(N)
+    c = F.fftn(A, np.zeros(F.complex_shape(), dtype=np.complex128))
+    ref = oracle.slab.fftn([A], N, 1)[0]
+    assert oracle.rel_l2(c, ref) <= 1e-12
+    assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape())), A) <= 1e-12
+    for d in ("2/3-rule", "3/2-rule"):
+        shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
+        got = F.ifftn(ref, np.zeros(shp), dealias=d)
+        assert oracle.rel_l2(got, oracle.slab.ifftn([ref], N, 1, dealias=d)[0]) <= 1e-12, d
+    up = np.random.default_rng(4).random(F.real_shape_padded())
+    got = F.fftn(up, np.zeros(F.complex_shape(), dtype=np.complex128), dealias="3/2-rule")
+    assert oracle.rel_l2(got, oracle.slab.fftn([up], N, 1, dealias="3/2-rule")[0]) <= 1e-12
+    # variant 20: only launches whose rows are >= 1 MB apart take the cluster kernel
+    be.L.b200fft_set_variant(20)
+    n, pitch, J = 1024, 1 << 16, 24  # rows 1 MB apart (complex128), 24 live columns
+    x = torch.zeros((n, pitch), dtype=torch.complex128, device="cuda")
+    x[:, :J] = torch.from_numpy(tp._cplx(np.random.default_rng(5), (n, J), np.complex128)).cuda()
+    y = torch.zeros_like(x)
+    from mpifft4py_b200 import _cdefs as D
+    out = tp.run_strided(be, None, n, None, B=1, J=J, prec=D.DOUBLE,
+                         in_side=D.plain_side(x.data_ptr(), 0, pitch, n), out_side=D.plain_side(y.data_ptr(), 0, pitch, n))
+    del out
+    ref = np.fft.fft(x[:, :J].cpu().numpy(), axis=0)
+    assert tp._rel(y[:, :J].cpu().numpy(), ref) < 4e-14
+    assert float(y[:, J:].abs().max()) == 0.0  # nothing outside the live columns was written
+    be.L.b200fft_set_variant(0)
+
+
+if __name__ == "__main__":
+    assert torch.cuda.is_available()
+    {"cluster": cluster}[sys.argv[1]]()
+    print("VARIANT_WORKER_OK")
