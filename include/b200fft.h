@@ -30,6 +30,7 @@ enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-
 enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3,
        B200FFT_SLAB_C2C = 4 /* slab.C2C, slab.py:538-825: u and fu are both complex */ };
 enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
+enum { B200FFT_PIPELINE_X = 0, B200FFT_PIPELINE_KZ = 1 };
 enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1,
        B200FFT_TRANSPORT_STORE = 2 /* fused: the producing FFT pass stores into the peers' buffers */ };
 
@@ -160,6 +161,10 @@ typedef struct {
   int chunks;      /* pipeline depth of the exchange (the MPI collectives of slab.py:281-332,406-471
                       cut into `chunks` pieces, each overlapped with the FFT passes of the next
                       piece on a second stream); 0 = automatic, 1 = no overlap */
+  int pipeline;    /* how a slab exchange is cut into pieces: B200FFT_PIPELINE_X (default) by local x
+                      planes -- z(c), y(c) | exchange(c), then one x pass; B200FFT_PIPELINE_KZ by kz
+                      ranges -- one z pass, then y(c) | exchange(c) | x(c), so the exchange overlaps
+                      FFT passes on BOTH sides (three-stage pipeline; receive layout is chunk-major) */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

@@ -6,6 +6,7 @@ SINGLE, DOUBLE = 0, 1
 SLAB, PENCIL_X, PENCIL_Y, LINE, SLAB_C2C = 0, 1, 2, 3, 4
 DEALIAS_NONE, DEALIAS_3_2, DEALIAS_2_3 = 0, 1, 2
 TRANSPORT_NCCL, TRANSPORT_P2P, TRANSPORT_STORE = 0, 1, 2
+PIPELINE_X, PIPELINE_KZ = 0, 1
 
 ERR_ARG, ERR_RANKS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = 1, 2, 3, 4, 5, 6
 
@@ -40,7 +41,7 @@ class PlanDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("precision", C.c_int), ("N", C.c_longlong * 3),
                 ("nranks", C.c_int), ("rank", C.c_int), ("P1", C.c_int), ("P2", C.c_int),
                 ("padsize", C.c_double), ("drop_nyquist", C.c_int), ("transport", C.c_int),
-                ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int)]
+                ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int)]
 
 
 def no_mask():

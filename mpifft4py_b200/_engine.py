@@ -58,6 +58,11 @@ class Transform(object):
         d.drop_nyquist = int(drop_nyquist)
         d.transport = D.TRANSPORT_NCCL
         d.chunks = int(getattr(self, "exchange_chunks", 0) or os.environ.get("B200FFT_CHUNKS", "0"))
+        # slab exchanges are cut by local x planes ("x": z, y | exchange, then x) or by kz ranges ("kz":
+        # z, then y | exchange | x -- the exchange overlaps FFT passes on both sides)
+        pipe = str(getattr(self, "exchange_pipeline", None) or os.environ.get("B200FFT_PIPELINE", "x")).lower()
+        assert pipe in ("x", "kz"), "exchange_pipeline must be 'x' or 'kz'"
+        d.pipeline = D.PIPELINE_KZ if pipe == "kz" else D.PIPELINE_X
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree

@@ -491,6 +491,11 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       pl->sched_ev.push_back(e);
     }
   }
+  if (pg.fork_ev >= 0) {  // the program's first step runs on the second stream: order it after the caller's work
+    cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)pg.fork_ev], st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(pl->comm_stream, pl->sched_ev[(size_t)pg.fork_ev], 0);
+    if (e != cudaSuccess) return cuda_fail(e, "fork event");
+  }
   bool use_p2p = false;
   for (const Step& s : pg.steps) use_p2p = use_p2p || (s.type == ST_EXCH);
   use_p2p = use_p2p && (pl->d.transport == B200FFT_TRANSPORT_P2P || pl->d.transport == B200FFT_TRANSPORT_STORE);
@@ -662,6 +667,8 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
   const bool peer_mapped = d->transport == B200FFT_TRANSPORT_P2P || d->transport == B200FFT_TRANSPORT_STORE;
   if (d->transport != B200FFT_TRANSPORT_NCCL && !peer_mapped)
     return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
+  if (d->pipeline != B200FFT_PIPELINE_X && d->pipeline != B200FFT_PIPELINE_KZ)
+    return fail(B200FFT_ERR_ARG, "unknown pipeline %d", d->pipeline);
   if (peer_mapped && d->nranks > 1 && d->kind != B200FFT_SLAB && d->kind != B200FFT_SLAB_C2C)
     return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) and fused (STORE) transports are built for slab plans; use NCCL for pencil / line");
   if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_NCCL)

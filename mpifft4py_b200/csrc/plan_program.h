@@ -92,6 +92,8 @@ struct Program {
   std::vector<Step> steps;
   long long need[NBUF] = {0, 0, 0, 0, 0};  // complex elements needed in W0..W2
   int nevents = 0;
+  int fork_ev = -1;  // >= 0: recorded on the caller's stream when the program starts and awaited by the
+                     // second stream (programs whose first step runs there)
   bool built = false;
   int error = 0;
   std::string errmsg;
@@ -207,6 +209,13 @@ inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, b
   return 1;
 }
 
+// kz pipeline: number of kz ranges (each at least 8 entries wide so that tiles stay full)
+inline int kz_chunks(int requested, long long Nf) {
+  long long c = requested > 0 ? requested : 4;
+  if (c > Nf / 8) c = Nf / 8;
+  return c < 1 ? 1 : (int)c;
+}
+
 // Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
 inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
   Builder b(pg);
@@ -263,6 +272,81 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           b.strided(pN1, pN0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), nat(BUF_W1, 0, N1 * Nf, Nf, (int)N1), yfold);
           b.use(BUF_W1, (long long)pN0 * N1 * Nf);
           b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
+        }
+      } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
+        // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
+        // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
+        // exchange(c) (second stream) overlaps y(c+1..) before it and x(..c-1) after it; with the fused
+        // transport the y passes ARE the transfer (NVLink-bound) and run on the second stream beside the
+        // HBM-bound x passes.
+        const int recvbuf = BUF_W2;
+        const int C = kz_chunks(d.chunks, Nf);
+        const long long kc = Nf / C;
+        b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
+        if (!store) b.use(BUF_W1, P * blk);
+        b.use(recvbuf, P * blk);
+        b.fixed = 0;
+        Step& z = zfwd((long long)pNp0 * pN1, 0, BUF_W0, 0);
+        int z_ev = -1;
+        if (store) z_ev = z.rec_ev = pg.nevents++;
+        std::vector<int> xev((size_t)C);
+        for (int c = 0; c < C; ++c) {
+          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+          SideT o;
+          o.chunk = (int)Np1;
+          o.nchunk = P;
+          o.nphys = (int)N1;
+          for (int q = 0; q < P; ++q) {
+            o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
+            o.base[q].off = coff + q * blkc;
+            if (store && q != me) {
+              o.base[q].buf = recvbuf;
+              o.base[q].off = coff + me * blkc;
+              o.base[q].peer = q;
+            }
+            o.sb[q] = Np1 * kcc;
+            o.si[q] = kcc;
+          }
+          b.fixed = 1;
+          Step& y = b.strided(pN1, pNp0, kcc, 0, nat(BUF_W0, k0, pN1 * Nf, Nf, pN1), o, yfold);
+          y.wait_credits = store && c == 0;
+          if (store) {
+            y.stream = 1;
+            if (c == 0) y.wait_ev = z_ev;
+          }
+          y.rec_ev = pg.nevents++;
+          b.fixed = 2;
+          Step& x = b.exch(0, P, me);
+          x.stream = 1;
+          x.wait_ev = y.rec_ev;
+          x.rec_ev = pg.nevents++;
+          xev[(size_t)c] = x.rec_ev;
+          x.first_exch = (c == 0);
+          x.fused = store;
+          for (int q = 0; q < P; ++q) {
+            x.send[q].buf = BUF_W1; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
+            x.recv[q].buf = recvbuf; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
+            x.rpeer[q].buf = recvbuf; x.rpeer[q].off = coff + me * blkc;
+          }
+        }
+        for (int c = 0; c < C; ++c) {
+          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+          SideT g;
+          g.chunk = pNp0;
+          g.nchunk = P;
+          g.nphys = pN0;
+          for (int q = 0; q < P; ++q) {
+            g.base[q].buf = recvbuf;
+            g.base[q].off = coff + q * blkc;
+            g.sb[q] = kcc;
+            g.si[q] = Np1 * kcc;
+          }
+          b.fixed = 3;
+          Step& fx = b.strided(pN0, Np1, kcc, 0, g, nat(BUF_OUT, k0, Nf, Np1 * Nf, (int)N0), xfold, padded ? 1.0 / p3 : 1.0);
+          fx.wait_ev = xev[(size_t)c];
+          fx.last_reader = (c == C - 1);
         }
       } else {  // slab.py:389-483
         // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
@@ -335,6 +419,84 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
           zinv((long long)pN0 * pN1, 0, BUF_W1, 0, scale);
         }
+      } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
+        // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
+        const int C = kz_chunks(d.chunks, Nf);
+        const long long kc = Nf / C;
+        const int ybuf = BUF_W2;
+        if (!store) b.use(BUF_W0, P * blk);
+        b.use(BUF_W1, P * blk);
+        b.use(ybuf, (long long)pNp0 * pN1 * Nf);
+        if (store) pg.fork_ev = pg.nevents++;  // the x passes (the transfer) run on the second stream
+        std::vector<int> xev((size_t)C);
+        for (int c = 0; c < C; ++c) {
+          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+          SideT o;
+          o.chunk = pNp0;
+          o.nchunk = P;
+          o.nphys = pN0;
+          for (int q = 0; q < P; ++q) {
+            o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+            o.base[q].off = coff + q * blkc;
+            if (store && q != me) {
+              o.base[q].buf = BUF_W1;
+              o.base[q].off = coff + me * blkc;
+              o.base[q].peer = q;
+            }
+            o.sb[q] = kcc;
+            o.si[q] = Np1 * kcc;
+          }
+          b.fixed = 0;
+          Step& sx = b.strided(pN0, Np1, kcc, 1, nat(BUF_IN, k0, Nf, Np1 * Nf, (int)N0), o);
+          if (masked) {  // batch index = local ky, column index = kz - k0
+            sx.mask.on = 1;
+            sx.mask.jdiv = 0x3fffffff;
+            band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+            band(N1, false, sx.mask.b_lo, sx.mask.b_hi);
+            sx.mask.b_off = (int)(me * Np1);
+            band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
+            sx.mask.jr_off = (int)k0;
+          }
+          sx.wait_credits = store && c == 0;
+          if (store) {
+            sx.stream = 1;
+            if (c == 0) sx.wait_ev = pg.fork_ev;
+          }
+          sx.rec_ev = pg.nevents++;
+          b.fixed = 1;
+          Step& x = b.exch(0, P, me);
+          x.stream = 1;
+          x.wait_ev = sx.rec_ev;
+          x.rec_ev = pg.nevents++;
+          xev[(size_t)c] = x.rec_ev;
+          x.first_exch = (c == 0);
+          x.fused = store;
+          for (int q = 0; q < P; ++q) {
+            x.send[q].buf = BUF_W0; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
+            x.recv[q].buf = BUF_W1; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
+            x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = coff + me * blkc;
+          }
+        }
+        for (int c = 0; c < C; ++c) {
+          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+          SideT g;
+          g.chunk = (int)Np1;
+          g.nchunk = P;
+          g.nphys = (int)N1;
+          for (int q = 0; q < P; ++q) {
+            g.base[q].buf = BUF_W1;
+            g.base[q].off = coff + q * blkc;
+            g.sb[q] = Np1 * kcc;
+            g.si[q] = kcc;
+          }
+          b.fixed = 2;
+          Step& y = b.strided(pN1, pNp0, kcc, 1, g, nat(ybuf, k0, pN1 * Nf, Nf, pN1));
+          y.wait_ev = xev[(size_t)c];
+        }
+        b.fixed = 3;
+        zinv((long long)pNp0 * pN1, 0, ybuf, 0, scale).last_reader = 1;
       } else {  // slab.py:270-345
         // x pass, then per chunk of local x planes: exchange (communication stream) -> y and z
         // passes; the exchange of chunk c+1 overlaps the passes of chunk c

@@ -31,7 +31,7 @@ def check(name, got, ref, tol, rank):
         raise SystemExit("rank %d: %s: rel L2 %.3e > %.1e (shapes %r %r)" % (rank, name, err, tol, got.shape, ref.shape))
 
 
-def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None):
+def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None, pipeline=None):
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
@@ -40,6 +40,8 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, tra
         F = m.Slab_R2C(np.array(N), L3, comm, prec, communication=communication or "Alltoallw")
         if transport:
             F.transport = transport  # read when the device plan is created (first transform)
+        if pipeline:
+            F.exchange_pipeline = pipeline
         g = oracle.slab.Geometry(N, P)
         cshape = [g.complex_shape()] * P
         fwd = lambda u, d=None: oracle.slab.fftn(u, N, P, dealias=d, precision=prec)
@@ -150,7 +152,7 @@ def run_golden(comm):
                   z["A23"][rs], tol, r)
 
 
-def run_c2c(comm, N, prec, transport=None):
+def run_c2c(comm, N, prec, transport=None, pipeline=None):
     """slab.C2C (slab.py:538-825) on all ranks against the oracle, every dealias mode."""
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
@@ -159,6 +161,8 @@ def run_c2c(comm, N, prec, transport=None):
     F = m.Slab_C2C(np.array(N), L3, comm, prec)
     if transport:
         F.transport = transport
+    if pipeline:
+        F.exchange_pipeline = pipeline
     g = oracle.slab.GeometryC2C(N, P)
     A = rand_c(rng, N, ct)
     u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
@@ -196,11 +200,13 @@ def main():
     P = comm.Get_size()
     N = (32, 64, 128)
     if len(sys.argv) > 1 and sys.argv[1] == "--transport":
-        # one slab transport only (tests/test_zz_gpu_transports.py): "store" = fused peer stores, "nccl"
+        # one slab transport x pipeline only (tests/test_zz_gpu_transports.py): "store" = fused peer stores;
+        # "kz" = three-stage pipeline over kz ranges
+        tr, pipe = sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else None)
         for prec in ("double", "single"):
-            run_3d(comm, "slab", N, prec, transport=sys.argv[2])
-        run_3d(comm, "slab", (64, 64, 64), "double", transport=sys.argv[2])
-        run_c2c(comm, N, "double", transport=sys.argv[2])
+            run_3d(comm, "slab", N, prec, transport=tr, pipeline=pipe)
+        run_3d(comm, "slab", (64, 64, 64), "double", transport=tr, pipeline=pipe)
+        run_c2c(comm, N, "double", transport=tr, pipeline=pipe)
         comm.barrier()
         dist.destroy_process_group()
         print("GPU_WORKER_OK", local)

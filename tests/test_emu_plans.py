@@ -15,7 +15,7 @@ from mpifft4py_b200 import _cdefs as D
 TOL = {"double": 5e-14, "single": 5e-6}
 
 
-def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0):
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0):
     d = D.PlanDesc()
     d.kind = kind
     d.precision = D.DOUBLE if prec == "double" else D.SINGLE
@@ -26,8 +26,9 @@ def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0):
     d.P1, d.P2 = P1, P2
     d.padsize = 1.5
     d.drop_nyquist = drop
-    d.transport = 0
+    d.transport = transport
     d.chunks = chunks
+    d.pipeline = pipeline
     return d
 
 
@@ -268,3 +269,47 @@ def test_slab_fused_store_runs_in_emulator(P, chunks, kind):
     _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()] * P, it), inv(fu, dealias="2/3-rule"), TOL[prec])
     _check(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, it), inv(fu, dealias="3/2-rule"), TOL[prec])
     _check(run_plan(d, 0, D.DEALIAS_3_2, padded, [cs] * P, ct), fwd(padded, dealias="3/2-rule"), TOL[prec])
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE])
+@pytest.mark.parametrize("chunks", [0, 1, 3])
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("kind,N", [("r2c", (16, 16, 64)), ("r2c", (8, 32, 128)), ("c2c", (16, 16, 32))])
+def test_slab_kz_pipeline_runs_in_emulator(kind, N, P, chunks, transport):
+    """Three-stage pipeline (B200FFT_PIPELINE_KZ): one z pass, then y(c) | exchange(c) | x(c) per kz range
+    with chunk-major exchange buffers (uneven last range), every transport, every dealias mode."""
+    prec = "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(11 + P + chunks)
+    c2c = kind == "c2c"
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=D.PIPELINE_KZ, transport=transport)
+    if c2c:
+        cs = (N[0], N[1] // P, N[2])
+        A = _rand_c(rng, N, ct)
+        fwd = lambda u, **k: oracle.slab.c2c_fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.c2c_ifftn(fu, N, P, precision=prec, **k)
+        padded = [_rand_c(rng, g.real_shape_padded(), ct) for _ in range(P)]
+        it = ct
+    else:
+        cs = g.complex_shape()
+        A = rng.random(N).astype(rt)
+        fwd = lambda u, **k: oracle.slab.fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.ifftn(fu, N, P, precision=prec, **k)
+        padded = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+        it = rt
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    got = run_plan(d, 0, D.DEALIAS_NONE, u, [cs] * P, ct)
+    _check(got, fwd(u), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, got, [g.real_shape()] * P, it), u, TOL[prec])
+    fu = [_rand_c(rng, cs, ct) for _ in range(P)]
+    _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()] * P, it), inv(fu, dealias="2/3-rule"), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, it), inv(fu, dealias="3/2-rule"), TOL[prec])
+    _check(run_plan(d, 0, D.DEALIAS_3_2, padded, [cs] * P, ct), fwd(padded, dealias="3/2-rule"), TOL[prec])
+    if transport != D.TRANSPORT_NCCL:
+        lib = emu_util.load()
+        for inverse in (0, 1):
+            for dealias in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+                n = C.c_int()
+                assert lib.emu_check_p2p(C.byref(d), inverse, dealias, C.byref(n)) == 0
+                assert 1 <= n.value <= max(chunks, 4)

@@ -12,18 +12,22 @@ from test_gpu_multi import HERE, _free_port
 pytestmark = pytest.mark.gpu
 
 
-# "store" was written after round 1's GPU minutes were spent (emulator-checked only): a device failure
-# of this opt-in transport is reported as xfail, a pass as XPASS.
-@pytest.mark.parametrize("transport", ["nccl", pytest.param("store", marks=pytest.mark.xfail(
-    strict=False, reason="opt-in transport; first device run pending"))])
+# "store" and the "kz" pipeline were written after round 1's GPU minutes were spent (emulator-checked
+# only): a device failure of these opt-in modes is reported as xfail, a pass as XPASS.
+_PENDING = pytest.mark.xfail(strict=False, reason="opt-in mode; first device run pending")
+
+
+@pytest.mark.parametrize("transport,pipeline", [
+    ("nccl", "x"), pytest.param("store", "x", marks=_PENDING), pytest.param("nccl", "kz", marks=_PENDING),
+    pytest.param("p2p", "kz", marks=_PENDING), pytest.param("store", "kz", marks=_PENDING)])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
-def test_slab_transport_parity(nproc, transport):
+def test_slab_transport_parity(nproc, transport, pipeline):
     import torch
     if torch.cuda.device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "gpu_dist_worker.py"), "--transport", transport]
+           os.path.join(HERE, "gpu_dist_worker.py"), "--transport", transport, pipeline]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     text = out.stdout.decode("utf-8", "replace")
     assert out.returncode == 0, text[-6000:]
