@@ -70,12 +70,16 @@ class Transform(object):
         # "store" is the fused transport: same peer mappings, but the y (forward) / x (inverse) FFT
         # pass stores each peer's block straight into that peer's receive buffer over NVLink, so no
         # copy step, send buffer or per-copy launch cost remains (include/b200fft.h).
-        choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT", "p2p")).lower()
+        # Pencil and line plans use NCCL unless a peer-mapped transport is asked for (they address their
+        # sub-communicators' peers through the same world-wide mappings).
+        slab = kind in (D.SLAB, D.SLAB_C2C)
+        choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT") or
+                     ("p2p" if slab else "nccl")).lower()
         assert choice in ("p2p", "nccl", "store"), "transport must be 'p2p', 'store' or 'nccl'"
         h = None
-        if kind in (D.SLAB, D.SLAB_C2C) and int(nranks) > 1 and choice in ("p2p", "store"):
+        if int(nranks) > 1 and choice in ("p2p", "store"):
             d.transport = D.TRANSPORT_P2P if choice == "p2p" else D.TRANSPORT_STORE
-            d.comm = None
+            d.comm = d.comm0 = d.comm1 = None
             h = C.c_void_p()
             L = _lib.lib()
             mine = C.create_string_buffer(256)

@@ -421,15 +421,18 @@ int run_exchange_p2p(b200fft_plan* pl, const Step& s, const void* in, void* out,
   if (s.first_exch && !s.fused)  // peers must have finished reading what the previous transform sent them
     if (int rc = wait_credits(pl, s1)) return rc;
   // fused transport: the FFT pass this step waited for has stored the blocks already
+  // peers are members q of the step's (sub)communicator; buffers and flags are indexed by world rank
+  const int me_w = pl->d.rank;
   for (int k = 1; k < s.npeers && !s.fused; ++k) {  // staggered peer order: no two ranks target the same GPU at once
     const int q = (s.me + k) % s.npeers;
-    char* dst = (char*)pp.peer_ws[q][s.rpeer[q].buf - BUF_W0] + (size_t)s.rpeer[q].off * csz;
+    const int w = world_rank(pl->d, s.comm, me_w, q);
+    char* dst = (char*)pp.peer_ws[w][s.rpeer[q].buf - BUF_W0] + (size_t)s.rpeer[q].off * csz;
     cudaError_t e = cudaMemcpyAsync(dst, resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, cudaMemcpyDeviceToDevice, s1);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(peer)");
   }
   for (int q = 0; q < s.npeers; ++q)
     if (q != s.me)
-      if (int rc = post_flag(pl, s1, (unsigned*)pp.peer_flags[q] + s.me, seq)) return rc;
+      if (int rc = post_flag(pl, s1, (unsigned*)pp.peer_flags[world_rank(pl->d, s.comm, me_w, q)] + me_w, seq)) return rc;
   return 0;
 }
 
@@ -446,7 +449,8 @@ int finish_exchange_p2p(b200fft_plan* pl, const Step& s, cudaStream_t s1, int id
   unsigned* fl = reinterpret_cast<unsigned*>(pp.flags);
   for (int q = 0; q < s.npeers; ++q)
     if (q != s.me)
-      if (CUresult r = g_cu.WaitValue32((CUstream)pp.wait_stream, (CUdeviceptr)(fl + q), pp.seq, CU_STREAM_WAIT_VALUE_GEQ))
+      if (CUresult r = g_cu.WaitValue32((CUstream)pp.wait_stream, (CUdeviceptr)(fl + world_rank(pl->d, s.comm, pl->d.rank, q)), pp.seq,
+                                        CU_STREAM_WAIT_VALUE_GEQ))
         return cu_fail(r, "cuStreamWaitValue32(arrived)");
   if (s.rec_ev >= 0) {
     cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], pp.wait_stream);
@@ -669,8 +673,8 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
     return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
   if (d->pipeline != B200FFT_PIPELINE_X && d->pipeline != B200FFT_PIPELINE_KZ)
     return fail(B200FFT_ERR_ARG, "unknown pipeline %d", d->pipeline);
-  if (peer_mapped && d->nranks > 1 && d->kind != B200FFT_SLAB && d->kind != B200FFT_SLAB_C2C)
-    return fail(B200FFT_ERR_UNSUPPORTED, "the copy-engine (P2P) and fused (STORE) transports are built for slab plans; use NCCL for pencil / line");
+  if (peer_mapped && d->nranks > B200FFT_MAXP)
+    return fail(B200FFT_ERR_RANKS, "peer-mapped transports address at most %d ranks", B200FFT_MAXP);
   if (d->nranks > 1 && d->transport == B200FFT_TRANSPORT_NCCL)
     if (int rc = load_nccl()) return rc;
   if (d->nranks > 1 && peer_mapped)

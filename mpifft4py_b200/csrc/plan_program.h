@@ -216,6 +216,51 @@ inline int kz_chunks(int requested, long long Nf) {
   return c < 1 ? 1 : (int)c;
 }
 
+// world rank of peer q of communicator `comm` (0: world, 1: comm0 = ranks with equal rank / P1,
+// 2: comm1 = ranks with equal rank % P1; pencil.py:184-195) as seen from world rank `me`
+inline int world_rank(const b200fft_plan_desc_t& d, int comm, int me, int q) {
+  if (comm == 0) return q;
+  if (comm == 1) return (me / d.P1) * d.P1 + q;
+  return q * d.P1 + (me % d.P1);
+}
+
+// Peer-mapped transports of the pencil / line programs (the slab programs set these fields as they are
+// built).  Copy engines: first_exch / last_reader bracket the buffers' hand-over between transforms.
+// Fused stores: the pass right before an exchange step writes the per-peer blocks into its send buffer;
+// point those store bases at the place the block would be copied to -- `rpeer` in the peer's memory --
+// and the exchange step is left with the flags only.
+inline int finish_peer_mapped(const b200fft_plan_desc_t& d, Program& pg) {
+  const bool store = d.transport == B200FFT_TRANSPORT_STORE;
+  bool first = true, credits = false;
+  for (size_t i = 0; i < pg.steps.size(); ++i) {
+    Step& x = pg.steps[i];
+    if (x.type != ST_EXCH) continue;
+    x.first_exch = first;
+    first = false;
+    // arrival is awaited on the plan's wait stream: the consuming pass needs an event to follow it
+    if (x.rec_ev < 0 && i + 1 < pg.steps.size() && pg.steps[i + 1].wait_ev < 0) {
+      x.rec_ev = pg.nevents++;
+      pg.steps[i + 1].wait_ev = x.rec_ev;
+    }
+    if (!store) continue;
+    if (i == 0) return fail(B200FFT_ERR_ARG, "exchange without a producing pass");
+    Step& y = pg.steps[i - 1];
+    SideT& o = (y.type == ST_STRIDED) ? y.out : y.cside;
+    if (y.type == ST_EXCH || y.type == ST_C2R || o.nchunk != x.npeers) return fail(B200FFT_ERR_ARG, "producing pass does not match its exchange");
+    for (int q = 0; q < x.npeers; ++q) {
+      if (q == x.me) continue;
+      if (o.base[q].buf != x.send[q].buf || o.base[q].off != x.send[q].off) return fail(B200FFT_ERR_ARG, "producing pass does not fill the send blocks");
+      o.base[q] = x.rpeer[q];
+      o.base[q].peer = world_rank(d, x.comm, d.rank, q);
+    }
+    x.fused = 1;
+    if (!credits) y.wait_credits = 1;
+    credits = true;
+  }
+  if (!first) pg.steps.back().last_reader = 1;  // every reader of received data has run by then
+  return 0;
+}
+
 // Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
 inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
   Builder b(pg);
@@ -579,6 +624,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
     return 0;
   }
 
+  const bool peer_mapped = (d.transport == B200FFT_TRANSPORT_P2P || d.transport == B200FFT_TRANSPORT_STORE) && P > 1;
   if (d.kind == B200FFT_PENCIL_X || d.kind == B200FFT_PENCIL_Y) {
     const bool alignX = d.kind == B200FFT_PENCIL_X;
     const int P1 = d.P1, P2 = d.P2;
@@ -627,7 +673,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
       const long long blk2 = (long long)pa * y1 * kzl;     // comm0 exchange block
       const long long blk1 = rowsz * kzl;                  // comm1 block [pa][pbq][kzl]
       if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
-        const int recv2 = padded ? BUF_W2 : BUF_OUT;
+        const int recv2 = (padded || peer_mapped) ? BUF_W2 : BUF_OUT;  // peers write plan-owned buffers only
         b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
         b.use(BUF_W0, rowsz * nk);
         b.use(BUF_W1, P2 * blk1);
@@ -635,6 +681,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P2; ++q) {
           x1.send[q].buf = BUF_W0; x1.send[q].off = rowsz * zoff[q]; x1.scnt[q] = rowsz * zc[q];
           x1.recv[q].buf = BUF_W1; x1.recv[q].off = q * blk1; x1.rcnt[q] = blk1;
+          x1.rpeer[q].buf = BUF_W1; x1.rpeer[q].off = c1 * rowsz * zc[q];
         }
         SideT g;  // gather y from the P2 peers
         g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
@@ -651,6 +698,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P1; ++q) {
           x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
           x2.recv[q].buf = recv2; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+          x2.rpeer[q].buf = recv2; x2.rpeer[q].off = c0 * blk2;
         }
         b.strided(pN0, 1, y1 * kzl, 0, nat(recv2, 0, 0, y1 * kzl, pN0), nat(BUF_OUT, 0, 0, y1 * kzl, (int)N0),
                   padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
@@ -676,6 +724,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P1; ++q) {
           x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
           x2.recv[q].buf = BUF_W1; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+          x2.rpeer[q].buf = BUF_W1; x2.rpeer[q].off = c0 * blk2;
         }
         SideT g;
         g.chunk = (int)y1; g.nchunk = P1; g.nphys = (int)N1;
@@ -694,6 +743,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P2; ++q) {
           x1.send[q].buf = BUF_W0; x1.send[q].off = q * blk1; x1.scnt[q] = blk1;
           x1.recv[q].buf = BUF_W2; x1.recv[q].off = rowsz * zoff[q]; x1.rcnt[q] = rowsz * zc[q];
+          x1.rpeer[q].buf = BUF_W2; x1.rpeer[q].off = rowsz * zoff[c1];
         }
         b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
       }
@@ -709,6 +759,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P1; ++q) {
           xa.send[q].buf = BUF_W0; xa.send[q].off = rowsz * zoff[q]; xa.scnt[q] = rowsz * zc[q];
           xa.recv[q].buf = BUF_W1; xa.recv[q].off = q * blk1; xa.rcnt[q] = blk1;
+          xa.rpeer[q].buf = BUF_W1; xa.rpeer[q].off = c0 * rowsz * zc[q];
         }
         SideT o;
         o.chunk = (int)x2l; o.nchunk = P2; o.nphys = (int)N0;
@@ -722,6 +773,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P2; ++q) {
           xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
           xb.recv[q].buf = BUF_W2; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+          xb.rpeer[q].buf = BUF_W2; xb.rpeer[q].off = c1 * blk;
         }
         SideT g;
         g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
@@ -749,6 +801,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P2; ++q) {
           xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
           xb.recv[q].buf = BUF_W1; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+          xb.rpeer[q].buf = BUF_W1; xb.rpeer[q].off = c1 * blk;
         }
         SideT o2;
         o2.chunk = pa; o2.nchunk = P1; o2.nphys = pN0;
@@ -764,11 +817,12 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P1; ++q) {
           xa.send[q].buf = BUF_W0; xa.send[q].off = q * blk1; xa.scnt[q] = blk1;
           xa.recv[q].buf = BUF_W2; xa.recv[q].off = rowsz * zoff[q]; xa.rcnt[q] = rowsz * zc[q];
+          xa.rpeer[q].buf = BUF_W2; xa.rpeer[q].off = rowsz * zoff[c0];
         }
         b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
       }
     }
-    return 0;
+    return peer_mapped ? finish_peer_mapped(d, pg) : 0;
   }
 
   if (d.kind == B200FFT_LINE) {
@@ -795,7 +849,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           b.strided(pN0, 1, Nf, 0, nat(BUF_W0, 0, 0, Nf, pN0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 2, 1.0 / p2);
         }
       } else {  // line.py:193-258
-        const int recvbuf = padded ? BUF_W1 : BUF_OUT;
+        const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
         SideT o;
         o.chunk = (int)kc; o.nchunk = P; o.nphys = (int)Nf;
         for (int q = 0; q < P; ++q) {
@@ -810,6 +864,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P; ++q) {
           x.send[q].buf = BUF_W0; x.send[q].off = (long long)pNp0 * koff[q]; x.scnt[q] = (long long)pNp0 * kcl[q];
           x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf; x.rcnt[q] = (long long)pNp0 * Npf;
+          x.rpeer[q].buf = recvbuf; x.rpeer[q].off = (long long)me * pNp0 * kcl[q];
         }
         b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
                   padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
@@ -848,6 +903,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         for (int q = 0; q < P; ++q) {
           x.send[q].buf = BUF_W0; x.send[q].off = q * blk; x.scnt[q] = blk;
           x.recv[q].buf = BUF_W1; x.recv[q].off = (long long)pNp0 * koff[q]; x.rcnt[q] = (long long)pNp0 * kcl[q];
+          x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = (long long)pNp0 * koff[me];
         }
         SideT g;
         g.chunk = (int)kc; g.nchunk = P; g.nphys = (int)Nf;
@@ -855,7 +911,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         b.rows(false, pNp0, pN1, (int)Nf, BUF_OUT, g, iscale);
       }
     }
-    return 0;
+    return peer_mapped ? finish_peer_mapped(d, pg) : 0;
   }
   return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
 }

@@ -79,7 +79,7 @@ class R2CY(Transform):
         self._init_alignment()
         self._create_plan(self._kind, N, self.num_processes, self.rank, P1=self.P1, P2=self.P2,
                           drop_nyquist=int(self.communication == 'AlltoallN'),
-                          comm0=self.comm0, comm1=self.comm1)
+                          comm=comm, comm0=self.comm0, comm1=self.comm1)
 
     def _init_alignment(self):
         pass

@@ -188,10 +188,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
       } else {
         for (int q = 0; q < s.npeers; ++q) {
           if (q == s.me) continue;
-          int w;  // world rank of peer q of this communicator (pencil.py:192-195)
-          if (s.comm == 0) w = q;
-          else if (s.comm == 1) w = (r / d0->P1) * d0->P1 + q;
-          else w = q * d0->P1 + (r % d0->P1);
+          const int w = world_rank(*d0, s.comm, r, q);  // pencil.py:192-195
           const Step& t = pg[w].steps[si];
           if (t.type != ST_EXCH || t.rcnt[s.me] != s.scnt[q]) return 91;
           if (s.fused) continue;  // the producing pass stored straight into the peer's buffer
@@ -234,7 +231,7 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
           if (in.base[q].peer >= 0) return 110;  // no remote loads
         for (int q = 0; q < o.nchunk; ++q) {
           if (o.base[q].peer < 0) continue;
-          if (d0->transport != B200FFT_TRANSPORT_STORE || s.type != ST_STRIDED || o.base[q].peer != q || q == r) return 111;
+          if (d0->transport != B200FFT_TRANSPORT_STORE || s.type == ST_C2R) return 111;
           if (!credits) return 112;
           ++peer_stores;
           // the next exchange step of this program is the one that announces these stores
@@ -242,27 +239,29 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
           while (sx < nsteps && pg[r].steps[sx].type != ST_EXCH) ++sx;
           if (sx == nsteps) return 113;
           const Step& x = pg[r].steps[sx];
-          const Step& t = pg[q].steps[sx];
-          if (!x.fused || t.type != ST_EXCH || !t.fused) return 114;
-          // chunk q of the store side covers rows [q*chunk, ...) with pitch si and batch pitch sb: it must be the
-          // block peer q receives from r
-          if (o.base[q].buf != t.recv[r].buf || o.base[q].off != t.recv[r].off) return 115;
-          if (o.base[q].buf < BUF_W0 || t.recv[r].off + t.rcnt[r] > pg[q].need[t.recv[r].buf]) return 116;
+          const int w = world_rank(*d0, x.comm, r, q);  // chunk q belongs to member q of that exchange's communicator
+          if (o.base[q].peer != w || w == r || o.nchunk != x.npeers) return 111;
+          const Step& t = pg[w].steps[sx];
+          if (!x.fused || t.type != ST_EXCH || !t.fused || t.comm != x.comm) return 114;
+          // it must be the block peer w receives from this rank (member x.me of the communicator)
+          if (o.base[q].buf != t.recv[x.me].buf || o.base[q].off != t.recv[x.me].off) return 115;
+          if (o.base[q].buf < BUF_W0 || t.recv[x.me].off + t.rcnt[x.me] > pg[w].need[t.recv[x.me].buf]) return 116;
         }
         continue;
       }
       if ((d0->transport == B200FFT_TRANSPORT_STORE) != (s.fused != 0)) return 117;
       ++ex;
       first += s.first_exch;
-      if (s.comm != 0) return 101;  // only world exchanges (slab) are built for this transport
+      if (s.rec_ev < 0) return 101;  // arrival is awaited on another stream: the consumer needs the event
       for (int q = 0; q < s.npeers; ++q) {
         if (q == s.me) continue;
-        const Step& t = pg[q].steps[si];
-        if (t.type != ST_EXCH) return 102;
+        const int w = world_rank(*d0, s.comm, r, q);
+        const Step& t = pg[w].steps[si];
+        if (t.type != ST_EXCH || t.comm != s.comm || world_rank(*d0, t.comm, w, s.me) != r) return 102;
         if (s.rpeer[q].buf != t.recv[s.me].buf || s.rpeer[q].off != t.recv[s.me].off) return 103;
         if (s.scnt[q] != t.rcnt[s.me]) return 104;
         if (s.rpeer[q].buf < BUF_W0) return 105;  // peers may only write plan-owned buffers
-        if (s.rpeer[q].off + s.scnt[q] > pg[q].need[s.rpeer[q].buf]) return 106;
+        if (s.rpeer[q].off + s.scnt[q] > pg[w].need[s.rpeer[q].buf]) return 106;
       }
     }
     if (ex > 0 && (first != 1 || last != 1)) return 107;

@@ -48,6 +48,8 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, tra
         inv = lambda f, d=None: oracle.slab.ifftn(f, N, P, dealias=d, precision=prec)
     else:
         F = m.Pencil_R2C(np.array(N), L3, comm, prec, P1=P1, communication=communication, alignment=alignment)
+        if transport:
+            F.transport = transport
         g = oracle.pencil.Geometry(N, P, alignment, P1, communication)
         cshape = [g.complex_shape(q) for q in range(P)]
         kw = dict(alignment=alignment, P1=P1, communication=communication, precision=prec)
@@ -87,12 +89,14 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, tra
         check(tag + " 6 round trips", ta.cpu().numpy(), u[r], tol, r)
 
 
-def run_line(comm, N, prec):
+def run_line(comm, N, prec, transport=None):
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
     rng = np.random.default_rng(17)
     F = m.Line_R2C(np.array(N), L3[:2], comm, prec)
+    if transport:
+        F.transport = transport
     g = oracle.line.Geometry(N, P)
     cshape = [g.complex_shape(q) for q in range(P)]
     A = rng.random(N).astype(rt)
@@ -207,6 +211,14 @@ def main():
             run_3d(comm, "slab", N, prec, transport=tr, pipeline=pipe)
         run_3d(comm, "slab", (64, 64, 64), "double", transport=tr, pipeline=pipe)
         run_c2c(comm, N, "double", transport=tr, pipeline=pipe)
+        if tr != "nccl" and pipe != "kz":  # pencil / line over the same peer mappings (their default is NCCL)
+            run_line(comm, (64, 128), "double", transport=tr)
+            if P >= 4:
+                for al in "XY":
+                    for cm in ("Alltoall", "AlltoallN"):
+                        run_3d(comm, "pencil", N, "double", al, None, cm, transport=tr)
+                if P == 8:
+                    run_3d(comm, "pencil", N, "single", "X", 2, "Alltoall", transport=tr)
         comm.barrier()
         dist.destroy_process_group()
         print("GPU_WORKER_OK", local)

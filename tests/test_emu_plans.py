@@ -97,6 +97,30 @@ def test_slab(N, P, prec, chunks):
 @pytest.mark.parametrize("alignment", ["X", "Y"])
 @pytest.mark.parametrize("N", [(8, 16, 32), (16, 16, 16)])
 def test_pencil(N, alignment, P, P1, comm):
+    _pencil_body(N, alignment, P, P1, comm, D.TRANSPORT_NCCL)
+
+
+def _check_peer_mapped(d, modes):
+    lib = emu_util.load()
+    for inverse in (0, 1):
+        for dealias in modes:
+            n = C.c_int()
+            rc = lib.emu_check_p2p(C.byref(d), inverse, dealias, C.byref(n))
+            assert rc == 0, (rc, inverse, dealias)
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_P2P, D.TRANSPORT_STORE])
+@pytest.mark.parametrize("comm", ["Alltoallw", "AlltoallN"])
+@pytest.mark.parametrize("P,P1", [(4, None), (8, None), (8, 2)])
+@pytest.mark.parametrize("alignment", ["X", "Y"])
+def test_pencil_peer_mapped_transports(alignment, P, P1, comm, transport):
+    """Copy-engine and fused-store transports over the pencil grid's sub-communicators: buffers and flags
+    are addressed by world rank; with fused stores the z pass (kz chunks) and the strided passes write
+    the peers' receive buffers directly."""
+    _pencil_body((8, 16, 32), alignment, P, P1, comm, transport)
+
+
+def _pencil_body(N, alignment, P, P1, comm, transport):
     prec = "double"
     rt, ct = oracle.common.dtypes(prec)
     g = oracle.pencil.Geometry(N, P, alignment, P1, comm)
@@ -104,7 +128,10 @@ def test_pencil(N, alignment, P, P1, comm):
     if (N[2] // 2) % zparts or any(n % g.P1 or n % g.P2 for n in N):
         pytest.skip("illegal decomposition")
     rng = np.random.default_rng(sum(N) + P + (P1 or 0))
-    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"))
+    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"),
+              transport=transport)
+    if transport != D.TRANSPORT_NCCL:
+        _check_peer_mapped(d, (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3))
     kw = dict(alignment=alignment, P1=P1, communication=comm, precision=prec)
     tol = TOL[prec]
     A = rng.random(N).astype(rt)
@@ -138,12 +165,24 @@ def test_pencil_single_precision():
 @pytest.mark.parametrize("P", [1, 2, 4, 8])
 @pytest.mark.parametrize("N", [(16, 32), (64, 32)])
 def test_line(N, P, prec):
+    _line_body(N, P, prec, D.TRANSPORT_NCCL)
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_P2P, D.TRANSPORT_STORE])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_line_peer_mapped_transports(P, transport):
+    _line_body((64, 32), P, "double", transport)
+
+
+def _line_body(N, P, prec, transport):
     if N[1] % (2 * P) or N[0] % P:
         pytest.skip("illegal decomposition")
     rt, ct = oracle.common.dtypes(prec)
     g = oracle.line.Geometry(N, P)
     rng = np.random.default_rng(sum(N) + P)
-    d = _desc(D.LINE, N, P, prec)
+    d = _desc(D.LINE, N, P, prec, transport=transport if P > 1 else 0)
+    if transport != D.TRANSPORT_NCCL and P > 1:
+        _check_peer_mapped(d, (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3))
     tol = TOL[prec]
     A = rng.random(N).astype(rt)
     u = [A[g.real_local_slice(r)] for r in range(P)]

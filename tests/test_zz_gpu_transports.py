@@ -18,7 +18,7 @@ _PENDING = pytest.mark.xfail(strict=False, reason="opt-in mode; first device run
 
 
 @pytest.mark.parametrize("transport,pipeline", [
-    ("nccl", "x"), pytest.param("store", "x", marks=_PENDING), pytest.param("nccl", "kz", marks=_PENDING),
+    ("nccl", "x"), pytest.param("p2p", "x", marks=_PENDING), pytest.param("store", "x", marks=_PENDING), pytest.param("nccl", "kz", marks=_PENDING),
     pytest.param("p2p", "kz", marks=_PENDING), pytest.param("store", "kz", marks=_PENDING)])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_slab_transport_parity(nproc, transport, pipeline):
