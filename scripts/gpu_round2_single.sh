@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 opener, ONE GPU (gpurun --timeout 1500 -- 'bash scripts/gpu_round2_single.sh'):
+# device runs of the opt-in kernels written blind at the end of round 1, then A/B timings.
+# Everything goes to gpurun_out/r02_single/.
+O=gpurun_out/r02_single
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/gpu.txt 2>&1
+# 1. parity first: the default path, then the experimental variants (subprocess, xfail until verified)
+timeout 1200 python -m pytest tests -m gpu -q -rxX > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+tail -25 $O/pytest_gpu.log
+# 2. cluster strided pass (variant 20: far launches only) against the default, plain and 3/2-rule
+for v in 0 20; do
+  for w in slab1024_f64 slab1024_f64_32; do
+    B200FFT_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
+        > $O/bench_${w}_v$v.json 2> $O/bench_${w}_v$v.err
+    echo "== $w variant $v"; python scripts/show_passes.py $O/bench_${w}_v$v.json; tail -2 $O/bench_${w}_v$v.err
+  done
+done
+# 3. ncu: launch list of the default bench, full capture of the x pass in both variants
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fft_ -c 60 --csv --log-file $O/launches_1024.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launch.log 2>&1
+for v in 0 20; do
+  B200FFT_VARIANT=$v timeout 900 ncu --set full --clock-control none --import-source on -k regex:fft_ -s 18 -c 6 -o $O/prof_1024_v$v -f \
+      python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_v$v.log 2>&1
+done
+ls -la $O
