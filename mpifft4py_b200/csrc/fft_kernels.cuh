@@ -528,6 +528,8 @@ struct RowCfg {
   static constexpr int RPC_ = RPC_T < RPC_S ? RPC_T : RPC_S;
   static constexpr int RPC = (RPC_ * TC >= 32) ? ((RPC_ * TC) / 32 * 32) / TC : RPC_;  // whole warps
   static constexpr int NT = TC * RPC;
+  // threads sharing one row; they may use a barrier of their own when they are whole warps
+  static constexpr bool ROWBAR_OK = RPC > 1 && TC % 32 == 0 && RPC <= 15;
   static constexpr int SW = 128 / CB;
   static constexpr int SMEM1 = RPC * SROW * CB;
   static constexpr bool PIPE = 2 * SMEM1 + 1024 <= 227 * 1024;
@@ -540,6 +542,7 @@ struct RowCfg {
 
 template <class real, class P>
 struct R2CK {  // forward: real rows -> complex rows
+  static constexpr int GROUP = RowCfg<real, P>::TC;
   // Stage 0 loads its butterfly inputs straight from HBM into registers (coalesced 16-byte loads,
   // all issued before the first use): staging the row through shared memory first, as C2R does,
   // measured 20% slower here because the kernel is bound by LSU wavefronts, not by load latency.
@@ -612,6 +615,7 @@ struct R2CK {  // forward: real rows -> complex rows
 
 template <class real, class P>
 struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's scale carries 1/n)
+  static constexpr int GROUP = RowCfg<real, P>::TC;
   using Cfg = RowCfg<real, P>;
   using C = cx<real>;
   using Params = RowParams<real>;
@@ -696,6 +700,7 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
 template <class real, class P>
 struct RowC2CK {
   using Cfg = RowCfg<real, P>;
+  static constexpr int GROUP = Cfg::TC;
   using SK = StridedK<real, P>;
   using C = cx<real>;
   using Params = StridedParams<real>;
@@ -747,17 +752,31 @@ struct RowC2CK {
 // device entry + host launcher
 // ------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-template <class K, int s>
+// Barrier between two phases.  RB ("row barriers", row kernels only): the TC threads that share a row
+// are whole warps and touch nothing but their own row of shared memory, so they synchronise among
+// themselves on a named barrier (id 1 + row) instead of stalling the whole CTA -- the rows of a CTA
+// then drift apart and overlap one row's butterflies with another's loads and stores.
+template <class K, bool RB>
+__device__ __forceinline__ void phase_barrier() {
+  if constexpr (RB) {
+    static_assert(K::GROUP % 32 == 0 && K::NT / K::GROUP <= 15, "row groups must be whole warps, at most 15 per CTA");
+    asm volatile("bar.sync %0, %1;\n" ::"r"((int)threadIdx.x / K::GROUP + 1), "n"(K::GROUP) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
+template <class K, int s, bool RB = false>
 __device__ __forceinline__ void run_phases(const typename K::Params& p, void* sm, int bx, int by) {
   K::template phase<s>(p, sm, (int)threadIdx.x, bx, by);
   if constexpr (s == 0) async_copy_wait();  // phase 0 of the row kernels only issues its loads
   if constexpr (s + 1 < K::NPHASE) {
-    __syncthreads();
-    run_phases<K, s + 1>(p, sm, bx, by);
+    phase_barrier<K, RB>();
+    run_phases<K, s + 1, RB>(p, sm, bx, by);
   }
 }
 
-template <class K>
+template <class K, bool RB = false>
 __global__ void __launch_bounds__(K::NT, K::MINB) fft_kernel(const __grid_constant__ typename K::Params p) {
   extern __shared__ __align__(128) unsigned char smraw[];
   if constexpr (K::PIPE) {
@@ -779,16 +798,16 @@ __global__ void __launch_bounds__(K::NT, K::MINB) fft_kernel(const __grid_consta
       }
       asm volatile("cp.async.commit_group;\n" ::: "memory");
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-      __syncthreads();
+      phase_barrier<K, RB>();
       K::decode(p, g, bx, by);
-      run_phases<K, 1>(p, smraw + buf * K::SMEM1, bx, by);
-      __syncthreads();  // every read of this buffer is done before the next iteration refills it
+      run_phases<K, 1, RB>(p, smraw + buf * K::SMEM1, bx, by);
+      phase_barrier<K, RB>();  // every read of this buffer is done before the next iteration refills it
       buf ^= 1;
     }
   } else {
     int bx, by;
     K::decode(p, blockIdx.x, bx, by);
-    run_phases<K, 0>(p, smraw, bx, by);
+    run_phases<K, 0, RB>(p, smraw, bx, by);
   }
 }
 

@@ -2,6 +2,7 @@
 tests/test_zz_gpu_experimental.py, so that a fault cannot take the main test process down).
 
     python tests/gpu_variant_worker.py cluster    # 2-CTA cluster strided pass (variant 21 / 20)
+    python tests/gpu_variant_worker.py rowbar     # row kernels with per-row named barriers (variant 30)
 """
 import os
 import sys
@@ -57,7 +58,48 @@ def cluster():
     be.L.b200fft_set_variant(0)
 
 
+def rowbar():
+    """Row kernels (R2C / C2R) whose rows synchronise on their own named barrier: many more rows than
+    one wave of persistent CTAs, so that rows of one CTA really run out of step."""
+    import mpifft4py_b200 as m
+    from mpifft4py_b200 import _cdefs as D
+    from mpifft4py_b200.comm import SelfComm
+    be = tp._Gpu()
+    be.L.b200fft_set_variant(30)
+    for prec in "ds":
+        for h in (256, 384, 512, 768, 1024, 1536):
+            tp.test_rows_r2c_c2r(be, h, prec)
+    tp.test_rows_truncate_and_zero_pad(be, 256)
+    tp.test_rows_uneven_kz_chunks(be)
+    for n, rows in ((1024, 40000), (1536, 30011)):
+        x = torch.rand((rows, n), dtype=torch.float64, device="cuda")
+        X = torch.zeros((rows, n // 2 + 1), dtype=torch.complex128, device="cuda")
+        y = torch.zeros_like(x)
+        tp.run_rows(be, "exec_r2c", _P(x), D.plain_side(X.data_ptr(), n // 2 + 1, 1, n // 2 + 1), n, rows,
+                    n // 2 + 1, D.DOUBLE)
+        ref = torch.fft.rfft(x, dim=1)
+        assert float(torch.linalg.vector_norm(X - ref) / torch.linalg.vector_norm(ref)) < 1e-14
+        tp.run_rows(be, "exec_c2r", _P(y), D.plain_side(X.data_ptr(), n // 2 + 1, 1, n // 2 + 1), n, rows,
+                    n // 2 + 1, D.DOUBLE, scale=1.0 / n)
+        assert float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x)) < 1e-14
+    N = (64, 64, 1024)
+    F = m.Slab_R2C(np.array(N), np.array([2 * np.pi] * 3), SelfComm(), "double")
+    A = np.random.default_rng(8).random(N)
+    c = F.fftn(A, np.zeros(F.complex_shape(), dtype=np.complex128))
+    assert oracle.rel_l2(c, oracle.slab.fftn([A], N, 1)[0]) <= 1e-12
+    assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape())), A) <= 1e-12
+    be.L.b200fft_set_variant(0)
+
+
+class _P(object):
+    """device tensor with the two attributes run_rows reads from a numpy array"""
+
+    def __init__(self, t):
+        self.t, self.shape = t, tuple(t.shape)
+        self.ctypes = type("c", (), {"data": t.data_ptr()})()
+
+
 if __name__ == "__main__":
     assert torch.cuda.is_available()
-    {"cluster": cluster}[sys.argv[1]]()
+    {"cluster": cluster, "rowbar": rowbar}[sys.argv[1]]()
     print("VARIANT_WORKER_OK")
