@@ -397,9 +397,11 @@ struct StridedK {
 // cluster barrier before it (both tiles have landed) and one after it (all remote writes are done).
 // Pad / truncate / fold / mask / inverse index maps are those of StridedK, evaluated for the full
 // length n; the two folded modes +-N/2 are even frequencies and stay in one butterfly of CTA 0.
-template <class real, class PS>
+// RB = 64 gives long columns (n >= 2048) near-stride tiles of today's width but half the rows per CTA,
+// i.e. three resident CTAs where the whole column in one CTA leaves room for one.
+template <class real, class PS, int RB = 128>
 struct ClusterStridedK {
-  using SK = StridedK<real, PS, 0, 128>;
+  using SK = StridedK<real, PS, 0, RB>;
   using Cfg = typename SK::Cfg;
   using C = cx<real>;
   using Params = StridedParams<real>;
@@ -411,7 +413,7 @@ struct ClusterStridedK {
   static constexpr int SMEM = Cfg::SMEM;
   static constexpr int MINB = Cfg::MINB;
   static_assert(Cfg::TAB, "cluster tiles keep their row-address table in shared memory");
-  static_assert(Cfg::SW == 1, "128-byte rows need no swizzle");
+  static_assert(Cfg::T * Cfg::CB == RB, "tile rows are RB bytes");
 
   B2_HD static unsigned long long blocks(const Params& p) { return 2ull * SK::blocks(p); }
   B2_HD static void decode(const Params& p, unsigned blk, int& bx, int& by) { SK::decode(p, blk / 2, bx, by); }
@@ -419,7 +421,8 @@ struct ClusterStridedK {
   // `sm`: this CTA's tile, `peer`: the other CTA's tile (distributed shared memory), `rank`: 0 / 1
   template <int s>
   B2_HD static void phase(const Params& p, void* smraw, void* peerraw, int tid, int rank, int bx, int by) {
-    constexpr int T = Cfg::T, CB = Cfg::CB, TC = Cfg::TC;
+    constexpr int T = Cfg::T, CB = Cfg::CB, TC = Cfg::TC, SW = Cfg::SW;
+    constexpr int M0 = PS::template M<0>;
     const int c = tid % T;
     const int t = tid / T;
     const int j0 = bx * T;
@@ -444,7 +447,7 @@ struct ClusterStridedK {
       for (int i = t; i < H; i += TC) {
         const addr_t a = tab[i];
         const bool ok = (a != 0) && !colzero;
-        async_copy<CB>(sm + i * T, ok ? a + (addr_t)c * CB : fallback, ok);
+        async_copy<CB>(sm + swz<M0, SW>(i) * T, ok ? a + (addr_t)c * CB : fallback, ok);
       }
     } else if constexpr (s == 2) {  // store-row addresses: CTA `rank` owns output frequencies 2k' + rank
       for (int k = tid; k < H; k += NT) tab[k] = SK::template out_row_n<N>(p, b, 2 * k + rank, j0);
@@ -456,9 +459,10 @@ struct ClusterStridedK {
       C* hi = rank == 0 ? oth : own;  // rows i + H  (CTA 1's tile)
 #pragma unroll 4
       for (int i = rank * (H / 2) + t; i < (rank + 1) * (H / 2); i += TC) {
-        const C a = lo[i * T], bq = hi[i * T];
-        lo[i * T] = cadd(a, bq);
-        hi[i * T] = cmul(csub(a, bq), p.tw[i * p.tws]);
+        const int ps = swz<M0, SW>(i) * T;  // both tiles use the sub-plan's swizzle
+        const C a = lo[ps], bq = hi[ps];
+        lo[ps] = cadd(a, bq);
+        hi[ps] = cmul(csub(a, bq), p.tw[i * p.tws]);
       }
     } else {
       constexpr int st = s - 4;
@@ -472,7 +476,7 @@ struct ClusterStridedK {
         *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
       };
       const int fold = rank != 0 ? 0 : (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
-      fft_stage<real, PS, st, TC, T, 1, false, (st == PS::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, fold);
+      fft_stage<real, PS, st, TC, T, SW, false, (st == PS::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, fold);
     }
   }
 };

@@ -92,6 +92,12 @@ static int strided(const b200fft_strided_desc_t& d) {
     B200FFT_CLUSTER_PLANS(X)
 #undef X
   }
+  if (g_emu_variant == 23) {  // 64-byte rows
+#define X(nn, ...) \
+  if (d.n == nn) return emulate_cluster<ClusterStridedK<real, Plan<__VA_ARGS__>, 64>>(p);
+    B200FFT_CLUSTER_PLANS(X)
+#undef X
+  }
   switch (d.n) {
 #define X(n, ...) \
   case n:         \

@@ -25,7 +25,9 @@ def cluster():
     import mpifft4py_b200 as m
     from mpifft4py_b200.comm import SelfComm
     be = tp._Gpu()
-    be.L.b200fft_set_variant(21)  # every strided pass whose length has a cluster plan
+    be.L.b200fft_set_variant(23)  # 64-byte tile rows
+    cc.run_all(be)
+    be.L.b200fft_set_variant(21)  # every strided pass whose length has a cluster plan, 128-byte rows
     cc.run_all(be)
     # whole transforms whose x pass is a cluster launch (1024 plain, 1536 with the 3/2-rule), against the oracle
     N = (1024, 16, 16)

@@ -9,10 +9,11 @@ import emu_util
 import test_passes as tp
 
 
-@pytest.fixture(scope="module")
-def be21():
+@pytest.fixture(scope="module", params=[21, 23], ids=["rows128", "rows64"])
+def be21(request):
+    """variant 21: 128-byte tile rows (far strides); 23: 64-byte rows (long columns at near strides)"""
     lib = emu_util.load()
-    old = lib.emu_set_variant(21)
+    old = lib.emu_set_variant(request.param)
     yield tp._Emu()
     lib.emu_set_variant(old)
 
