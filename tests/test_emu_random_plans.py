@@ -1,0 +1,76 @@
+"""Seeded random sweep over the slab plan space -- mesh x ranks x transport x pipeline x chunk count x
+kind x dealias mode -- in the CPU emulator against the oracle.  The fixed cases of test_emu_plans.py pin
+the common configurations; this one looks for index-map mistakes in the corners (uneven kz ranges, chunk
+counts that do not divide the local planes, non-cubic meshes, 3*2^k sizes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import emu_util
+import oracle
+from mpifft4py_b200 import _cdefs as D
+from test_emu_plans import TOL, _check, _desc, _rand_c, run_plan
+
+SIZES = [8, 12, 16, 24, 32, 48]
+
+
+def _cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        N = tuple(int(rng.choice(SIZES)) for _ in range(3))
+        P = int(rng.choice([2, 4, 8]))
+        if N[0] % P or N[1] % P or P > N[0] // 2:
+            continue
+        transport = int(rng.choice([D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE]))
+        pipeline = int(rng.choice([D.PIPELINE_X, D.PIPELINE_KZ]))
+        chunks = int(rng.choice([0, 1, 2, 3, 4, 5]))
+        kind = str(rng.choice(["r2c", "c2c"]))
+        prec = "double" if rng.random() < 0.75 else "single"
+        out.append((N, P, transport, pipeline, chunks, kind, prec))
+    return out
+
+
+def _supported(n):
+    while n % 2 == 0:
+        n //= 2
+    return n in (1, 3)
+
+
+@pytest.mark.parametrize("N,P,transport,pipeline,chunks,kind,prec", _cases(40, 2026),
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
+def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec):
+    rt, ct = oracle.common.dtypes(prec)
+    c2c = kind == "c2c"
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(sum(N) * P + chunks)
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport)
+    tol = TOL[prec]
+    if c2c:
+        cs, it = (N[0], N[1] // P, N[2]), ct
+        new_in = lambda shape: _rand_c(rng, shape, ct)
+        fwd = lambda u, **k: oracle.slab.c2c_fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.c2c_ifftn(fu, N, P, precision=prec, **k)
+    else:
+        cs, it = g.complex_shape(), rt
+        new_in = lambda shape: rng.random(shape).astype(rt)
+        fwd = lambda u, **k: oracle.slab.fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.ifftn(fu, N, P, precision=prec, **k)
+    u = [new_in(g.real_shape()) for _ in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, [cs] * P, ct), fwd(u), tol)
+    fu = [_rand_c(rng, cs, ct) for _ in range(P)]
+    _check(run_plan(d, 1, D.DEALIAS_NONE, fu, [g.real_shape()] * P, it), inv(fu), tol)
+    _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()] * P, it), inv(fu, dealias="2/3-rule"), tol)
+    modes = [D.DEALIAS_NONE, D.DEALIAS_2_3]
+    if all(_supported(3 * n // 2) and n % 2 == 0 for n in N):  # padded lengths need a radix plan too
+        up = [new_in(g.real_shape_padded()) for _ in range(P)]
+        _check(run_plan(d, 0, D.DEALIAS_3_2, up, [cs] * P, ct), fwd(up, dealias="3/2-rule"), tol)
+        _check(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, it), inv(fu, dealias="3/2-rule"), tol)
+        modes.append(D.DEALIAS_3_2)
+    if transport != D.TRANSPORT_NCCL:
+        lib = emu_util.load()
+        for inverse in (0, 1):
+            for m in modes:
+                n = C.c_int()
+                assert lib.emu_check_p2p(C.byref(d), inverse, m, C.byref(n)) == 0
