@@ -12,5 +12,6 @@ from .mpibase import work_arrays, datatypes, empty, zeros
 from .serialFFT import fft, ifft, rfft, irfft, rfft2, irfft2, rfftn, irfftn, fft2, ifft2, fftn, ifftn
 from numpy.fft import fftfreq, rfftfreq
 from . import comm
+from . import device  # device-resident mesh / wavenumber / mask helpers and work arrays
 
 __version__ = '0.1.0'
