@@ -167,6 +167,11 @@ typedef struct {
                       planes -- z(c), y(c) | exchange(c), then one x pass; B200FFT_PIPELINE_KZ by kz
                       ranges -- one z pass, then y(c) | exchange(c) | x(c), so the exchange overlaps
                       FFT passes on BOTH sides (three-stage pipeline; receive layout is chunk-major) */
+  int l2_planes;   /* slab plans: > 0 runs the z and y passes per group of this many local x planes
+                      (z(g), y(g), z(g+1), ...) so that the y pass finds the z pass's output -- and the
+                      inverse z pass the y pass's -- still in the 126 MB L2: the intermediate
+                      (rfft2 / irfft2 of slab.py:366-370,247-268) then costs no HBM round trip.
+                      0 = one launch per pass */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

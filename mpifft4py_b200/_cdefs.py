@@ -41,7 +41,8 @@ class PlanDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("precision", C.c_int), ("N", C.c_longlong * 3),
                 ("nranks", C.c_int), ("rank", C.c_int), ("P1", C.c_int), ("P2", C.c_int),
                 ("padsize", C.c_double), ("drop_nyquist", C.c_int), ("transport", C.c_int),
-                ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int)]
+                ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int),
+                ("l2_planes", C.c_int)]
 
 
 def no_mask():

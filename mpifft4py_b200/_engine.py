@@ -63,6 +63,9 @@ class Transform(object):
         pipe = str(getattr(self, "exchange_pipeline", None) or os.environ.get("B200FFT_PIPELINE", "x")).lower()
         assert pipe in ("x", "kz"), "exchange_pipeline must be 'x' or 'kz'"
         d.pipeline = D.PIPELINE_KZ if pipe == "kz" else D.PIPELINE_X
+        # L2 blocking of the z and y passes of slab plans: run them per group of this many x planes so
+        # that the y pass reads what the z pass just wrote from L2 instead of HBM (0 = whole array)
+        d.l2_planes = int(getattr(self, "l2_planes", 0) or os.environ.get("B200FFT_L2_PLANES", "0"))
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree
@@ -190,7 +193,7 @@ class Transform(object):
         """[(type, ms, algorithmic_bytes, length, pass)] of the last transform; type in
         {'c2c', 'r2c', 'c2r', 'exchange'}; ms < 0 unless set_timing(True); the chunks of a
         pipelined pass share `pass`."""
-        M = 64
+        M = 4096
         n = C.c_int()
         ty = (C.c_int * M)()
         ms = (C.c_float * M)()

@@ -226,9 +226,7 @@ struct b200fft_plan {
   } p2p;
   cudaStream_t comm_stream = nullptr;   // exchanges of pipelined programs run here
   std::vector<cudaEvent_t> sched_ev;    // ordering events between the two streams
-  cudaEvent_t ev[2 * 64];
-  int nev = 0;
-  bool ev_made = false;
+  std::vector<cudaEvent_t> ev;  // timing events, two per step (grown on demand)
   float last_fft_ms = -1.f, last_exch_ms = -1.f;
   std::vector<std::pair<int, int>> ev_marks;  // (event index start, is_exchange)
   std::vector<int> st_type, st_len, st_pass;
@@ -475,10 +473,12 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   pl->st_pass.clear();
   pl->st_bytes.clear();
   int evi = 0;
-  if (pl->timing && !pl->ev_made) {
-    for (int i = 0; i < 128; ++i) cudaEventCreate(&pl->ev[i]);
-    pl->ev_made = true;
-  }
+  if (pl->timing)
+    while (pl->ev.size() < 2 * pg.steps.size()) {
+      cudaEvent_t e;
+      if (cudaError_t rc = cudaEventCreate(&e)) return cuda_fail(rc, "cudaEventCreate");
+      pl->ev.push_back(e);
+    }
   // scheduling resources of pipelined programs: a high-priority communication stream (its few
   // NCCL CTAs must win SM slots against the FFT grids) and one event per cross-stream edge
   if (pg.nevents > 0) {
@@ -514,7 +514,7 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
     }
     if (use_p2p && s.wait_credits)  // this pass stores into the peers' receive buffers
       if (int rc = wait_credits(pl, st)) return rc;
-    if (pl->timing && evi + 2 <= 128) cudaEventRecord(pl->ev[evi], st);
+    if (pl->timing) cudaEventRecord(pl->ev[(size_t)evi], st);
     int rc = 0;
     if (s.type == ST_STRIDED) {
       b200fft_strided_desc_t d;
@@ -562,8 +562,8 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       pl->st_pass.push_back(s.pass);
       pl->st_bytes.push_back(bytes);
     }
-    if (pl->timing && evi + 2 <= 128) {
-      cudaEventRecord(pl->ev[evi + 1], st);
+    if (pl->timing) {
+      cudaEventRecord(pl->ev[(size_t)evi + 1], st);
       pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
       evi += 2;
     }
@@ -699,8 +699,7 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
   cudaDeviceSynchronize();
   for (int w = 0; w < 3; ++w)
     if (plan->ws[w]) cudaFree(plan->ws[w]);
-  if (plan->ev_made)
-    for (int i = 0; i < 128; ++i) cudaEventDestroy(plan->ev[i]);
+  for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
   if (plan->p2p.connected) {

@@ -305,17 +305,34 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
       z.real.off = row0 * pN2;
       return z;
     };
+    // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
+    // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
+    // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
+    auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
+      const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn) ? d.l2_planes : xn;
+      for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
+    };
     if (!inverse) {
       if (P == 1) {
         if (!padded) {  // slab.py:366-370
-          zfwd(N0 * N1, 0, BUF_OUT, 0);
-          b.strided((int)N1, N0, Nf, 0, nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1));
+          zy_groups(0, N0, [&](long long g0, long long gn) {
+            b.fixed = 0;
+            zfwd(gn * N1, g0 * N1, BUF_OUT, g0 * N1 * Nf);
+            b.fixed = 1;
+            b.strided((int)N1, gn, Nf, 0, nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
+          });
+          b.fixed = 2;
           b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
         } else {  // slab.py:371-387
-          zfwd((long long)pN0 * pN1, 0, BUF_W0, 0);
           b.use(BUF_W0, (long long)pN0 * pN1 * Nf);
-          b.strided(pN1, pN0, Nf, 0, nat(BUF_W0, 0, pN1 * Nf, Nf, pN1), nat(BUF_W1, 0, N1 * Nf, Nf, (int)N1), yfold);
           b.use(BUF_W1, (long long)pN0 * N1 * Nf);
+          zy_groups(0, pN0, [&](long long g0, long long gn) {
+            b.fixed = 0;
+            zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
+            b.fixed = 1;
+            b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), nat(BUF_W1, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), yfold);
+          });
+          b.fixed = 2;
           b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
         }
       } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
@@ -403,31 +420,34 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         b.use(recvbuf, P * blk);
         for (int c = 0; c < C; ++c) {
           const long long x0 = c * xc;
-          b.fixed = 0;
-          zfwd(xc * pN1, x0 * pN1, BUF_W0, x0 * pN1 * Nf);
-          SideT o;
-          o.chunk = (int)Np1;
-          o.nchunk = P;
-          o.nphys = (int)N1;
-          for (int q = 0; q < P; ++q) {
-            o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
-            o.base[q].off = q * blk + x0 * Np1 * Nf;
-            if (store && q != me) {  // block `me` of peer q's receive buffer
-              o.base[q].buf = recvbuf;
-              o.base[q].off = me * blk + x0 * Np1 * Nf;
-              o.base[q].peer = q;
+          int y_ev = -1;
+          zy_groups(x0, xc, [&](long long g0, long long gn) {
+            b.fixed = 0;
+            zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
+            SideT o;
+            o.chunk = (int)Np1;
+            o.nchunk = P;
+            o.nphys = (int)N1;
+            for (int q = 0; q < P; ++q) {
+              o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
+              o.base[q].off = q * blk + g0 * Np1 * Nf;
+              if (store && q != me) {  // block `me` of peer q's receive buffer
+                o.base[q].buf = recvbuf;
+                o.base[q].off = me * blk + g0 * Np1 * Nf;
+                o.base[q].peer = q;
+              }
+              o.sb[q] = Np1 * Nf;
+              o.si[q] = Nf;
             }
-            o.sb[q] = Np1 * Nf;
-            o.si[q] = Nf;
-          }
-          b.fixed = 1;
-          Step& y = b.strided(pN1, xc, Nf, 0, nat(BUF_W0, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
-          y.wait_credits = store && c == 0;
-          y.rec_ev = pg.nevents++;
+            b.fixed = 1;
+            Step& y = b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
+            y.wait_credits = store && c == 0 && g0 == x0;
+            if (g0 + gn == x0 + xc) y_ev = y.rec_ev = pg.nevents++;  // the exchange follows the chunk's last group
+          });
           b.fixed = 2;
           Step& x = b.exch(0, P, me);
           x.stream = 1;
-          x.wait_ev = y.rec_ev;
+          x.wait_ev = y_ev;
           x.rec_ev = pg.nevents++;
           x.first_exch = (c == 0);
           x.fused = store;
@@ -457,12 +477,20 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
         }
         if (!padded) {
-          b.strided((int)N1, N0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1));
-          zinv(N0 * N1, 0, BUF_W0, 0, scale);
+          zy_groups(0, N0, [&](long long g0, long long gn) {
+            b.fixed = 1;
+            b.strided((int)N1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
+            b.fixed = 2;
+            zinv(gn * N1, g0 * N1, BUF_W0, g0 * N1 * Nf, scale);
+          });
         } else {
-          b.strided(pN1, pN0, Nf, 1, nat(BUF_W0, 0, N1 * Nf, Nf, (int)N1), nat(BUF_W1, 0, pN1 * Nf, Nf, pN1));
           b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
-          zinv((long long)pN0 * pN1, 0, BUF_W1, 0, scale);
+          zy_groups(0, pN0, [&](long long g0, long long gn) {
+            b.fixed = 1;
+            b.strided(pN1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W1, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
+            b.fixed = 2;
+            zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
+          });
         }
       } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
         // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
@@ -600,24 +628,26 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
         }
         for (int c = 0; c < C; ++c) {
           const long long x0 = c * xc;
-          SideT g;
-          g.chunk = (int)Np1;
-          g.nchunk = P;
-          g.nphys = (int)N1;
-          for (int q = 0; q < P; ++q) {
-            g.base[q].buf = BUF_W1;
-            g.base[q].off = q * blk + x0 * Np1 * Nf;
-            g.sb[q] = Np1 * Nf;
-            g.si[q] = Nf;
-          }
-          b.fixed = 2;
-          Step& y = b.strided(pN1, xc, Nf, 1, g, nat(ybuf, x0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
-          y.wait_ev = xev[(size_t)c];
-          b.fixed = 3;
-          Step& z = zinv(xc * pN1, x0 * pN1, ybuf, x0 * pN1 * Nf, scale);
-          // credits go back after the last z pass, not the last y pass: W2 (this program's y output)
-          // is the forward program's receive buffer, which the peers fill as soon as they hold credits
-          z.last_reader = (c == C - 1);
+          zy_groups(x0, xc, [&](long long g0, long long gn) {
+            SideT g;
+            g.chunk = (int)Np1;
+            g.nchunk = P;
+            g.nphys = (int)N1;
+            for (int q = 0; q < P; ++q) {
+              g.base[q].buf = BUF_W1;
+              g.base[q].off = q * blk + g0 * Np1 * Nf;
+              g.sb[q] = Np1 * Nf;
+              g.si[q] = Nf;
+            }
+            b.fixed = 2;
+            Step& y = b.strided(pN1, gn, Nf, 1, g, nat(ybuf, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
+            if (g0 == x0) y.wait_ev = xev[(size_t)c];
+            b.fixed = 3;
+            Step& z = zinv(gn * pN1, g0 * pN1, ybuf, g0 * pN1 * Nf, scale);
+            // credits go back after the last z pass, not the last y pass: W2 (this program's y output)
+            // is the forward program's receive buffer, which the peers fill as soon as they hold credits
+            z.last_reader = (c == C - 1) && (g0 + gn == x0 + xc);
+          });
         }
       }
     }

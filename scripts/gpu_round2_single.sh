@@ -17,6 +17,14 @@ for v in 0 20 30; do
     echo "== $w variant $v"; python scripts/show_passes.py $O/bench_${w}_v$v.json; tail -2 $O/bench_${w}_v$v.err
   done
 done
+# 2b. L2 blocking of the z / y passes: groups of x planes (0 = off)
+for g in 2 4 6 8 12 16; do
+  for w in slab1024_f64 slab1024_f64_32; do
+    B200FFT_L2_PLANES=$g timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
+        > $O/bench_${w}_l2_$g.json 2> $O/bench_${w}_l2_$g.err
+    echo "== $w l2_planes $g"; python scripts/show_passes.py $O/bench_${w}_l2_$g.json; tail -2 $O/bench_${w}_l2_$g.err
+  done
+done
 # 3. ncu: launch list of the default bench, full capture of the x pass in both variants
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fft_ -c 60 --csv --log-file $O/launches_1024.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launch.log 2>&1

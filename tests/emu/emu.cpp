@@ -249,8 +249,15 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
           if (o.base[q].peer != w || w == r || o.nchunk != x.npeers) return 111;
           const Step& t = pg[w].steps[sx];
           if (!x.fused || t.type != ST_EXCH || !t.fused || t.comm != x.comm) return 114;
-          // it must be the block peer w receives from this rank (member x.me of the communicator)
-          if (o.base[q].buf != t.recv[x.me].buf || o.base[q].off != t.recv[x.me].off) return 115;
+          // it must lie inside the block peer w receives from this rank (member x.me of the communicator);
+          // all of it, when the pass is not one of several L2 groups of the chunk
+          const long long rows_q = (q == o.nchunk - 1) ? o.nphys - (long long)q * o.chunk : o.chunk;
+          const long long nb = s.type == ST_STRIDED ? s.B : s.rows, nj = s.type == ST_STRIDED ? s.J : 1;
+          const long long ext = (nb - 1) * o.sb[q] + (rows_q - 1) * o.si[q] + nj;
+          if (o.base[q].buf != t.recv[x.me].buf || o.base[q].off < t.recv[x.me].off ||
+              o.base[q].off + ext > t.recv[x.me].off + t.rcnt[x.me])
+            return 115;
+          if (d0->l2_planes <= 0 && (o.base[q].off != t.recv[x.me].off || ext != t.rcnt[x.me])) return 120;
           if (o.base[q].buf < BUF_W0 || t.recv[x.me].off + t.rcnt[x.me] > pg[w].need[t.recv[x.me].buf]) return 116;
         }
         continue;

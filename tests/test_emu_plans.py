@@ -15,7 +15,7 @@ from mpifft4py_b200 import _cdefs as D
 TOL = {"double": 5e-14, "single": 5e-6}
 
 
-def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0):
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0, l2_planes=0):
     d = D.PlanDesc()
     d.kind = kind
     d.precision = D.DOUBLE if prec == "double" else D.SINGLE
@@ -29,6 +29,7 @@ def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=
     d.transport = transport
     d.chunks = chunks
     d.pipeline = pipeline
+    d.l2_planes = l2_planes
     return d
 
 
@@ -352,3 +353,34 @@ def test_slab_kz_pipeline_runs_in_emulator(kind, N, P, chunks, transport):
                 n = C.c_int()
                 assert lib.emu_check_p2p(C.byref(d), inverse, dealias, C.byref(n)) == 0
                 assert 1 <= n.value <= max(chunks, 4)
+
+
+@pytest.mark.parametrize("l2_planes", [1, 3, 4])
+@pytest.mark.parametrize("kind", ["r2c", "c2c"])
+def test_slab_single_rank_l2_groups(kind, l2_planes):
+    """P = 1 with the z and y passes run per group of x planes (L2 blocking): same results; the step list
+    alternates z(g), y(g) and keeps one x pass."""
+    N, P, prec = (16, 8, 32), 1, "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(5)
+    c2c = kind == "c2c"
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, l2_planes=l2_planes)
+    if c2c:
+        cs, it = tuple(N), ct
+        new_in = lambda shape: _rand_c(rng, shape, ct)
+        fwd = lambda u, **k: oracle.slab.c2c_fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.c2c_ifftn(fu, N, P, precision=prec, **k)
+    else:
+        cs, it = g.complex_shape(), rt
+        new_in = lambda shape: rng.random(shape).astype(rt)
+        fwd = lambda u, **k: oracle.slab.fftn(u, N, P, precision=prec, **k)
+        inv = lambda fu, **k: oracle.slab.ifftn(fu, N, P, precision=prec, **k)
+    u = [new_in(g.real_shape())]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, [cs], ct), fwd(u), TOL[prec])
+    fu = [_rand_c(rng, cs, ct)]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp], it), inv(fu, dealias=name), TOL[prec])
+    up = [new_in(g.real_shape_padded())]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [cs], ct), fwd(up, dealias="3/2-rule"), TOL[prec])

@@ -1,5 +1,5 @@
 """Seeded random sweep over the slab plan space -- mesh x ranks x transport x pipeline x chunk count x
-kind x dealias mode -- in the CPU emulator against the oracle.  The fixed cases of test_emu_plans.py pin
+L2 group size x kind x dealias mode -- in the CPU emulator against the oracle.  The fixed cases of test_emu_plans.py pin
 the common configurations; this one looks for index-map mistakes in the corners (uneven kz ranges, chunk
 counts that do not divide the local planes, non-cubic meshes, 3*2^k sizes)."""
 import ctypes as C
@@ -28,7 +28,8 @@ def _cases(count, seed):
         chunks = int(rng.choice([0, 1, 2, 3, 4, 5]))
         kind = str(rng.choice(["r2c", "c2c"]))
         prec = "double" if rng.random() < 0.75 else "single"
-        out.append((N, P, transport, pipeline, chunks, kind, prec))
+        l2 = int(rng.choice([0, 0, 1, 2, 3]))
+        out.append((N, P, transport, pipeline, chunks, kind, prec, l2))
     return out
 
 
@@ -38,14 +39,15 @@ def _supported(n):
     return n in (1, 3)
 
 
-@pytest.mark.parametrize("N,P,transport,pipeline,chunks,kind,prec", _cases(40, 2026),
+@pytest.mark.parametrize("N,P,transport,pipeline,chunks,kind,prec,l2", _cases(60, 2026),
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
-def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec):
+def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec, l2):
     rt, ct = oracle.common.dtypes(prec)
     c2c = kind == "c2c"
     g = oracle.slab.Geometry(N, P)
     rng = np.random.default_rng(sum(N) * P + chunks)
-    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport)
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport,
+              l2_planes=l2)
     tol = TOL[prec]
     if c2c:
         cs, it = (N[0], N[1] // P, N[2]), ct
