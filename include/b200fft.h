@@ -172,6 +172,9 @@ typedef struct {
                       inverse z pass the y pass's -- still in the 126 MB L2: the intermediate
                       (rfft2 / irfft2 of slab.py:366-370,247-268) then costs no HBM round trip.
                       0 = one launch per pass */
+  int l2_streams;  /* single-rank L2-blocked plans: 2 = the two passes of a group run on two streams so
+                      that the next group's first pass overlaps this group's second (at most two groups
+                      in flight); 0 / 1 = one stream */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

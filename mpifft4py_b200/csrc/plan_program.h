@@ -261,6 +261,37 @@ inline int finish_peer_mapped(const b200fft_plan_desc_t& d, Program& pg) {
   return 0;
 }
 
+// Two-stream schedule of an L2-blocked single-rank program (d.l2_streams == 2).  On one stream every
+// small launch drains before the next starts; here the first pass of a group runs on the caller's
+// stream and the second on the plan's second stream, so group g+1's first pass fills the SMs that
+// group g's second pass leaves idle.  At most two groups are in flight (the first pass of group g+2
+// waits for the second pass of group g), which bounds the L2 footprint.
+//   forward  [z0 y0 z1 y1 ... x]:  z on stream 0, y on stream 1, x after the last y
+//   inverse  [x y0 z0 y1 z1 ...]:  y on stream 1, z on stream 0
+inline void two_stream_groups(Program& pg, int inverse) {
+  const int n = (int)pg.steps.size(), G = (n - 1) / 2;
+  if (G < 2 || n != 2 * G + 1) return;
+  std::vector<int> first_ev((size_t)G), second_ev((size_t)G);
+  for (int g = 0; g < G; ++g) {
+    first_ev[(size_t)g] = pg.nevents++;
+    second_ev[(size_t)g] = pg.nevents++;
+  }
+  const int base = inverse ? 1 : 0;
+  int x_ev = -1;
+  if (inverse) x_ev = pg.steps[0].rec_ev = pg.nevents++;
+  for (int g = 0; g < G; ++g) {
+    Step& a = pg.steps[(size_t)(base + 2 * g)];      // first pass of the group  (forward z, inverse y)
+    Step& c = pg.steps[(size_t)(base + 2 * g + 1)];  // second pass              (forward y, inverse z)
+    a.rec_ev = first_ev[(size_t)g];
+    c.wait_ev = first_ev[(size_t)g];
+    c.rec_ev = second_ev[(size_t)g];
+    if (g >= 2) a.wait_ev = second_ev[(size_t)g - 2];
+    (inverse ? a : c).stream = 1;
+    if (inverse && g == 0) a.wait_ev = x_ev;
+  }
+  if (!inverse) pg.steps[(size_t)n - 1].wait_ev = second_ev[(size_t)G - 1];
+}
+
 // Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
 inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
   Builder b(pg);
@@ -335,6 +366,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
           b.fixed = 2;
           b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
         }
+        if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 0);
       } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
         // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
         // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
@@ -492,6 +524,7 @@ inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias,
             zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
           });
         }
+        if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 1);
       } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
         // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
         const int C = kz_chunks(d.chunks, Nf);

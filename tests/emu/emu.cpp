@@ -287,6 +287,111 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
   return 0;
 }
 
+}  // extern "C"
+
+// Schedule check of every rank's program: the device runs steps on two streams ordered by events
+// (Step::stream / wait_ev / rec_ev), the emulator in program order -- so a missing dependency would
+// pass every emulator run and race on the GPU.  This derives the happens-before relation the device
+// actually enforces (stream order + event edges; a wait on an event that is recorded LATER in program
+// order is a no-op in CUDA and counts as an error) and requires it between any two steps of a rank
+// that touch overlapping parts of the same local buffer with at least one write.  Regions are
+// bounding intervals (conservative).  Peer stores of the fused transport are ordered by the flag /
+// credit protocol, not by this rank's streams, and are left out.
+namespace {
+struct Region { int buf; long long lo, hi; bool write; };
+
+void side_regions(const SideT& s, long long nb, long long nj, bool write, long long unit, std::vector<Region>& out) {
+  for (int q = 0; q < s.nchunk; ++q) {
+    if (s.base[q].peer >= 0) continue;
+    const long long rows_q = (q == s.nchunk - 1) ? s.nphys - (long long)q * s.chunk : s.chunk;
+    const long long ext = (nb - 1) * s.sb[q] + (rows_q - 1) * s.si[q] + nj;
+    out.push_back(Region{s.base[q].buf, s.base[q].off * unit, (s.base[q].off + ext) * unit, write});
+  }
+}
+
+std::vector<Region> step_regions(const Step& s) {
+  std::vector<Region> r;
+  if (s.type == ST_STRIDED) {
+    side_regions(s.in, s.B, s.J, false, 2, r);
+    side_regions(s.out, s.B, s.J, true, 2, r);
+  } else if (s.type == ST_R2C || s.type == ST_C2R) {  // real side in real units, complex side in 2 real units
+    r.push_back(Region{s.real.buf, s.real.off, s.real.off + (s.rows - 1) * s.rpitch + s.n, s.type == ST_C2R});
+    side_regions(s.cside, s.rows, 1, s.type == ST_R2C, 2, r);
+  } else {
+    for (int q = 0; q < s.npeers; ++q) {
+      if (q == s.me) continue;
+      if (!s.fused) r.push_back(Region{s.send[q].buf, s.send[q].off * 2, (s.send[q].off + s.scnt[q]) * 2, false});
+      r.push_back(Region{s.recv[q].buf, s.recv[q].off * 2, (s.recv[q].off + s.rcnt[q]) * 2, true});
+    }
+  }
+  return r;
+}
+}  // namespace
+
+extern "C" int emu_check_schedule(const b200fft_plan_desc_t* d0, int inverse, int dealias) {
+  if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;
+  for (int rank = 0; rank < d0->nranks; ++rank) {
+    b200fft_plan_desc_t d = *d0;
+    d.rank = rank;
+    Program pg;
+    if (int rc = build_program(d, inverse, dealias, pg)) return rc;
+    const int n = (int)pg.steps.size();
+    std::vector<std::vector<char>> hb((size_t)n, std::vector<char>((size_t)n, 0));  // hb[i][j]: i happens before j
+    int last_on[2] = {-1, -1};
+    for (int j = 0; j < n; ++j) {
+      const Step& s = pg.steps[(size_t)j];
+      const int st = s.stream == 1 ? 1 : 0;
+      std::vector<int> preds;
+      if (last_on[st] >= 0) preds.push_back(last_on[st]);
+      for (int ev : {s.wait_ev, s.wait_ev2}) {
+        if (ev < 0) continue;
+        int rec = -1;
+        for (int i = 0; i < j; ++i)
+          if (pg.steps[(size_t)i].rec_ev == ev) rec = i;
+        if (ev == pg.fork_ev) continue;  // recorded at program start
+        if (rec < 0) {
+          std::fprintf(stderr, "schedule: rank %d step %d waits for event %d that no earlier step records\n", rank, j, ev);
+          return 201;
+        }
+        preds.push_back(rec);
+      }
+      // a step on the second stream with no predecessor at all would run unordered against the caller's
+      // earlier work: only allowed behind the fork event
+      if (st == 1 && preds.empty() && !(pg.fork_ev >= 0 && s.wait_ev == pg.fork_ev)) {
+        std::fprintf(stderr, "schedule: rank %d step %d starts the second stream without an event\n", rank, j);
+        return 202;
+      }
+      for (int i : preds) {
+        hb[(size_t)i][(size_t)j] = 1;
+        for (int k = 0; k < n; ++k)
+          if (hb[(size_t)k][(size_t)i]) hb[(size_t)k][(size_t)j] = 1;
+      }
+      last_on[st] = j;
+    }
+    // the caller's stream must end up behind everything: its last step (or a later one) follows every step
+    for (int i = 0; i < n; ++i)
+      if (i != last_on[0] && !hb[(size_t)i][(size_t)last_on[0]]) {
+        std::fprintf(stderr, "schedule: rank %d step %d is not joined into the caller's stream\n", rank, i);
+        return 203;
+      }
+    std::vector<std::vector<Region>> regs((size_t)n);
+    for (int i = 0; i < n; ++i) regs[(size_t)i] = step_regions(pg.steps[(size_t)i]);
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) {
+        if (hb[(size_t)i][(size_t)j]) continue;
+        for (const Region& a : regs[(size_t)i])
+          for (const Region& c : regs[(size_t)j])
+            if (a.buf == c.buf && (a.write || c.write) && a.lo < c.hi && c.lo < a.hi) {
+              std::fprintf(stderr, "schedule: rank %d steps %d and %d touch buffer %d [%lld,%lld) / [%lld,%lld) unordered\n", rank, i, j,
+                           a.buf, a.lo, a.hi, c.lo, c.hi);
+              return 204;
+            }
+      }
+  }
+  return 0;
+}
+
+extern "C" {
 // kernel launch geometry, for DESIGN.md / tests
 int emu_strided_config(int precision, int n, int* T, int* TC, int* smem) {
   switch (n) {
