@@ -4,7 +4,8 @@
 N=${1:-2}
 O=gpurun_out/r02_multi_$N
 mkdir -p $O
-timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_zz_gpu_transports.py -m gpu -q -rxX > $O/pytest.log 2>&1
+B200FFT_EXPERIMENTAL=1 timeout 2400 python -m pytest tests/test_gpu_multi.py tests/test_zz_gpu_transports.py -m gpu -q -rxXs \
+    -k "test_multi_gpu_parity[$N] or test_slab_transport_parity[$N-" > $O/pytest.log 2>&1
 tail -25 $O/pytest.log
 run() {  # transport pipeline chunks workload
   B200FFT_TRANSPORT=$1 B200FFT_PIPELINE=$2 B200FFT_CHUNKS=$3 timeout 300 python -m torch.distributed.run --nnodes=1 \

@@ -17,6 +17,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.parametrize("what", ["cluster", "rowbar"])
 def test_variant_on_device(what):
     out = subprocess.run([sys.executable, os.path.join(HERE, "gpu_variant_worker.py"), what],
-                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
     text = out.stdout.decode("utf-8", "replace")
     assert out.returncode == 0 and "VARIANT_WORKER_OK" in text, text[-6000:]

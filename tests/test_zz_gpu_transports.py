@@ -12,9 +12,12 @@ from test_gpu_multi import HERE, _free_port
 pytestmark = pytest.mark.gpu
 
 
-# "store" and the "kz" pipeline were written after round 1's GPU minutes were spent (emulator-checked
-# only): a device failure of these opt-in modes is reported as xfail, a pass as XPASS.
-_PENDING = pytest.mark.xfail(strict=False, reason="opt-in mode; first device run pending")
+# "store", the "kz" pipeline and "p2p" for pencil / line were written after round 1's GPU minutes were
+# spent (emulator-checked only).  A protocol mistake between ranks would show up as a hang that only the
+# subprocess timeout ends, so these opt-in modes run on request only (B200FFT_EXPERIMENTAL=1, set by
+# scripts/gpu_round2_multi.sh) and do not put the default suite's wall clock at risk.
+_PENDING = pytest.mark.skipif(not os.environ.get("B200FFT_EXPERIMENTAL"),
+                              reason="opt-in mode, first device run pending: set B200FFT_EXPERIMENTAL=1")
 
 
 @pytest.mark.parametrize("transport,pipeline", [
@@ -28,7 +31,7 @@ def test_slab_transport_parity(nproc, transport, pipeline):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "gpu_dist_worker.py"), "--transport", transport, pipeline]
-    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=420)
     text = out.stdout.decode("utf-8", "replace")
     assert out.returncode == 0, text[-6000:]
     assert text.count("GPU_WORKER_OK") == nproc, text[-6000:]
