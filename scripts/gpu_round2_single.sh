@@ -25,6 +25,10 @@ for g in 2 4 6 8 12 16 -2 -3 -4 -6; do   # negative: the two-stream schedule wit
     echo "== $w l2_planes $g"; python scripts/show_passes.py $O/bench_${w}_l2_$g.json; tail -2 $O/bench_${w}_l2_$g.err
   done
 done
+# 2c. which side of a far-strided pass pays: loads or stores (default kernels, cluster kernels 128 / 64 B)
+for v in 0 20 21 23; do
+  B200FFT_VARIANT=$v timeout 300 python scripts/microbench_strided.py 1024 d 2>&1 | tee -a $O/micro_strided.log
+done
 # 3. ncu: launch list of the default bench, full capture of the x pass in both variants
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fft_ -c 60 --csv --log-file $O/launches_1024.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launch.log 2>&1
