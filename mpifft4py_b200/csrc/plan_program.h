@@ -292,691 +292,724 @@ inline void two_stream_groups(Program& pg, int inverse) {
   if (!inverse) pg.steps[(size_t)n - 1].wait_ev = second_ev[(size_t)G - 1];
 }
 
-// Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
-inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
+// ------------------------------------------------------------------------------------------------
+// slab.R2C / slab.C2C programs (slab.py:214-485, 538-825)
+// ------------------------------------------------------------------------------------------------
+inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
   Builder b(pg);
   const bool padded = dealias == B200FFT_DEALIAS_3_2;
   const bool masked = inverse && dealias == B200FFT_DEALIAS_2_3;
   const double p = padded ? d.padsize : 1.0;
   const int P = d.nranks, me = d.rank;
   const long long N0 = d.N[0], N1 = d.N[1], N2 = d.N[2];
-
-  if (d.kind == B200FFT_SLAB || d.kind == B200FFT_SLAB_C2C) {
-    // slab.C2C (slab.py:538-825) reuses every R2C shape with Nf = N[2] (slab.py:565-567); its z pass is
-    // a contiguous-row C2C, its truncations fold in y and z at P > 1 (copy_from_padded, :816-823) and
-    // keep mode -N/2 in x (:796-797) and everywhere at P == 1 (the `ks` gather, :735-738)
-    const bool c2c = d.kind == B200FFT_SLAB_C2C;
-    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = c2c ? N2 : N2 / 2 + 1;
-    const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
-    if (padded && P > 1 && P > N0 / 2)  // slab.py:311,446
-      return fail(B200FFT_ERR_ARG, "Number of processors cannot be larger than N[0]//2 for 3/2-rule");
-    const double p3 = p * p * p;
-    const long long blk = (long long)pNp0 * Np1 * Nf;
-    const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
-    // fused transport: the y (forward) / x (inverse) pass stores each peer's block into that peer's
-    // receive buffer -- exactly where the copy-engine transport's DMA would put it (`rpeer`)
-    const bool store = d.transport == B200FFT_TRANSPORT_STORE && P > 1;
-    const bool p2p = (d.transport == B200FFT_TRANSPORT_P2P || store) && P > 1;  // peers write into plan-owned buffers only
-    const int yfold = !padded ? 0 : (c2c && P == 1) ? 2 : 1;
-    const int xfold = !padded ? 0 : c2c ? 2 : 1;
-    const int zfold = !padded ? 0 : (P == 1) ? 2 : 1;
-    // z pass over `rows` rows starting at row `row0` of the caller's array; the spectrum side is
-    // [rows][Nf] at `coff` of buffer `cbuf`
-    auto zfwd = [&](long long rows, long long row0, int cbuf, long long coff) -> Step& {
-      if (c2c)
-        return b.strided(pN2, rows, 1, 0, nat(BUF_IN, row0 * pN2, pN2, 1, pN2), nat(cbuf, coff, Nf, 1, (int)Nf), zfold);
-      Step& z = b.rows(true, rows, pN2, (int)Nf, BUF_IN, nat(cbuf, coff, Nf, 1, (int)Nf));
-      z.real.off = row0 * pN2;
-      return z;
-    };
-    auto zinv = [&](long long rows, long long row0, int cbuf, long long coff, double scale) -> Step& {
-      if (c2c)
-        return b.strided(pN2, rows, 1, 1, nat(cbuf, coff, Nf, 1, (int)Nf), nat(BUF_OUT, row0 * pN2, pN2, 1, pN2), 0, scale);
-      Step& z = b.rows(false, rows, pN2, (int)Nf, BUF_OUT, nat(cbuf, coff, Nf, 1, (int)Nf), scale);
-      z.real.off = row0 * pN2;
-      return z;
-    };
-    // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
-    // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
-    // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
-    auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
-      const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn) ? d.l2_planes : xn;
-      for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
-    };
-    if (!inverse) {
-      if (P == 1) {
-        if (!padded) {  // slab.py:366-370
-          zy_groups(0, N0, [&](long long g0, long long gn) {
-            b.fixed = 0;
-            zfwd(gn * N1, g0 * N1, BUF_OUT, g0 * N1 * Nf);
-            b.fixed = 1;
-            b.strided((int)N1, gn, Nf, 0, nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
-          });
-          b.fixed = 2;
-          b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
-        } else {  // slab.py:371-387
-          b.use(BUF_W0, (long long)pN0 * pN1 * Nf);
-          b.use(BUF_W1, (long long)pN0 * N1 * Nf);
-          zy_groups(0, pN0, [&](long long g0, long long gn) {
-            b.fixed = 0;
-            zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
-            b.fixed = 1;
-            b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), nat(BUF_W1, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), yfold);
-          });
-          b.fixed = 2;
-          b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
+  // slab.C2C (slab.py:538-825) reuses every R2C shape with Nf = N[2] (slab.py:565-567); its z pass is
+  // a contiguous-row C2C, its truncations fold in y and z at P > 1 (copy_from_padded, :816-823) and
+  // keep mode -N/2 in x (:796-797) and everywhere at P == 1 (the `ks` gather, :735-738)
+  const bool c2c = d.kind == B200FFT_SLAB_C2C;
+  const long long Np0 = N0 / P, Np1 = N1 / P, Nf = c2c ? N2 : N2 / 2 + 1;
+  const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
+  if (padded && P > 1 && P > N0 / 2)  // slab.py:311,446
+    return fail(B200FFT_ERR_ARG, "Number of processors cannot be larger than N[0]//2 for 3/2-rule");
+  const double p3 = p * p * p;
+  const long long blk = (long long)pNp0 * Np1 * Nf;
+  const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
+  // fused transport: the y (forward) / x (inverse) pass stores each peer's block into that peer's
+  // receive buffer -- exactly where the copy-engine transport's DMA would put it (`rpeer`)
+  const bool store = d.transport == B200FFT_TRANSPORT_STORE && P > 1;
+  const bool p2p = (d.transport == B200FFT_TRANSPORT_P2P || store) && P > 1;  // peers write into plan-owned buffers only
+  const int yfold = !padded ? 0 : (c2c && P == 1) ? 2 : 1;
+  const int xfold = !padded ? 0 : c2c ? 2 : 1;
+  const int zfold = !padded ? 0 : (P == 1) ? 2 : 1;
+  // z pass over `rows` rows starting at row `row0` of the caller's array; the spectrum side is
+  // [rows][Nf] at `coff` of buffer `cbuf`
+  auto zfwd = [&](long long rows, long long row0, int cbuf, long long coff) -> Step& {
+    if (c2c)
+      return b.strided(pN2, rows, 1, 0, nat(BUF_IN, row0 * pN2, pN2, 1, pN2), nat(cbuf, coff, Nf, 1, (int)Nf), zfold);
+    Step& z = b.rows(true, rows, pN2, (int)Nf, BUF_IN, nat(cbuf, coff, Nf, 1, (int)Nf));
+    z.real.off = row0 * pN2;
+    return z;
+  };
+  auto zinv = [&](long long rows, long long row0, int cbuf, long long coff, double scale) -> Step& {
+    if (c2c)
+      return b.strided(pN2, rows, 1, 1, nat(cbuf, coff, Nf, 1, (int)Nf), nat(BUF_OUT, row0 * pN2, pN2, 1, pN2), 0, scale);
+    Step& z = b.rows(false, rows, pN2, (int)Nf, BUF_OUT, nat(cbuf, coff, Nf, 1, (int)Nf), scale);
+    z.real.off = row0 * pN2;
+    return z;
+  };
+  // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
+  // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
+  // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
+  auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
+    const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn) ? d.l2_planes : xn;
+    for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
+  };
+  if (!inverse) {
+    if (P == 1) {
+      if (!padded) {  // slab.py:366-370
+        zy_groups(0, N0, [&](long long g0, long long gn) {
+          b.fixed = 0;
+          zfwd(gn * N1, g0 * N1, BUF_OUT, g0 * N1 * Nf);
+          b.fixed = 1;
+          b.strided((int)N1, gn, Nf, 0, nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
+        });
+        b.fixed = 2;
+        b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
+      } else {  // slab.py:371-387
+        b.use(BUF_W0, (long long)pN0 * pN1 * Nf);
+        b.use(BUF_W1, (long long)pN0 * N1 * Nf);
+        zy_groups(0, pN0, [&](long long g0, long long gn) {
+          b.fixed = 0;
+          zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
+          b.fixed = 1;
+          b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), nat(BUF_W1, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), yfold);
+        });
+        b.fixed = 2;
+        b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
+      }
+      if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 0);
+    } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
+      // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
+      // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
+      // exchange(c) (second stream) overlaps y(c+1..) before it and x(..c-1) after it; with the fused
+      // transport the y passes ARE the transfer (NVLink-bound) and run on the second stream beside the
+      // HBM-bound x passes.
+      const int recvbuf = BUF_W2;
+      const int C = kz_chunks(d.chunks, Nf);
+      const long long kc = Nf / C;
+      b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
+      if (!store) b.use(BUF_W1, P * blk);
+      b.use(recvbuf, P * blk);
+      b.fixed = 0;
+      Step& z = zfwd((long long)pNp0 * pN1, 0, BUF_W0, 0);
+      int z_ev = -1;
+      if (store) z_ev = z.rec_ev = pg.nevents++;
+      std::vector<int> xev((size_t)C);
+      for (int c = 0; c < C; ++c) {
+        const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+        const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+        SideT o;
+        o.chunk = (int)Np1;
+        o.nchunk = P;
+        o.nphys = (int)N1;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
+          o.base[q].off = coff + q * blkc;
+          if (store && q != me) {
+            o.base[q].buf = recvbuf;
+            o.base[q].off = coff + me * blkc;
+            o.base[q].peer = q;
+          }
+          o.sb[q] = Np1 * kcc;
+          o.si[q] = kcc;
         }
-        if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 0);
-      } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
-        // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
-        // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
-        // exchange(c) (second stream) overlaps y(c+1..) before it and x(..c-1) after it; with the fused
-        // transport the y passes ARE the transfer (NVLink-bound) and run on the second stream beside the
-        // HBM-bound x passes.
-        const int recvbuf = BUF_W2;
-        const int C = kz_chunks(d.chunks, Nf);
-        const long long kc = Nf / C;
-        b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
-        if (!store) b.use(BUF_W1, P * blk);
-        b.use(recvbuf, P * blk);
-        b.fixed = 0;
-        Step& z = zfwd((long long)pNp0 * pN1, 0, BUF_W0, 0);
-        int z_ev = -1;
-        if (store) z_ev = z.rec_ev = pg.nevents++;
-        std::vector<int> xev((size_t)C);
-        for (int c = 0; c < C; ++c) {
-          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
-          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+        b.fixed = 1;
+        Step& y = b.strided(pN1, pNp0, kcc, 0, nat(BUF_W0, k0, pN1 * Nf, Nf, pN1), o, yfold);
+        y.wait_credits = store && c == 0;
+        if (store) {
+          y.stream = 1;
+          if (c == 0) y.wait_ev = z_ev;
+        }
+        y.rec_ev = pg.nevents++;
+        b.fixed = 2;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = y.rec_ev;
+        x.rec_ev = pg.nevents++;
+        xev[(size_t)c] = x.rec_ev;
+        x.first_exch = (c == 0);
+        x.fused = store;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W1; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
+          x.recv[q].buf = recvbuf; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
+          x.rpeer[q].buf = recvbuf; x.rpeer[q].off = coff + me * blkc;
+        }
+      }
+      for (int c = 0; c < C; ++c) {
+        const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+        const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+        SideT g;
+        g.chunk = pNp0;
+        g.nchunk = P;
+        g.nphys = pN0;
+        for (int q = 0; q < P; ++q) {
+          g.base[q].buf = recvbuf;
+          g.base[q].off = coff + q * blkc;
+          g.sb[q] = kcc;
+          g.si[q] = Np1 * kcc;
+        }
+        b.fixed = 3;
+        Step& fx = b.strided(pN0, Np1, kcc, 0, g, nat(BUF_OUT, k0, Nf, Np1 * Nf, (int)N0), xfold, padded ? 1.0 / p3 : 1.0);
+        fx.wait_ev = xev[(size_t)c];
+        fx.last_reader = (c == C - 1);
+      }
+    } else {  // slab.py:389-483
+      // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
+      const int recvbuf = (padded || p2p) ? BUF_W2 : BUF_OUT;
+      const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p, store);
+      const long long xc = pNp0 / C;
+      b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
+      if (!store) b.use(BUF_W1, P * blk);  // send buffer
+      b.use(recvbuf, P * blk);
+      for (int c = 0; c < C; ++c) {
+        const long long x0 = c * xc;
+        int y_ev = -1;
+        zy_groups(x0, xc, [&](long long g0, long long gn) {
+          b.fixed = 0;
+          zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
           SideT o;
           o.chunk = (int)Np1;
           o.nchunk = P;
           o.nphys = (int)N1;
           for (int q = 0; q < P; ++q) {
             o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
-            o.base[q].off = coff + q * blkc;
-            if (store && q != me) {
+            o.base[q].off = q * blk + g0 * Np1 * Nf;
+            if (store && q != me) {  // block `me` of peer q's receive buffer
               o.base[q].buf = recvbuf;
-              o.base[q].off = coff + me * blkc;
+              o.base[q].off = me * blk + g0 * Np1 * Nf;
               o.base[q].peer = q;
             }
-            o.sb[q] = Np1 * kcc;
-            o.si[q] = kcc;
+            o.sb[q] = Np1 * Nf;
+            o.si[q] = Nf;
           }
           b.fixed = 1;
-          Step& y = b.strided(pN1, pNp0, kcc, 0, nat(BUF_W0, k0, pN1 * Nf, Nf, pN1), o, yfold);
-          y.wait_credits = store && c == 0;
-          if (store) {
-            y.stream = 1;
-            if (c == 0) y.wait_ev = z_ev;
-          }
-          y.rec_ev = pg.nevents++;
-          b.fixed = 2;
-          Step& x = b.exch(0, P, me);
-          x.stream = 1;
-          x.wait_ev = y.rec_ev;
-          x.rec_ev = pg.nevents++;
-          xev[(size_t)c] = x.rec_ev;
-          x.first_exch = (c == 0);
-          x.fused = store;
-          for (int q = 0; q < P; ++q) {
-            x.send[q].buf = BUF_W1; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
-            x.recv[q].buf = recvbuf; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
-            x.rpeer[q].buf = recvbuf; x.rpeer[q].off = coff + me * blkc;
-          }
+          Step& y = b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
+          y.wait_credits = store && c == 0 && g0 == x0;
+          if (g0 + gn == x0 + xc) y_ev = y.rec_ev = pg.nevents++;  // the exchange follows the chunk's last group
+        });
+        b.fixed = 2;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = y_ev;
+        x.rec_ev = pg.nevents++;
+        x.first_exch = (c == 0);
+        x.fused = store;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W1; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
+          x.recv[q].buf = recvbuf; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;
+          x.rpeer[q].buf = recvbuf; x.rpeer[q].off = me * blk + x0 * Np1 * Nf;
         }
-        for (int c = 0; c < C; ++c) {
-          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
-          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
-          SideT g;
-          g.chunk = pNp0;
-          g.nchunk = P;
-          g.nphys = pN0;
-          for (int q = 0; q < P; ++q) {
-            g.base[q].buf = recvbuf;
-            g.base[q].off = coff + q * blkc;
-            g.sb[q] = kcc;
-            g.si[q] = Np1 * kcc;
-          }
-          b.fixed = 3;
-          Step& fx = b.strided(pN0, Np1, kcc, 0, g, nat(BUF_OUT, k0, Nf, Np1 * Nf, (int)N0), xfold, padded ? 1.0 / p3 : 1.0);
-          fx.wait_ev = xev[(size_t)c];
-          fx.last_reader = (c == C - 1);
-        }
-      } else {  // slab.py:389-483
-        // z and y passes of chunk c (a range of local x planes) run while chunk c-1 is exchanged
-        const int recvbuf = (padded || p2p) ? BUF_W2 : BUF_OUT;
-        const int C = pick_chunks(d.chunks, pNp0, blk * csz, p2p, store);
-        const long long xc = pNp0 / C;
-        b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
-        if (!store) b.use(BUF_W1, P * blk);  // send buffer
-        b.use(recvbuf, P * blk);
-        for (int c = 0; c < C; ++c) {
-          const long long x0 = c * xc;
-          int y_ev = -1;
-          zy_groups(x0, xc, [&](long long g0, long long gn) {
-            b.fixed = 0;
-            zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
-            SideT o;
-            o.chunk = (int)Np1;
-            o.nchunk = P;
-            o.nphys = (int)N1;
-            for (int q = 0; q < P; ++q) {
-              o.base[q].buf = (q == me) ? recvbuf : BUF_W1;
-              o.base[q].off = q * blk + g0 * Np1 * Nf;
-              if (store && q != me) {  // block `me` of peer q's receive buffer
-                o.base[q].buf = recvbuf;
-                o.base[q].off = me * blk + g0 * Np1 * Nf;
-                o.base[q].peer = q;
-              }
-              o.sb[q] = Np1 * Nf;
-              o.si[q] = Nf;
-            }
-            b.fixed = 1;
-            Step& y = b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), o, yfold);
-            y.wait_credits = store && c == 0 && g0 == x0;
-            if (g0 + gn == x0 + xc) y_ev = y.rec_ev = pg.nevents++;  // the exchange follows the chunk's last group
-          });
-          b.fixed = 2;
-          Step& x = b.exch(0, P, me);
-          x.stream = 1;
-          x.wait_ev = y_ev;
-          x.rec_ev = pg.nevents++;
-          x.first_exch = (c == 0);
-          x.fused = store;
-          for (int q = 0; q < P; ++q) {
-            x.send[q].buf = BUF_W1; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
-            x.recv[q].buf = recvbuf; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;
-            x.rpeer[q].buf = recvbuf; x.rpeer[q].off = me * blk + x0 * Np1 * Nf;
-          }
-        }
-        const int last_ev = pg.nevents - 1;  // exchanges run in order on one stream
-        b.fixed = 3;
-        Step& fx = b.strided(pN0, 1, Np1 * Nf, 0, nat(recvbuf, 0, 0, Np1 * Nf, pN0), nat(BUF_OUT, 0, 0, Np1 * Nf, (int)N0),
-                             xfold, padded ? 1.0 / p3 : 1.0);
-        fx.wait_ev = last_ev;
-        fx.last_reader = 1;
       }
-    } else {
-      const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
-      if (P == 1) {  // slab.py:247-268
-        Step& sx = b.strided(pN0, 1, N1 * Nf, 1, nat(BUF_IN, 0, 0, N1 * Nf, (int)N0), nat(BUF_W0, 0, 0, N1 * Nf, pN0));
-        b.use(BUF_W0, (long long)pN0 * N1 * Nf);
-        if (masked) {
-          sx.mask.on = 1;
-          sx.mask.jdiv = (int)Nf;
-          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
-          band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
-        }
-        if (!padded) {
-          zy_groups(0, N0, [&](long long g0, long long gn) {
-            b.fixed = 1;
-            b.strided((int)N1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
-            b.fixed = 2;
-            zinv(gn * N1, g0 * N1, BUF_W0, g0 * N1 * Nf, scale);
-          });
-        } else {
-          b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
-          zy_groups(0, pN0, [&](long long g0, long long gn) {
-            b.fixed = 1;
-            b.strided(pN1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W1, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
-            b.fixed = 2;
-            zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
-          });
-        }
-        if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 1);
-      } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
-        // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
-        const int C = kz_chunks(d.chunks, Nf);
-        const long long kc = Nf / C;
-        const int ybuf = BUF_W2;
-        if (!store) b.use(BUF_W0, P * blk);
-        b.use(BUF_W1, P * blk);
-        b.use(ybuf, (long long)pNp0 * pN1 * Nf);
-        if (store) pg.fork_ev = pg.nevents++;  // the x passes (the transfer) run on the second stream
-        std::vector<int> xev((size_t)C);
-        for (int c = 0; c < C; ++c) {
-          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
-          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
-          SideT o;
-          o.chunk = pNp0;
-          o.nchunk = P;
-          o.nphys = pN0;
-          for (int q = 0; q < P; ++q) {
-            o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
-            o.base[q].off = coff + q * blkc;
-            if (store && q != me) {
-              o.base[q].buf = BUF_W1;
-              o.base[q].off = coff + me * blkc;
-              o.base[q].peer = q;
-            }
-            o.sb[q] = kcc;
-            o.si[q] = Np1 * kcc;
-          }
-          b.fixed = 0;
-          Step& sx = b.strided(pN0, Np1, kcc, 1, nat(BUF_IN, k0, Nf, Np1 * Nf, (int)N0), o);
-          if (masked) {  // batch index = local ky, column index = kz - k0
-            sx.mask.on = 1;
-            sx.mask.jdiv = 0x3fffffff;
-            band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-            band(N1, false, sx.mask.b_lo, sx.mask.b_hi);
-            sx.mask.b_off = (int)(me * Np1);
-            band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
-            sx.mask.jr_off = (int)k0;
-          }
-          sx.wait_credits = store && c == 0;
-          if (store) {
-            sx.stream = 1;
-            if (c == 0) sx.wait_ev = pg.fork_ev;
-          }
-          sx.rec_ev = pg.nevents++;
+      const int last_ev = pg.nevents - 1;  // exchanges run in order on one stream
+      b.fixed = 3;
+      Step& fx = b.strided(pN0, 1, Np1 * Nf, 0, nat(recvbuf, 0, 0, Np1 * Nf, pN0), nat(BUF_OUT, 0, 0, Np1 * Nf, (int)N0),
+                           xfold, padded ? 1.0 / p3 : 1.0);
+      fx.wait_ev = last_ev;
+      fx.last_reader = 1;
+    }
+  } else {
+    const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+    if (P == 1) {  // slab.py:247-268
+      Step& sx = b.strided(pN0, 1, N1 * Nf, 1, nat(BUF_IN, 0, 0, N1 * Nf, (int)N0), nat(BUF_W0, 0, 0, N1 * Nf, pN0));
+      b.use(BUF_W0, (long long)pN0 * N1 * Nf);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = (int)Nf;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+        band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
+      }
+      if (!padded) {
+        zy_groups(0, N0, [&](long long g0, long long gn) {
           b.fixed = 1;
-          Step& x = b.exch(0, P, me);
-          x.stream = 1;
-          x.wait_ev = sx.rec_ev;
-          x.rec_ev = pg.nevents++;
-          xev[(size_t)c] = x.rec_ev;
-          x.first_exch = (c == 0);
-          x.fused = store;
-          for (int q = 0; q < P; ++q) {
-            x.send[q].buf = BUF_W0; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
-            x.recv[q].buf = BUF_W1; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
-            x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = coff + me * blkc;
-          }
-        }
-        for (int c = 0; c < C; ++c) {
-          const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
-          const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
-          SideT g;
-          g.chunk = (int)Np1;
-          g.nchunk = P;
-          g.nphys = (int)N1;
-          for (int q = 0; q < P; ++q) {
-            g.base[q].buf = BUF_W1;
-            g.base[q].off = coff + q * blkc;
-            g.sb[q] = Np1 * kcc;
-            g.si[q] = kcc;
-          }
+          b.strided((int)N1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
           b.fixed = 2;
-          Step& y = b.strided(pN1, pNp0, kcc, 1, g, nat(ybuf, k0, pN1 * Nf, Nf, pN1));
-          y.wait_ev = xev[(size_t)c];
-        }
-        b.fixed = 3;
-        zinv((long long)pNp0 * pN1, 0, ybuf, 0, scale).last_reader = 1;
-      } else {  // slab.py:270-345
-        // x pass, then per chunk of local x planes: exchange (communication stream) -> y and z
-        // passes; the exchange of chunk c+1 overlaps the passes of chunk c
+          zinv(gn * N1, g0 * N1, BUF_W0, g0 * N1 * Nf, scale);
+        });
+      } else {
+        b.use(BUF_W1, (long long)pN0 * pN1 * Nf);
+        zy_groups(0, pN0, [&](long long g0, long long gn) {
+          b.fixed = 1;
+          b.strided(pN1, gn, Nf, 1, nat(BUF_W0, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_W1, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
+          b.fixed = 2;
+          zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
+        });
+      }
+      if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 1);
+    } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
+      // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
+      const int C = kz_chunks(d.chunks, Nf);
+      const long long kc = Nf / C;
+      const int ybuf = BUF_W2;
+      if (!store) b.use(BUF_W0, P * blk);
+      b.use(BUF_W1, P * blk);
+      b.use(ybuf, (long long)pNp0 * pN1 * Nf);
+      if (store) pg.fork_ev = pg.nevents++;  // the x passes (the transfer) run on the second stream
+      std::vector<int> xev((size_t)C);
+      for (int c = 0; c < C; ++c) {
+        const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+        const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
         SideT o;
         o.chunk = pNp0;
         o.nchunk = P;
         o.nphys = pN0;
         for (int q = 0; q < P; ++q) {
           o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
-          o.base[q].off = q * blk;
-          if (store && q != me) {  // block `me` of peer q's receive buffer
+          o.base[q].off = coff + q * blkc;
+          if (store && q != me) {
             o.base[q].buf = BUF_W1;
-            o.base[q].off = me * blk;
+            o.base[q].off = coff + me * blkc;
             o.base[q].peer = q;
           }
-          o.sb[q] = 0;
-          o.si[q] = Np1 * Nf;
+          o.sb[q] = kcc;
+          o.si[q] = Np1 * kcc;
         }
-        Step& sx = b.strided(pN0, 1, Np1 * Nf, 1, nat(BUF_IN, 0, 0, Np1 * Nf, (int)N0), o);
-        sx.wait_credits = store;
-        if (masked) {
+        b.fixed = 0;
+        Step& sx = b.strided(pN0, Np1, kcc, 1, nat(BUF_IN, k0, Nf, Np1 * Nf, (int)N0), o);
+        if (masked) {  // batch index = local ky, column index = kz - k0
           sx.mask.on = 1;
-          sx.mask.jdiv = (int)Nf;
+          sx.mask.jdiv = 0x3fffffff;
           band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
-          sx.mask.jq_off = (int)(me * Np1);
+          band(N1, false, sx.mask.b_lo, sx.mask.b_hi);
+          sx.mask.b_off = (int)(me * Np1);
           band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
+          sx.mask.jr_off = (int)k0;
+        }
+        sx.wait_credits = store && c == 0;
+        if (store) {
+          sx.stream = 1;
+          if (c == 0) sx.wait_ev = pg.fork_ev;
         }
         sx.rec_ev = pg.nevents++;
-        const int x_ev = sx.rec_ev;
-        if (!store) b.use(BUF_W0, P * blk);  // send buffer
-        b.use(BUF_W1, P * blk);
-        // the y pass of chunk c writes W0 rows that the sends of later chunks still read when the
-        // padded planes are larger than the send blocks: give its output a buffer of its own then
-        const int ybuf = BUF_W2;
-        b.use(ybuf, (long long)pNp0 * pN1 * Nf);
-        // (fused transport: the x pass has moved everything, one flag step covers all planes)
-        const int C = store ? 1 : pick_chunks(d.chunks, pNp0, blk * csz, p2p);
-        const long long xc = pNp0 / C;
-        std::vector<int> xev((size_t)C);
-        for (int c = 0; c < C; ++c) {  // all exchanges are queued first: they only depend on the x pass
-          const long long x0 = c * xc;
-          b.fixed = 1;
-          Step& x = b.exch(0, P, me);
-          x.stream = 1;
-          x.wait_ev = (c == 0) ? x_ev : -1;
-          x.rec_ev = pg.nevents++;
-          xev[(size_t)c] = x.rec_ev;
-          x.first_exch = (c == 0);
-          x.fused = store;
+        b.fixed = 1;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = sx.rec_ev;
+        x.rec_ev = pg.nevents++;
+        xev[(size_t)c] = x.rec_ev;
+        x.first_exch = (c == 0);
+        x.fused = store;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = coff + q * blkc; x.scnt[q] = blkc;
+          x.recv[q].buf = BUF_W1; x.recv[q].off = coff + q * blkc; x.rcnt[q] = blkc;
+          x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = coff + me * blkc;
+        }
+      }
+      for (int c = 0; c < C; ++c) {
+        const long long k0 = c * kc, kcc = (c == C - 1) ? Nf - k0 : kc;
+        const long long coff = (long long)P * pNp0 * Np1 * k0, blkc = (long long)pNp0 * Np1 * kcc;
+        SideT g;
+        g.chunk = (int)Np1;
+        g.nchunk = P;
+        g.nphys = (int)N1;
+        for (int q = 0; q < P; ++q) {
+          g.base[q].buf = BUF_W1;
+          g.base[q].off = coff + q * blkc;
+          g.sb[q] = Np1 * kcc;
+          g.si[q] = kcc;
+        }
+        b.fixed = 2;
+        Step& y = b.strided(pN1, pNp0, kcc, 1, g, nat(ybuf, k0, pN1 * Nf, Nf, pN1));
+        y.wait_ev = xev[(size_t)c];
+      }
+      b.fixed = 3;
+      zinv((long long)pNp0 * pN1, 0, ybuf, 0, scale).last_reader = 1;
+    } else {  // slab.py:270-345
+      // x pass, then per chunk of local x planes: exchange (communication stream) -> y and z
+      // passes; the exchange of chunk c+1 overlaps the passes of chunk c
+      SideT o;
+      o.chunk = pNp0;
+      o.nchunk = P;
+      o.nphys = pN0;
+      for (int q = 0; q < P; ++q) {
+        o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+        o.base[q].off = q * blk;
+        if (store && q != me) {  // block `me` of peer q's receive buffer
+          o.base[q].buf = BUF_W1;
+          o.base[q].off = me * blk;
+          o.base[q].peer = q;
+        }
+        o.sb[q] = 0;
+        o.si[q] = Np1 * Nf;
+      }
+      Step& sx = b.strided(pN0, 1, Np1 * Nf, 1, nat(BUF_IN, 0, 0, Np1 * Nf, (int)N0), o);
+      sx.wait_credits = store;
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = (int)Nf;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+        sx.mask.jq_off = (int)(me * Np1);
+        band(N2, !c2c, sx.mask.jr_lo, sx.mask.jr_hi);
+      }
+      sx.rec_ev = pg.nevents++;
+      const int x_ev = sx.rec_ev;
+      if (!store) b.use(BUF_W0, P * blk);  // send buffer
+      b.use(BUF_W1, P * blk);
+      // the y pass of chunk c writes W0 rows that the sends of later chunks still read when the
+      // padded planes are larger than the send blocks: give its output a buffer of its own then
+      const int ybuf = BUF_W2;
+      b.use(ybuf, (long long)pNp0 * pN1 * Nf);
+      // (fused transport: the x pass has moved everything, one flag step covers all planes)
+      const int C = store ? 1 : pick_chunks(d.chunks, pNp0, blk * csz, p2p);
+      const long long xc = pNp0 / C;
+      std::vector<int> xev((size_t)C);
+      for (int c = 0; c < C; ++c) {  // all exchanges are queued first: they only depend on the x pass
+        const long long x0 = c * xc;
+        b.fixed = 1;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = (c == 0) ? x_ev : -1;
+        x.rec_ev = pg.nevents++;
+        xev[(size_t)c] = x.rec_ev;
+        x.first_exch = (c == 0);
+        x.fused = store;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
+          x.recv[q].buf = BUF_W1; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;
+          x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = me * blk + x0 * Np1 * Nf;
+        }
+      }
+      for (int c = 0; c < C; ++c) {
+        const long long x0 = c * xc;
+        zy_groups(x0, xc, [&](long long g0, long long gn) {
+          SideT g;
+          g.chunk = (int)Np1;
+          g.nchunk = P;
+          g.nphys = (int)N1;
           for (int q = 0; q < P; ++q) {
-            x.send[q].buf = BUF_W0; x.send[q].off = q * blk + x0 * Np1 * Nf; x.scnt[q] = xc * Np1 * Nf;
-            x.recv[q].buf = BUF_W1; x.recv[q].off = q * blk + x0 * Np1 * Nf; x.rcnt[q] = xc * Np1 * Nf;
-            x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = me * blk + x0 * Np1 * Nf;
+            g.base[q].buf = BUF_W1;
+            g.base[q].off = q * blk + g0 * Np1 * Nf;
+            g.sb[q] = Np1 * Nf;
+            g.si[q] = Nf;
           }
-        }
-        for (int c = 0; c < C; ++c) {
-          const long long x0 = c * xc;
-          zy_groups(x0, xc, [&](long long g0, long long gn) {
-            SideT g;
-            g.chunk = (int)Np1;
-            g.nchunk = P;
-            g.nphys = (int)N1;
-            for (int q = 0; q < P; ++q) {
-              g.base[q].buf = BUF_W1;
-              g.base[q].off = q * blk + g0 * Np1 * Nf;
-              g.sb[q] = Np1 * Nf;
-              g.si[q] = Nf;
-            }
-            b.fixed = 2;
-            Step& y = b.strided(pN1, gn, Nf, 1, g, nat(ybuf, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
-            if (g0 == x0) y.wait_ev = xev[(size_t)c];
-            b.fixed = 3;
-            Step& z = zinv(gn * pN1, g0 * pN1, ybuf, g0 * pN1 * Nf, scale);
-            // credits go back after the last z pass, not the last y pass: W2 (this program's y output)
-            // is the forward program's receive buffer, which the peers fill as soon as they hold credits
-            z.last_reader = (c == C - 1) && (g0 + gn == x0 + xc);
-          });
-        }
+          b.fixed = 2;
+          Step& y = b.strided(pN1, gn, Nf, 1, g, nat(ybuf, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
+          if (g0 == x0) y.wait_ev = xev[(size_t)c];
+          b.fixed = 3;
+          Step& z = zinv(gn * pN1, g0 * pN1, ybuf, g0 * pN1 * Nf, scale);
+          // credits go back after the last z pass, not the last y pass: W2 (this program's y output)
+          // is the forward program's receive buffer, which the peers fill as soon as they hold credits
+          z.last_reader = (c == C - 1) && (g0 + gn == x0 + xc);
+        });
       }
     }
-    return 0;
   }
+  return 0;
+}
 
+// ------------------------------------------------------------------------------------------------
+// pencil.R2CX / R2CY programs (pencil.py:386-883, 1001-1477)
+// ------------------------------------------------------------------------------------------------
+inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
+  Builder b(pg);
+  const bool padded = dealias == B200FFT_DEALIAS_3_2;
+  const bool masked = inverse && dealias == B200FFT_DEALIAS_2_3;
+  const double p = padded ? d.padsize : 1.0;
+  const int P = d.nranks, me = d.rank;
+  const long long N0 = d.N[0], N1 = d.N[1], N2 = d.N[2];
   const bool peer_mapped = (d.transport == B200FFT_TRANSPORT_P2P || d.transport == B200FFT_TRANSPORT_STORE) && P > 1;
-  if (d.kind == B200FFT_PENCIL_X || d.kind == B200FFT_PENCIL_Y) {
-    const bool alignX = d.kind == B200FFT_PENCIL_X;
-    const int P1 = d.P1, P2 = d.P2;
-    const int c0 = me % P1, c1 = me / P1;
-    const long long Nf = N2 / 2 + 1;
-    const long long a = N0 / P1, bq = N1 / P2;      // real block: (a, bq, N2)
-    const int pa = ipad(p, a), pbq = ipad(p, bq);
-    const int pN0 = ipad(p, N0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
-    const int zparts = alignX ? P2 : P1, zme = alignX ? c1 : c0;
-    const long long C = Nf / zparts;
-    long long zc[PMAXP], zoff[PMAXP + 1];
-    zoff[0] = 0;
+  const bool alignX = d.kind == B200FFT_PENCIL_X;
+  const int P1 = d.P1, P2 = d.P2;
+  const int c0 = me % P1, c1 = me / P1;
+  const long long Nf = N2 / 2 + 1;
+  const long long a = N0 / P1, bq = N1 / P2;      // real block: (a, bq, N2)
+  const int pa = ipad(p, a), pbq = ipad(p, bq);
+  const int pN0 = ipad(p, N0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
+  const int zparts = alignX ? P2 : P1, zme = alignX ? c1 : c0;
+  const long long C = Nf / zparts;
+  long long zc[PMAXP], zoff[PMAXP + 1];
+  zoff[0] = 0;
+  for (int q = 0; q < zparts; ++q) {
+    zc[q] = C + ((q == zparts - 1 && !d.drop_nyquist) ? Nf % zparts : 0);
+    zoff[q + 1] = zoff[q] + zc[q];
+  }
+  const long long kzl = zc[zme];
+  const int nk = (int)zoff[zparts];  // Nf, or Nf-1 for the AlltoallN layout
+  const double p3 = p * p * p;
+  const long long rowsz = (long long)pa * pbq;  // z rows per rank
+  
+  const double iscale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+
+  // z pass stores / loads: kz cut into zparts chunks, one per peer of the z communicator
+  auto zside = [&](int selfbuf, long long selfoff, int otherbuf, bool recv_layout) {
+    SideT s;
+    s.chunk = (int)C;
+    s.nchunk = zparts;
+    s.nphys = nk;
     for (int q = 0; q < zparts; ++q) {
-      zc[q] = C + ((q == zparts - 1 && !d.drop_nyquist) ? Nf % zparts : 0);
-      zoff[q + 1] = zoff[q] + zc[q];
+      if (recv_layout) {  // blocks from q: [rowsz][zc[q]] at rowsz*zoff[q]
+        s.base[q].buf = otherbuf;
+        s.base[q].off = rowsz * zoff[q];
+      } else {
+        s.base[q].buf = (q == zme) ? selfbuf : otherbuf;
+        s.base[q].off = (q == zme) ? selfoff : rowsz * zoff[q];
+      }
+      s.sb[q] = zc[q];
+      s.si[q] = 1;
     }
-    const long long kzl = zc[zme];
-    const int nk = (int)zoff[zparts];  // Nf, or Nf-1 for the AlltoallN layout
-    const double p3 = p * p * p;
-    const long long rowsz = (long long)pa * pbq;  // z rows per rank
-    
-    const double iscale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+    return s;
+  };
 
-    // z pass stores / loads: kz cut into zparts chunks, one per peer of the z communicator
-    auto zside = [&](int selfbuf, long long selfoff, int otherbuf, bool recv_layout) {
-      SideT s;
-      s.chunk = (int)C;
-      s.nchunk = zparts;
-      s.nphys = nk;
-      for (int q = 0; q < zparts; ++q) {
-        if (recv_layout) {  // blocks from q: [rowsz][zc[q]] at rowsz*zoff[q]
-          s.base[q].buf = otherbuf;
-          s.base[q].off = rowsz * zoff[q];
-        } else {
-          s.base[q].buf = (q == zme) ? selfbuf : otherbuf;
-          s.base[q].off = (q == zme) ? selfoff : rowsz * zoff[q];
-        }
-        s.sb[q] = zc[q];
-        s.si[q] = 1;
+  if (alignX) {
+    const long long y1 = N1 / P1;
+    const long long blk2 = (long long)pa * y1 * kzl;     // comm0 exchange block
+    const long long blk1 = rowsz * kzl;                  // comm1 block [pa][pbq][kzl]
+    if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
+      const int recv2 = (padded || peer_mapped) ? BUF_W2 : BUF_OUT;  // peers write plan-owned buffers only
+      b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
+      b.use(BUF_W0, rowsz * nk);
+      b.use(BUF_W1, P2 * blk1);
+      Step& x1 = b.exch(2, P2, c1);
+      for (int q = 0; q < P2; ++q) {
+        x1.send[q].buf = BUF_W0; x1.send[q].off = rowsz * zoff[q]; x1.scnt[q] = rowsz * zc[q];
+        x1.recv[q].buf = BUF_W1; x1.recv[q].off = q * blk1; x1.rcnt[q] = blk1;
+        x1.rpeer[q].buf = BUF_W1; x1.rpeer[q].off = c1 * rowsz * zc[q];
       }
-      return s;
-    };
-
-    if (alignX) {
-      const long long y1 = N1 / P1;
-      const long long blk2 = (long long)pa * y1 * kzl;     // comm0 exchange block
-      const long long blk1 = rowsz * kzl;                  // comm1 block [pa][pbq][kzl]
-      if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
-        const int recv2 = (padded || peer_mapped) ? BUF_W2 : BUF_OUT;  // peers write plan-owned buffers only
-        b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
-        b.use(BUF_W0, rowsz * nk);
-        b.use(BUF_W1, P2 * blk1);
-        Step& x1 = b.exch(2, P2, c1);
-        for (int q = 0; q < P2; ++q) {
-          x1.send[q].buf = BUF_W0; x1.send[q].off = rowsz * zoff[q]; x1.scnt[q] = rowsz * zc[q];
-          x1.recv[q].buf = BUF_W1; x1.recv[q].off = q * blk1; x1.rcnt[q] = blk1;
-          x1.rpeer[q].buf = BUF_W1; x1.rpeer[q].off = c1 * rowsz * zc[q];
-        }
-        SideT g;  // gather y from the P2 peers
-        g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
-        for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk1; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
-        SideT o;  // split y over the P1 peers
-        o.chunk = (int)y1; o.nchunk = P1; o.nphys = (int)N1;
-        for (int q = 0; q < P1; ++q) {
-          o.base[q].buf = (q == c0) ? recv2 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = y1 * kzl; o.si[q] = kzl;
-        }
-        b.strided(pN1, pa, kzl, 0, g, o, padded ? 1 : 0);
-        b.use(BUF_W0, P1 * blk2);
-        b.use(recv2, P1 * blk2);
-        Step& x2 = b.exch(1, P1, c0);
-        for (int q = 0; q < P1; ++q) {
-          x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
-          x2.recv[q].buf = recv2; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
-          x2.rpeer[q].buf = recv2; x2.rpeer[q].off = c0 * blk2;
-        }
-        b.strided(pN0, 1, y1 * kzl, 0, nat(recv2, 0, 0, y1 * kzl, pN0), nat(BUF_OUT, 0, 0, y1 * kzl, (int)N0),
-                  padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
-      } else {  // pencil.py:1082-1105 (+ padded :1196-1223)
-        SideT o;
-        o.chunk = pa; o.nchunk = P1; o.nphys = pN0;
-        for (int q = 0; q < P1; ++q) {
-          o.base[q].buf = (q == c0) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = 0; o.si[q] = y1 * kzl;
-        }
-        Step& sx = b.strided(pN0, 1, y1 * kzl, 1, nat(BUF_IN, 0, 0, y1 * kzl, (int)N0), o);
-        if (masked) {
-          sx.mask.on = 1;
-          sx.mask.jdiv = (int)kzl;
-          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-          band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
-          sx.mask.jq_off = (int)(c0 * y1);
-          band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
-          sx.mask.jr_off = (int)(c1 * C);
-        }
-        b.use(BUF_W0, P1 * blk2);
-        b.use(BUF_W1, P1 * blk2);
-        Step& x2 = b.exch(1, P1, c0);
-        for (int q = 0; q < P1; ++q) {
-          x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
-          x2.recv[q].buf = BUF_W1; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
-          x2.rpeer[q].buf = BUF_W1; x2.rpeer[q].off = c0 * blk2;
-        }
-        SideT g;
-        g.chunk = (int)y1; g.nchunk = P1; g.nphys = (int)N1;
-        for (int q = 0; q < P1; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk2; g.sb[q] = y1 * kzl; g.si[q] = kzl; }
-        SideT o2;
-        o2.chunk = pbq; o2.nchunk = P2; o2.nphys = pN1;
-        for (int q = 0; q < P2; ++q) {
-          o2.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0;
-          o2.base[q].off = (q == c1) ? rowsz * zoff[c1] : q * blk1;
-          o2.sb[q] = pbq * kzl; o2.si[q] = kzl;
-        }
-        b.strided(pN1, pa, kzl, 1, g, o2);
-        b.use(BUF_W0, P2 * blk1);
-        b.use(BUF_W2, rowsz * nk);
-        Step& x1 = b.exch(2, P2, c1);
-        for (int q = 0; q < P2; ++q) {
-          x1.send[q].buf = BUF_W0; x1.send[q].off = q * blk1; x1.scnt[q] = blk1;
-          x1.recv[q].buf = BUF_W2; x1.recv[q].off = rowsz * zoff[q]; x1.rcnt[q] = rowsz * zc[q];
-          x1.rpeer[q].buf = BUF_W2; x1.rpeer[q].off = rowsz * zoff[c1];
-        }
-        b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
+      SideT g;  // gather y from the P2 peers
+      g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+      for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk1; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
+      SideT o;  // split y over the P1 peers
+      o.chunk = (int)y1; o.nchunk = P1; o.nphys = (int)N1;
+      for (int q = 0; q < P1; ++q) {
+        o.base[q].buf = (q == c0) ? recv2 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = y1 * kzl; o.si[q] = kzl;
       }
-    } else {  // alignment Y
-      const long long x2l = N0 / P2;                        // final local x extent
-      const long long blk = x2l * pbq * kzl;                // comm1 exchange block
-      const long long blk1 = rowsz * kzl;                   // comm0 block [pa][pbq][kzl]
-      if (!inverse) {  // pencil.py:730-754 (+ padded :853-881)
-        b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
-        b.use(BUF_W0, rowsz * nk);
-        b.use(BUF_W1, P1 * blk1);
-        Step& xa = b.exch(1, P1, c0);
-        for (int q = 0; q < P1; ++q) {
-          xa.send[q].buf = BUF_W0; xa.send[q].off = rowsz * zoff[q]; xa.scnt[q] = rowsz * zc[q];
-          xa.recv[q].buf = BUF_W1; xa.recv[q].off = q * blk1; xa.rcnt[q] = blk1;
-          xa.rpeer[q].buf = BUF_W1; xa.rpeer[q].off = c0 * rowsz * zc[q];
-        }
-        SideT o;
-        o.chunk = (int)x2l; o.nchunk = P2; o.nphys = (int)N0;
-        for (int q = 0; q < P2; ++q) {
-          o.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = 0; o.si[q] = pbq * kzl;
-        }
-        b.strided(pN0, 1, pbq * kzl, 0, nat(BUF_W1, 0, 0, pbq * kzl, pN0), o, padded ? 1 : 0);
-        b.use(BUF_W0, P2 * blk);
-        b.use(BUF_W2, P2 * blk);
-        Step& xb = b.exch(2, P2, c1);
-        for (int q = 0; q < P2; ++q) {
-          xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
-          xb.recv[q].buf = BUF_W2; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
-          xb.rpeer[q].buf = BUF_W2; xb.rpeer[q].off = c1 * blk;
-        }
-        SideT g;
-        g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
-        for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W2; g.base[q].off = q * blk; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
-        b.strided(pN1, x2l, kzl, 0, g, nat(BUF_OUT, 0, N1 * kzl, kzl, (int)N1), padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
-      } else {  // pencil.py:483-507 (+ padded :597-629)
-        SideT o;
-        o.chunk = pbq; o.nchunk = P2; o.nphys = pN1;
-        for (int q = 0; q < P2; ++q) {
-          o.base[q].buf = (q == c1) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = pbq * kzl; o.si[q] = kzl;
-        }
-        Step& sy = b.strided(pN1, x2l, kzl, 1, nat(BUF_IN, 0, N1 * kzl, kzl, (int)N1), o);
-        if (masked) {
-          sy.mask.on = 1;
-          sy.mask.jdiv = 0x3fffffff;
-          band(N0, false, sy.mask.b_lo, sy.mask.b_hi);
-          sy.mask.b_off = (int)(c1 * x2l);
-          band(N1, false, sy.mask.i_lo, sy.mask.i_hi);
-          band(N2, true, sy.mask.jr_lo, sy.mask.jr_hi);
-          sy.mask.jr_off = (int)(c0 * C);
-        }
-        b.use(BUF_W0, P2 * blk);
-        b.use(BUF_W1, P2 * blk);
-        Step& xb = b.exch(2, P2, c1);
-        for (int q = 0; q < P2; ++q) {
-          xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
-          xb.recv[q].buf = BUF_W1; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
-          xb.rpeer[q].buf = BUF_W1; xb.rpeer[q].off = c1 * blk;
-        }
-        SideT o2;
-        o2.chunk = pa; o2.nchunk = P1; o2.nphys = pN0;
-        for (int q = 0; q < P1; ++q) {
-          o2.base[q].buf = (q == c0) ? BUF_W2 : BUF_W0;
-          o2.base[q].off = (q == c0) ? rowsz * zoff[c0] : q * blk1;
-          o2.sb[q] = 0; o2.si[q] = pbq * kzl;
-        }
-        b.strided(pN0, 1, pbq * kzl, 1, nat(BUF_W1, 0, 0, pbq * kzl, (int)N0), o2);
-        b.use(BUF_W0, P1 * blk1);
-        b.use(BUF_W2, rowsz * nk);
-        Step& xa = b.exch(1, P1, c0);
-        for (int q = 0; q < P1; ++q) {
-          xa.send[q].buf = BUF_W0; xa.send[q].off = q * blk1; xa.scnt[q] = blk1;
-          xa.recv[q].buf = BUF_W2; xa.recv[q].off = rowsz * zoff[q]; xa.rcnt[q] = rowsz * zc[q];
-          xa.rpeer[q].buf = BUF_W2; xa.rpeer[q].off = rowsz * zoff[c0];
-        }
-        b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
+      b.strided(pN1, pa, kzl, 0, g, o, padded ? 1 : 0);
+      b.use(BUF_W0, P1 * blk2);
+      b.use(recv2, P1 * blk2);
+      Step& x2 = b.exch(1, P1, c0);
+      for (int q = 0; q < P1; ++q) {
+        x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
+        x2.recv[q].buf = recv2; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+        x2.rpeer[q].buf = recv2; x2.rpeer[q].off = c0 * blk2;
       }
+      b.strided(pN0, 1, y1 * kzl, 0, nat(recv2, 0, 0, y1 * kzl, pN0), nat(BUF_OUT, 0, 0, y1 * kzl, (int)N0),
+                padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+    } else {  // pencil.py:1082-1105 (+ padded :1196-1223)
+      SideT o;
+      o.chunk = pa; o.nchunk = P1; o.nphys = pN0;
+      for (int q = 0; q < P1; ++q) {
+        o.base[q].buf = (q == c0) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = 0; o.si[q] = y1 * kzl;
+      }
+      Step& sx = b.strided(pN0, 1, y1 * kzl, 1, nat(BUF_IN, 0, 0, y1 * kzl, (int)N0), o);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = (int)kzl;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+        sx.mask.jq_off = (int)(c0 * y1);
+        band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        sx.mask.jr_off = (int)(c1 * C);
+      }
+      b.use(BUF_W0, P1 * blk2);
+      b.use(BUF_W1, P1 * blk2);
+      Step& x2 = b.exch(1, P1, c0);
+      for (int q = 0; q < P1; ++q) {
+        x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2; x2.scnt[q] = blk2;
+        x2.recv[q].buf = BUF_W1; x2.recv[q].off = q * blk2; x2.rcnt[q] = blk2;
+        x2.rpeer[q].buf = BUF_W1; x2.rpeer[q].off = c0 * blk2;
+      }
+      SideT g;
+      g.chunk = (int)y1; g.nchunk = P1; g.nphys = (int)N1;
+      for (int q = 0; q < P1; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk2; g.sb[q] = y1 * kzl; g.si[q] = kzl; }
+      SideT o2;
+      o2.chunk = pbq; o2.nchunk = P2; o2.nphys = pN1;
+      for (int q = 0; q < P2; ++q) {
+        o2.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0;
+        o2.base[q].off = (q == c1) ? rowsz * zoff[c1] : q * blk1;
+        o2.sb[q] = pbq * kzl; o2.si[q] = kzl;
+      }
+      b.strided(pN1, pa, kzl, 1, g, o2);
+      b.use(BUF_W0, P2 * blk1);
+      b.use(BUF_W2, rowsz * nk);
+      Step& x1 = b.exch(2, P2, c1);
+      for (int q = 0; q < P2; ++q) {
+        x1.send[q].buf = BUF_W0; x1.send[q].off = q * blk1; x1.scnt[q] = blk1;
+        x1.recv[q].buf = BUF_W2; x1.recv[q].off = rowsz * zoff[q]; x1.rcnt[q] = rowsz * zc[q];
+        x1.rpeer[q].buf = BUF_W2; x1.rpeer[q].off = rowsz * zoff[c1];
+      }
+      b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
     }
-    return peer_mapped ? finish_peer_mapped(d, pg) : 0;
+  } else {  // alignment Y
+    const long long x2l = N0 / P2;                        // final local x extent
+    const long long blk = x2l * pbq * kzl;                // comm1 exchange block
+    const long long blk1 = rowsz * kzl;                   // comm0 block [pa][pbq][kzl]
+    if (!inverse) {  // pencil.py:730-754 (+ padded :853-881)
+      b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
+      b.use(BUF_W0, rowsz * nk);
+      b.use(BUF_W1, P1 * blk1);
+      Step& xa = b.exch(1, P1, c0);
+      for (int q = 0; q < P1; ++q) {
+        xa.send[q].buf = BUF_W0; xa.send[q].off = rowsz * zoff[q]; xa.scnt[q] = rowsz * zc[q];
+        xa.recv[q].buf = BUF_W1; xa.recv[q].off = q * blk1; xa.rcnt[q] = blk1;
+        xa.rpeer[q].buf = BUF_W1; xa.rpeer[q].off = c0 * rowsz * zc[q];
+      }
+      SideT o;
+      o.chunk = (int)x2l; o.nchunk = P2; o.nphys = (int)N0;
+      for (int q = 0; q < P2; ++q) {
+        o.base[q].buf = (q == c1) ? BUF_W2 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = 0; o.si[q] = pbq * kzl;
+      }
+      b.strided(pN0, 1, pbq * kzl, 0, nat(BUF_W1, 0, 0, pbq * kzl, pN0), o, padded ? 1 : 0);
+      b.use(BUF_W0, P2 * blk);
+      b.use(BUF_W2, P2 * blk);
+      Step& xb = b.exch(2, P2, c1);
+      for (int q = 0; q < P2; ++q) {
+        xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
+        xb.recv[q].buf = BUF_W2; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+        xb.rpeer[q].buf = BUF_W2; xb.rpeer[q].off = c1 * blk;
+      }
+      SideT g;
+      g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+      for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W2; g.base[q].off = q * blk; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
+      b.strided(pN1, x2l, kzl, 0, g, nat(BUF_OUT, 0, N1 * kzl, kzl, (int)N1), padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+    } else {  // pencil.py:483-507 (+ padded :597-629)
+      SideT o;
+      o.chunk = pbq; o.nchunk = P2; o.nphys = pN1;
+      for (int q = 0; q < P2; ++q) {
+        o.base[q].buf = (q == c1) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk; o.sb[q] = pbq * kzl; o.si[q] = kzl;
+      }
+      Step& sy = b.strided(pN1, x2l, kzl, 1, nat(BUF_IN, 0, N1 * kzl, kzl, (int)N1), o);
+      if (masked) {
+        sy.mask.on = 1;
+        sy.mask.jdiv = 0x3fffffff;
+        band(N0, false, sy.mask.b_lo, sy.mask.b_hi);
+        sy.mask.b_off = (int)(c1 * x2l);
+        band(N1, false, sy.mask.i_lo, sy.mask.i_hi);
+        band(N2, true, sy.mask.jr_lo, sy.mask.jr_hi);
+        sy.mask.jr_off = (int)(c0 * C);
+      }
+      b.use(BUF_W0, P2 * blk);
+      b.use(BUF_W1, P2 * blk);
+      Step& xb = b.exch(2, P2, c1);
+      for (int q = 0; q < P2; ++q) {
+        xb.send[q].buf = BUF_W0; xb.send[q].off = q * blk; xb.scnt[q] = blk;
+        xb.recv[q].buf = BUF_W1; xb.recv[q].off = q * blk; xb.rcnt[q] = blk;
+        xb.rpeer[q].buf = BUF_W1; xb.rpeer[q].off = c1 * blk;
+      }
+      SideT o2;
+      o2.chunk = pa; o2.nchunk = P1; o2.nphys = pN0;
+      for (int q = 0; q < P1; ++q) {
+        o2.base[q].buf = (q == c0) ? BUF_W2 : BUF_W0;
+        o2.base[q].off = (q == c0) ? rowsz * zoff[c0] : q * blk1;
+        o2.sb[q] = 0; o2.si[q] = pbq * kzl;
+      }
+      b.strided(pN0, 1, pbq * kzl, 1, nat(BUF_W1, 0, 0, pbq * kzl, (int)N0), o2);
+      b.use(BUF_W0, P1 * blk1);
+      b.use(BUF_W2, rowsz * nk);
+      Step& xa = b.exch(1, P1, c0);
+      for (int q = 0; q < P1; ++q) {
+        xa.send[q].buf = BUF_W0; xa.send[q].off = q * blk1; xa.scnt[q] = blk1;
+        xa.recv[q].buf = BUF_W2; xa.recv[q].off = rowsz * zoff[q]; xa.rcnt[q] = rowsz * zc[q];
+        xa.rpeer[q].buf = BUF_W2; xa.rpeer[q].off = rowsz * zoff[c0];
+      }
+      b.rows(false, rowsz, pN2, nk, BUF_OUT, zside(0, 0, BUF_W2, true), iscale);
+    }
   }
+  return peer_mapped ? finish_peer_mapped(d, pg) : 0;
+}
 
-  if (d.kind == B200FFT_LINE) {
-    const long long Np0 = N0 / P, Np1 = N1 / P, Nf = N1 / 2 + 1;
-    const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1);
-    const long long kc = Np1 / 2;
-    long long kcl[PMAXP], koff[PMAXP + 1];
-    koff[0] = 0;
-    for (int q = 0; q < P; ++q) {
-      kcl[q] = kc + (q == P - 1 ? 1 : 0);
-      koff[q + 1] = koff[q] + kcl[q];
-    }
-    const long long Npf = (P == 1) ? Nf : kcl[me];
-    const double p2 = p * p;
-    const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
-    if (!inverse) {
-      if (P == 1) {  // line.py:182-191
-        if (!padded) {
-          b.rows(true, N0, (int)N1, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
-          b.strided((int)N0, 1, Nf, 0, nat(BUF_OUT, 0, 0, Nf, (int)N0), nat(BUF_OUT, 0, 0, Nf, (int)N0));
-        } else {
-          b.rows(true, pN0, pN1, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
-          b.use(BUF_W0, (long long)pN0 * Nf);
-          b.strided(pN0, 1, Nf, 0, nat(BUF_W0, 0, 0, Nf, pN0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 2, 1.0 / p2);
-        }
-      } else {  // line.py:193-258
-        const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
-        SideT o;
-        o.chunk = (int)kc; o.nchunk = P; o.nphys = (int)Nf;
-        for (int q = 0; q < P; ++q) {
-          o.base[q].buf = (q == me) ? recvbuf : BUF_W0;
-          o.base[q].off = (q == me) ? (long long)me * pNp0 * Npf : (long long)pNp0 * koff[q];
-          o.sb[q] = kcl[q]; o.si[q] = 1;
-        }
-        b.rows(true, pNp0, pN1, (int)Nf, BUF_IN, o);
-        b.use(BUF_W0, (long long)pNp0 * Nf);
-        b.use(recvbuf, (long long)pN0 * Npf);
-        Step& x = b.exch(0, P, me);
-        for (int q = 0; q < P; ++q) {
-          x.send[q].buf = BUF_W0; x.send[q].off = (long long)pNp0 * koff[q]; x.scnt[q] = (long long)pNp0 * kcl[q];
-          x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf; x.rcnt[q] = (long long)pNp0 * Npf;
-          x.rpeer[q].buf = recvbuf; x.rpeer[q].off = (long long)me * pNp0 * kcl[q];
-        }
-        b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
-                  padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
-      }
-    } else {
-      if (P == 1) {  // line.py:274-283
-        Step& sx = b.strided(pN0, 1, Nf, 1, nat(BUF_IN, 0, 0, Nf, (int)N0), nat(BUF_W0, 0, 0, Nf, pN0));
+// ------------------------------------------------------------------------------------------------
+// line.R2C programs (line.py:179-340)
+// ------------------------------------------------------------------------------------------------
+inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
+  Builder b(pg);
+  const bool padded = dealias == B200FFT_DEALIAS_3_2;
+  const bool masked = inverse && dealias == B200FFT_DEALIAS_2_3;
+  const double p = padded ? d.padsize : 1.0;
+  const int P = d.nranks, me = d.rank;
+  const long long N0 = d.N[0], N1 = d.N[1];
+  const bool peer_mapped = (d.transport == B200FFT_TRANSPORT_P2P || d.transport == B200FFT_TRANSPORT_STORE) && P > 1;
+  const long long Np0 = N0 / P, Np1 = N1 / P, Nf = N1 / 2 + 1;
+  const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1);
+  const long long kc = Np1 / 2;
+  long long kcl[PMAXP], koff[PMAXP + 1];
+  koff[0] = 0;
+  for (int q = 0; q < P; ++q) {
+    kcl[q] = kc + (q == P - 1 ? 1 : 0);
+    koff[q + 1] = koff[q] + kcl[q];
+  }
+  const long long Npf = (P == 1) ? Nf : kcl[me];
+  const double p2 = p * p;
+  const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
+  if (!inverse) {
+    if (P == 1) {  // line.py:182-191
+      if (!padded) {
+        b.rows(true, N0, (int)N1, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
+        b.strided((int)N0, 1, Nf, 0, nat(BUF_OUT, 0, 0, Nf, (int)N0), nat(BUF_OUT, 0, 0, Nf, (int)N0));
+      } else {
+        b.rows(true, pN0, pN1, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
         b.use(BUF_W0, (long long)pN0 * Nf);
-        if (masked) {
-          sx.mask.on = 1;
-          sx.mask.jdiv = 0x3fffffff;
-          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-          band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
-        }
-        b.rows(false, pN0, pN1, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), iscale);
-      } else {  // line.py:285-338
-        const long long blk = (long long)pNp0 * Npf;
-        SideT o;
-        o.chunk = pNp0; o.nchunk = P; o.nphys = pN0;
-        for (int q = 0; q < P; ++q) {
-          o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
-          o.base[q].off = (q == me) ? (long long)pNp0 * koff[me] : q * blk;
-          o.sb[q] = 0; o.si[q] = Npf;
-        }
-        Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
-        if (masked) {
-          sx.mask.on = 1;
-          sx.mask.jdiv = 0x3fffffff;
-          band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-          band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
-          sx.mask.jr_off = (int)(me * kc);
-        }
-        b.use(BUF_W0, P * blk);
-        b.use(BUF_W1, (long long)pNp0 * Nf);
-        Step& x = b.exch(0, P, me);
-        for (int q = 0; q < P; ++q) {
-          x.send[q].buf = BUF_W0; x.send[q].off = q * blk; x.scnt[q] = blk;
-          x.recv[q].buf = BUF_W1; x.recv[q].off = (long long)pNp0 * koff[q]; x.rcnt[q] = (long long)pNp0 * kcl[q];
-          x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = (long long)pNp0 * koff[me];
-        }
-        SideT g;
-        g.chunk = (int)kc; g.nchunk = P; g.nphys = (int)Nf;
-        for (int q = 0; q < P; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = (long long)pNp0 * koff[q]; g.sb[q] = kcl[q]; g.si[q] = 1; }
-        b.rows(false, pNp0, pN1, (int)Nf, BUF_OUT, g, iscale);
+        b.strided(pN0, 1, Nf, 0, nat(BUF_W0, 0, 0, Nf, pN0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 2, 1.0 / p2);
       }
+    } else {  // line.py:193-258
+      const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
+      SideT o;
+      o.chunk = (int)kc; o.nchunk = P; o.nphys = (int)Nf;
+      for (int q = 0; q < P; ++q) {
+        o.base[q].buf = (q == me) ? recvbuf : BUF_W0;
+        o.base[q].off = (q == me) ? (long long)me * pNp0 * Npf : (long long)pNp0 * koff[q];
+        o.sb[q] = kcl[q]; o.si[q] = 1;
+      }
+      b.rows(true, pNp0, pN1, (int)Nf, BUF_IN, o);
+      b.use(BUF_W0, (long long)pNp0 * Nf);
+      b.use(recvbuf, (long long)pN0 * Npf);
+      Step& x = b.exch(0, P, me);
+      for (int q = 0; q < P; ++q) {
+        x.send[q].buf = BUF_W0; x.send[q].off = (long long)pNp0 * koff[q]; x.scnt[q] = (long long)pNp0 * kcl[q];
+        x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf; x.rcnt[q] = (long long)pNp0 * Npf;
+        x.rpeer[q].buf = recvbuf; x.rpeer[q].off = (long long)me * pNp0 * kcl[q];
+      }
+      b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
+                padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
     }
-    return peer_mapped ? finish_peer_mapped(d, pg) : 0;
+  } else {
+    if (P == 1) {  // line.py:274-283
+      Step& sx = b.strided(pN0, 1, Nf, 1, nat(BUF_IN, 0, 0, Nf, (int)N0), nat(BUF_W0, 0, 0, Nf, pN0));
+      b.use(BUF_W0, (long long)pN0 * Nf);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = 0x3fffffff;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
+      }
+      b.rows(false, pN0, pN1, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), iscale);
+    } else {  // line.py:285-338
+      const long long blk = (long long)pNp0 * Npf;
+      SideT o;
+      o.chunk = pNp0; o.nchunk = P; o.nphys = pN0;
+      for (int q = 0; q < P; ++q) {
+        o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+        o.base[q].off = (q == me) ? (long long)pNp0 * koff[me] : q * blk;
+        o.sb[q] = 0; o.si[q] = Npf;
+      }
+      Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = 0x3fffffff;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        sx.mask.jr_off = (int)(me * kc);
+      }
+      b.use(BUF_W0, P * blk);
+      b.use(BUF_W1, (long long)pNp0 * Nf);
+      Step& x = b.exch(0, P, me);
+      for (int q = 0; q < P; ++q) {
+        x.send[q].buf = BUF_W0; x.send[q].off = q * blk; x.scnt[q] = blk;
+        x.recv[q].buf = BUF_W1; x.recv[q].off = (long long)pNp0 * koff[q]; x.rcnt[q] = (long long)pNp0 * kcl[q];
+        x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = (long long)pNp0 * koff[me];
+      }
+      SideT g;
+      g.chunk = (int)kc; g.nchunk = P; g.nphys = (int)Nf;
+      for (int q = 0; q < P; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = (long long)pNp0 * koff[q]; g.sb[q] = kcl[q]; g.si[q] = 1; }
+      b.rows(false, pNp0, pN1, (int)Nf, BUF_OUT, g, iscale);
+    }
   }
-  return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
+  return peer_mapped ? finish_peer_mapped(d, pg) : 0;
+}
+
+// Build the step list of one (direction, dealias) program.  Mirrors oracle/slab.py etc.
+inline int build_program(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
+  switch (d.kind) {
+    case B200FFT_SLAB:
+    case B200FFT_SLAB_C2C:
+      return build_slab(d, inverse, dealias, pg);
+    case B200FFT_PENCIL_X:
+    case B200FFT_PENCIL_Y:
+      return build_pencil(d, inverse, dealias, pg);
+    case B200FFT_LINE:
+      return build_line(d, inverse, dealias, pg);
+    default:
+      return fail(B200FFT_ERR_ARG, "unknown plan kind %d", d.kind);
+  }
 }
 
 
