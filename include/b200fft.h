@@ -130,6 +130,17 @@ B200FFT_API int b200fft_stream_sync(void* stream);
 B200FFT_API int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
+/* The z and y passes of a single-rank slab transform (rfft2 / irfft2 of slab.py:366-370,247-268) as ONE
+ * persistent kernel that keeps the intermediate in L2: the planes (batch entries of `cols`) are cut into
+ * groups of `planes_per_group` and the blocks of both passes are pulled from one queue ordered so that
+ * the second pass of a group runs right after the first (held back by a counter until it is complete).
+ * `rows` is the R2C (forward) or C2R (inverse_order != 0) pass over rows = planes * rows-per-plane,
+ * `cols` the strided pass along y with B = planes; forward runs rows then cols, inverse cols then rows.
+ * `ctl` is device scratch of 4097 32-bit words.  Returns B200FFT_ERR_UNSUPPORTED when no fused kernel
+ * exists for the size pair or there would be more than 4096 groups (callers then run the two passes
+ * separately). */
+B200FFT_API int b200fft_exec_fused_zy(const b200fft_rows_desc_t* rows, const b200fft_strided_desc_t* cols, int inverse_order,
+                                      int planes_per_group, void* ctl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Communicators: replace the mpi4py communicator (comm.Alltoall / Alltoallw / Sendrecv_replace /
@@ -172,9 +183,11 @@ typedef struct {
                       inverse z pass the y pass's -- still in the 126 MB L2: the intermediate
                       (rfft2 / irfft2 of slab.py:366-370,247-268) then costs no HBM round trip.
                       0 = one launch per pass */
-  int l2_streams;  /* single-rank L2-blocked plans: 2 = the two passes of a group run on two streams so
-                      that the next group's first pass overlaps this group's second (at most two groups
-                      in flight); 0 / 1 = one stream */
+  int l2_mode;     /* how the groups of an L2-blocked single-rank plan are issued: 0 / 1 = launches on one
+                      stream; 2 = the two passes of a group on two streams, so that the next group's first
+                      pass overlaps this group's second (at most two groups in flight); 3 = ONE persistent
+                      kernel that pulls the blocks of both passes from a queue in dependency order
+                      (b200fft_exec_fused_zy): no launch gaps, no partly empty last waves */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

@@ -66,7 +66,7 @@ class Transform(object):
         # L2 blocking of the z and y passes of slab plans: run them per group of this many x planes so
         # that the y pass reads what the z pass just wrote from L2 instead of HBM (0 = whole array)
         d.l2_planes = int(getattr(self, "l2_planes", 0) or os.environ.get("B200FFT_L2_PLANES", "0"))
-        d.l2_streams = int(getattr(self, "l2_streams", 0) or os.environ.get("B200FFT_L2_STREAMS", "0"))
+        d.l2_mode = int(getattr(self, "l2_mode", 0) or os.environ.get("B200FFT_L2_MODE", "0"))
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree

@@ -129,6 +129,33 @@ int exec_rows(const b200fft_rows_desc_t& d, bool fwd, cudaStream_t st) {
   return map_launch_rc(rc, fwd ? "R2C pass" : "C2R pass", d.n);
 }
 
+// z + y passes as one persistent kernel through L2; B200FFT_ERR_UNSUPPORTED (without touching memory) when
+// there is no fused kernel for the pair or the grids do not split into `groups`
+int exec_fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg, void* ctl,
+                  cudaStream_t st) {
+  if (const char* e = check_rows(r)) return fail(B200FFT_ERR_ARG, "fused row pass: %s", e);
+  if (const char* e = check_strided(c)) return fail(B200FFT_ERR_ARG, "fused strided pass: %s", e);
+  if (r.precision != c.precision || !ctl || ppg < 1 || c.B < 1 || r.rows % c.B)
+    return fail(B200FFT_ERR_ARG, "fused passes: bad arguments (rows must be a whole number per plane)");
+  if (contiguous_rows(c)) return fail(B200FFT_ERR_UNSUPPORTED, "fused passes: the column pass must be strided");
+  int rc;
+  if (r.precision == B200FFT_DOUBLE) {
+    const cx<double>*twr, *twc;
+    if (int e = get_tw<double>(r.n, &twr)) return e;
+    if (int e = get_tw<double>(c.n, &twc)) return e;
+    rc = launch_fused_zy_f64(r.n / 2, c.n, convert_rows<double>(r, twr, 1, !inverse_order), convert_strided<double>(c, twc, 1),
+                             inverse_order, ppg, (unsigned*)ctl, st);
+  } else {
+    const cx<float>*twr, *twc;
+    if (int e = get_tw<float>(r.n, &twr)) return e;
+    if (int e = get_tw<float>(c.n, &twc)) return e;
+    rc = launch_fused_zy_f32(r.n / 2, c.n, convert_rows<float>(r, twr, 1, !inverse_order), convert_strided<float>(c, twc, 1),
+                             inverse_order, ppg, (unsigned*)ctl, st);
+  }
+  if (rc == -1 || rc == -3) return fail(B200FFT_ERR_UNSUPPORTED, "no fused z+y kernel for rows of %d and columns of %d, %d planes per group", r.n, c.n, ppg);
+  return map_launch_rc(rc, "fused z+y passes", c.n);
+}
+
 // ---- NCCL through dlopen: the library loads (and does P == 1 work) without NCCL ---------------
 struct NcclApi {
   void* h = nullptr;
@@ -224,6 +251,7 @@ struct b200fft_plan {
     unsigned seq = 0;                        // exchange steps executed so far (identical on all ranks)
     unsigned calls = 0;                      // transforms with exchanges executed so far
   } p2p;
+  unsigned* fuse_ctl = nullptr;         // queue head + per-group counters of fused z+y launches
   cudaStream_t comm_stream = nullptr;   // exchanges of pipelined programs run here
   std::vector<cudaEvent_t> sched_ev;    // ordering events between the two streams
   std::vector<cudaEvent_t> ev;  // timing events, two per step (grown on demand)
@@ -457,6 +485,45 @@ int finish_exchange_p2p(b200fft_plan* pl, const Step& s, cudaStream_t s1, int id
   return 0;
 }
 
+b200fft_strided_desc_t strided_desc(const b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz) {
+  b200fft_strided_desc_t d;
+  std::memset(&d, 0, sizeof(d));
+  d.precision = pl->d.precision;
+  d.n = s.n;
+  d.B = s.B;
+  d.J = s.J;
+  d.inverse = s.inverse;
+  d.fold_mode = s.fold;
+  d.scale = s.scale;
+  fill_side(pl, s.in, d.in, in, out, csz);
+  fill_side(pl, s.out, d.out, in, out, csz);
+  d.mask = s.mask;
+  return d;
+}
+
+b200fft_rows_desc_t rows_desc(const b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz) {
+  b200fft_rows_desc_t d;
+  std::memset(&d, 0, sizeof(d));
+  d.precision = pl->d.precision;
+  d.n = s.n;
+  d.rows = s.rows;
+  d.nk = s.nk;
+  d.scale = s.scale;
+  d.real_base = resolve(pl, s.real, in, out, csz / 2);
+  d.rpitch = s.rpitch;
+  fill_side(pl, s.cside, d.cside, in, out, csz);
+  return d;
+}
+
+double step_bytes(const Step& s, size_t csz) {  // algorithmic bytes: operand read once, result written once
+  if (s.type == ST_STRIDED) return (double)s.B * s.J * ((double)s.in.nphys + (double)s.out.nphys) * (double)csz;
+  if (s.type == ST_R2C || s.type == ST_C2R) return (double)s.rows * ((double)s.n * (csz / 2) + (double)s.nk * csz);
+  double b = 0;
+  for (int q = 0; q < s.npeers; ++q)
+    if (q != s.me) b += (double)s.scnt[q] * csz;
+  return b;
+}
+
 int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void* out, cudaStream_t st) {
   if (dealias < 0 || dealias > 2) return fail(B200FFT_ERR_ARG, "dealias must be None, '3/2-rule' or '2/3-rule'");
   if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;  // forward 2/3 == plain (slab.py:389)
@@ -464,7 +531,6 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   if (int rc = ensure_program(pl, inverse, dealias)) return rc;
   const Program& pg = pl->prog[inverse][dealias];
   const size_t csz = pl->d.precision == B200FFT_DOUBLE ? 16 : 8;
-  const size_t rsz = csz / 2;
   pl->last_kernels = 0;
   pl->last_exch = 0;
   pl->ev_marks.clear();
@@ -506,7 +572,8 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
   if (use_p2p && !pl->p2p.connected) return fail(B200FFT_ERR_ARG, "P2P plan used before b200fft_plan_p2p_connect");
   int nexch = 0;
   cudaStream_t caller = st;
-  for (const Step& s : pg.steps) {
+  for (size_t si = 0; si < pg.steps.size(); ++si) {
+    const Step& s = pg.steps[si];
     st = (s.stream == 1 && pl->comm_stream) ? pl->comm_stream : caller;
     if (s.wait_ev >= 0) {
       cudaError_t e = cudaStreamWaitEvent(st, pl->sched_ev[(size_t)s.wait_ev], 0);
@@ -516,33 +583,34 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       if (int rc = wait_credits(pl, st)) return rc;
     if (pl->timing) cudaEventRecord(pl->ev[(size_t)evi], st);
     int rc = 0;
-    if (s.type == ST_STRIDED) {
-      b200fft_strided_desc_t d;
-      std::memset(&d, 0, sizeof(d));
-      d.precision = pl->d.precision;
-      d.n = s.n;
-      d.B = s.B;
-      d.J = s.J;
-      d.inverse = s.inverse;
-      d.fold_mode = s.fold;
-      d.scale = s.scale;
-      fill_side(pl, s.in, d.in, in, out, csz);
-      fill_side(pl, s.out, d.out, in, out, csz);
-      d.mask = s.mask;
-      rc = exec_strided(d, st);
+    bool fused = false;
+    if (s.fuse_planes > 0 && si + 1 < pg.steps.size()) {
+      // z + y (inverse: y + z) as one persistent kernel through L2; two launches if no such kernel exists
+      const Step& t = pg.steps[si + 1];
+      const Step& rs = (s.type == ST_STRIDED) ? t : s;
+      const Step& cs = (s.type == ST_STRIDED) ? s : t;
+      if (!pl->fuse_ctl) {
+        cudaError_t e = cudaMalloc(&pl->fuse_ctl, sizeof(unsigned) * FUSE_CTL_WORDS);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fuse control words)");
+      }
+      if (cs.type == ST_STRIDED && (rs.type == ST_R2C || rs.type == ST_C2R)) {
+        rc = exec_fused_zy(rows_desc(pl, rs, in, out, csz), strided_desc(pl, cs, in, out, csz), s.type == ST_STRIDED, s.fuse_planes,
+                           pl->fuse_ctl, st);
+        if (rc == 0) {
+          fused = true;
+          pl->last_kernels++;
+        } else if (rc == B200FFT_ERR_UNSUPPORTED) {
+          rc = 0;
+        }
+      }
+    }
+    if (rc || fused) {
+      // error, or both steps done by the fused launch
+    } else if (s.type == ST_STRIDED) {
+      rc = exec_strided(strided_desc(pl, s, in, out, csz), st);
       pl->last_kernels++;
     } else if (s.type == ST_R2C || s.type == ST_C2R) {
-      b200fft_rows_desc_t d;
-      std::memset(&d, 0, sizeof(d));
-      d.precision = pl->d.precision;
-      d.n = s.n;
-      d.rows = s.rows;
-      d.nk = s.nk;
-      d.scale = s.scale;
-      d.real_base = resolve(pl, s.real, in, out, rsz);
-      d.rpitch = s.rpitch;
-      fill_side(pl, s.cside, d.cside, in, out, csz);
-      rc = exec_rows(d, s.type == ST_R2C, st);
+      rc = exec_rows(rows_desc(pl, s, in, out, csz), s.type == ST_R2C, st);
       pl->last_kernels++;
     } else if (use_p2p) {
       rc = run_exchange_p2p(pl, s, in, out, csz, st);
@@ -552,16 +620,11 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       pl->last_exch++;
     }
     if (rc) return rc;
-    {  // algorithmic bytes of the step: operand read once, result written once
-      double bytes = 0;
-      if (s.type == ST_STRIDED) bytes = (double)s.B * s.J * ((double)s.in.nphys + (double)s.out.nphys) * (double)csz;
-      else if (s.type == ST_R2C || s.type == ST_C2R) bytes = (double)s.rows * ((double)s.n * rsz + (double)s.nk * csz);
-      else for (int q = 0; q < s.npeers; ++q) if (q != s.me) bytes += (double)s.scnt[q] * csz;
-      pl->st_type.push_back((int)s.type);
-      pl->st_len.push_back(s.type == ST_EXCH ? s.npeers : s.n);
-      pl->st_pass.push_back(s.pass);
-      pl->st_bytes.push_back(bytes);
-    }
+    pl->st_type.push_back((int)s.type);
+    pl->st_len.push_back(s.type == ST_EXCH ? s.npeers : s.n);
+    pl->st_pass.push_back(s.pass);
+    // (a fused launch is reported as its first pass, with the bytes of both)
+    pl->st_bytes.push_back(step_bytes(s, csz) + (fused ? step_bytes(pg.steps[si + 1], csz) : 0.0));
     if (pl->timing) {
       cudaEventRecord(pl->ev[(size_t)evi + 1], st);
       pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
@@ -573,6 +636,7 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], st);
       if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
     }
+    if (fused) ++si;  // the next step ran inside the fused launch (single-rank programs: no events or credits on it)
     if (use_p2p && s.last_reader) {  // hand the receive buffers back to the peers
       for (int q = 0; q < pl->d.nranks; ++q)
         if (q != pl->d.rank)
@@ -629,6 +693,12 @@ int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream) {
 int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream) {
   if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
   return exec_rows(*d, false, (cudaStream_t)stream);
+}
+
+int b200fft_exec_fused_zy(const b200fft_rows_desc_t* rows, const b200fft_strided_desc_t* cols, int inverse_order, int planes_per_group,
+                          void* ctl, void* stream) {
+  if (!rows || !cols) return fail(B200FFT_ERR_ARG, "null descriptor");
+  return exec_fused_zy(*rows, *cols, inverse_order, planes_per_group, ctl, (cudaStream_t)stream);
 }
 
 int b200fft_comm_unique_id(void* id128) {
@@ -710,6 +780,7 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
       if (plan->p2p.peer_flags[q]) cudaIpcCloseMemHandle(plan->p2p.peer_flags[q]);
     }
   }
+  if (plan->fuse_ctl) cudaFree(plan->fuse_ctl);
   if (plan->p2p.flags) cudaFree(plan->p2p.flags);
   if (plan->p2p.wait_stream) cudaStreamDestroy(plan->p2p.wait_stream);
   if (plan->comm_stream) cudaStreamDestroy(plan->comm_stream);

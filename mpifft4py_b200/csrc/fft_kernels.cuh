@@ -212,6 +212,82 @@ B2_HD void async_copy_wait() {
 }
 
 // ------------------------------------------------------------------------------------------
+// fused pair of passes through L2 (persistent kernel)
+// ------------------------------------------------------------------------------------------
+// Two consecutive passes A, B over the same planes (forward: z then y; inverse: y then z) are cut into
+// G groups of planes.  One persistent kernel executes the blocks of BOTH grids from a single queue,
+//     A(0) | A(1) B(0) | A(2) B(1) | ... | B(G-1)          ("super-steps" 0 .. G)
+// so that B(g) reads what A(g) wrote while it is still in L2 (a group is a few planes, tens of MB), A
+// runs one group ahead and no launch boundary drains the SMs.  Work is counted in units -- rows for a
+// row pass, blocks for a strided pass -- because a block of a row pass (RPC rows) may straddle two
+// groups: such a block of A runs with the earlier group and credits both, such a block of B runs with
+// the later group and waits for both.  done[g] counts finished units of pass A in group g; a block of
+// B spins until its groups are complete.  Every block it can wait for sits earlier in the queue, i.e.
+// is already running on some SM and never waits itself, so the queue cannot deadlock.
+struct FuseSide {
+  unsigned n;      // blocks in the pass's grid
+  unsigned upb;    // units per block
+  unsigned upg;    // units per group (>= upb)
+  unsigned units;  // units in total
+  // first block whose first / last unit lies in a group >= k
+  B2_HD unsigned lo_first(unsigned k) const {
+    const unsigned long long v = ((unsigned long long)k * upg + upb - 1) / upb;
+    return v < n ? (unsigned)v : n;
+  }
+  B2_HD unsigned lo_last(unsigned k) const {
+    const unsigned long long v = ((unsigned long long)k * upg) / upb;
+    return v < n ? (unsigned)v : n;
+  }
+  // groups touched by block `blk` and its units in the first of them
+  B2_HD void groups(unsigned blk, unsigned& g1, unsigned& g2, unsigned& u_in_g1, unsigned& u_in_g2) const {
+    const unsigned u0 = blk * upb, u1 = (u0 + upb < units) ? u0 + upb : units;
+    g1 = u0 / upg;
+    g2 = (u1 - 1) / upg;
+    u_in_g1 = (g1 == g2) ? u1 - u0 : g2 * upg - u0;
+    u_in_g2 = (g1 == g2) ? 0 : u1 - g2 * upg;
+  }
+  B2_HD unsigned need(unsigned g) const {  // units of group g
+    const unsigned long long lo = (unsigned long long)g * upg;
+    return (unsigned)((lo + upg <= units) ? upg : units - lo);
+  }
+};
+
+struct FuseCtl {
+  unsigned* ctr;   // next queue index
+  unsigned* done;  // per group: finished units of pass A
+  unsigned G;
+  FuseSide a, b;
+};
+
+// queue start of super-step k (k in 0 .. G+1): A blocks starting in groups < k and B blocks ending in groups < k-1
+B2_HD unsigned fuse_qstart(const FuseCtl& c, unsigned k) {
+  if (k == 0) return 0;
+  const unsigned na = (k > c.G) ? c.a.n : c.a.lo_first(k);
+  const unsigned nb = (k - 1 >= c.G) ? c.b.n : c.b.lo_last(k - 1);
+  return na + nb;
+}
+
+// queue index -> (pass B?, block of that pass's grid)
+B2_HD void fuse_decode(const FuseCtl& c, unsigned i, bool& isB, unsigned& blk) {
+  // blocks per super-step ~ upg_a/upb_a + upg_b/upb_b: estimate, then correct
+  const unsigned long long per = (unsigned long long)c.a.upg * c.b.upb + (unsigned long long)c.b.upg * c.a.upb;
+  unsigned long long k64 = ((unsigned long long)i * c.a.upb * c.b.upb) / (per ? per : 1);
+  unsigned k = k64 > c.G ? c.G : (unsigned)k64;
+  while (k > 0 && fuse_qstart(c, k) > i) --k;
+  while (k < c.G && fuse_qstart(c, k + 1) <= i) ++k;
+  const unsigned off = i - fuse_qstart(c, k);
+  const unsigned a0 = (k > c.G) ? c.a.n : c.a.lo_first(k);
+  const unsigned a1 = (k + 1 > c.G) ? c.a.n : c.a.lo_first(k + 1);
+  if (off < a1 - a0) {
+    isB = false;
+    blk = a0 + off;
+  } else {
+    isB = true;
+    blk = c.b.lo_last(k - 1) + (off - (a1 - a0));  // (k >= 1 here: super-step 0 holds blocks of A only)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // strided C2C pass
 // ------------------------------------------------------------------------------------------
 template <class real>
@@ -283,6 +359,12 @@ struct StridedK {
     const unsigned nt = (unsigned)((p.J + Cfg::T - 1) / Cfg::T);
     by = (int)(blk / nt);
     bx = (int)(blk - (unsigned)by * nt);
+  }
+  // work units of the fused pair kernel: one per block, (column tiles) per plane
+  B2_HD static FuseSide fuse_side(const Params& p, long long planes, long long planes_per_group) {
+    const unsigned nt = (unsigned)((p.J + Cfg::T - 1) / Cfg::T);
+    (void)planes;
+    return FuseSide{(unsigned)blocks(p), 1u, (unsigned)(planes_per_group * nt), (unsigned)blocks(p)};
   }
 
   // address of load row i (logical index of the transform input) for column j0; 0 = zero fill:
@@ -567,6 +649,10 @@ struct R2CK {  // forward: real rows -> complex rows
     bx = (int)blk;
     by = 0;
   }
+  // work units of the fused pair kernel: rows (RPC per block)
+  B2_HD static FuseSide fuse_side(const Params& p, long long planes, long long planes_per_group) {
+    return FuseSide{(unsigned)blocks(p), (unsigned)Cfg::RPC, (unsigned)(planes_per_group * (p.rows / planes)), (unsigned)p.rows};
+  }
 
   template <int s>
   B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
@@ -635,6 +721,10 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
   B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
     bx = (int)blk;
     by = 0;
+  }
+  // work units of the fused pair kernel: rows (RPC per block)
+  B2_HD static FuseSide fuse_side(const Params& p, long long planes, long long planes_per_group) {
+    return FuseSide{(unsigned)blocks(p), (unsigned)Cfg::RPC, (unsigned)(planes_per_group * (p.rows / planes)), (unsigned)p.rows};
   }
 
   template <int s>
@@ -752,6 +842,7 @@ struct RowC2CK {
   }
 };
 
+
 // ------------------------------------------------------------------------------------------
 // device entry + host launcher
 // ------------------------------------------------------------------------------------------
@@ -830,6 +921,84 @@ __device__ __forceinline__ void run_cluster_phases(const typename K::Params& p, 
       __syncthreads();
     }
     run_cluster_phases<K, s + 1>(p, sm, peer, rank, bx, by);
+  }
+}
+
+
+// phases of pass K inside a CTA of NTL >= K::NT threads: the surplus threads only keep the barriers
+template <class K, int s, int NTL>
+__device__ __forceinline__ void run_phases_in(const typename K::Params& p, void* sm, int bx, int by) {
+  if (NTL == K::NT || (int)threadIdx.x < K::NT) {
+    K::template phase<s>(p, sm, (int)threadIdx.x, bx, by);
+    if constexpr (s == 0) async_copy_wait();
+  }
+  if constexpr (s + 1 < K::NPHASE) {
+    __syncthreads();
+    run_phases_in<K, s + 1, NTL>(p, sm, bx, by);
+  }
+}
+
+// one block of pass K; not inlined, so that each pass keeps the register allocation of its own kernel
+// instead of the union of both (the 1536-point pair spilled 384 bytes when inlined)
+template <class K, int NTL>
+__device__ __noinline__ void run_block_in(const typename K::Params& p, void* sm, unsigned blk) {
+  int bx, by;
+  K::decode(p, blk, bx, by);
+  run_phases_in<K, 0, NTL>(p, sm, bx, by);
+}
+
+template <class KA, class KB>
+struct FusePair {
+  static constexpr int NT = KA::NT > KB::NT ? KA::NT : KB::NT;
+  static constexpr int SMEM = KA::SMEM1 > KB::SMEM1 ? KA::SMEM1 : KB::SMEM1;  // one work item at a time: no double buffer
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB_K = KA::MINB < KB::MINB ? KA::MINB : KB::MINB;
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ < MINB_K ? MINB_ : MINB_K);
+};
+
+template <class KA, class KB>
+__global__ void __launch_bounds__(FusePair<KA, KB>::NT, FusePair<KA, KB>::MINB)
+    fused_pair_kernel(const __grid_constant__ typename KA::Params pa, const __grid_constant__ typename KB::Params pb,
+                      const __grid_constant__ FuseCtl c) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ unsigned s_blk;  // block to run: bit 31 = pass B, 0xffffffff = queue exhausted
+  const unsigned total = c.a.n + c.b.n;
+  for (;;) {
+    __syncthreads();  // the previous item is done with shared memory and with s_blk
+    if (threadIdx.x == 0) {  // one thread takes the next item, decodes it and, for pass B, waits for its groups
+      const unsigned i = atomicAdd(c.ctr, 1u);
+      unsigned v = 0xffffffffu;
+      if (i < total) {
+        bool isB;
+        unsigned blk, g1, g2, u1, u2;
+        fuse_decode(c, i, isB, blk);
+        if (isB) {
+          c.b.groups(blk, g1, g2, u1, u2);
+          for (unsigned g = g1; g <= g2; ++g)
+            while (*reinterpret_cast<volatile unsigned*>(c.done + g) < c.a.need(g)) __nanosleep(200);
+          __threadfence();
+        }
+        v = blk | (isB ? 0x80000000u : 0u);
+      }
+      s_blk = v;
+    }
+    __syncthreads();
+    const unsigned v = s_blk;
+    if (v == 0xffffffffu) break;
+    const unsigned blk = v & 0x7fffffffu;
+    if (!(v & 0x80000000u)) {
+      run_block_in<KA, FusePair<KA, KB>::NT>(pa, smraw, blk);
+      __threadfence();  // this thread's stores are visible device-wide ...
+      __syncthreads();  // ... for every thread of the block, before its units are counted
+      if (threadIdx.x == 0) {
+        unsigned g1, g2, u1, u2;
+        c.a.groups(blk, g1, g2, u1, u2);
+        atomicAdd(c.done + g1, u1);
+        if (g2 != g1) atomicAdd(c.done + g2, u2);
+      }
+    } else {
+      run_block_in<KB, FusePair<KA, KB>::NT>(pb, smraw, blk);
+    }
   }
 }
 

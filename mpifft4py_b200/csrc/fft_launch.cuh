@@ -56,4 +56,48 @@ int launch_cluster_k(const typename K::Params& p, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// Fused pair of passes (fused_pair_kernel) over `planes` planes in groups of `planes_per_group`.  `ctl`
+// points at FUSE_CTL_WORDS words of device memory (queue head + per-group counters); -3 when there would
+// be more groups than that or a group smaller than one block.
+
+template <class KA, class KB>
+int launch_fused_pair(const typename KA::Params& pa, const typename KB::Params& pb, long long planes, long long planes_per_group,
+                      unsigned* ctl, cudaStream_t st) {
+  using F = FusePair<KA, KB>;
+  if (F::SMEM > SMEM_LIMIT) return -1;
+  if (planes < 1 || planes_per_group < 1) return -3;
+  const long long groups = (planes + planes_per_group - 1) / planes_per_group;
+  FuseCtl c;
+  c.a = KA::fuse_side(pa, planes, planes_per_group);
+  c.b = KB::fuse_side(pb, planes, planes_per_group);
+  if (groups + 1 > FUSE_CTL_WORDS || c.a.n == 0 || c.b.n == 0 || c.a.upg < c.a.upb || c.b.upg < c.b.upb ||
+      (unsigned long long)c.a.n + c.b.n > 2147483647ull)
+    return -3;
+  static bool configured = false;
+  static unsigned long long resident = 0;
+  if (!configured) {
+    if (F::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(fused_pair_kernel<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+      if (e != cudaSuccess) return (int)e;
+    }
+    int dev = 0, sms = 0, occ = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pair_kernel<KA, KB>, F::NT, F::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    resident = (unsigned long long)sms * (unsigned long long)(occ < 1 ? 1 : occ);
+    configured = true;
+  }
+  cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(unsigned) * (size_t)(1 + groups), st);
+  if (e != cudaSuccess) return (int)e;
+  c.ctr = ctl;
+  c.done = ctl + 1;
+  c.G = (unsigned)groups;
+  // every CTA of the grid must be resident (a waiting block relies on the blocks before it making progress)
+  const unsigned long long total = (unsigned long long)c.a.n + c.b.n;
+  const unsigned long long grid = total < resident ? total : resident;
+  fused_pair_kernel<KA, KB><<<(unsigned)grid, F::NT, F::SMEM, st>>>(pa, pb, c);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace b200fft

@@ -33,3 +33,16 @@
 // sub-transform each CTA runs after the cross stage).  The factor 3 stays in the last stage (fold).
 #define B200FFT_CLUSTER_PLANS(X) \
   X(1024, 8, 8, 8) X(1536, 8, 8, 12) X(2048, 16, 8, 8) X(3072, 16, 8, 12)
+
+// Fused z + y passes through L2 (fused_pair_kernel), compiled for the benchmark sizes: rows of 2*H reals
+// next to columns of NY points.  X(H, NY, H-point row plan, NY-point column plan); the aliases repeat the
+// radices of B200FFT_PLANS (template commas do not survive macro arguments).
+namespace b200fft {
+using FR256 = Plan<16, 16>;
+using FR512 = Plan<8, 8, 8>;
+using FR768 = Plan<8, 8, 12>;
+using FC512 = Plan<8, 8, 8>;
+using FC1024 = Plan<16, 8, 8>;
+using FC1536 = Plan<16, 8, 12>;
+}  // namespace b200fft
+#define B200FFT_FUSED_PAIRS(X) X(256, 512, FR256, FC512) X(512, 1024, FR512, FC1024) X(768, 1536, FR768, FC1536)

@@ -71,6 +71,10 @@ struct Step {
   // after it.  Lets the exchange of one chunk overlap the FFT passes of the next.
   int stream = 0, wait_ev = -1, wait_ev2 = -1, rec_ev = -1;
   int pass = 0;  // logical pass of the transform this step belongs to (chunks of one pass share it)
+  // > 0: this step and the next (a row pass and a strided pass over the same planes) run as ONE persistent
+  // kernel that keeps the intermediate in L2, the planes cut into groups of this many (l2_mode 3); the
+  // executor falls back to two launches when no fused kernel exists for the sizes
+  int fuse_planes = 0;
   // exchange
   int comm = 0;  // 0: world, 1: comm0, 2: comm1
   int npeers = 0, me = 0;
@@ -261,7 +265,7 @@ inline int finish_peer_mapped(const b200fft_plan_desc_t& d, Program& pg) {
   return 0;
 }
 
-// Two-stream schedule of an L2-blocked single-rank program (d.l2_streams == 2).  On one stream every
+// Two-stream schedule of an L2-blocked single-rank program (d.l2_mode == 2).  On one stream every
 // small launch drains before the next starts; here the first pass of a group runs on the caller's
 // stream and the second on the plan's second stream, so group g+1's first pass fills the SMs that
 // group g's second pass leaves idle.  At most two groups are in flight (the first pass of group g+2
@@ -339,8 +343,9 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
   // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
   // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
+  const bool fused_zy = d.l2_mode == 3 && d.l2_planes > 0 && P == 1 && !c2c;
   auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
-    const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn) ? d.l2_planes : xn;
+    const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn && !fused_zy) ? d.l2_planes : xn;
     for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
   };
   if (!inverse) {
@@ -352,6 +357,7 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 1;
           b.strided((int)N1, gn, Nf, 0, nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
         });
+        if (fused_zy) pg.steps[0].fuse_planes = d.l2_planes;
         b.fixed = 2;
         b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
       } else {  // slab.py:371-387
@@ -363,10 +369,11 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 1;
           b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), nat(BUF_W1, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), yfold);
         });
+        if (fused_zy) pg.steps[0].fuse_planes = d.l2_planes;
         b.fixed = 2;
         b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
       }
-      if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 0);
+      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 0);
     } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
       // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
       // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
@@ -524,7 +531,8 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
         });
       }
-      if (d.l2_planes > 0 && d.l2_streams == 2) two_stream_groups(pg, 1);
+      if (fused_zy) pg.steps[1].fuse_planes = d.l2_planes;
+      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 1);
     } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
       // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
       const int C = kz_chunks(d.chunks, Nf);

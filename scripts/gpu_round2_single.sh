@@ -18,9 +18,10 @@ for v in 0 20 30; do
   done
 done
 # 2b. L2 blocking of the z / y passes: groups of x planes (0 = off)
-for g in 2 4 6 8 12 16 -2 -3 -4 -6; do   # negative: the two-stream schedule with |g| planes per group
+for g in 2 4 6 8 12 16 -2 -3 -4 -6 f2 f3 f4 f6 f8 f12; do   # -g: two streams; fg: one fused persistent kernel
   for w in slab1024_f64 slab1024_f64_32; do
-    B200FFT_L2_STREAMS=$([ $g -lt 0 ] && echo 2 || echo 1) B200FFT_L2_PLANES=${g#-} timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
+    case $g in -*) mode=2;; f*) mode=3;; *) mode=1;; esac
+    B200FFT_L2_MODE=$mode B200FFT_L2_PLANES=${g#[-f]} timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
         > $O/bench_${w}_l2_$g.json 2> $O/bench_${w}_l2_$g.err
     echo "== $w l2_planes $g"; python scripts/show_passes.py $O/bench_${w}_l2_$g.json; tail -2 $O/bench_${w}_l2_$g.err
   done

@@ -62,7 +62,59 @@ static int emulate_cluster(const typename K::Params& p) {
   return 0;
 }
 
+// Fused pair of passes (fused_pair_kernel): the queue is walked in index order by ONE worker, which is a
+// legal schedule of the persistent kernel; on the way it checks what the device relies on -- the decode
+// visits every block of both grids exactly once, and every block of pass B finds the pass-A counters of
+// the groups it reads complete (i.e. all blocks it would wait for have a smaller queue index).
+template <class KA, class KB>
+static int emulate_fused_pair(const typename KA::Params& pa, const typename KB::Params& pb, long long planes, long long ppg) {
+  if (planes < 1 || ppg < 1) return -3;
+  FuseCtl c;
+  c.ctr = nullptr;
+  c.done = nullptr;
+  c.G = (unsigned)((planes + ppg - 1) / ppg);
+  c.a = KA::fuse_side(pa, planes, ppg);
+  c.b = KB::fuse_side(pb, planes, ppg);
+  if (c.G + 1 > 4097 || c.a.n == 0 || c.b.n == 0 || c.a.upg < c.a.upb || c.b.upg < c.b.upb) return -3;
+  std::vector<unsigned> done(c.G, 0);
+  std::vector<char> seenA(c.a.n, 0), seenB(c.b.n, 0);
+  const size_t smem = (size_t)(KA::SMEM1 > KB::SMEM1 ? KA::SMEM1 : KB::SMEM1) + 256;
+  std::vector<unsigned char> sm(smem);
+  for (unsigned i = 0; i < c.a.n + c.b.n; ++i) {
+    bool isB;
+    unsigned blk, g1, g2, u1, u2;
+    fuse_decode(c, i, isB, blk);
+    for (auto& x : sm) x = 0x7f;
+    int bx, by;
+    if (!isB) {
+      if (blk >= c.a.n || seenA[blk]++) return 97;
+      KA::decode(pa, blk, bx, by);
+      emu_phases<KA, 0>(pa, sm, bx, by);
+      c.a.groups(blk, g1, g2, u1, u2);
+      if (g2 >= c.G || g2 > g1 + 1) return 94;
+      done[g1] += u1;
+      if (g2 != g1) done[g2] += u2;
+    } else {
+      if (blk >= c.b.n || seenB[blk]++) return 98;
+      c.b.groups(blk, g1, g2, u1, u2);
+      if (g2 >= c.G) return 95;
+      for (unsigned g = g1; g <= g2; ++g)
+        if (done[g] != c.a.need(g)) return 96;  // the device would wait for a block that is queued later: deadlock
+      KB::decode(pb, blk, bx, by);
+      emu_phases<KB, 0>(pb, sm, bx, by);
+    }
+  }
+  for (char x : seenA) if (!x) return 99;
+  for (char x : seenB) if (!x) return 99;
+  for (unsigned g = 0; g < c.G; ++g) if (done[g] != c.a.need(g)) return 93;
+  return 0;
+}
+
+template <class real>
+static int fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg);
+
 static int g_emu_variant = 0;
+static int g_emu_fused_runs = 0;  // fused launches executed by emu_plan_run (tests check the path was taken)
 
 template <class real>
 static const cx<real>* table(int len) {
@@ -124,7 +176,65 @@ static int rows(const b200fft_rows_desc_t& d) {
   }
 }
 
+template <class real>
+static int fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg) {
+  if (contiguous_rows(c) || c.B < 1 || r.rows % c.B) return -1;
+  auto pr = convert_rows<real>(r, table<real>(r.n), 1, !inverse_order);
+  auto pc = convert_strided<real>(c, table<real>(c.n), 1);
+#define X(h, ny, PR, PC)                                                                                  \
+  if (r.n / 2 == h && c.n == ny)                                                                          \
+    return inverse_order ? emulate_fused_pair<StridedK<real, PC>, C2RK<real, PR>>(pc, pr, c.B, ppg)       \
+                         : emulate_fused_pair<R2CK<real, PR>, StridedK<real, PC>>(pr, pc, c.B, ppg);
+  B200FFT_FUSED_PAIRS(X)
+#undef X
+  return -1;
+}
+
 extern "C" {
+// -1: no fused kernel for the size pair, -3: too many / too small groups (callers fall back)
+int emu_exec_fused_zy(const b200fft_rows_desc_t* r, const b200fft_strided_desc_t* c, int inverse_order, int ppg) {
+  if (const char* e = check_rows(*r)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
+  if (const char* e = check_strided(*c)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
+  return r->precision == B200FFT_DOUBLE ? fused_zy<double>(*r, *c, inverse_order, ppg) : fused_zy<float>(*r, *c, inverse_order, ppg);
+}
+int emu_fused_runs() { return g_emu_fused_runs; }
+// Queue of the fused pair kernel without running any FFT: rows * planes rows in blocks of `rpc` rows next to
+// `tiles` column tiles per plane, groups of `ppg` planes, either order.  Checks that the queue visits every
+// block of both passes once and that no block of the second pass precedes a block it waits for.
+int emu_check_fuse_queue(long long rows_per_plane, int rpc, long long planes, long long ppg, int tiles, int rows_first) {
+  FuseCtl c;
+  c.ctr = c.done = nullptr;
+  c.G = (unsigned)((planes + ppg - 1) / ppg);
+  const long long rows = rows_per_plane * planes;
+  const FuseSide r{(unsigned)((rows + rpc - 1) / rpc), (unsigned)rpc, (unsigned)(ppg * rows_per_plane), (unsigned)rows};
+  const FuseSide t{(unsigned)(planes * tiles), 1u, (unsigned)(ppg * tiles), (unsigned)(planes * tiles)};
+  c.a = rows_first ? r : t;
+  c.b = rows_first ? t : r;
+  if (c.a.upg < c.a.upb || c.b.upg < c.b.upb) return -3;
+  std::vector<unsigned> done(c.G, 0);
+  std::vector<char> seenA(c.a.n, 0), seenB(c.b.n, 0);
+  for (unsigned i = 0; i < c.a.n + c.b.n; ++i) {
+    bool isB;
+    unsigned blk, g1, g2, u1, u2;
+    fuse_decode(c, i, isB, blk);
+    if (!isB) {
+      if (blk >= c.a.n || seenA[blk]++) return 97;
+      c.a.groups(blk, g1, g2, u1, u2);
+      if (g2 >= c.G || g2 > g1 + 1) return 94;
+      done[g1] += u1;
+      if (g2 != g1) done[g2] += u2;
+    } else {
+      if (blk >= c.b.n || seenB[blk]++) return 98;
+      c.b.groups(blk, g1, g2, u1, u2);
+      if (g2 >= c.G) return 95;
+      for (unsigned g = g1; g <= g2; ++g)
+        if (done[g] != c.a.need(g)) return 96;
+    }
+  }
+  for (char x : seenA) if (!x) return 99;
+  for (char x : seenB) if (!x) return 99;
+  return 0;
+}
 int emu_set_variant(int v) {  // 21: lengths with a cluster plan run the 2-CTA cluster kernel
   const int old = g_emu_variant;
   g_emu_variant = v;
@@ -175,10 +285,35 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
   };
   const size_t nsteps = pg[0].steps.size();
   for (int r = 1; r < P; ++r) if (pg[r].steps.size() != nsteps) return 90;
+  auto strided_of = [&](int r, const Step& s) {
+    b200fft_strided_desc_t d;
+    std::memset(&d, 0, sizeof(d));
+    d.precision = d0->precision; d.n = s.n; d.B = s.B; d.J = s.J; d.inverse = s.inverse;
+    d.fold_mode = s.fold; d.scale = s.scale; d.in = side(r, s.in); d.out = side(r, s.out); d.mask = s.mask;
+    return d;
+  };
+  auto rows_of = [&](int r, const Step& s) {
+    b200fft_rows_desc_t d;
+    std::memset(&d, 0, sizeof(d));
+    d.precision = d0->precision; d.n = s.n; d.rows = s.rows; d.nk = s.nk; d.scale = s.scale;
+    d.real_base = resolve(r, s.real, csz / 2); d.rpitch = s.rpitch; d.cside = side(r, s.cside);
+    return d;
+  };
   for (size_t si = 0; si < nsteps; ++si) {
     for (int r = 0; r < P; ++r) {
       const Step& s = pg[r].steps[si];
       int rc = 0;
+      if (s.fuse_planes > 0 && si + 1 < nsteps && P == 1) {  // as b200fft.cu: fused launch, else two passes
+        const Step& t = pg[r].steps[si + 1];
+        const Step& rs = (s.type == ST_STRIDED) ? t : s;
+        const Step& cs = (s.type == ST_STRIDED) ? s : t;
+        auto rd = rows_of(r, rs);
+        auto cd = strided_of(r, cs);
+        rc = emu_exec_fused_zy(&rd, &cd, s.type == ST_STRIDED, s.fuse_planes);
+        if (rc == 0) { ++g_emu_fused_runs; ++si; continue; }
+        if (rc != -1 && rc != -3) return rc;
+        rc = 0;
+      }
       if (s.type == ST_STRIDED) {
         b200fft_strided_desc_t d;
         std::memset(&d, 0, sizeof(d));

@@ -3,6 +3,7 @@ tests/test_zz_gpu_experimental.py, so that a fault cannot take the main test pro
 
     python tests/gpu_variant_worker.py cluster    # 2-CTA cluster strided pass (variant 21 / 20)
     python tests/gpu_variant_worker.py rowbar     # row kernels with per-row named barriers (variant 30)
+    python tests/gpu_variant_worker.py l2         # L2-blocked z / y passes: grouped launches, two streams, fused kernel
 """
 import os
 import sys
@@ -93,6 +94,46 @@ def rowbar():
     be.L.b200fft_set_variant(0)
 
 
+def l2():
+    """L2 blocking of the z and y passes (plan options l2_planes / l2_mode) against the oracle and against
+    the unblocked plan; the fused persistent kernel (mode 3) is run repeatedly and must reproduce its own
+    result bit for bit (a dependency race would show up as a varying result)."""
+    import mpifft4py_b200 as m
+    from mpifft4py_b200.comm import SelfComm
+    L3 = np.array([2 * np.pi] * 3)
+    for N, prec, planes in (((16, 512, 512), "double", 2), ((16, 512, 512), "single", 3), ((12, 1024, 1024), "double", 5),
+                            ((4, 1024, 1024), "double", 1)):
+        rt, ct = oracle.common.dtypes(prec)
+        tol = 1e-12 if prec == "double" else 1e-5
+        A = np.random.default_rng(21).random(N).astype(rt)
+        ref = oracle.slab.fftn([A], N, 1, precision=prec)[0]
+        for mode in (1, 2, 3):
+            F = m.Slab_R2C(np.array(N), L3, SelfComm(), prec)
+            F.l2_planes, F.l2_mode = planes, mode
+            c = F.fftn(A, np.zeros(F.complex_shape(), dtype=ct))
+            assert oracle.rel_l2(c, ref) <= tol, (N, prec, mode)
+            assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape(), dtype=rt)), A) <= tol, (N, prec, mode)
+            for d in ("2/3-rule", "3/2-rule"):
+                shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
+                got = F.ifftn(ref, np.zeros(shp, dtype=rt), dealias=d)
+                assert oracle.rel_l2(got, oracle.slab.ifftn([ref], N, 1, dealias=d, precision=prec)[0]) <= tol, (N, prec, mode, d)
+                if d == "3/2-rule":
+                    back = F.fftn(got, np.zeros(F.complex_shape(), dtype=ct), dealias=d)
+                    assert oracle.rel_l2(back, oracle.slab.fftn([got], N, 1, dealias=d, precision=prec)[0]) <= 10 * tol
+            if mode == 3:
+                k, _ = F.last_launches()
+                assert k == 2, "fused launch expected (z+y in one kernel, then x): %d kernels" % k
+                tu = torch.from_numpy(A).cuda()
+                tf = torch.zeros(tuple(int(s) for s in F.complex_shape()), dtype=torch.complex128 if prec == "double" else torch.complex64,
+                                 device="cuda")
+                F.fftn(tu, tf)
+                first = tf.clone()
+                for _ in range(20):
+                    tf.zero_()
+                    F.fftn(tu, tf)
+                    assert torch.equal(tf, first)
+
+
 class _P(object):
     """device tensor with the two attributes run_rows reads from a numpy array"""
 
@@ -103,5 +144,5 @@ class _P(object):
 
 if __name__ == "__main__":
     assert torch.cuda.is_available()
-    {"cluster": cluster, "rowbar": rowbar}[sys.argv[1]]()
+    {"cluster": cluster, "rowbar": rowbar, "l2": l2}[sys.argv[1]]()
     print("VARIANT_WORKER_OK")

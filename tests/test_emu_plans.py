@@ -384,3 +384,46 @@ def test_slab_single_rank_l2_groups(kind, l2_planes):
         _check(run_plan(d, 1, mode, fu, [shp], it), inv(fu, dealias=name), TOL[prec])
     up = [new_in(g.real_shape_padded())]
     _check(run_plan(d, 0, D.DEALIAS_3_2, up, [cs], ct), fwd(up, dealias="3/2-rule"), TOL[prec])
+
+
+@pytest.mark.parametrize("N,l2_planes,prec", [((8, 512, 512), 2, "double"), ((8, 512, 512), 4, "single"),
+                                              ((4, 1024, 1024), 1, "double"), ((6, 512, 512), 4, "double")])
+def test_slab_single_rank_fused_zy(N, l2_planes, prec):
+    """l2_mode 3: the z and y passes as one persistent kernel (queue order A(0) | A(1) B(0) | ...); the
+    emulator walks the queue in order and checks that every block runs once and never ahead of the blocks
+    it depends on.  Row blocks of RPC rows straddle plane groups (1024-point rows: 3 per block; 6 planes in
+    groups of 4 leave a short last group): such blocks credit / wait for two groups."""
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, 1)
+    rng = np.random.default_rng(12)
+    d = _desc(D.SLAB, N, 1, prec, l2_planes=l2_planes)
+    d.l2_mode = 3
+    lib = emu_util.load()
+    before = lib.emu_fused_runs()
+    u = [rng.random(g.real_shape()).astype(rt)]
+    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)
+    _check(c, oracle.slab.fftn(u, N, 1, precision=prec), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()], rt), u, TOL[prec])
+    fu = [_rand_c(rng, g.complex_shape(), ct)]
+    _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()], rt), oracle.slab.ifftn(fu, N, 1, dealias="2/3-rule", precision=prec),
+           TOL[prec])
+    assert lib.emu_fused_runs() - before == 3
+    assert lib.emu_check_schedule(C.byref(d), 0, D.DEALIAS_NONE) == 0 and lib.emu_check_schedule(C.byref(d), 1, D.DEALIAS_NONE) == 0
+
+
+def test_slab_single_rank_fused_zy_padded():
+    """3/2-rule: rows of 1536 reals next to columns of 1536 points (the (768, 1536) fused pair), 3 plane groups"""
+    N, prec = (2, 1024, 1024), "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, 1)
+    rng = np.random.default_rng(13)
+    d = _desc(D.SLAB, N, 1, prec, l2_planes=1)
+    d.l2_mode = 3
+    lib = emu_util.load()
+    before = lib.emu_fused_runs()
+    fu = [_rand_c(rng, g.complex_shape(), ct)]
+    up = run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)
+    _check(up, oracle.slab.ifftn(fu, N, 1, dealias="3/2-rule", precision=prec), TOL[prec])
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct), oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec),
+           TOL[prec])
+    assert lib.emu_fused_runs() - before == 2

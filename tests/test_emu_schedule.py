@@ -32,7 +32,7 @@ def test_slab_schedules(kind, P, transport, pipeline, chunks, l2, streams):
     if P == 1 and (transport or pipeline or chunks):
         pytest.skip("single rank: no exchange")
     d = _desc(kind, (32, 16, 64), P, "double", chunks=chunks, pipeline=pipeline, transport=transport, l2_planes=l2)
-    d.l2_streams = streams
+    d.l2_mode = streams
     _check(d)
 
 
@@ -44,7 +44,7 @@ def test_headline_sizes():
             continue
         d = _desc(D.SLAB, (1024, 1024, 1024), P, "double", chunks=chunks, pipeline=pipeline, transport=transport,
                   l2_planes=l2)
-        d.l2_streams = streams
+        d.l2_mode = streams
         _check(d)
 
 
