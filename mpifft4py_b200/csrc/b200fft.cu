@@ -584,11 +584,18 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
     if (pl->timing) cudaEventRecord(pl->ev[(size_t)evi], st);
     int rc = 0;
     bool fused = false;
-    if (s.fuse_planes > 0 && si + 1 < pg.steps.size()) {
+    if (s.fuse_planes > 0 && si + 1 < pg.steps.size() && pg.steps[si + 1].stream == s.stream) {
       // z + y (inverse: y + z) as one persistent kernel through L2; two launches if no such kernel exists
       const Step& t = pg.steps[si + 1];
       const Step& rs = (s.type == ST_STRIDED) ? t : s;
       const Step& cs = (s.type == ST_STRIDED) ? s : t;
+      // the second pass's own preconditions hold for the whole launch
+      if (t.wait_ev >= 0) {
+        cudaError_t e = cudaStreamWaitEvent(st, pl->sched_ev[(size_t)t.wait_ev], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+      }
+      if (use_p2p && t.wait_credits)
+        if (int rc2 = wait_credits(pl, st)) return rc2;
       if (!pl->fuse_ctl) {
         cudaError_t e = cudaMalloc(&pl->fuse_ctl, sizeof(unsigned) * FUSE_CTL_WORDS);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fuse control words)");
@@ -636,8 +643,16 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], st);
       if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
     }
-    if (fused) ++si;  // the next step ran inside the fused launch (single-rank programs: no events or credits on it)
-    if (use_p2p && s.last_reader) {  // hand the receive buffers back to the peers
+    bool last_reader = s.last_reader != 0;
+    if (fused) {  // the next step ran inside the fused launch: its event and credits follow the launch
+      const Step& t = pg.steps[++si];
+      if (t.rec_ev >= 0) {
+        cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)t.rec_ev], st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+      }
+      last_reader = last_reader || t.last_reader != 0;
+    }
+    if (use_p2p && last_reader) {  // hand the receive buffers back to the peers
       for (int q = 0; q < pl->d.nranks; ++q)
         if (q != pl->d.rank)
           if (int rc2 = post_flag(pl, st, (unsigned*)pl->p2p.peer_flags[q] + B200FFT_MAXP + pl->d.rank, pl->p2p.calls + 1)) return rc2;

@@ -343,7 +343,7 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
   // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
   // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
-  const bool fused_zy = d.l2_mode == 3 && d.l2_planes > 0 && P == 1 && !c2c;
+  const bool fused_zy = d.l2_mode == 3 && d.l2_planes > 0 && !c2c;
   auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
     const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn && !fused_zy) ? d.l2_planes : xn;
     for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
@@ -462,7 +462,9 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         int y_ev = -1;
         zy_groups(x0, xc, [&](long long g0, long long gn) {
           b.fixed = 0;
+          const size_t zi = pg.steps.size();
           zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
+          if (fused_zy) pg.steps[zi].fuse_planes = d.l2_planes;  // z(c) + y(c) as one kernel through L2
           SideT o;
           o.chunk = (int)Np1;
           o.nchunk = P;
@@ -683,6 +685,7 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 2;
           Step& y = b.strided(pN1, gn, Nf, 1, g, nat(ybuf, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
           if (g0 == x0) y.wait_ev = xev[(size_t)c];
+          if (fused_zy) y.fuse_planes = d.l2_planes;  // y(c) + z(c) as one kernel through L2
           b.fixed = 3;
           Step& z = zinv(gn * pN1, g0 * pN1, ybuf, g0 * pN1 * Nf, scale);
           // credits go back after the last z pass, not the last y pass: W2 (this program's y output)

@@ -300,20 +300,31 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
     return d;
   };
   for (size_t si = 0; si < nsteps; ++si) {
-    for (int r = 0; r < P; ++r) {
-      const Step& s = pg[r].steps[si];
-      int rc = 0;
-      if (s.fuse_planes > 0 && si + 1 < nsteps && P == 1) {  // as b200fft.cu: fused launch, else two passes
+    if (pg[0].steps[si].fuse_planes > 0 && si + 1 < nsteps) {  // as b200fft.cu: fused launch, else two passes
+      bool all = true;
+      for (int r = 0; r < P && all; ++r) {  // (the same sizes on every rank: all fuse or none does)
+        const Step& s = pg[r].steps[si];
         const Step& t = pg[r].steps[si + 1];
         const Step& rs = (s.type == ST_STRIDED) ? t : s;
         const Step& cs = (s.type == ST_STRIDED) ? s : t;
+        if (cs.type != ST_STRIDED || (rs.type != ST_R2C && rs.type != ST_C2R)) { all = false; break; }
         auto rd = rows_of(r, rs);
         auto cd = strided_of(r, cs);
-        rc = emu_exec_fused_zy(&rd, &cd, s.type == ST_STRIDED, s.fuse_planes);
-        if (rc == 0) { ++g_emu_fused_runs; ++si; continue; }
-        if (rc != -1 && rc != -3) return rc;
-        rc = 0;
+        const int rc = emu_exec_fused_zy(&rd, &cd, s.type == ST_STRIDED, s.fuse_planes);
+        if (rc == -1 || rc == -3) {
+          if (r != 0) return 92;
+          all = false;
+        } else if (rc) {
+          return rc;
+        } else {
+          ++g_emu_fused_runs;
+        }
       }
+      if (all) { ++si; continue; }
+    }
+    for (int r = 0; r < P; ++r) {
+      const Step& s = pg[r].steps[si];
+      int rc = 0;
       if (s.type == ST_STRIDED) {
         b200fft_strided_desc_t d;
         std::memset(&d, 0, sizeof(d));

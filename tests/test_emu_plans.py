@@ -427,3 +427,29 @@ def test_slab_single_rank_fused_zy_padded():
     _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct), oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec),
            TOL[prec])
     assert lib.emu_fused_runs() - before == 2
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_STORE])
+def test_slab_multi_rank_fused_zy(transport):
+    """P = 2: inside each exchange chunk the z and y passes run as one fused kernel (the y pass storing
+    into the per-peer blocks, or straight into the peer's buffer with the fused transport)."""
+    N, P, prec = (16, 512, 512), 2, "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(14)
+    d = _desc(D.SLAB, N, P, prec, chunks=2, transport=transport, l2_planes=2)
+    d.l2_mode = 3
+    lib = emu_util.load()
+    before = lib.emu_fused_runs()
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
+    _check(c, oracle.slab.fftn(u, N, P, precision=prec), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()] * P, rt), u, TOL[prec])
+    # forward: two chunks; inverse: two chunks, or one with the fused transport (its x pass moves everything at once)
+    assert lib.emu_fused_runs() - before == (2 + (1 if transport == D.TRANSPORT_STORE else 2)) * P
+    for inverse in (0, 1):
+        assert lib.emu_check_schedule(C.byref(d), inverse, D.DEALIAS_NONE) == 0
+        if transport != D.TRANSPORT_NCCL:
+            n = C.c_int()
+            assert lib.emu_check_p2p(C.byref(d), inverse, D.DEALIAS_NONE, C.byref(n)) == 0
