@@ -17,6 +17,14 @@ for w in slab1024_f64 slab1024_f64_32; do
   run nccl x 0 $w; run p2p x 0 $w; run store x 1 $w
   for c in 2 4 8; do run nccl kz $c $w; run p2p kz $c $w; run store kz $c $w; done
 done
+# fused z+y kernel through L2 inside each exchange chunk (groups of 4 / 8 planes), best transports
+for g in 4 8; do
+  for t in p2p store; do
+    B200FFT_L2_MODE=3 B200FFT_L2_PLANES=$g run $t x 0 slab1024_f64
+    mv $O/bench_slab1024_f64_${t}_x_c0.json $O/bench_slab1024_f64_${t}_x_c0_l2f$g.json
+  done
+done
+run p2p x 0 slab1024_f64   # (restores the plain result file name)
 if [ "$N" -ge 4 ]; then
   for t in nccl p2p store; do run $t x 0 pencilX1024_f64; done
 fi
