@@ -974,8 +974,14 @@ __global__ void __launch_bounds__(FusePair<KA, KB>::NT, FusePair<KA, KB>::MINB)
         fuse_decode(c, i, isB, blk);
         if (isB) {
           c.b.groups(blk, g1, g2, u1, u2);
+          // (bounded: a protocol error must end as a launch failure, never as a GPU that spins forever --
+          // 2^26 polls of >= 200 ns are more than ten seconds, a healthy wait is microseconds)
+          unsigned polls = 0;
           for (unsigned g = g1; g <= g2; ++g)
-            while (*reinterpret_cast<volatile unsigned*>(c.done + g) < c.a.need(g)) __nanosleep(200);
+            while (*reinterpret_cast<volatile unsigned*>(c.done + g) < c.a.need(g)) {
+              __nanosleep(200);
+              if (++polls > (1u << 26)) __trap();
+            }
           __threadfence();
         }
         v = blk | (isB ? 0x80000000u : 0u);
