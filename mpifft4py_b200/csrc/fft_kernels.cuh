@@ -211,6 +211,33 @@ B2_HD void async_copy_wait() {
 #endif
 }
 
+// Streaming ("touched once", evict-first) global accesses.  Used by the fused z+y kernel for the data that
+// only passes through -- the real input of the forward z pass, the real output of the inverse one, the y
+// pass's final stores -- so that it does not push the intermediate the two passes share out of L2.
+template <class real>
+B2_HD cx<real> load_streaming(const cx<real>* p) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (sizeof(real) == 8) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return cx<real>{v.x, v.y};
+  } else {
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    return cx<real>{v.x, v.y};
+  }
+#else
+  return *p;
+#endif
+}
+template <class real>
+B2_HD void store_streaming(cx<real>* p, cx<real> v) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (sizeof(real) == 8) __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+  else __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+#else
+  *p = v;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // fused pair of passes through L2 (persistent kernel)
 // ------------------------------------------------------------------------------------------
@@ -338,7 +365,7 @@ struct StridedCfg {
   static constexpr int MINB = MB > 0 ? MB : (MINB_ < 1 ? 1 : (MINB_ > 3 ? 3 : MINB_));
 };
 
-template <class real, class P, int MB = 0, int RB = 0>
+template <class real, class P, int MB = 0, int RB = 0, bool STREAM_ST = false>
 struct StridedK {
   using Cfg = StridedCfg<real, P, MB, RB>;
   using C = cx<real>;
@@ -451,7 +478,8 @@ struct StridedK {
         else a = out_row(p, b, k, j0);
         if (a == 0) return;
         if (p.scale != (real)1) v = cscale(v, p.scale);
-        *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
+        if constexpr (STREAM_ST) store_streaming(reinterpret_cast<C*>(a + (addr_t)c * CB), v);
+        else *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
       };
       // reversed output index: the slot that survives a "keep -N/2" truncation is the other one
       const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
@@ -626,7 +654,7 @@ struct RowCfg {
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > MINB_CAP ? MINB_CAP : MINB_);
 };
 
-template <class real, class P>
+template <class real, class P, bool STREAM_LD = false>
 struct R2CK {  // forward: real rows -> complex rows
   static constexpr int GROUP = RowCfg<real, P>::TC;
   // Stage 0 loads its butterfly inputs straight from HBM into registers (coalesced 16-byte loads,
@@ -664,7 +692,11 @@ struct R2CK {  // forward: real rows -> complex rows
     C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
     if constexpr (s < P::S) {
       const C* src = reinterpret_cast<const C*>(reinterpret_cast<const real*>(p.rin) + row * p.rpitch);
-      auto in = [&](int i) -> C { return live ? src[i] : C{0, 0}; };  // z[i] = x[2i] + i*x[2i+1]
+      auto in = [&](int i) -> C {  // z[i] = x[2i] + i*x[2i+1]
+        if (!live) return C{0, 0};
+        if constexpr (STREAM_LD) return load_streaming(src + i);
+        else return src[i];
+      };
       auto out = [](int, C) {};
       // every stage writes shared memory (the split step needs all of F)
       fft_stage<real, P, s, TC, 1, Cfg::SW, (s == 0), false>(t, sm, p.tw, 2 * p.tws, in, out, 0);
@@ -703,7 +735,7 @@ struct R2CK {  // forward: real rows -> complex rows
   }
 };
 
-template <class real, class P>
+template <class real, class P, bool STREAM_ST = false>
 struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's scale carries 1/n)
   static constexpr int GROUP = RowCfg<real, P>::TC;
   using Cfg = RowCfg<real, P>;
@@ -778,7 +810,8 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
         if (!live) return;
         // z = swap(FFT(swap G)) ; x[2m] = Re z, x[2m+1] = Im z
         C z = C{v.y * p.scale, v.x * p.scale};
-        *reinterpret_cast<C*>(dst + 2 * (long long)m) = z;
+        if constexpr (STREAM_ST) store_streaming(reinterpret_cast<C*>(dst + 2 * (long long)m), z);
+        else *reinterpret_cast<C*>(dst + 2 * (long long)m) = z;
       };
       fft_stage<real, P, st, TC, 1, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, 0);
     }
