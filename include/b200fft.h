@@ -52,7 +52,8 @@ B200FFT_API int b200fft_supported_length(int n);
  * alternative kernel or radix plan where one is compiled; 0 = the defaults.  Returns the old value.
  * 20: strided passes with rows >= 1 MB apart run on 2-CTA clusters (128-byte rows split over
  * distributed shared memory); 22: also near-stride passes of n >= 2048, with 64-byte rows; 21 / 23: all
- * strided passes that have a cluster plan do (128- / 64-byte rows; testing aids); 30: the threads of a
+ * strided passes that have a cluster plan do (128- / 64-byte rows; testing aids); 31: register-staged
+ * C2R kernel (loads its spectrum pairs straight into registers, like the R2C kernel, no staging copy); 30: the threads of a
  * row of the R2C / C2R passes synchronise on a named barrier of their own instead of the CTA's. */
 B200FFT_API int b200fft_set_variant(int v);
 

@@ -818,6 +818,88 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
   }
 };
 
+// C2R, register-staged ("direct") form -- the mirror image of R2CK: each thread loads the spectrum pairs
+// (X[k], X[H-k]) it merges straight from HBM into registers (all loads issued before the first use, both
+// streams coalesced), merges them there and writes G to shared memory once.  Against C2RK this drops the
+// staging copy's shared-memory round trip (one write + two reads per pair) and one barrier; it has no
+// asynchronous double buffer and relies on CTA residency for overlap, exactly like R2CK (which reaches
+// 0.84 of the HBM figure where C2RK reaches 0.67).  Opt-in: B200FFT_VARIANT=31.
+template <class real, class P>
+struct C2RDK {
+  static constexpr int GROUP = RowCfg<real, P>::TC;
+  using Cfg = RowCfg<real, P>;
+  using C = cx<real>;
+  using Params = RowParams<real>;
+  static constexpr int NPHASE = P::S + 1;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM1;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = false;
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > Cfg::MINB_CAP ? Cfg::MINB_CAP : MINB_);
+  B2_HD static unsigned long long blocks(const Params& p) {
+    return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC);
+  }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int H = Cfg::H, TC = Cfg::TC;
+    constexpr int M0 = P::template M<0>;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.rows;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
+    if constexpr (s == 0) {
+      const Side& o = p.cside;
+      // X[k], or 0 in the z zero pad (copy_to_padded axis 2, slab.py:524-525) / for rows past the end
+      auto load = [&](int k) -> C {
+        if (!live || k >= p.nk) return C{0, 0};
+        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+        return *(reinterpret_cast<const C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk));
+      };
+      constexpr int NK = H / 2 + 1;
+      constexpr int ROUNDS = (NK + TC - 1) / TC;
+      C a[ROUNDS], bq[ROUNDS];
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int k = t + rr * TC;
+        if (k < NK) {
+          a[rr] = load(k);
+          bq[rr] = load(H - k);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int k = t + rr * TC;
+        if (k >= NK) break;
+        if (k == 0) {  // imaginary parts of DC / Nyquist ignored (C2R)
+          sm[swz<M0, Cfg::SW>(0)] = cswap(C{a[rr].x + bq[rr].x, a[rr].x - bq[rr].x});
+        } else {
+          // G[k] = (X[k] + conj X[H-k]) + i W_n^-k (X[k] - conj X[H-k]); stored swapped (inverse by swapping)
+          const C e = C{a[rr].x + bq[rr].x, a[rr].y - bq[rr].y};
+          const C d = C{a[rr].x - bq[rr].x, a[rr].y + bq[rr].y};
+          const C o2 = cmul(cconj(p.tw[k * p.tws]), d);
+          sm[swz<M0, Cfg::SW>(k)] = cswap(cadd(e, mul_pi(o2)));
+          if (k != H - k) sm[swz<M0, Cfg::SW>(H - k)] = cswap(cadd(cconj(e), mul_pi(cconj(o2))));
+        }
+      }
+    } else {
+      constexpr int st = s - 1;
+      real* dst = reinterpret_cast<real*>(p.rout) + row * p.rpitch;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int m, C v) {
+        if (!live) return;
+        *reinterpret_cast<C*>(dst + 2 * (long long)m) = C{v.y * p.scale, v.x * p.scale};
+      };
+      fft_stage<real, P, st, TC, 1, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, 0);
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // contiguous-row C2C pass (the z pass of slab.C2C, slab.py:538-825): the strided pass's index maps
 // (zero pad on load, truncate / fold on store, reversed output index for the inverse, scale) on

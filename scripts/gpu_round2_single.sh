@@ -8,9 +8,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 # 1. parity first: the default path, then the experimental variants (subprocess, xfail until verified)
 timeout 1200 python -m pytest tests -m gpu -q -rxX > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -25 $O/pytest_gpu.log
-# 2. cluster strided pass (variant 20: far launches only) and per-row barriers in the row kernels (30)
+# 2. cluster strided pass (variant 20: far launches only), per-row barriers in the row kernels (30),
+#    register-staged C2R (31)
 #    against the default, plain and 3/2-rule
-for v in 0 20 30; do
+for v in 0 20 30 31; do
   for w in slab1024_f64 slab1024_f64_32; do
     B200FFT_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
         > $O/bench_${w}_v$v.json 2> $O/bench_${w}_v$v.err

@@ -168,6 +168,7 @@ static int rows(const b200fft_rows_desc_t& d) {
 #define X(n, ...)                                                     \
   case n:                                                             \
     if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);        \
+    else if (g_emu_variant == 31) return emulate<C2RDK<real, Plan<__VA_ARGS__>>>(p); \
     else return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);
     B200FFT_ROW_PLANS(X)
 #undef X

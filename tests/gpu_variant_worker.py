@@ -2,7 +2,7 @@
 tests/test_zz_gpu_experimental.py, so that a fault cannot take the main test process down).
 
     python tests/gpu_variant_worker.py cluster    # 2-CTA cluster strided pass (variant 21 / 20)
-    python tests/gpu_variant_worker.py rowbar     # row kernels with per-row named barriers (variant 30)
+    python tests/gpu_variant_worker.py rowbar     # row kernels: per-row named barriers (30), register-staged C2R (31)
     python tests/gpu_variant_worker.py l2         # L2-blocked z / y passes: grouped launches, two streams, fused kernel
 """
 import os
@@ -62,13 +62,19 @@ def cluster():
 
 
 def rowbar():
-    """Row kernels (R2C / C2R) whose rows synchronise on their own named barrier: many more rows than
-    one wave of persistent CTAs, so that rows of one CTA really run out of step."""
+    """Row-kernel variants: 30 = the rows of a CTA synchronise on their own named barrier (many more rows
+    than one wave of persistent CTAs, so that rows really run out of step); 31 = register-staged C2R."""
+    be = tp._Gpu()
+    for variant in (30, 31):
+        _rows_checks(be, variant)
+    be.L.b200fft_set_variant(0)
+
+
+def _rows_checks(be, variant):
     import mpifft4py_b200 as m
     from mpifft4py_b200 import _cdefs as D
     from mpifft4py_b200.comm import SelfComm
-    be = tp._Gpu()
-    be.L.b200fft_set_variant(30)
+    be.L.b200fft_set_variant(variant)
     for prec in "ds":
         for h in (256, 384, 512, 768, 1024, 1536):
             tp.test_rows_r2c_c2r(be, h, prec)
@@ -91,7 +97,8 @@ def rowbar():
     c = F.fftn(A, np.zeros(F.complex_shape(), dtype=np.complex128))
     assert oracle.rel_l2(c, oracle.slab.fftn([A], N, 1)[0]) <= 1e-12
     assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape())), A) <= 1e-12
-    be.L.b200fft_set_variant(0)
+    up = F.ifftn(c, np.zeros(F.real_shape_padded()), dealias="3/2-rule")
+    assert oracle.rel_l2(up, oracle.slab.ifftn([c], N, 1, dealias="3/2-rule")[0]) <= 1e-12
 
 
 def l2():
@@ -112,6 +119,9 @@ def l2():
             F.l2_planes, F.l2_mode = planes, mode
             c = F.fftn(A, np.zeros(F.complex_shape(), dtype=ct))
             assert oracle.rel_l2(c, ref) <= tol, (N, prec, mode)
+            if mode == 3:
+                k, _ = F.last_launches()
+                assert k == 2, "fused launch expected (z+y in one kernel, then x): %d kernels" % k
             assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape(), dtype=rt)), A) <= tol, (N, prec, mode)
             for d in ("2/3-rule", "3/2-rule"):
                 shp = F.real_shape_padded() if d == "3/2-rule" else F.real_shape()
@@ -121,8 +131,6 @@ def l2():
                     back = F.fftn(got, np.zeros(F.complex_shape(), dtype=ct), dealias=d)
                     assert oracle.rel_l2(back, oracle.slab.fftn([got], N, 1, dealias=d, precision=prec)[0]) <= 10 * tol
             if mode == 3:
-                k, _ = F.last_launches()
-                assert k == 2, "fused launch expected (z+y in one kernel, then x): %d kernels" % k
                 tu = torch.from_numpy(A).cuda()
                 tf = torch.zeros(tuple(int(s) for s in F.complex_shape()), dtype=torch.complex128 if prec == "double" else torch.complex64,
                                  device="cuda")

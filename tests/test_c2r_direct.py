@@ -1,0 +1,30 @@
+"""Register-staged C2R kernel (csrc/fft_kernels.cuh: C2RDK, kernel variant 31) in the CPU emulator: every
+row plan, zero-padded spectra (3/2-rule), per-peer kz chunks.  The device run is part of
+tests/gpu_variant_worker.py rowbar."""
+import pytest
+
+import emu_util
+import test_passes as tp
+
+
+@pytest.fixture(scope="module")
+def be31():
+    lib = emu_util.load()
+    old = lib.emu_set_variant(31)
+    yield tp._Emu()
+    lib.emu_set_variant(old)
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+@pytest.mark.parametrize("h", [2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 256, 384, 512, 768, 1024, 1536, 2048])
+def test_c2r_direct_all_plans(be31, h, prec):
+    tp.test_rows_r2c_c2r(be31, h, prec)
+
+
+@pytest.mark.parametrize("N", [8, 32, 256, 1024])
+def test_c2r_direct_zero_pad(be31, N):
+    tp.test_rows_truncate_and_zero_pad(be31, N)
+
+
+def test_c2r_direct_uneven_kz_chunks(be31):
+    tp.test_rows_uneven_kz_chunks(be31)
