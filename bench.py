@@ -455,6 +455,12 @@ def run_ours(args):
     if P > 1:
         dist.barrier()
     cfg = describe(name, P)
+    # opt-in kernels / schedules that were active (environment switches): a line measured
+    # with any of them says so
+    tuning = {k: os.environ[k] for k in ("B200FFT_VARIANT", "B200FFT_L2_PLANES", "B200FFT_L2_MODE", "B200FFT_TRANSPORT",
+                                          "B200FFT_PIPELINE", "B200FFT_CHUNKS") if os.environ.get(k)}
+    if tuning:
+        cfg["tuning"] = tuning
     if P > 1:
         ex = [s for s in F.last_steps() if s[0] == "exchange"]
         cfg["exchange"] = {"transport": getattr(F, "transport_used", "nccl"),
