@@ -25,4 +25,10 @@ int launch_fused_zy_f32(int H, int NY, const RowParams<float>& pr, const Strided
 bool plan_exists(int n);
 // tuning switch (B200FFT_VARIANT environment variable, b200fft_set_variant): 0 = default kernels
 int kernel_variant();
+// switches that combine: variant = 100 + bits
+enum { VAR_CLUSTER_FAR = 1, VAR_CLUSTER_LONG = 2, VAR_ROW_BARRIERS = 4, VAR_C2R_DIRECT = 8 };
+inline bool variant_has(int flag) {
+  const int v = kernel_variant();
+  return v >= 100 && v < 200 && ((v - 100) & flag) != 0;
+}
 }  // namespace b200fft

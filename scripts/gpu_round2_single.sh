@@ -8,6 +8,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 # 1. parity first: the default path, then the experimental variants (subprocess, xfail until verified)
 timeout 1200 python -m pytest tests -m gpu -q -rxX > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -25 $O/pytest_gpu.log
+# 2a. everything below in one process first (one import, one set of arrays): the quick overall picture
+timeout 1500 python scripts/ab_single.py --steps 5 > $O/ab_single.jsonl 2> $O/ab_single.txt; tail -80 $O/ab_single.txt
 # 2. cluster strided pass (variant 20: far launches only), per-row barriers in the row kernels (30),
 #    register-staged C2R (31)
 #    against the default, plain and 3/2-rule
