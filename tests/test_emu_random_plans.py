@@ -76,3 +76,54 @@ def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec, l2):
             for m in modes:
                 n = C.c_int()
                 assert lib.emu_check_p2p(C.byref(d), inverse, m, C.byref(n)) == 0
+
+
+def _pencil_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        N = tuple(int(rng.choice([8, 16, 32, 48])) for _ in range(3))
+        P1, P2 = [(2, 2), (4, 2), (2, 4), (4, 4), (2, 8)][int(rng.integers(0, 5))]
+        alignment = str(rng.choice(["X", "Y"]))
+        zparts = P2 if alignment == "X" else P1
+        if any(n % P1 or n % P2 for n in N) or (N[2] // 2) % zparts:
+            continue
+        comm = str(rng.choice(["Alltoall", "Alltoallw", "AlltoallN"]))
+        transport = int(rng.choice([D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE]))
+        prec = "double" if rng.random() < 0.75 else "single"
+        out.append((N, P1, P2, alignment, comm, transport, prec))
+    return out
+
+
+@pytest.mark.parametrize("N,P1,P2,alignment,comm,transport,prec", _pencil_cases(30, 77),
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
+def test_random_pencil_plan(N, P1, P2, alignment, comm, transport, prec):
+    P = P1 * P2
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.pencil.Geometry(N, P, alignment, P1, comm)
+    assert (g.P1, g.P2) == (P1, P2)
+    rng = np.random.default_rng(sum(N) + P)
+    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, P1, P2, int(comm == "AlltoallN"), transport=transport)
+    kw = dict(alignment=alignment, P1=P1, communication=comm, precision=prec)
+    tol = TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.pencil.fftn(u, N, P, **kw), tol)
+    fu = [_rand_c(rng, s, ct) for s in cshape]
+    modes = [(D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule")]
+    if all(_supported(3 * n // 2) for n in N):
+        modes.append((D.DEALIAS_3_2, "3/2-rule"))
+    for mode, name in modes:
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.pencil.ifftn(fu, N, P, dealias=name, **kw), tol)
+    if len(modes) == 3:
+        up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+        _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), oracle.pencil.fftn(up, N, P, dealias="3/2-rule", **kw), tol)
+    lib = emu_util.load()
+    for inverse in (0, 1):
+        for mode, _ in modes:
+            assert lib.emu_check_schedule(C.byref(d), inverse, mode) == 0
+            if transport != D.TRANSPORT_NCCL:
+                n = C.c_int()
+                assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0
