@@ -232,8 +232,8 @@ struct b200fft_comm {
 struct b200fft_plan {
   b200fft_plan_desc_t d;
   Program prog[2][3];  // [forward=0 / inverse=1][dealias]
-  void* ws[3] = {nullptr, nullptr, nullptr};
-  size_t wbytes[3] = {0, 0, 0};
+  void* ws[NWORK] = {};
+  size_t wbytes[NWORK] = {};
   int last_kernels = 0, last_exch = 0;
   int timing = 0;
   // copy-engine (P2P) transport: peers' work buffers and flag words mapped through CUDA IPC.
@@ -243,7 +243,7 @@ struct b200fft_plan {
   struct {
     bool connected = false;
     void* flags = nullptr;                   // uint32 arrived[MAXP] then credit[MAXP]
-    void* peer_ws[B200FFT_MAXP][3] = {};
+    void* peer_ws[B200FFT_MAXP][NPEERBUF] = {};
     void* peer_flags[B200FFT_MAXP] = {};
     cudaStream_t wait_stream = nullptr;
     std::vector<cudaEvent_t> send_ev;
@@ -347,7 +347,7 @@ int ensure_program(b200fft_plan* pl, int inverse, int dealias) {
   }
   // grow the work buffers
   const size_t csz = pl->d.precision == B200FFT_DOUBLE ? 16 : 8;
-  for (int w = 0; w < 3; ++w) {
+  for (int w = 0; w < NWORK; ++w) {
     const size_t need = (size_t)pg.need[BUF_W0 + w] * csz;
     if (need > pl->wbytes[w]) {
       if (pl->p2p.connected) return fail(B200FFT_ERR_NOMEM, "P2P plans size their buffers at connect time (need %zu > %zu)", need, pl->wbytes[w]);
@@ -782,7 +782,7 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
 int b200fft_plan_destroy(b200fft_plan_t plan) {
   if (!plan) return 0;
   cudaDeviceSynchronize();
-  for (int w = 0; w < 3; ++w)
+  for (int w = 0; w < NWORK; ++w)
     if (plan->ws[w]) cudaFree(plan->ws[w]);
   for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
@@ -790,7 +790,7 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
   if (plan->p2p.connected) {
     for (int q = 0; q < plan->d.nranks; ++q) {
       if (q == plan->d.rank) continue;
-      for (int w = 0; w < 3; ++w)
+      for (int w = 0; w < NPEERBUF; ++w)
         if (plan->p2p.peer_ws[q][w]) cudaIpcCloseMemHandle(plan->p2p.peer_ws[q][w]);
       if (plan->p2p.peer_flags[q]) cudaIpcCloseMemHandle(plan->p2p.peer_flags[q]);
     }
@@ -805,7 +805,9 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
 
 size_t b200fft_plan_workspace_bytes(b200fft_plan_t plan) {
   if (!plan) return 0;
-  return plan->wbytes[0] + plan->wbytes[1] + plan->wbytes[2];
+  size_t total = 0;
+  for (int w = 0; w < NWORK; ++w) total += plan->wbytes[w];
+  return total;
 }
 
 int b200fft_exec_forward(b200fft_plan_t plan, const void* u, void* fu, int dealias, void* stream) {
@@ -823,16 +825,17 @@ int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256) {
   if ((plan->d.transport != B200FFT_TRANSPORT_P2P && plan->d.transport != B200FFT_TRANSPORT_STORE) || plan->d.nranks < 2)
     return fail(B200FFT_ERR_ARG, "not a multi-rank P2P plan");
   // size the work buffers for every program now: their addresses are what the peers map
-  size_t need[3] = {256, 256, 256};
+  size_t need[NWORK];
+  for (int w = 0; w < NWORK; ++w) need[w] = 256;
   const size_t csz = plan->d.precision == B200FFT_DOUBLE ? 16 : 8;
   for (int inv = 0; inv < 2; ++inv)
     for (int de = 0; de < 3; ++de) {
       if (de == B200FFT_DEALIAS_3_2 && std::fabs(plan->d.padsize - 1.5) > 1e-12) continue;
       Program pg;
       if (build_program(plan->d, inv, de, pg) || check_lengths(pg)) continue;
-      for (int w = 0; w < 3; ++w) need[w] = std::max(need[w], (size_t)pg.need[BUF_W0 + w] * csz);
+      for (int w = 0; w < NWORK; ++w) need[w] = std::max(need[w], (size_t)pg.need[BUF_W0 + w] * csz);
     }
-  for (int w = 0; w < 3; ++w) {
+  for (int w = 0; w < NWORK; ++w) {
     if (plan->ws[w]) cudaFree(plan->ws[w]);
     cudaError_t e = cudaMalloc(&plan->ws[w], need[w]);
     if (e != cudaSuccess) return fail(B200FFT_ERR_NOMEM, "cudaMalloc(%zu bytes of work space): %s", need[w], cudaGetErrorString(e));
@@ -843,7 +846,7 @@ int b200fft_plan_p2p_handles(b200fft_plan_t plan, void* handles256) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(flags)");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");
   cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(handles256);
-  for (int w = 0; w < 3; ++w)
+  for (int w = 0; w < NPEERBUF; ++w)  // (W3 is a local send buffer: peers never address it)
     if ((e = cudaIpcGetMemHandle(&h[w], plan->ws[w])) != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
   if ((e = cudaIpcGetMemHandle(&h[3], plan->p2p.flags)) != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle(flags)");
   return 0;
@@ -855,7 +858,7 @@ int b200fft_plan_p2p_connect(b200fft_plan_t plan, const void* all_handles) {
   const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
   for (int q = 0; q < plan->d.nranks; ++q) {
     if (q == plan->d.rank) continue;
-    for (int w = 0; w < 3; ++w) {
+    for (int w = 0; w < NPEERBUF; ++w) {
       cudaError_t e = cudaIpcOpenMemHandle(&plan->p2p.peer_ws[q][w], h[4 * q + w], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (is NVLink / P2P available between the GPUs?)");
     }

@@ -33,7 +33,11 @@ namespace b200fft {
 // ================================================================================================
 // plan programs
 // ================================================================================================
-enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_W0 = 2, BUF_W1 = 3, BUF_W2 = 4, NBUF = 5 };
+// W0..W2 may be written by peers (peer-mapped transports export exactly these three); W3 is a local
+// send buffer of the pipelined pencil programs
+enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_W0 = 2, BUF_W1 = 3, BUF_W2 = 4, BUF_W3 = 5, NBUF = 6 };
+constexpr int NWORK = NBUF - BUF_W0;  // work buffers of a plan
+constexpr int NPEERBUF = 3;           // ... of which the first three are mapped by the peers
 
 struct Ref {
   int buf = BUF_IN;
@@ -94,7 +98,7 @@ struct Step {
 
 struct Program {
   std::vector<Step> steps;
-  long long need[NBUF] = {0, 0, 0, 0, 0};  // complex elements needed in W0..W2
+  long long need[NBUF] = {0, 0, 0, 0, 0, 0};  // complex elements needed in W0..W3
   int nevents = 0;
   int fork_ev = -1;  // >= 0: recorded on the caller's stream when the program starts and awaited by the
                      // second stream (programs whose first step runs there)
@@ -755,7 +759,147 @@ inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, 
     const long long y1 = N1 / P1;
     const long long blk2 = (long long)pa * y1 * kzl;     // comm0 exchange block
     const long long blk1 = rowsz * kzl;                  // comm1 block [pa][pbq][kzl]
-    if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
+    // Pipelined programs (d.chunks > 1; NCCL and copy-engine transports): the local x planes are cut into
+    // CH chunks and both exchanges run per chunk on the second stream -- forward z(c) | e1(c) | y(c) |
+    // e2(c) then one x pass, inverse one x pass then e2(c) | y(c) | e1(c) | z(c) -- so each exchange
+    // overlaps the FFT passes of the neighbouring chunks.  The send buffer of the second exchange of a
+    // direction must not alias the first one's any more (W3 where W2 is taken).
+    int CH = (d.chunks > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+    while (CH > 1 && pa % CH) --CH;
+    const long long xc = pa / CH;
+    // kz-chunked side of the z pass restricted to local planes [x0, x0 + xc)
+    auto zside_x = [&](SideT sd, long long x0) {
+      for (int q = 0; q < zparts; ++q) sd.base[q].off += x0 * pbq * zc[q];
+      return sd;
+    };
+    if (!inverse && CH > 1) {  // pencil.py:1312-1337 (+ padded :1440-1475), pipelined
+      const int recv2 = (padded || peer_mapped) ? BUF_W2 : BUF_OUT;
+      const int send2 = (recv2 == BUF_OUT) ? BUF_W2 : BUF_W3;
+      b.use(BUF_W0, rowsz * nk);
+      b.use(BUF_W1, P2 * blk1);
+      b.use(send2, P1 * blk2);
+      b.use(recv2, P1 * blk2);
+      std::vector<int> e1ev((size_t)CH);
+      for (int c = 0; c < CH; ++c) {
+        const long long x0 = c * xc;
+        b.fixed = 0;
+        Step& z = b.rows(true, xc * pbq, pN2, nk, BUF_IN, zside_x(zside(BUF_W1, zme * blk1, BUF_W0, false), x0));
+        z.real.off = x0 * pbq * pN2;
+        z.rec_ev = pg.nevents++;
+        const int zev = z.rec_ev;
+        b.fixed = 1;
+        Step& x1 = b.exch(2, P2, c1);
+        x1.stream = 1;
+        x1.wait_ev = zev;
+        e1ev[(size_t)c] = x1.rec_ev = pg.nevents++;
+        for (int q = 0; q < P2; ++q) {
+          x1.send[q].buf = BUF_W0; x1.send[q].off = rowsz * zoff[q] + x0 * pbq * zc[q]; x1.scnt[q] = xc * pbq * zc[q];
+          x1.recv[q].buf = BUF_W1; x1.recv[q].off = q * blk1 + x0 * pbq * kzl; x1.rcnt[q] = xc * pbq * kzl;
+          x1.rpeer[q].buf = BUF_W1; x1.rpeer[q].off = c1 * rowsz * zc[q] + x0 * pbq * zc[q];
+        }
+      }
+      int last_ev = -1;
+      for (int c = 0; c < CH; ++c) {
+        const long long x0 = c * xc;
+        SideT g;
+        g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+        for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk1 + x0 * pbq * kzl; g.sb[q] = pbq * kzl; g.si[q] = kzl; }
+        SideT o;
+        o.chunk = (int)y1; o.nchunk = P1; o.nphys = (int)N1;
+        for (int q = 0; q < P1; ++q) {
+          o.base[q].buf = (q == c0) ? recv2 : send2; o.base[q].off = q * blk2 + x0 * y1 * kzl; o.sb[q] = y1 * kzl; o.si[q] = kzl;
+        }
+        b.fixed = 2;
+        Step& y = b.strided(pN1, xc, kzl, 0, g, o, padded ? 1 : 0);
+        y.wait_ev = e1ev[(size_t)c];
+        y.rec_ev = pg.nevents++;
+        const int yev = y.rec_ev;
+        b.fixed = 3;
+        Step& x2 = b.exch(1, P1, c0);
+        x2.stream = 1;
+        x2.wait_ev = yev;
+        last_ev = x2.rec_ev = pg.nevents++;
+        for (int q = 0; q < P1; ++q) {
+          x2.send[q].buf = send2; x2.send[q].off = q * blk2 + x0 * y1 * kzl; x2.scnt[q] = xc * y1 * kzl;
+          x2.recv[q].buf = recv2; x2.recv[q].off = q * blk2 + x0 * y1 * kzl; x2.rcnt[q] = xc * y1 * kzl;
+          x2.rpeer[q].buf = recv2; x2.rpeer[q].off = c0 * blk2 + x0 * y1 * kzl;
+        }
+      }
+      b.fixed = 4;
+      Step& fx = b.strided(pN0, 1, y1 * kzl, 0, nat(recv2, 0, 0, y1 * kzl, pN0), nat(BUF_OUT, 0, 0, y1 * kzl, (int)N0),
+                           padded ? 1 : 0, padded ? 1.0 / p3 : 1.0);
+      fx.wait_ev = last_ev;  // exchanges complete in order on the second stream
+    } else if (inverse && CH > 1) {  // pencil.py:1082-1105 (+ padded :1196-1223), pipelined
+      SideT o;
+      o.chunk = pa; o.nchunk = P1; o.nphys = pN0;
+      for (int q = 0; q < P1; ++q) {
+        o.base[q].buf = (q == c0) ? BUF_W1 : BUF_W0; o.base[q].off = q * blk2; o.sb[q] = 0; o.si[q] = y1 * kzl;
+      }
+      b.fixed = 0;
+      Step& sx = b.strided(pN0, 1, y1 * kzl, 1, nat(BUF_IN, 0, 0, y1 * kzl, (int)N0), o);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = (int)kzl;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, false, sx.mask.jq_lo, sx.mask.jq_hi);
+        sx.mask.jq_off = (int)(c0 * y1);
+        band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        sx.mask.jr_off = (int)(c1 * C);
+      }
+      const int xev = sx.rec_ev = pg.nevents++;
+      b.use(BUF_W0, P1 * blk2);
+      b.use(BUF_W1, P1 * blk2);
+      b.use(BUF_W3, P2 * blk1);      // send buffer of the second exchange
+      b.use(BUF_W2, rowsz * nk);
+      std::vector<int> e2ev((size_t)CH), e1ev((size_t)CH);
+      for (int c = 0; c < CH; ++c) {  // all first exchanges are queued at once: they only depend on the x pass
+        const long long x0 = c * xc;
+        b.fixed = 1;
+        Step& x2 = b.exch(1, P1, c0);
+        x2.stream = 1;
+        x2.wait_ev = (c == 0) ? xev : -1;
+        e2ev[(size_t)c] = x2.rec_ev = pg.nevents++;
+        for (int q = 0; q < P1; ++q) {
+          x2.send[q].buf = BUF_W0; x2.send[q].off = q * blk2 + x0 * y1 * kzl; x2.scnt[q] = xc * y1 * kzl;
+          x2.recv[q].buf = BUF_W1; x2.recv[q].off = q * blk2 + x0 * y1 * kzl; x2.rcnt[q] = xc * y1 * kzl;
+          x2.rpeer[q].buf = BUF_W1; x2.rpeer[q].off = c0 * blk2 + x0 * y1 * kzl;
+        }
+      }
+      for (int c = 0; c < CH; ++c) {
+        const long long x0 = c * xc;
+        SideT g;
+        g.chunk = (int)y1; g.nchunk = P1; g.nphys = (int)N1;
+        for (int q = 0; q < P1; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = q * blk2 + x0 * y1 * kzl; g.sb[q] = y1 * kzl; g.si[q] = kzl; }
+        SideT o2;
+        o2.chunk = pbq; o2.nchunk = P2; o2.nphys = pN1;
+        for (int q = 0; q < P2; ++q) {
+          o2.base[q].buf = (q == c1) ? BUF_W2 : BUF_W3;
+          o2.base[q].off = ((q == c1) ? rowsz * zoff[c1] : q * blk1) + x0 * pbq * kzl;
+          o2.sb[q] = pbq * kzl; o2.si[q] = kzl;
+        }
+        b.fixed = 2;
+        Step& y = b.strided(pN1, xc, kzl, 1, g, o2);
+        y.wait_ev = e2ev[(size_t)c];
+        const int yev = y.rec_ev = pg.nevents++;
+        b.fixed = 3;
+        Step& x1 = b.exch(2, P2, c1);
+        x1.stream = 1;
+        x1.wait_ev = yev;
+        e1ev[(size_t)c] = x1.rec_ev = pg.nevents++;
+        for (int q = 0; q < P2; ++q) {
+          x1.send[q].buf = BUF_W3; x1.send[q].off = q * blk1 + x0 * pbq * kzl; x1.scnt[q] = xc * pbq * kzl;
+          x1.recv[q].buf = BUF_W2; x1.recv[q].off = rowsz * zoff[q] + x0 * pbq * zc[q]; x1.rcnt[q] = xc * pbq * zc[q];
+          x1.rpeer[q].buf = BUF_W2; x1.rpeer[q].off = rowsz * zoff[c1] + x0 * pbq * kzl;
+        }
+      }
+      for (int c = 0; c < CH; ++c) {
+        const long long x0 = c * xc;
+        b.fixed = 4;
+        Step& z = b.rows(false, xc * pbq, pN2, nk, BUF_OUT, zside_x(zside(0, 0, BUF_W2, true), x0), iscale);
+        z.real.off = x0 * pbq * pN2;
+        z.wait_ev = e1ev[(size_t)c];
+      }
+    } else if (!inverse) {  // pencil.py:1312-1337 (+ padded :1440-1475)
       const int recv2 = (padded || peer_mapped) ? BUF_W2 : BUF_OUT;  // peers write plan-owned buffers only
       b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
       b.use(BUF_W0, rowsz * nk);

@@ -260,7 +260,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
   if (!inverse && dealias == B200FFT_DEALIAS_2_3) dealias = B200FFT_DEALIAS_NONE;
   const size_t csz = d0->precision == B200FFT_DOUBLE ? 16 : 8;
   std::vector<Program> pg((size_t)P);
-  std::vector<std::vector<unsigned char>> ws((size_t)P * 3);
+  std::vector<std::vector<unsigned char>> ws((size_t)P * NWORK);
   for (int r = 0; r < P; ++r) {
     b200fft_plan_desc_t d = *d0;
     d.rank = r;
@@ -268,13 +268,13 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
       std::fprintf(stderr, "emu plan: %s\n", plan_err().c_str());
       return rc;
     }
-    for (int w = 0; w < 3; ++w) ws[(size_t)r * 3 + w].assign((size_t)pg[r].need[BUF_W0 + w] * csz + 64, 0xff);  // NaN poison
+    for (int w = 0; w < NWORK; ++w) ws[(size_t)r * NWORK + w].assign((size_t)pg[r].need[BUF_W0 + w] * csz + 64, 0xff);  // NaN poison
   }
   auto resolve = [&](int r, const Ref& ref, size_t esz) -> void* {
     char* base;
     if (ref.buf == BUF_IN) base = (char*)ins[r];
     else if (ref.buf == BUF_OUT) base = (char*)outs[r];
-    else base = (char*)ws[(size_t)(ref.peer >= 0 ? ref.peer : r) * 3 + (ref.buf - BUF_W0)].data();  // peer: fused transport
+    else base = (char*)ws[(size_t)(ref.peer >= 0 ? ref.peer : r) * NWORK + (ref.buf - BUF_W0)].data();  // peer: fused transport
     return base + (size_t)ref.off * esz;
   };
   auto side = [&](int r, const SideT& s) {
@@ -405,7 +405,7 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
               o.base[q].off + ext > t.recv[x.me].off + t.rcnt[x.me])
             return 115;
           if (d0->l2_planes <= 0 && (o.base[q].off != t.recv[x.me].off || ext != t.rcnt[x.me])) return 120;
-          if (o.base[q].buf < BUF_W0 || t.recv[x.me].off + t.rcnt[x.me] > pg[w].need[t.recv[x.me].buf]) return 116;
+          if (o.base[q].buf < BUF_W0 || o.base[q].buf > BUF_W2 || t.recv[x.me].off + t.rcnt[x.me] > pg[w].need[t.recv[x.me].buf]) return 116;
         }
         continue;
       }
@@ -420,7 +420,7 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
         if (t.type != ST_EXCH || t.comm != s.comm || world_rank(*d0, t.comm, w, s.me) != r) return 102;
         if (s.rpeer[q].buf != t.recv[s.me].buf || s.rpeer[q].off != t.recv[s.me].off) return 103;
         if (s.scnt[q] != t.rcnt[s.me]) return 104;
-        if (s.rpeer[q].buf < BUF_W0) return 105;  // peers may only write plan-owned buffers
+        if (s.rpeer[q].buf < BUF_W0 || s.rpeer[q].buf > BUF_W2) return 105;  // peers may only write the mapped plan buffers
         if (s.rpeer[q].off + s.scnt[q] > pg[w].need[s.rpeer[q].buf]) return 106;
       }
     }

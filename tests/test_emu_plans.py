@@ -453,3 +453,37 @@ def test_slab_multi_rank_fused_zy(transport):
         if transport != D.TRANSPORT_NCCL:
             n = C.c_int()
             assert lib.emu_check_p2p(C.byref(d), inverse, D.DEALIAS_NONE, C.byref(n)) == 0
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P])
+@pytest.mark.parametrize("chunks", [2, 4])
+@pytest.mark.parametrize("comm", ["Alltoallw", "AlltoallN"])
+@pytest.mark.parametrize("P,P1", [(4, None), (8, None), (8, 2)])
+def test_pencil_x_pipelined(P, P1, comm, chunks, transport):
+    """Pencil X programs with both exchanges cut into chunks of local x planes and overlapped with the FFT
+    passes of the neighbouring chunks (second stream): same results, clean schedule, peer invariants."""
+    N, prec = (16, 16, 32), "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.pencil.Geometry(N, P, "X", P1, comm)
+    rng = np.random.default_rng(P + chunks)
+    d = _desc(D.PENCIL_X, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"), chunks=chunks, transport=transport)
+    kw = dict(alignment="X", P1=P1, communication=comm, precision=prec)
+    tol = TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.pencil.fftn(u, N, P, **kw), tol)
+    fu = [_rand_c(rng, s, ct) for s in cshape]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.pencil.ifftn(fu, N, P, dealias=name, **kw), tol)
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), oracle.pencil.fftn(up, N, P, dealias="3/2-rule", **kw), tol)
+    lib = emu_util.load()
+    for inverse in (0, 1):
+        for mode in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+            assert lib.emu_check_schedule(C.byref(d), inverse, mode) == 0, (inverse, mode)
+            if transport != D.TRANSPORT_NCCL:
+                n = C.c_int()
+                assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0, (inverse, mode)
+                assert n.value >= 4 and n.value % 2 == 0  # two exchanges per chunk; the chunk count divides the local planes
