@@ -318,6 +318,8 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   const int pN0 = ipad(p, N0), pNp0 = ipad(p, Np0), pN1 = ipad(p, N1), pN2 = ipad(p, N2);
   if (padded && P > 1 && P > N0 / 2)  // slab.py:311,446
     return fail(B200FFT_ERR_ARG, "Number of processors cannot be larger than N[0]//2 for 3/2-rule");
+  if (padded && (long long)pNp0 * P != pN0)  // int(padsize * N0 / P) must tile the padded mesh (real_shape_padded, slab.py:104-107)
+    return fail(B200FFT_ERR_ARG, "3/2-rule: padsize * N[0] / ranks must be an integer");
   const double p3 = p * p * p;
   const long long blk = (long long)pNp0 * Np1 * Nf;
   const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
@@ -732,6 +734,9 @@ inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, 
   const int nk = (int)zoff[zparts];  // Nf, or Nf-1 for the AlltoallN layout
   const double p3 = p * p * p;
   const long long rowsz = (long long)pa * pbq;  // z rows per rank
+  if (padded && ((long long)pa * P1 != pN0 || (long long)pbq * P2 != pN1 || (long long)ipad(p, N1 / P1) * P1 != pN1 ||
+                 (long long)ipad(p, N0 / P2) * P2 != pN0))  // the padded blocks must tile the padded mesh (pencil.py:273-275)
+    return fail(B200FFT_ERR_ARG, "3/2-rule: padsize * N / P1 and padsize * N / P2 must be integers");
   
   const double iscale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
 
@@ -978,7 +983,170 @@ inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, 
     const long long x2l = N0 / P2;                        // final local x extent
     const long long blk = x2l * pbq * kzl;                // comm1 exchange block
     const long long blk1 = rowsz * kzl;                   // comm0 block [pa][pbq][kzl]
-    if (!inverse) {  // pencil.py:730-754 (+ padded :853-881)
+    // Pipelined programs (d.chunks > 1; NCCL and copy-engine transports).  No local axis survives both
+    // exchanges here except kz, so every rank's kz range is cut into CH sub-ranges and all exchange
+    // buffers become sub-range-major -- [c][peer][...][kz in c] -- which keeps every (sub-range, peer)
+    // message contiguous.  forward: z | ea(c) | x(c) | eb(c) | y(c);  inverse: y(c) | eb(c) | x(c) | ea(c) | z:
+    // a three-stage pipeline on both sides of the x pass.  The z pass addresses the P1*CH kz chunks of
+    // its complex side directly (hence P1*CH <= 16).
+    int CH = (d.chunks > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+    while (CH > 1 && (C % CH || (long long)P1 * CH > PMAXP)) --CH;
+    const long long kzc = C / CH;
+    auto kq = [&](int c, int q) { return kzc + ((c == CH - 1) ? zc[q] - C : 0); };   // width of sub-range c on rank q
+    auto zoffc = [&](int c, int q) { return rowsz * ((long long)c * P1 * kzc + (long long)q * kzc); };  // [c][q][rowsz][kq]
+    if (CH > 1) {
+      std::vector<long long> k0((size_t)CH), kcc((size_t)CH);
+      for (int c = 0; c < CH; ++c) {
+        k0[(size_t)c] = c * kzc;
+        kcc[(size_t)c] = kq(c, c0);
+      }
+      auto roff = [&](int c, int q) { return (long long)P1 * rowsz * k0[(size_t)c] + (long long)q * rowsz * kcc[(size_t)c]; };
+      auto off2 = [&](int c, int q) { return (long long)P2 * x2l * pbq * k0[(size_t)c] + (long long)q * x2l * pbq * kcc[(size_t)c]; };
+      // complex side of the z pass: chunk (q, c) of kzc entries (the last one takes the Nyquist entry)
+      auto zside_c = [&](bool recv_layout, int otherbuf) {
+        SideT sd;
+        sd.chunk = (int)kzc;
+        sd.nchunk = P1 * CH;
+        sd.nphys = nk;
+        for (int q = 0; q < P1; ++q)
+          for (int c = 0; c < CH; ++c) {
+            const int pidx = q * CH + c;
+            if (recv_layout) {
+              sd.base[pidx].buf = BUF_W2; sd.base[pidx].off = zoffc(c, q);
+            } else {
+              sd.base[pidx].buf = (q == c0) ? BUF_W1 : otherbuf;
+              sd.base[pidx].off = (q == c0) ? roff(c, c0) : zoffc(c, q);
+            }
+            sd.sb[pidx] = kq(c, q);
+            sd.si[pidx] = 1;
+          }
+        return sd;
+      };
+      if (!inverse) {  // pencil.py:730-754 (+ padded :853-881), pipelined
+        b.use(BUF_W0, rowsz * nk);
+        b.use(BUF_W1, P1 * blk1);
+        b.use(BUF_W3, P2 * blk);
+        b.use(BUF_W2, P2 * blk);
+        b.fixed = 0;
+        Step& z = b.rows(true, rowsz, pN2, nk, BUF_IN, zside_c(false, BUF_W0));
+        const int zev = z.rec_ev = pg.nevents++;
+        std::vector<int> eaev((size_t)CH), ebev((size_t)CH);
+        for (int c = 0; c < CH; ++c) {  // all first exchanges only depend on the z pass
+          b.fixed = 1;
+          Step& xa = b.exch(1, P1, c0);
+          xa.stream = 1;
+          xa.wait_ev = (c == 0) ? zev : -1;
+          eaev[(size_t)c] = xa.rec_ev = pg.nevents++;
+          for (int q = 0; q < P1; ++q) {
+            xa.send[q].buf = BUF_W0; xa.send[q].off = zoffc(c, q); xa.scnt[q] = rowsz * kq(c, q);
+            xa.recv[q].buf = BUF_W1; xa.recv[q].off = roff(c, q); xa.rcnt[q] = rowsz * kcc[(size_t)c];
+            xa.rpeer[q].buf = BUF_W1; xa.rpeer[q].off = (long long)P1 * rowsz * k0[(size_t)c] + (long long)c0 * rowsz * kq(c, q);
+          }
+        }
+        for (int c = 0; c < CH; ++c) {
+          const long long kc_ = kcc[(size_t)c];
+          SideT g;
+          g.chunk = pa; g.nchunk = P1; g.nphys = pN0;
+          for (int q = 0; q < P1; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = roff(c, q); g.sb[q] = 0; g.si[q] = pbq * kc_; }
+          SideT o;
+          o.chunk = (int)x2l; o.nchunk = P2; o.nphys = (int)N0;
+          for (int q = 0; q < P2; ++q) {
+            o.base[q].buf = (q == c1) ? BUF_W2 : BUF_W3; o.base[q].off = off2(c, q); o.sb[q] = 0; o.si[q] = pbq * kc_;
+          }
+          b.fixed = 2;
+          Step& fx = b.strided(pN0, 1, pbq * kc_, 0, g, o, padded ? 1 : 0);
+          fx.wait_ev = eaev[(size_t)c];
+          const int xev = fx.rec_ev = pg.nevents++;
+          b.fixed = 3;
+          Step& xb = b.exch(2, P2, c1);
+          xb.stream = 1;
+          xb.wait_ev = xev;
+          ebev[(size_t)c] = xb.rec_ev = pg.nevents++;
+          for (int q = 0; q < P2; ++q) {
+            xb.send[q].buf = BUF_W3; xb.send[q].off = off2(c, q); xb.scnt[q] = x2l * pbq * kc_;
+            xb.recv[q].buf = BUF_W2; xb.recv[q].off = off2(c, q); xb.rcnt[q] = x2l * pbq * kc_;
+            xb.rpeer[q].buf = BUF_W2; xb.rpeer[q].off = off2(c, c1);
+          }
+        }
+        for (int c = 0; c < CH; ++c) {
+          const long long kc_ = kcc[(size_t)c];
+          SideT g;
+          g.chunk = pbq; g.nchunk = P2; g.nphys = pN1;
+          for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W2; g.base[q].off = off2(c, q); g.sb[q] = pbq * kc_; g.si[q] = kc_; }
+          b.fixed = 4;
+          Step& fy = b.strided(pN1, x2l, kc_, 0, g, nat(BUF_OUT, k0[(size_t)c], N1 * kzl, kzl, (int)N1), padded ? 1 : 0,
+                               padded ? 1.0 / p3 : 1.0);
+          fy.wait_ev = ebev[(size_t)c];
+        }
+      } else {  // pencil.py:483-507 (+ padded :597-629), pipelined
+        b.use(BUF_W0, P2 * blk);
+        b.use(BUF_W1, P2 * blk);
+        b.use(BUF_W3, P1 * blk1);
+        b.use(BUF_W2, rowsz * nk);
+        std::vector<int> ebev((size_t)CH);
+        int last_ev = -1;
+        for (int c = 0; c < CH; ++c) {
+          const long long kc_ = kcc[(size_t)c];
+          SideT o;
+          o.chunk = pbq; o.nchunk = P2; o.nphys = pN1;
+          for (int q = 0; q < P2; ++q) {
+            o.base[q].buf = (q == c1) ? BUF_W1 : BUF_W0; o.base[q].off = off2(c, q); o.sb[q] = pbq * kc_; o.si[q] = kc_;
+          }
+          b.fixed = 0;
+          Step& sy = b.strided(pN1, x2l, kc_, 1, nat(BUF_IN, k0[(size_t)c], N1 * kzl, kzl, (int)N1), o);
+          if (masked) {
+            sy.mask.on = 1;
+            sy.mask.jdiv = 0x3fffffff;
+            band(N0, false, sy.mask.b_lo, sy.mask.b_hi);
+            sy.mask.b_off = (int)(c1 * x2l);
+            band(N1, false, sy.mask.i_lo, sy.mask.i_hi);
+            band(N2, true, sy.mask.jr_lo, sy.mask.jr_hi);
+            sy.mask.jr_off = (int)(c0 * C + k0[(size_t)c]);
+          }
+          const int yev = sy.rec_ev = pg.nevents++;
+          b.fixed = 1;
+          Step& xb = b.exch(2, P2, c1);
+          xb.stream = 1;
+          xb.wait_ev = yev;
+          ebev[(size_t)c] = xb.rec_ev = pg.nevents++;
+          for (int q = 0; q < P2; ++q) {
+            xb.send[q].buf = BUF_W0; xb.send[q].off = off2(c, q); xb.scnt[q] = x2l * pbq * kc_;
+            xb.recv[q].buf = BUF_W1; xb.recv[q].off = off2(c, q); xb.rcnt[q] = x2l * pbq * kc_;
+            xb.rpeer[q].buf = BUF_W1; xb.rpeer[q].off = off2(c, c1);
+          }
+        }
+        for (int c = 0; c < CH; ++c) {
+          const long long kc_ = kcc[(size_t)c];
+          SideT g;
+          g.chunk = (int)x2l; g.nchunk = P2; g.nphys = (int)N0;
+          for (int q = 0; q < P2; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = off2(c, q); g.sb[q] = 0; g.si[q] = pbq * kc_; }
+          SideT o2;
+          o2.chunk = pa; o2.nchunk = P1; o2.nphys = pN0;
+          for (int q = 0; q < P1; ++q) {
+            o2.base[q].buf = (q == c0) ? BUF_W2 : BUF_W3;
+            o2.base[q].off = (q == c0) ? zoffc(c, c0) : roff(c, q);
+            o2.sb[q] = 0; o2.si[q] = pbq * kc_;
+          }
+          b.fixed = 2;
+          Step& sx = b.strided(pN0, 1, pbq * kc_, 1, g, o2);
+          sx.wait_ev = ebev[(size_t)c];
+          const int xev = sx.rec_ev = pg.nevents++;
+          b.fixed = 3;
+          Step& xa = b.exch(1, P1, c0);
+          xa.stream = 1;
+          xa.wait_ev = xev;
+          last_ev = xa.rec_ev = pg.nevents++;
+          for (int q = 0; q < P1; ++q) {
+            xa.send[q].buf = BUF_W3; xa.send[q].off = roff(c, q); xa.scnt[q] = rowsz * kc_;
+            xa.recv[q].buf = BUF_W2; xa.recv[q].off = zoffc(c, q); xa.rcnt[q] = rowsz * kq(c, q);
+            xa.rpeer[q].buf = BUF_W2; xa.rpeer[q].off = zoffc(c, c0);
+          }
+        }
+        b.fixed = 4;
+        Step& z = b.rows(false, rowsz, pN2, nk, BUF_OUT, zside_c(true, BUF_W2), iscale);
+        z.wait_ev = last_ev;  // exchanges complete in order on the second stream
+      }
+    } else if (!inverse) {  // pencil.py:730-754 (+ padded :853-881)
       b.rows(true, rowsz, pN2, nk, BUF_IN, zside(BUF_W1, zme * blk1, BUF_W0, false));
       b.use(BUF_W0, rowsz * nk);
       b.use(BUF_W1, P1 * blk1);
@@ -1073,6 +1241,7 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
     koff[q + 1] = koff[q] + kcl[q];
   }
   const long long Npf = (P == 1) ? Nf : kcl[me];
+  if (padded && (long long)pNp0 * P != pN0) return fail(B200FFT_ERR_ARG, "3/2-rule: padsize * N[0] / ranks must be an integer");
   const double p2 = p * p;
   const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
   if (!inverse) {

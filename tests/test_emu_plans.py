@@ -459,15 +459,18 @@ def test_slab_multi_rank_fused_zy(transport):
 @pytest.mark.parametrize("chunks", [2, 4])
 @pytest.mark.parametrize("comm", ["Alltoallw", "AlltoallN"])
 @pytest.mark.parametrize("P,P1", [(4, None), (8, None), (8, 2)])
-def test_pencil_x_pipelined(P, P1, comm, chunks, transport):
-    """Pencil X programs with both exchanges cut into chunks of local x planes and overlapped with the FFT
-    passes of the neighbouring chunks (second stream): same results, clean schedule, peer invariants."""
-    N, prec = (16, 16, 32), "double"
+@pytest.mark.parametrize("alignment", ["X", "Y"])
+def test_pencil_pipelined(alignment, P, P1, comm, chunks, transport):
+    """Pencil programs with both exchanges cut into chunks -- local x planes for alignment X, kz sub-ranges
+    with sub-range-major buffers for alignment Y -- and overlapped with the FFT passes of the neighbouring
+    chunks (second stream): same results, clean schedule, peer invariants."""
+    N, prec = (16, 16, 64), "double"
     rt, ct = oracle.common.dtypes(prec)
-    g = oracle.pencil.Geometry(N, P, "X", P1, comm)
+    g = oracle.pencil.Geometry(N, P, alignment, P1, comm)
     rng = np.random.default_rng(P + chunks)
-    d = _desc(D.PENCIL_X, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"), chunks=chunks, transport=transport)
-    kw = dict(alignment="X", P1=P1, communication=comm, precision=prec)
+    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, g.P1, g.P2, int(comm == "AlltoallN"), chunks=chunks,
+              transport=transport)
+    kw = dict(alignment=alignment, P1=P1, communication=comm, precision=prec)
     tol = TOL[prec]
     A = rng.random(N).astype(rt)
     u = [A[g.real_local_slice(r)] for r in range(P)]

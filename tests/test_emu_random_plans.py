@@ -91,19 +91,21 @@ def _pencil_cases(count, seed):
         comm = str(rng.choice(["Alltoall", "Alltoallw", "AlltoallN"]))
         transport = int(rng.choice([D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE]))
         prec = "double" if rng.random() < 0.75 else "single"
-        out.append((N, P1, P2, alignment, comm, transport, prec))
+        chunks = int(rng.choice([0, 0, 2, 3, 4]))
+        out.append((N, P1, P2, alignment, comm, transport, prec, chunks))
     return out
 
 
-@pytest.mark.parametrize("N,P1,P2,alignment,comm,transport,prec", _pencil_cases(30, 77),
+@pytest.mark.parametrize("N,P1,P2,alignment,comm,transport,prec,chunks", _pencil_cases(40, 77),
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
-def test_random_pencil_plan(N, P1, P2, alignment, comm, transport, prec):
+def test_random_pencil_plan(N, P1, P2, alignment, comm, transport, prec, chunks):
     P = P1 * P2
     rt, ct = oracle.common.dtypes(prec)
     g = oracle.pencil.Geometry(N, P, alignment, P1, comm)
     assert (g.P1, g.P2) == (P1, P2)
     rng = np.random.default_rng(sum(N) + P)
-    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, P1, P2, int(comm == "AlltoallN"), transport=transport)
+    d = _desc(D.PENCIL_X if alignment == "X" else D.PENCIL_Y, N, P, prec, P1, P2, int(comm == "AlltoallN"), transport=transport,
+              chunks=chunks)
     kw = dict(alignment=alignment, P1=P1, communication=comm, precision=prec)
     tol = TOL[prec]
     A = rng.random(N).astype(rt)
@@ -112,8 +114,17 @@ def test_random_pencil_plan(N, P1, P2, alignment, comm, transport, prec):
     _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.pencil.fftn(u, N, P, **kw), tol)
     fu = [_rand_c(rng, s, ct) for s in cshape]
     modes = [(D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule")]
-    if all(_supported(3 * n // 2) for n in N):
+    # the padded blocks must tile the padded mesh: 1.5 * N / P1 and 1.5 * N / P2 integral
+    if all(_supported(3 * n // 2) for n in N) and all((3 * n) % (2 * q) == 0 for n in N[:2] for q in (P1, P2)):
         modes.append((D.DEALIAS_3_2, "3/2-rule"))
+    else:
+        lib0 = emu_util.load()
+        if all(_supported(3 * n // 2) for n in N):  # supported lengths, untileable blocks: refused, not overrun
+            ins = [np.zeros(s_, dtype=ct) for s_ in cshape]
+            outs = [np.zeros(g.real_shape_padded(), dtype=rt) for _ in range(P)]
+            ip = (C.c_void_p * P)(*[a.ctypes.data for a in ins])
+            op = (C.c_void_p * P)(*[a.ctypes.data for a in outs])
+            assert lib0.emu_plan_run(C.byref(d), 1, D.DEALIAS_3_2, ip, op) == D.ERR_ARG
     for mode, name in modes:
         shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
         _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.pencil.ifftn(fu, N, P, dealias=name, **kw), tol)
