@@ -27,5 +27,6 @@ done
 run p2p x 0 slab1024_f64   # (restores the plain result file name)
 if [ "$N" -ge 4 ]; then
   for t in nccl p2p store; do run $t x 0 pencilX1024_f64; done
+  for c in 2 4; do run nccl x $c pencilX1024_f64; run p2p x $c pencilX1024_f64; done   # pipelined pencil programs
 fi
 ls -la $O

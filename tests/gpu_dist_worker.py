@@ -31,7 +31,7 @@ def check(name, got, ref, tol, rank):
         raise SystemExit("rank %d: %s: rel L2 %.3e > %.1e (shapes %r %r)" % (rank, name, err, tol, got.shape, ref.shape))
 
 
-def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None, pipeline=None):
+def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None, pipeline=None, chunks=0):
     P, r = comm.Get_size(), comm.Get_rank()
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
@@ -50,12 +50,14 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, tra
         F = m.Pencil_R2C(np.array(N), L3, comm, prec, P1=P1, communication=communication, alignment=alignment)
         if transport:
             F.transport = transport
+        if chunks:
+            F.exchange_chunks = chunks  # pipelined pencil programs
         g = oracle.pencil.Geometry(N, P, alignment, P1, communication)
         cshape = [g.complex_shape(q) for q in range(P)]
         kw = dict(alignment=alignment, P1=P1, communication=communication, precision=prec)
         fwd = lambda u, d=None: oracle.pencil.fftn(u, N, P, dealias=d, **kw)
         inv = lambda f, d=None: oracle.pencil.ifftn(f, N, P, dealias=d, **kw)
-    tag = "%s %s %s %s %s P=%d" % (kind, alignment, communication, transport, prec, P)
+    tag = "%s %s %s %s chunks=%d %s P=%d" % (kind, alignment, communication, transport, chunks, prec, P)
     assert tuple(int(s) for s in F.complex_shape()) == tuple(cshape[r])
     A = rng.random(N).astype(rt)
     u = [np.ascontiguousarray(A[g.real_local_slice(q)]) for q in range(P)]
@@ -207,6 +209,17 @@ def main():
         # one slab transport x pipeline only (tests/test_zz_gpu_transports.py): "store" = fused peer stores;
         # "kz" = three-stage pipeline over kz ranges
         tr, pipe = sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else None)
+        if pipe == "pencil-chunks":  # pipelined pencil programs (x-plane chunks for 'X', kz sub-ranges for 'Y')
+            if P >= 4:
+                for al in "XY":
+                    for cm in ("Alltoallw", "AlltoallN"):
+                        for ch in (2, 4):
+                            run_3d(comm, "pencil", (32, 64, 128), "double", al, None, cm, transport=tr, chunks=ch)
+                run_3d(comm, "pencil", (32, 64, 128), "single", "Y", None, "Alltoall", transport=tr, chunks=2)
+            comm.barrier()
+            dist.destroy_process_group()
+            print("GPU_WORKER_OK", local)
+            return
         for prec in ("double", "single"):
             run_3d(comm, "slab", N, prec, transport=tr, pipeline=pipe)
         run_3d(comm, "slab", (64, 64, 64), "double", transport=tr, pipeline=pipe)

@@ -22,7 +22,8 @@ _PENDING = pytest.mark.skipif(not os.environ.get("B200FFT_EXPERIMENTAL"),
 
 @pytest.mark.parametrize("transport,pipeline", [
     ("nccl", "x"), pytest.param("p2p", "x", marks=_PENDING), pytest.param("store", "x", marks=_PENDING), pytest.param("nccl", "kz", marks=_PENDING),
-    pytest.param("p2p", "kz", marks=_PENDING), pytest.param("store", "kz", marks=_PENDING)])
+    pytest.param("p2p", "kz", marks=_PENDING), pytest.param("store", "kz", marks=_PENDING),
+    pytest.param("nccl", "pencil-chunks", marks=_PENDING), pytest.param("p2p", "pencil-chunks", marks=_PENDING)])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_slab_transport_parity(nproc, transport, pipeline):
     import torch
