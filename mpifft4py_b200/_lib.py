@@ -27,15 +27,8 @@ class B200FFTError(RuntimeError):
     pass
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise B200FFTError(
-            "CUDA library %s is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "or `make -C mpifft4py_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+def declare(L):
+    """Argument / result types of include/b200fft.h on a loaded library."""
     L.b200fft_version.restype = C.c_int
     L.b200fft_last_error.restype = C.c_char_p
     L.b200fft_supported_length.argtypes = [C.c_int]
@@ -64,6 +57,18 @@ def lib():
     L.b200fft_plan_last_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200FFTError(
+            "CUDA library %s is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C mpifft4py_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    declare(L)
     for name in SYMBOLS:
         getattr(L, name)
     _lib = L
