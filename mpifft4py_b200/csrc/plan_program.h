@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -97,7 +98,9 @@ struct Step {
 };
 
 struct Program {
-  std::vector<Step> steps;
+  // a deque: the builders keep references to steps while they append further ones (push_back on a
+  // deque leaves references to existing elements valid; a vector's reallocation does not)
+  std::deque<Step> steps;
   long long need[NBUF] = {0, 0, 0, 0, 0, 0};  // complex elements needed in W0..W3
   int nevents = 0;
   int fork_ev = -1;  // >= 0: recorded on the caller's stream when the program starts and awaited by the
