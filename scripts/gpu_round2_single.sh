@@ -8,6 +8,12 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 # 1. parity first: the default path, then the experimental variants (subprocess, xfail until verified)
 timeout 1200 python -m pytest tests -m gpu -q -rxX > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 tail -25 $O/pytest_gpu.log
+# 1b. compute-sanitizer over small launches of every kernel family and variant (shared-memory races, barrier
+#     misuse, out-of-bounds): the checks the CPU emulator cannot make
+for tool in racecheck synccheck memcheck; do
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python tests/gpu_sanitize_worker.py > $O/sanitize_$tool.log 2>&1
+  echo "compute-sanitizer $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|SANITIZE_WORKER_OK|variant .* ok|Error" $O/sanitize_$tool.log | tail -12
+done
 # 2a. everything below in one process first (one import, one set of arrays): the quick overall picture
 timeout 1500 python scripts/ab_single.py --steps 5 > $O/ab_single.jsonl 2> $O/ab_single.txt; tail -80 $O/ab_single.txt
 # 2. cluster strided pass (variant 20: far launches only), per-row barriers in the row kernels (30),
