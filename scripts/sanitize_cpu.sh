@@ -6,7 +6,7 @@
 set -e
 cd "$(dirname "$0")/.."
 LIB=/tmp/libb200fft_shim_asan.so
-g++ -std=c++17 -O1 -g -fsanitize=address,undefined -shared -fPIC -x c++ -I tests/emu/cuda_shim tests/emu/host_shim.cpp -o $LIB -ldl
+g++ -std=c++17 -O1 -g -fsanitize=address,undefined -shared -fPIC -x c++ -I tests/emu/cuda_shim tests/emu/host_shim.cpp -o $LIB -ldl -pthread
 cat > /tmp/b200fft_asan_driver.py <<PY
 import sys, ctypes
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
@@ -19,6 +19,6 @@ host_shim_util._shim = L
 import pytest
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "-m", "not gpu", "tests/test_emu_plans.py", "tests/test_emu_random_plans.py",
                       "tests/test_emu_schedule.py", "tests/test_fuse_queue.py", "tests/test_passes.py", "tests/test_cluster_pass.py",
-                      "tests/test_c2r_direct.py", "tests/test_c2c.py", "tests/test_host_shim.py"]))
+                      "tests/test_c2r_direct.py", "tests/test_c2c.py", "tests/test_host_shim.py", "tests/test_host_shim_multi.py"]))
 PY
 LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 python -u /tmp/b200fft_asan_driver.py

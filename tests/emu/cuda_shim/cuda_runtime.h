@@ -42,6 +42,7 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
 }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { return e ? cudaSuccess : 1; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "IPC": the ranks of a host-shim test are threads of one process, so a handle is the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorNotSupported; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

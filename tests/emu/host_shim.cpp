@@ -74,4 +74,115 @@ int launch_fused_zy_f32(int H, int NY, const RowParams<float>& pr, const Strided
 }
 }  // namespace b200fft
 
+// ---- stand-ins for libcuda's stream memory operations and for NCCL, reached through the library's own
+// dlopen / dlsym calls (interposed below): the ranks of a test are threads of this process ------------
+#include <dlfcn.h>
+#include <sched.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include <cuda.h>
+#include <nccl.h>
+
+namespace shim {
+// everything executes at the call, so a wait is a blocking poll on the word the peer thread writes;
+// bounded, so that a protocol mistake fails a test instead of hanging it
+static CUresult wait_value32(CUstream, CUdeviceptr addr, cuuint32_t value, unsigned) {
+  const auto t0 = std::chrono::steady_clock::now();
+  while (*reinterpret_cast<volatile cuuint32_t*>(addr) < value) {
+    sched_yield();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) return 999;
+  }
+  return 0;
+}
+static CUresult write_value32(CUstream, CUdeviceptr addr, cuuint32_t value, unsigned) {
+  *reinterpret_cast<volatile cuuint32_t*>(addr) = value;
+  return 0;
+}
+
+struct Comm { std::string id; int nranks, rank; };
+struct Msg { const void* src; size_t bytes; bool taken; };
+static std::mutex mu;
+static std::condition_variable cv;
+static std::map<std::tuple<std::string, int, int>, Msg> box;  // (communicator id, from, to) -> pending send
+static thread_local std::vector<std::tuple<ncclComm_t, int, const void*, size_t>> sends;
+static thread_local std::vector<std::tuple<ncclComm_t, int, void*, size_t>> recvs;
+static int next_id = 0;
+
+static ncclResult_t get_unique_id(ncclUniqueId* id) {
+  std::lock_guard<std::mutex> lk(mu);
+  std::memset(id, 0, sizeof(*id));
+  std::snprintf(id->internal, sizeof(id->internal), "shim-comm-%d", next_id++);
+  return 0;
+}
+static ncclResult_t comm_init_rank(ncclComm_t* c, int nranks, ncclUniqueId id, int rank) {
+  *c = reinterpret_cast<ncclComm_t>(new Comm{std::string(id.internal), nranks, rank});
+  return 0;
+}
+static ncclResult_t comm_destroy(ncclComm_t c) { delete reinterpret_cast<Comm*>(c); return 0; }
+static ncclResult_t group_start() { sends.clear(); recvs.clear(); return 0; }
+static ncclResult_t send(const void* p, size_t n, ncclDataType_t, int peer, ncclComm_t c, shim_stream*) { sends.emplace_back(c, peer, p, n); return 0; }
+static ncclResult_t recv(void* p, size_t n, ncclDataType_t, int peer, ncclComm_t c, shim_stream*) { recvs.emplace_back(c, peer, p, n); return 0; }
+static ncclResult_t group_end() {  // post the sends, take the matching receives, wait until the sends were taken
+  std::unique_lock<std::mutex> lk(mu);
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(20);
+  for (auto& s : sends) {
+    Comm* c = reinterpret_cast<Comm*>(std::get<0>(s));
+    auto key = std::make_tuple(c->id, c->rank, std::get<1>(s));
+    if (!cv.wait_until(lk, deadline, [&] { return box.find(key) == box.end(); })) return 5;  // previous message still pending
+    box[key] = Msg{std::get<2>(s), std::get<3>(s), false};
+  }
+  cv.notify_all();
+  for (auto& r : recvs) {
+    Comm* c = reinterpret_cast<Comm*>(std::get<0>(r));
+    auto key = std::make_tuple(c->id, std::get<1>(r), c->rank);
+    if (!cv.wait_until(lk, deadline, [&] { auto it = box.find(key); return it != box.end() && !it->second.taken; })) return 6;
+    Msg& m = box[key];
+    if (m.bytes != std::get<3>(r)) return 7;  // send / receive counts must agree
+    std::memcpy(std::get<2>(r), m.src, m.bytes);
+    m.taken = true;
+  }
+  cv.notify_all();
+  for (auto& s : sends) {
+    Comm* c = reinterpret_cast<Comm*>(std::get<0>(s));
+    auto key = std::make_tuple(c->id, c->rank, std::get<1>(s));
+    if (!cv.wait_until(lk, deadline, [&] { return box[key].taken; })) return 8;
+    box.erase(key);
+  }
+  cv.notify_all();
+  return 0;
+}
+static const char* error_string(ncclResult_t r) { return r == 0 ? "ok" : "shim NCCL: unmatched or timed-out send/recv"; }
+
+static int nccl_handle, cuda_handle;
+static void* open(const char* name, int) {
+  if (std::strstr(name, "libnccl")) return &nccl_handle;
+  if (std::strstr(name, "libcuda")) return &cuda_handle;
+  return nullptr;
+}
+static void* sym(void* h, const char* name) {
+  const std::string n(name);
+  if (h == &cuda_handle) {
+    if (n == "cuStreamWaitValue32_v2") return reinterpret_cast<void*>(&wait_value32);
+    if (n == "cuStreamWriteValue32_v2") return reinterpret_cast<void*>(&write_value32);
+    return nullptr;
+  }
+  if (n == "ncclGetUniqueId") return reinterpret_cast<void*>(&get_unique_id);
+  if (n == "ncclCommInitRank") return reinterpret_cast<void*>(&comm_init_rank);
+  if (n == "ncclCommDestroy") return reinterpret_cast<void*>(&comm_destroy);
+  if (n == "ncclGroupStart") return reinterpret_cast<void*>(&group_start);
+  if (n == "ncclGroupEnd") return reinterpret_cast<void*>(&group_end);
+  if (n == "ncclSend") return reinterpret_cast<void*>(&send);
+  if (n == "ncclRecv") return reinterpret_cast<void*>(&recv);
+  if (n == "ncclGetErrorString") return reinterpret_cast<void*>(&error_string);
+  return nullptr;
+}
+}  // namespace shim
+#define dlopen shim::open
+#define dlsym shim::sym
+
 #include "../../mpifft4py_b200/csrc/b200fft.cu"

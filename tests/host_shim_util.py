@@ -29,7 +29,7 @@ def load():
     stale = (not os.path.exists(LIB)) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS)
     if stale:
         subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(HERE, "emu", "cuda_shim"),
-                        SRC, "-o", LIB, "-ldl"], check=True)
+                        SRC, "-o", LIB, "-ldl", "-pthread"], check=True)
     L = ctypes.CDLL(LIB)
     _lib.declare(L)
     for name in _lib.SYMBOLS:
