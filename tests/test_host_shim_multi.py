@@ -199,3 +199,41 @@ def test_line_ranks_as_threads(transport):
             L.b200fft_comm_destroy(c)
 
     R.run(rank)
+
+
+@pytest.mark.parametrize("transport,pipeline", [(D.TRANSPORT_P2P, D.PIPELINE_X), (D.TRANSPORT_STORE, D.PIPELINE_X),
+                                                (D.TRANSPORT_STORE, D.PIPELINE_KZ), (D.TRANSPORT_P2P, D.PIPELINE_KZ)])
+def test_skewed_ranks_many_transforms(transport, pipeline):
+    """30 transforms of mixed kinds per plan with the ranks deliberately out of step (random sleeps): a rank
+    that runs ahead must be held by the credit / sequence flags, never overwrite a buffer a slower peer
+    still reads, and nobody may deadlock (the stand-in waits are bounded)."""
+    import time
+    L = host_shim_util.load()
+    N, P = (16, 16, 32), 4
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(8)
+    A = rng.random(N)
+    u = [np.ascontiguousarray(A[g.real_local_slice(r)]) for r in range(P)]
+    ref = oracle.slab.fftn(u, N, P)
+    fu = [(rng.standard_normal(g.complex_shape()) + 1j * rng.standard_normal(g.complex_shape())) for _ in range(P)]
+    inv = {m: oracle.slab.ifftn(fu, N, P, dealias=n) for m, n in ((D.DEALIAS_NONE, None), (D.DEALIAS_3_2, "3/2-rule"))}
+    order = np.random.default_rng(9).integers(0, 3, size=30)  # the same sequence of calls on every rank
+    R = Ranks(P)
+
+    def rank(r):
+        h, _ = _make_plan(L, R, r, D.SLAB, N, P, transport, pipeline=pipeline, chunks=2)
+        nap = np.random.default_rng(100 + r)
+        for what in order:
+            time.sleep(float(nap.random()) * 0.004 * (r + 1))
+            if what == 0:
+                c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(g.complex_shape(), np.nan, dtype=np.complex128))
+                assert oracle.rel_l2(c, ref[r]) <= TOL
+            else:
+                mode = D.DEALIAS_NONE if what == 1 else D.DEALIAS_3_2
+                shp = g.real_shape_padded() if what == 2 else g.real_shape()
+                got = _exec(L, h, 1, mode, fu[r], np.full(shp, np.nan))
+                assert oracle.rel_l2(got, inv[mode][r]) <= TOL
+        R.bar.wait()
+        assert L.b200fft_plan_destroy(h) == 0
+
+    R.run(rank)
