@@ -237,3 +237,35 @@ def test_skewed_ranks_many_transforms(transport, pipeline):
         assert L.b200fft_plan_destroy(h) == 0
 
     R.run(rank)
+
+
+@pytest.mark.parametrize("transport,pipeline,chunks", [(D.TRANSPORT_NCCL, D.PIPELINE_X, 2), (D.TRANSPORT_P2P, D.PIPELINE_X, 2),
+                                                       (D.TRANSPORT_STORE, D.PIPELINE_X, 0), (D.TRANSPORT_STORE, D.PIPELINE_KZ, 2)])
+def test_c2c_single_precision_ranks_as_threads(transport, pipeline, chunks):
+    """slab.C2C in single precision on 4 ranks: complex rows in the z pass, keep-mode truncations."""
+    L = host_shim_util.load()
+    N, P, prec = (16, 16, 16), 4, "single"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.GeometryC2C(N, P)
+    rng = np.random.default_rng(10)
+    A = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(ct)
+    u = [np.ascontiguousarray(A[g.real_local_slice(r)]) for r in range(P)]
+    ref = oracle.slab.c2c_fftn(u, N, P, precision=prec)
+    padded = oracle.slab.c2c_ifftn(ref, N, P, dealias="3/2-rule", precision=prec)
+    R = Ranks(P)
+
+    def rank(r):
+        d_extra = dict(pipeline=pipeline, chunks=chunks, precision=D.SINGLE)
+        h, comms = _make_plan(L, R, r, D.SLAB_C2C, N, P, transport, **d_extra)
+        for rep in range(2):
+            c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(g.complex_shape(), np.nan, dtype=ct))
+            assert oracle.rel_l2(c, ref[r]) <= 5e-6
+            assert oracle.rel_l2(_exec(L, h, 1, D.DEALIAS_NONE, c, np.full(g.real_shape(), np.nan, dtype=ct)), u[r]) <= 5e-6
+            up = _exec(L, h, 1, D.DEALIAS_3_2, ref[r], np.full(g.real_shape_padded(), np.nan, dtype=ct))
+            assert oracle.rel_l2(up, padded[r]) <= 5e-6
+        R.bar.wait()
+        assert L.b200fft_plan_destroy(h) == 0
+        for c in comms:
+            L.b200fft_comm_destroy(c)
+
+    R.run(rank)
