@@ -1245,6 +1245,11 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   }
   const long long Npf = (P == 1) ? Nf : kcl[me];
   if (padded && (long long)pNp0 * P != pN0) return fail(B200FFT_ERR_ARG, "3/2-rule: padsize * N[0] / ranks must be an integer");
+  // pipelined programs (d.chunks > 1; NCCL and copy-engine transports): the local rows are cut into CH
+  // chunks whose exchange runs on the second stream beside the z pass of the next chunk
+  int CH = (d.chunks > 1 && P > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+  while (CH > 1 && pNp0 % CH) --CH;
+  const long long rc = pNp0 / CH;
   const double p2 = p * p;
   const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
   if (!inverse) {
@@ -1257,6 +1262,39 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         b.use(BUF_W0, (long long)pN0 * Nf);
         b.strided(pN0, 1, Nf, 0, nat(BUF_W0, 0, 0, Nf, pN0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 2, 1.0 / p2);
       }
+    } else if (CH > 1) {  // line.py:193-258, pipelined: z(c) | exchange(c) over chunks of local rows, then the x pass
+      const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
+      b.use(BUF_W0, (long long)pNp0 * Nf);
+      b.use(recvbuf, (long long)pN0 * Npf);
+      int last_ev = -1;
+      for (int c = 0; c < CH; ++c) {
+        const long long r0 = c * rc;
+        SideT o;
+        o.chunk = (int)kc; o.nchunk = P; o.nphys = (int)Nf;
+        for (int q = 0; q < P; ++q) {
+          o.base[q].buf = (q == me) ? recvbuf : BUF_W0;
+          o.base[q].off = ((q == me) ? (long long)me * pNp0 * Npf : (long long)pNp0 * koff[q]) + r0 * kcl[q];
+          o.sb[q] = kcl[q]; o.si[q] = 1;
+        }
+        b.fixed = 0;
+        Step& z = b.rows(true, rc, pN1, (int)Nf, BUF_IN, o);
+        z.real.off = r0 * pN1;
+        const int zev = z.rec_ev = pg.nevents++;
+        b.fixed = 1;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = zev;
+        last_ev = x.rec_ev = pg.nevents++;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = (long long)pNp0 * koff[q] + r0 * kcl[q]; x.scnt[q] = rc * kcl[q];
+          x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf + r0 * Npf; x.rcnt[q] = rc * Npf;
+          x.rpeer[q].buf = recvbuf; x.rpeer[q].off = (long long)me * pNp0 * kcl[q] + r0 * kcl[q];
+        }
+      }
+      b.fixed = 2;
+      Step& fx = b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
+                           padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
+      fx.wait_ev = last_ev;
     } else {  // line.py:193-258
       const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
       SideT o;
@@ -1289,6 +1327,51 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
       }
       b.rows(false, pN0, pN1, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), iscale);
+    } else if (CH > 1) {  // line.py:285-338, pipelined: the x pass, then exchange(c) | z(c) over chunks of local rows
+      const long long blk = (long long)pNp0 * Npf;
+      SideT o;
+      o.chunk = pNp0; o.nchunk = P; o.nphys = pN0;
+      for (int q = 0; q < P; ++q) {
+        o.base[q].buf = (q == me) ? BUF_W1 : BUF_W0;
+        o.base[q].off = (q == me) ? (long long)pNp0 * koff[me] : q * blk;
+        o.sb[q] = 0; o.si[q] = Npf;
+      }
+      b.fixed = 0;
+      Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
+      if (masked) {
+        sx.mask.on = 1;
+        sx.mask.jdiv = 0x3fffffff;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
+        sx.mask.jr_off = (int)(me * kc);
+      }
+      const int xev = sx.rec_ev = pg.nevents++;
+      b.use(BUF_W0, P * blk);
+      b.use(BUF_W1, (long long)pNp0 * Nf);
+      std::vector<int> eev((size_t)CH);
+      for (int c = 0; c < CH; ++c) {
+        const long long r0 = c * rc;
+        b.fixed = 1;
+        Step& x = b.exch(0, P, me);
+        x.stream = 1;
+        x.wait_ev = (c == 0) ? xev : -1;
+        eev[(size_t)c] = x.rec_ev = pg.nevents++;
+        for (int q = 0; q < P; ++q) {
+          x.send[q].buf = BUF_W0; x.send[q].off = q * blk + r0 * Npf; x.scnt[q] = rc * Npf;
+          x.recv[q].buf = BUF_W1; x.recv[q].off = (long long)pNp0 * koff[q] + r0 * kcl[q]; x.rcnt[q] = rc * kcl[q];
+          x.rpeer[q].buf = BUF_W1; x.rpeer[q].off = (long long)pNp0 * koff[me] + r0 * Npf;
+        }
+      }
+      for (int c = 0; c < CH; ++c) {
+        const long long r0 = c * rc;
+        SideT g;
+        g.chunk = (int)kc; g.nchunk = P; g.nphys = (int)Nf;
+        for (int q = 0; q < P; ++q) { g.base[q].buf = BUF_W1; g.base[q].off = (long long)pNp0 * koff[q] + r0 * kcl[q]; g.sb[q] = kcl[q]; g.si[q] = 1; }
+        b.fixed = 2;
+        Step& z = b.rows(false, rc, pN1, (int)Nf, BUF_OUT, g, iscale);
+        z.real.off = r0 * pN1;
+        z.wait_ev = eev[(size_t)c];
+      }
     } else {  // line.py:285-338
       const long long blk = (long long)pNp0 * Npf;
       SideT o;

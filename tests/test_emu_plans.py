@@ -490,3 +490,34 @@ def test_pencil_pipelined(alignment, P, P1, comm, chunks, transport):
                 n = C.c_int()
                 assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0, (inverse, mode)
                 assert n.value >= 4 and n.value % 2 == 0  # two exchanges per chunk; the chunk count divides the local planes
+
+
+@pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P])
+@pytest.mark.parametrize("chunks", [2, 4])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_line_pipelined(P, chunks, transport):
+    """line programs with the exchange cut into chunks of local rows and overlapped with the z pass."""
+    N, prec = (64, 32), "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.line.Geometry(N, P)
+    rng = np.random.default_rng(P * chunks)
+    d = _desc(D.LINE, N, P, prec, chunks=chunks, transport=transport)
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.line.fft2(u, N, P, precision=prec), TOL[prec])
+    fu = [_rand_c(rng, s_, ct) for s_ in cshape]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_3_2, "3/2-rule"), (D.DEALIAS_2_3, "2/3-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp] * P, rt), oracle.line.ifft2(fu, N, P, dealias=name, precision=prec), TOL[prec])
+    up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, cshape, ct), oracle.line.fft2(up, N, P, dealias="3/2-rule", precision=prec, exact=True),
+           TOL[prec])
+    lib = emu_util.load()
+    for inverse in (0, 1):
+        for mode in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+            assert lib.emu_check_schedule(C.byref(d), inverse, mode) == 0
+            if transport != D.TRANSPORT_NCCL:
+                n = C.c_int()
+                assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0
+                assert n.value >= 2

@@ -177,8 +177,9 @@ def test_pencil_ranks_as_threads(kind, P, P1, P2, drop, transport, chunks):
     R.run(rank)
 
 
+@pytest.mark.parametrize("chunks", [0, 2])
 @pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE])
-def test_line_ranks_as_threads(transport):
+def test_line_ranks_as_threads(transport, chunks):
     L = host_shim_util.load()
     N, P = (32, 64), 4
     g = oracle.line.Geometry(N, P)
@@ -188,7 +189,7 @@ def test_line_ranks_as_threads(transport):
     R = Ranks(P)
 
     def rank(r):
-        h, comms = _make_plan(L, R, r, D.LINE, N, P, transport)
+        h, comms = _make_plan(L, R, r, D.LINE, N, P, transport, chunks=chunks)
         for rep in range(3):
             c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(g.complex_shape(r), np.nan, dtype=np.complex128))
             assert oracle.rel_l2(c, ref[r]) <= TOL
