@@ -411,6 +411,15 @@ def run_ours(args):
                 "passes": passes,
                 "sum_fft_ms": round(sum(p["ms"] for p in ffts), 4),
                 "sum_exchange_ms": round(sum(p["ms"] for p in passes if p["type"] == "exchange"), 4)}
+    # whole-step roofline: time the algorithmic bytes need at the HBM figure plus the
+    # exchanged bytes at the link figure, serial and fully overlapped, against the measured step
+    t_hbm = sum(p["bytes"] for p in ffts) / (hbm_peak * 1e9) * 1e3
+    t_link = sum(p["bytes"] for p in passes if p["type"] == "exchange") / 770e9 * 1e3
+    roofline["step_model"] = {"hbm_ms": round(t_hbm, 4), "link_ms": round(t_link, 4), "serial_ms": round(t_hbm + t_link, 4),
+                              "overlapped_ms": round(max(t_hbm, t_link), 4),
+                              "frac_of_serial": round((t_hbm + t_link) / ms_per_step, 4),
+                              "frac_of_overlapped": round(max(t_hbm, t_link) / ms_per_step, 4),
+                              "link_peak_GBps_per_direction": 770.0}
     xs = [p for p in passes if p["type"] == "exchange" and p["ms"] > 0]
     if xs:
         roofline["nvlink"] = {"achieved_GBps_per_direction": round(sum(p["bytes"] for p in xs) / sum(p["ms"] for p in xs) / 1e6, 1),
