@@ -76,6 +76,11 @@ typedef struct {
   int chunk;
   int nchunk;
   int nphys; /* physical extent along the FFT axis; < n means zero-pad (load) / truncate (store) */
+  /* optional blocking of the contiguous index j (strided passes): jc > 0 places column j at
+   * (j / jc) * sj + (j % jc) instead of j -- a kz-blocked intermediate array [block][...][jc] whose rows
+   * along the transformed axis are closer together than in the natural layout.  0 = plain. */
+  int jc;
+  long long sj;
 } b200fft_side_t;
 
 /* 2/3-rule mask folded into a load (dealias_filter maths.pyx:9-19; get_dealias_filter
@@ -185,6 +190,9 @@ typedef struct {
                       inverse z pass the y pass's -- still in the 126 MB L2: the intermediate
                       (rfft2 / irfft2 of slab.py:366-370,247-268) then costs no HBM round trip.
                       0 = one launch per pass */
+  int kz_block;    /* single-rank slab plans: > 0 keeps the array between the passes kz-blocked,
+                      [kz block of this many entries][x][y][.], so that the x pass has only one far-strided
+                      side (the caller's array) and the y pass none; at most 16 blocks; 0 = natural layout */
   int l2_mode;     /* how the groups of an L2-blocked single-rank plan are issued: 0 / 1 = launches on one
                       stream; 2 = the two passes of a group on two streams, so that the next group's first
                       pass overlaps this group's second (at most two groups in flight); 3 = ONE persistent

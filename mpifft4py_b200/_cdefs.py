@@ -13,7 +13,7 @@ ERR_ARG, ERR_RANKS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = 1, 2, 3, 4,
 
 class Side(C.Structure):
     _fields_ = [("base", C.c_void_p * MAXP), ("sb", C.c_longlong * MAXP), ("si", C.c_longlong * MAXP),
-                ("chunk", C.c_int), ("nchunk", C.c_int), ("nphys", C.c_int)]
+                ("chunk", C.c_int), ("nchunk", C.c_int), ("nphys", C.c_int), ("jc", C.c_int), ("sj", C.c_longlong)]
 
 
 class Mask(C.Structure):
@@ -42,7 +42,7 @@ class PlanDesc(C.Structure):
                 ("nranks", C.c_int), ("rank", C.c_int), ("P1", C.c_int), ("P2", C.c_int),
                 ("padsize", C.c_double), ("drop_nyquist", C.c_int), ("transport", C.c_int),
                 ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int),
-                ("l2_planes", C.c_int), ("l2_mode", C.c_int)]
+                ("l2_planes", C.c_int), ("kz_block", C.c_int), ("l2_mode", C.c_int)]
 
 
 def no_mask():

@@ -67,6 +67,8 @@ class Transform(object):
         # that the y pass reads what the z pass just wrote from L2 instead of HBM (0 = whole array)
         d.l2_planes = int(getattr(self, "l2_planes", 0) or os.environ.get("B200FFT_L2_PLANES", "0"))
         d.l2_mode = int(getattr(self, "l2_mode", 0) or os.environ.get("B200FFT_L2_MODE", "0"))
+        # single-rank slab plans: kz-blocked intermediate array (only one far-strided side left in the x pass)
+        d.kz_block = int(getattr(self, "kz_block", 0) or os.environ.get("B200FFT_KZ_BLOCK", "0"))
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree

@@ -138,6 +138,7 @@ int exec_fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c,
   if (r.precision != c.precision || !ctl || ppg < 1 || c.B < 1 || r.rows % c.B)
     return fail(B200FFT_ERR_ARG, "fused passes: bad arguments (rows must be a whole number per plane)");
   if (contiguous_rows(c)) return fail(B200FFT_ERR_UNSUPPORTED, "fused passes: the column pass must be strided");
+  if (c.in.jc > 0 || c.out.jc > 0) return fail(B200FFT_ERR_UNSUPPORTED, "fused passes: no kernel for blocked column layouts");
   int rc;
   if (r.precision == B200FFT_DOUBLE) {
     const cx<double>*twr, *twc;
@@ -391,6 +392,8 @@ void fill_side(const b200fft_plan* pl, const SideT& s, b200fft_side_t& o, const 
   o.chunk = s.chunk;
   o.nchunk = s.nchunk;
   o.nphys = s.nphys;
+  o.jc = s.jc;
+  o.sj = s.sj;
 }
 
 int run_exchange(b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz, cudaStream_t st) {

@@ -159,7 +159,12 @@ struct Side {
   int chunk;
   int nchunk;
   int nphys;
+  int jc;        // > 0: column j lives at (j / jc) * sj + (j % jc)  (kz-blocked arrays; strided passes only)
+  long long sj;
 };
+
+// element offset of column j (each thread maps its own column, so a tile may straddle blocks)
+B2_HD long long side_jmap(const Side& sd, long long j) { return sd.jc > 0 ? (j / sd.jc) * sd.sj + (j % sd.jc) : j; }
 
 // 2/3-rule mask folded into a load (maths.pyx:9-19; masks slab.py:191-197, pencil.py:343-349,
 // line.py:131-136).  An element is zeroed when any enabled band contains its index:
@@ -365,7 +370,8 @@ struct StridedCfg {
   static constexpr int MINB = MB > 0 ? MB : (MINB_ < 1 ? 1 : (MINB_ > 3 ? 3 : MINB_));
 };
 
-template <class real, class P, int MB = 0, int RB = 0, bool STREAM_ST = false>
+// JS: the sides may use the blocked column map (Side::jc); compiled for the benchmark lengths only
+template <class real, class P, int MB = 0, int RB = 0, bool STREAM_ST = false, bool JS = false>
 struct StridedK {
   using Cfg = StridedCfg<real, P, MB, RB>;
   using C = cx<real>;
@@ -396,11 +402,11 @@ struct StridedK {
 
   // address of load row i (logical index of the transform input) for column j0; 0 = zero fill:
   // copy_to_padded (slab.py:517-523) and the kx / ky band of the 2/3-rule mask
-  B2_HD static addr_t in_row(const Params& p, long long b, int i, int j0) { return in_row_n<P::N>(p, b, i, j0); }
-  B2_HD static addr_t out_row(const Params& p, long long b, int k, int j0) { return out_row_n<P::N>(p, b, k, j0); }
+  B2_HD static addr_t in_row(const Params& p, long long b, int i, long long j0) { return in_row_n<P::N>(p, b, i, j0); }
+  B2_HD static addr_t out_row(const Params& p, long long b, int k, long long j0) { return out_row_n<P::N>(p, b, k, j0); }
   // (n: length of the whole transform -- the cluster kernel runs half-length plans on each CTA)
   template <int n>
-  B2_HD static addr_t in_row_n(const Params& p, long long b, int i, int j0) {
+  B2_HD static addr_t in_row_n(const Params& p, long long b, int i, long long j0) {
     int ip = i;
     if (p.in.nphys < n) {
       const int h = p.in.nphys / 2;
@@ -418,7 +424,7 @@ struct StridedK {
   // address of store row for output frequency k; 0 = dropped: copy_from_padded (slab.py:529-533).
   // The inverse transform is the forward one with the output index reversed (k -> -k mod n).
   template <int n>
-  B2_HD static addr_t out_row_n(const Params& p, long long b, int k, int j0) {
+  B2_HD static addr_t out_row_n(const Params& p, long long b, int k, long long j0) {
     int kp = p.inverse ? (k == 0 ? 0 : n - k) : k;
     if (p.out.nphys < n) {
       const int h = p.out.nphys / 2;
@@ -441,9 +447,13 @@ struct StridedK {
     const bool live = j0 + c < p.J;
     addr_t* tab = reinterpret_cast<addr_t*>(reinterpret_cast<unsigned char*>(smraw) + Cfg::TILE);
 
+    // row addresses are taken at column jin / jout and every thread adds its own column offset cin / cout;
+    // with blocked column layouts (JS) the rows are taken at column 0 and each column is mapped by itself
+    const long long jin = JS ? 0 : j0, jout = JS ? 0 : j0;
+    const long long cin = JS ? side_jmap(p.in, (long long)j0 + c) : c, cout = JS ? side_jmap(p.out, (long long)j0 + c) : c;
     if constexpr (s == 0) {  // load-row address table
       if constexpr (Cfg::TAB)
-        for (int i = tid; i < n; i += Cfg::NT) tab[i] = in_row(p, b, i, j0);
+        for (int i = tid; i < n; i += Cfg::NT) tab[i] = in_row(p, b, i, jin);
     } else if constexpr (s == 1) {  // whole tile global -> shared, asynchronously
       bool colzero = !live;
       if (p.mask.on && live) {
@@ -459,13 +469,13 @@ struct StridedK {
       for (int i = t; i < n; i += Cfg::TC) {
         addr_t a;
         if constexpr (Cfg::TAB) a = tab[i];
-        else a = in_row(p, b, i, j0);
+        else a = in_row(p, b, i, jin);
         const bool ok = (a != 0) && !colzero;
-        async_copy<CB>(sm + swz<M0, Cfg::SW>(i) * T, ok ? a + (addr_t)c * CB : fallback, ok);
+        async_copy<CB>(sm + swz<M0, Cfg::SW>(i) * T, ok ? a + (addr_t)(cin * CB) : fallback, ok);
       }
     } else if constexpr (s == 2) {  // store-row address table (overlaps the loads in flight)
       if constexpr (Cfg::TAB)
-        for (int k = tid; k < n; k += Cfg::NT) tab[k] = out_row(p, b, k, j0);
+        for (int k = tid; k < n; k += Cfg::NT) tab[k] = out_row(p, b, k, jout);
       async_copy_wait();
     } else {
       constexpr int st = s - 3;
@@ -475,11 +485,11 @@ struct StridedK {
         if (!live) return;
         addr_t a;
         if constexpr (Cfg::TAB) a = tab[k];
-        else a = out_row(p, b, k, j0);
+        else a = out_row(p, b, k, jout);
         if (a == 0) return;
         if (p.scale != (real)1) v = cscale(v, p.scale);
-        if constexpr (STREAM_ST) store_streaming(reinterpret_cast<C*>(a + (addr_t)c * CB), v);
-        else *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
+        if constexpr (STREAM_ST) store_streaming(reinterpret_cast<C*>(a + (addr_t)(cout * CB)), v);
+        else *reinterpret_cast<C*>(a + (addr_t)(cout * CB)) = v;
       };
       // reversed output index: the slot that survives a "keep -N/2" truncation is the other one
       const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;

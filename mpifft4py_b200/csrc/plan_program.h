@@ -51,6 +51,8 @@ struct SideT {
   long long sb[PMAXP] = {0};
   long long si[PMAXP] = {0};
   int chunk = 1, nchunk = 1, nphys = 1;
+  int jc = 0;        // > 0: blocked column map, column j at (j / jc) * sj + (j % jc)
+  long long sj = 0;
 };
 
 enum StepType { ST_STRIDED, ST_R2C, ST_C2R, ST_EXCH };
@@ -357,6 +359,67 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
     const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn && !fused_zy) ? d.l2_planes : xn;
     for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
   };
+  if (d.kz_block > 0 && P == 1 && !c2c) {
+    // kz-blocked intermediate (single rank): the array between the passes is [kz block][x][y][jc] instead of
+    // [x][y][Nf].  Along x its rows are N1*jc elements apart instead of N1*Nf (tens of KB instead of 8 MB
+    // at 1024^3), so the x pass -- whose other side is the caller's array and cannot move -- has only ONE
+    // far-strided side left; along y they are jc apart.  The row passes address the blocks as chunks of
+    // their complex side (hence at most 16 blocks), the strided passes through Side::jc.
+    const long long jc = d.kz_block;
+    const int nblk = (int)((Nf + jc - 1) / jc);
+    if (nblk > PMAXP) return fail(B200FFT_ERR_ARG, "kz_block: at most %d blocks (kz_block >= %lld here)", PMAXP, (Nf + PMAXP - 1) / PMAXP);
+    auto rows_side = [&](int buf, long long ROWS, long long row0) {  // complex side of a row pass over rows [row0, ...)
+      SideT sd;
+      sd.chunk = (int)jc; sd.nchunk = nblk; sd.nphys = (int)Nf;
+      for (int c = 0; c < nblk; ++c) { sd.base[c].buf = buf; sd.base[c].off = (long long)c * ROWS * jc + row0 * jc; sd.sb[c] = jc; sd.si[c] = 1; }
+      return sd;
+    };
+    auto cols_side = [&](int buf, long long ROWS, long long row0, long long sb_rows, long long si_rows, int nphys) {
+      SideT sd = nat(buf, row0 * jc, sb_rows * jc, si_rows * jc, nphys);
+      sd.jc = (int)jc;
+      sd.sj = ROWS * jc;
+      return sd;
+    };
+    const long long R0 = (long long)pN0 * pN1, R1 = (long long)pN0 * N1;  // rows of the array before / after the y truncation
+    const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+    if (!inverse) {
+      b.use(BUF_W0, (long long)nblk * R0 * jc);
+      if (padded) b.use(BUF_W1, (long long)nblk * R1 * jc);
+      const int ybuf = padded ? BUF_W1 : BUF_W0;
+      zy_groups(0, pN0, [&](long long g0, long long gn) {
+        b.fixed = 0;
+        Step& z = b.rows(true, gn * pN1, pN2, (int)Nf, BUF_IN, rows_side(BUF_W0, R0, g0 * pN1));
+        z.real.off = g0 * pN1 * pN2;
+        b.fixed = 1;
+        b.strided(pN1, gn, Nf, 0, cols_side(BUF_W0, R0, g0 * pN1, pN1, 1, pN1), cols_side(ybuf, R1, g0 * N1, N1, 1, (int)N1), yfold);
+      });
+      b.fixed = 2;
+      b.strided(pN0, N1, Nf, 0, cols_side(ybuf, R1, 0, 1, N1, pN0), nat(BUF_OUT, 0, Nf, N1 * Nf, (int)N0), xfold, padded ? 1.0 / p3 : 1.0);
+      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 0);
+    } else {
+      b.use(BUF_W0, (long long)nblk * R1 * jc);
+      if (padded) b.use(BUF_W1, (long long)nblk * R0 * jc);
+      const int zbuf = padded ? BUF_W1 : BUF_W0;
+      b.fixed = 0;
+      Step& sx = b.strided(pN0, N1, Nf, 1, nat(BUF_IN, 0, Nf, N1 * Nf, (int)N0), cols_side(BUF_W0, R1, 0, 1, N1, pN0));
+      if (masked) {  // batch index = ky, column index = kz
+        sx.mask.on = 1;
+        sx.mask.jdiv = 0x3fffffff;
+        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
+        band(N1, false, sx.mask.b_lo, sx.mask.b_hi);
+        band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+      }
+      zy_groups(0, pN0, [&](long long g0, long long gn) {
+        b.fixed = 1;
+        b.strided(pN1, gn, Nf, 1, cols_side(BUF_W0, R1, g0 * N1, N1, 1, (int)N1), cols_side(zbuf, R0, g0 * pN1, pN1, 1, pN1));
+        b.fixed = 2;
+        Step& z = b.rows(false, gn * pN1, pN2, (int)Nf, BUF_OUT, rows_side(zbuf, R0, g0 * pN1), scale);
+        z.real.off = g0 * pN1 * pN2;
+      });
+      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 1);
+    }
+    return 0;
+  }
   if (!inverse) {
     if (P == 1) {
       if (!padded) {  // slab.py:366-370

@@ -150,6 +150,17 @@ static int strided(const b200fft_strided_desc_t& d) {
     B200FFT_CLUSTER_PLANS(X)
 #undef X
   }
+  if (d.in.jc > 0 || d.out.jc > 0) {  // blocked column layouts: the JS form of the kernel (every length here)
+    switch (d.n) {
+#define X(n, ...) \
+  case n:         \
+    return emulate<StridedK<real, Plan<__VA_ARGS__>, 0, 0, false, true>>(p);
+      B200FFT_PLANS(X)
+#undef X
+      default:
+        return -1;
+    }
+  }
   switch (d.n) {
 #define X(n, ...) \
   case n:         \
@@ -179,7 +190,7 @@ static int rows(const b200fft_rows_desc_t& d) {
 
 template <class real>
 static int fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg) {
-  if (contiguous_rows(c) || c.B < 1 || r.rows % c.B) return -1;
+  if (contiguous_rows(c) || c.B < 1 || r.rows % c.B || c.in.jc > 0 || c.out.jc > 0) return -1;
   auto pr = convert_rows<real>(r, table<real>(r.n), 1, !inverse_order);
   auto pc = convert_strided<real>(c, table<real>(c.n), 1);
 #define X(h, ny, PR, PC)                                                                                  \
@@ -281,7 +292,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
     b200fft_side_t o;
     std::memset(&o, 0, sizeof(o));
     for (int q = 0; q < s.nchunk; ++q) { o.base[q] = resolve(r, s.base[q], csz); o.sb[q] = s.sb[q]; o.si[q] = s.si[q]; }
-    o.chunk = s.chunk; o.nchunk = s.nchunk; o.nphys = s.nphys;
+    o.chunk = s.chunk; o.nchunk = s.nchunk; o.nphys = s.nphys; o.jc = s.jc; o.sj = s.sj;
     return o;
   };
   const size_t nsteps = pg[0].steps.size();
@@ -451,6 +462,14 @@ void side_regions(const SideT& s, long long nb, long long nj, bool write, long l
   for (int q = 0; q < s.nchunk; ++q) {
     if (s.base[q].peer >= 0) continue;
     const long long rows_q = (q == s.nchunk - 1) ? s.nphys - (long long)q * s.chunk : s.chunk;
+    if (s.jc > 0) {  // blocked columns: one interval per block (the blocks of one pass are sj apart)
+      for (long long c = 0; c * s.jc < nj; ++c) {
+        const long long w = (nj - c * s.jc < s.jc) ? nj - c * s.jc : s.jc;
+        const long long lo = s.base[q].off + c * s.sj, ext = (nb - 1) * s.sb[q] + (rows_q - 1) * s.si[q] + w;
+        out.push_back(Region{s.base[q].buf, lo * unit, (lo + ext) * unit, write});
+      }
+      continue;
+    }
     const long long ext = (nb - 1) * s.sb[q] + (rows_q - 1) * s.si[q] + nj;
     out.push_back(Region{s.base[q].buf, s.base[q].off * unit, (s.base[q].off + ext) * unit, write});
   }

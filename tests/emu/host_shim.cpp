@@ -10,6 +10,17 @@
 namespace b200fft {
 template <class real>
 static int h_strided(int n, const StridedParams<real>& p) {
+  if (p.in.jc > 0 || p.out.jc > 0) {
+    switch (n) {
+#define X(nn, ...) \
+  case nn:         \
+    return emulate<StridedK<real, Plan<__VA_ARGS__>, 0, 0, false, true>>(p);
+      B200FFT_PLANS(X)
+#undef X
+      default:
+        return -1;
+    }
+  }
   switch (n) {
 #define X(nn, ...) \
   case nn:         \

@@ -15,7 +15,7 @@ from mpifft4py_b200 import _cdefs as D
 TOL = {"double": 5e-14, "single": 5e-6}
 
 
-def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0, l2_planes=0):
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0, l2_planes=0, kz_block=0, l2_mode=0):
     d = D.PlanDesc()
     d.kind = kind
     d.precision = D.DOUBLE if prec == "double" else D.SINGLE
@@ -30,6 +30,8 @@ def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=
     d.chunks = chunks
     d.pipeline = pipeline
     d.l2_planes = l2_planes
+    d.kz_block = kz_block
+    d.l2_mode = l2_mode
     return d
 
 
@@ -521,3 +523,41 @@ def test_line_pipelined(P, chunks, transport):
                 n = C.c_int()
                 assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0
                 assert n.value >= 2
+
+
+@pytest.mark.parametrize("l2", [(0, 0), (2, 1), (3, 2), (2, 3)])
+@pytest.mark.parametrize("kz_block,N", [(16, (8, 16, 64)), (8, (16, 8, 32)), (48, (4, 8, 128))])
+@pytest.mark.parametrize("prec", ["double", "single"])
+def test_slab_single_rank_kz_blocked_intermediate(prec, kz_block, N, l2):
+    """kz_block: the array between the passes is [kz block][x][y][jc]; row passes address the blocks as
+    chunks, strided passes through Side::jc; every dealias mode, with and without L2 grouping (mode 3 has
+    no fused kernel for blocked layouts and must fall back to two launches)."""
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, 1)
+    rng = np.random.default_rng(kz_block + N[0])
+    d = _desc(D.SLAB, N, 1, prec, kz_block=kz_block, l2_planes=l2[0], l2_mode=l2[1])
+    u = [rng.random(g.real_shape()).astype(rt)]
+    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)
+    _check(c, oracle.slab.fftn(u, N, 1, precision=prec), TOL[prec])
+    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()], rt), u, TOL[prec])
+    fu = [_rand_c(rng, g.complex_shape(), ct)]
+    for mode, name in ((D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        _check(run_plan(d, 1, mode, fu, [shp], rt), oracle.slab.ifftn(fu, N, 1, dealias=name, precision=prec), TOL[prec])
+    up = [rng.random(g.real_shape_padded()).astype(rt)]
+    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct), oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec),
+           TOL[prec])
+    lib = emu_util.load()
+    for inverse in (0, 1):
+        for mode in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
+            assert lib.emu_check_schedule(C.byref(d), inverse, mode) == 0
+
+
+def test_kz_block_needs_at_most_16_blocks():
+    d = _desc(D.SLAB, (8, 8, 1024), 1, "double", kz_block=16)  # 513 entries in blocks of 16: 33 blocks
+    lib = emu_util.load()
+    A = np.zeros((8, 8, 1024))
+    out = np.zeros((8, 8, 513), dtype=np.complex128)
+    ip = (C.c_void_p * 1)(A.ctypes.data)
+    op = (C.c_void_p * 1)(out.ctypes.data)
+    assert lib.emu_plan_run(C.byref(d), 0, D.DEALIAS_NONE, ip, op) == D.ERR_ARG

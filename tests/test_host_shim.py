@@ -136,3 +136,22 @@ def test_c2c_and_line_plans_and_error_codes():
     assert L.b200fft_exec_forward(h, C.c_void_p(A.ctypes.data), None, 0, None) == D.ERR_ARG
     assert L.b200fft_exec_forward(h, C.c_void_p(A.ctypes.data), C.c_void_p(A.ctypes.data), 9, None) == D.ERR_ARG
     L.b200fft_plan_destroy(h)
+
+
+@pytest.mark.parametrize("l2", [(0, 0), (2, 2)])
+def test_kz_blocked_plan_through_the_c_abi(l2):
+    L = host_shim_util.load()
+    N = (8, 16, 64)
+    rc, h = _plan(L, D.SLAB, N, "double", kz_block=16, l2_planes=l2[0], l2_mode=l2[1])
+    assert rc == 0, L.b200fft_last_error()
+    rng = np.random.default_rng(4)
+    A = rng.random(N)
+    g = oracle.slab.Geometry(N, 1)
+    c = _run(L, h, 0, D.DEALIAS_NONE, A, np.full(g.complex_shape(), np.nan, dtype=np.complex128))
+    assert oracle.rel_l2(c, np.fft.rfftn(A)) <= 5e-14
+    assert oracle.rel_l2(_run(L, h, 1, D.DEALIAS_NONE, c, np.full(N, np.nan)), A) <= 5e-14
+    up = _run(L, h, 1, D.DEALIAS_3_2, c, np.full(g.real_shape_padded(), np.nan))
+    assert oracle.rel_l2(up, oracle.slab.ifftn([c], N, 1, dealias="3/2-rule")[0]) <= 5e-14
+    back = _run(L, h, 0, D.DEALIAS_3_2, up, np.full(g.complex_shape(), np.nan, dtype=np.complex128))
+    assert oracle.rel_l2(back, oracle.slab.fftn([up], N, 1, dealias="3/2-rule")[0]) <= 5e-13
+    L.b200fft_plan_destroy(h)
