@@ -4,6 +4,7 @@ tests/test_zz_gpu_experimental.py, so that a fault cannot take the main test pro
     python tests/gpu_variant_worker.py cluster    # 2-CTA cluster strided pass (variant 21 / 20)
     python tests/gpu_variant_worker.py rowbar     # row kernels: per-row named barriers (30), register-staged C2R (31)
     python tests/gpu_variant_worker.py l2         # L2-blocked z / y passes: grouped launches, two streams, fused kernel
+    python tests/gpu_variant_worker.py kzblock    # kz-blocked intermediate array
 """
 import os
 import sys
@@ -142,6 +143,33 @@ def l2():
                     assert torch.equal(tf, first)
 
 
+def kzblock():
+    """kz-blocked intermediate array (plan option kz_block), alone and with L2 grouping, against the oracle."""
+    import mpifft4py_b200 as m
+    from mpifft4py_b200.comm import SelfComm
+    L3 = np.array([2 * np.pi] * 3)
+    for N, prec in (((16, 512, 512), "double"), ((8, 1024, 1024), "double"), ((16, 512, 512), "single")):
+        rt, ct = oracle.common.dtypes(prec)
+        tol = 1e-12 if prec == "double" else 1e-5
+        A = np.random.default_rng(22).random(N).astype(rt)
+        ref = oracle.slab.fftn([A], N, 1, precision=prec)[0]
+        for jc, planes, mode in ((48, 0, 0), (64, 0, 0), (48, 2, 1), (48, 3, 2)):
+            F = m.Slab_R2C(np.array(N), L3, SelfComm(), prec)
+            F.kz_block, F.l2_planes, F.l2_mode = jc, planes, mode
+            c = F.fftn(A, np.zeros(F.complex_shape(), dtype=ct))
+            assert oracle.rel_l2(c, ref) <= tol, (N, prec, jc, planes, mode)
+            assert oracle.rel_l2(F.ifftn(c, np.zeros(F.real_shape(), dtype=rt)), A) <= tol, (N, prec, jc, planes, mode)
+            got = F.ifftn(ref, np.zeros(F.real_shape(), dtype=rt), dealias="2/3-rule")
+            assert oracle.rel_l2(got, oracle.slab.ifftn([ref], N, 1, dealias="2/3-rule", precision=prec)[0]) <= tol
+        if N[1] == 1024:  # padded lengths 1536 have the blocked-column kernels too
+            F = m.Slab_R2C(np.array(N), L3, SelfComm(), prec)
+            F.kz_block = 48
+            up = F.ifftn(ref, np.zeros(F.real_shape_padded(), dtype=rt), dealias="3/2-rule")
+            assert oracle.rel_l2(up, oracle.slab.ifftn([ref], N, 1, dealias="3/2-rule", precision=prec)[0]) <= tol
+            back = F.fftn(up, np.zeros(F.complex_shape(), dtype=ct), dealias="3/2-rule")
+            assert oracle.rel_l2(back, oracle.slab.fftn([up], N, 1, dealias="3/2-rule", precision=prec)[0]) <= 10 * tol
+
+
 class _P(object):
     """device tensor with the two attributes run_rows reads from a numpy array"""
 
@@ -152,5 +180,5 @@ class _P(object):
 
 if __name__ == "__main__":
     assert torch.cuda.is_available()
-    {"cluster": cluster, "rowbar": rowbar, "l2": l2}[sys.argv[1]]()
+    {"cluster": cluster, "rowbar": rowbar, "l2": l2, "kzblock": kzblock}[sys.argv[1]]()
     print("VARIANT_WORKER_OK")

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # Written after round 1's GPU minutes were spent: checked in the CPU emulator only so far, so a device
 # failure is reported as xfail (and a pass as XPASS) instead of failing the suite of the default path.
 @pytest.mark.xfail(strict=False, reason="opt-in kernel variant; first device run pending")
-@pytest.mark.parametrize("what", ["cluster", "rowbar", "l2"])
+@pytest.mark.parametrize("what", ["cluster", "rowbar", "l2", "kzblock"])
 def test_variant_on_device(what):
     out = subprocess.run([sys.executable, os.path.join(HERE, "gpu_variant_worker.py"), what],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
