@@ -9,7 +9,7 @@ from .slab import C2C as Slab_C2C
 from .pencil import R2C as Pencil_R2C
 from .line import R2C as Line_R2C
 from .mpibase import work_arrays, datatypes, empty, zeros
-from .serialFFT import fft, ifft, rfft, irfft, rfft2, irfft2, rfftn, irfftn, fft2, ifft2, fftn, ifftn
+from .serialFFT import dct, fft, ifft, rfft, irfft, rfft2, irfft2, rfftn, irfftn, fft2, ifft2, fftn, ifftn
 from numpy.fft import fftfreq, rfftfreq
 from . import comm
 from . import device  # device-resident mesh / wavenumber / mask helpers and work arrays

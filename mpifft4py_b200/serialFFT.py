@@ -14,7 +14,7 @@ import numpy as np
 from . import _cdefs as D
 from . import _lib
 
-__all__ = ['fft', 'ifft', 'fft2', 'ifft2', 'fftn', 'ifftn',
+__all__ = ['dct', 'fft', 'ifft', 'fft2', 'ifft2', 'fftn', 'ifftn',
            'rfft', 'irfft', 'rfft2', 'irfft2', 'rfftn', 'irfftn']
 
 
@@ -190,3 +190,50 @@ def rfftn(a, b=None, axes=(0, 1, 2), overwrite_input=False, threads=1, planner_e
 
 def irfftn(a, b=None, axes=(0, 1, 2), overwrite_input=False, threads=1, planner_effort=None, **kw):
     return _finish(_irn(a, tuple(axes)), a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# dct (serialFFT/pyfftw_fft.py:205-244, numpy_fft.py:11-22): types 2 and 3 with scipy.fftpack's
+# unnormalised convention, through ONE complex FFT of the engine along `axis` (Makhoul's reordering);
+# complex input is transformed part by part like upstream (real and imaginary parts share the FFT).
+# Not on the R2C hot path (no caller in slab / pencil / line); provided because the function table of
+# the reference's serialFFT module has it.
+# ------------------------------------------------------------------------------------------------
+def _dct_core(x, type, axis, fft_inplace):
+    """``x``: complex tensor (device of the FFT); ``fft_inplace(t, axis, inverse)``: unnormalised forward /
+    1/n-normalised inverse complex FFT in place.  Returns the complex result (imaginary part = DCT of the
+    imaginary part of ``x``)."""
+    torch = _torch()
+    x = x.movedim(axis, -1)
+    N = x.shape[-1]
+    k = torch.arange(N, device=x.device, dtype=x.real.dtype)
+    ang = torch.pi * k / (2 * N)
+    if type == 2:
+        v = torch.cat([x[..., 0::2], x[..., 1::2].flip(-1)], dim=-1).contiguous()
+        Z = fft_inplace(v, v.dim() - 1, False)
+        Zr = torch.roll(Z.flip(-1), 1, -1).conj()            # conj Z[(N - k) % N]
+        e = torch.complex(torch.cos(ang), -torch.sin(ang))   # exp(-i pi k / 2N)
+        yr = 2 * ((Z + Zr) * 0.5 * e).real                   # FFT of the real part of v, rotated
+        yi = 2 * ((Z - Zr) * (-0.5j) * e).real               # ... of the imaginary part
+        y = torch.complex(yr, yi)
+    elif type == 3:
+        xr = torch.cat([torch.zeros_like(x[..., :1]), x[..., 1:].flip(-1)], dim=-1)   # x[N - k], x[N] := 0
+        e = torch.complex(torch.cos(ang), torch.sin(ang))    # exp(+i pi k / 2N)
+        W = ((x - 1j * xr) * e).contiguous()
+        w = fft_inplace(W, W.dim() - 1, True) * N            # unnormalised inverse
+        y = torch.empty_like(w)
+        y[..., 0::2] = w[..., :(N + 1) // 2]
+        y[..., 1::2] = w.flip(-1)[..., :N // 2]
+    else:
+        raise NotImplementedError("dct type %r: types 2 and 3 are implemented" % (type,))
+    return y.movedim(-1, axis)
+
+
+def dct(a, b, type=2, axis=0, overwrite_input=False, threads=1, planner_effort=None, **kw):
+    ct = _cdt(a)
+    is_complex = (a.is_complex() if _is_tensor(a) else np.iscomplexobj(a))
+    x = _to_device(a, ct)
+    if _is_tensor(a) and x.data_ptr() == a.data_ptr():
+        x = x.clone()
+    y = _dct_core(x, type, axis % x.dim(), _c2c_axis)
+    return _finish(y if is_complex else y.real.contiguous(), a, b)
