@@ -354,12 +354,14 @@ def test_rows_c2c_pad_truncate_fold(be, N):
 
 
 @pytest.mark.parametrize("n,prec", [(16, "d"), (96, "d"), (1024, "d"), (1024, "s"), (1536, "d"), (512, "s")])
-def test_blocked_column_layout(be, n, prec):
+def test_blocked_column_layout(be, n, prec, request):
     """Side::jc -- a kz-blocked array [block][b][n][jc] on either side of a strided pass: natural -> blocked on
     the store side, blocked -> natural on the load side, and blocked in place.  (The device library compiles
     this form for n = 512, 1024, 1536; the emulator for every length.)"""
     if be.name == "gpu" and n not in (512, 1024, 1536):
         pytest.skip("blocked column layouts are compiled for the benchmark lengths on the device")
+    if be.name == "gpu":  # written after round 1's GPU minutes were spent: emulator-checked only so far
+        request.applymarker(pytest.mark.xfail(strict=False, reason="opt-in kernel form; first device run pending"))
     ct = np.complex128 if prec == "d" else np.complex64
     tol = 2e-15 * np.log2(n) if prec == "d" else 6e-7 * np.log2(n)
     rng = np.random.default_rng(n)
