@@ -1,0 +1,33 @@
+"""The ctypes mirrors of include/b200fft.h (mpifft4py_b200/_cdefs.py) against the C compiler's view of the
+structs: total size and the offset of every field.  A field added on one side only would shift everything
+behind it silently."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+from mpifft4py_b200 import _cdefs as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PAIRS = [("b200fft_side_t", D.Side, {}), ("b200fft_mask_t", D.Mask, {}),
+         ("b200fft_strided_desc_t", D.StridedDesc, {"inp": "in"}), ("b200fft_rows_desc_t", D.RowsDesc, {}),
+         ("b200fft_plan_desc_t", D.PlanDesc, {})]
+
+
+def test_struct_layouts_match_the_header():
+    lines = ['#include <cstdio>', '#include <cstddef>', '#include "include/b200fft.h"', 'int main() {']
+    expected = []
+    for cname, ct, rename in PAIRS:
+        lines.append('  std::printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        expected.append("%s %d" % (cname, C.sizeof(ct)))
+        for fname, _ in ct._fields_:
+            cf = rename.get(fname, fname)
+            lines.append('  std::printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, cf, cname, cf))
+            expected.append("%s.%s %d" % (cname, cf, getattr(ct, fname).offset))
+    lines += ['  return 0;', '}']
+    with tempfile.TemporaryDirectory() as tmp:
+        src, exe = os.path.join(tmp, "layout.cpp"), os.path.join(tmp, "layout")
+        open(src, "w").write("\n".join(lines))
+        subprocess.run(["g++", "-I", ROOT, src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, stdout=subprocess.PIPE).stdout.decode().split("\n")
+    assert [ln for ln in out if ln] == expected
