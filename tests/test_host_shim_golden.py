@@ -24,7 +24,7 @@ KIND = {("slab", None): D.SLAB, ("pencil", "X"): D.PENCIL_X, ("pencil", "Y"): D.
 @pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE])
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
 def test_reference_golden_through_the_c_abi(path, transport):
-    z = np.load(path)
+    z = dict(np.load(path))  # (every array read here: NpzFile decompresses lazily and is not thread-safe)
     meta = json.loads(str(z["meta"]))
     P, prec, N = meta["P"], meta["precision"], meta["N"]
     if P == 1 and transport != D.TRANSPORT_NCCL:
@@ -76,7 +76,7 @@ C2C_FILES = sorted(glob.glob(os.path.join(os.path.dirname(GOLDEN), "golden_c2c",
 @pytest.mark.parametrize("path", C2C_FILES, ids=[os.path.basename(f)[:-4] for f in C2C_FILES])
 def test_reference_c2c_golden_through_the_c_abi(path, transport):
     """slab.C2C goldens (outputs of the unmodified reference, slab.py:538-825)."""
-    z = np.load(path)
+    z = dict(np.load(path))
     meta = json.loads(str(z["meta"]))
     P, prec, N = meta["P"], meta["precision"], meta["N"]
     if P == 1 and transport != D.TRANSPORT_NCCL:
