@@ -19,6 +19,6 @@ host_shim_util._shim = L
 import pytest
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "-m", "not gpu", "tests/test_emu_plans.py", "tests/test_emu_random_plans.py",
                       "tests/test_emu_schedule.py", "tests/test_fuse_queue.py", "tests/test_passes.py", "tests/test_cluster_pass.py",
-                      "tests/test_c2r_direct.py", "tests/test_c2c.py", "tests/test_host_shim.py", "tests/test_host_shim_multi.py"]))
+                      "tests/test_c2r_direct.py", "tests/test_c2c.py", "tests/test_host_shim.py", "tests/test_host_shim_multi.py", "tests/test_host_shim_golden.py"]))
 PY
 LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 python -u /tmp/b200fft_asan_driver.py
