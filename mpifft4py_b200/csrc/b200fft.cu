@@ -13,6 +13,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -42,14 +43,16 @@ bool plan_exists(int n) {
       return false;
   }
 }
-static int g_variant = -1;
+static std::atomic<int> g_variant{-1};
 int kernel_variant() {
-  if (g_variant < 0) {
+  int v = g_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = std::getenv("B200FFT_VARIANT");
-    g_variant = e ? std::atoi(e) : 0;
-    if (g_variant < 0) g_variant = 0;
+    v = e ? std::atoi(e) : 0;
+    if (v < 0) v = 0;
+    g_variant.store(v, std::memory_order_relaxed);
   }
-  return g_variant;
+  return v;
 }
 }  // namespace b200fft
 
@@ -680,7 +683,7 @@ int b200fft_supported_length(int n) { return plan_exists(n) ? 1 : 0; }
 
 int b200fft_set_variant(int v) {
   const int old = b200fft::kernel_variant();
-  b200fft::g_variant = v < 0 ? 0 : v;
+  b200fft::g_variant.store(v < 0 ? 0 : v, std::memory_order_relaxed);
   return old;
 }
 

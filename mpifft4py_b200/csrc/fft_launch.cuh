@@ -1,6 +1,10 @@
 // Kernel launcher shared by the per-precision translation units.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+
 #include "fft_kernels.cuh"
 #include "fft_plans.h"
 
@@ -8,26 +12,43 @@ namespace b200fft {
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// One-time set-up of a kernel instantiation on the current device (shared-memory opt-in, resident CTA count
+// of persistent kernels), safe against concurrent first launches and against processes that drive more than
+// one device.  `kernel`: the __global__ function; returns 0 or a cudaError_t; *resident = CTAs the device holds.
+template <class Kernel>
+int configure_kernel(Kernel kernel, int threads, int smem, bool want_resident, std::mutex& mu, std::map<int, unsigned long long>& done,
+                     unsigned long long* resident) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find(dev);
+  if (it == done.end()) {
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    unsigned long long res = 0;
+    if (want_resident) {
+      int sms = 0, occ = 0;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+      if (e != cudaSuccess) return (int)e;
+      res = (unsigned long long)sms * (unsigned long long)(occ < 1 ? 1 : occ);
+    }
+    it = done.emplace(dev, res).first;
+  }
+  *resident = it->second;
+  return 0;
+}
+
 template <class K, bool RB = false>
 int launch_k(const typename K::Params& p, cudaStream_t st) {
   if (K::SMEM > SMEM_LIMIT) return -1;
-  static bool configured = false;
-  static unsigned long long resident = 0;  // CTAs the device holds at once (persistent kernels)
-  if (!configured) {
-    if (K::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(fft_kernel<K, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-      if (e != cudaSuccess) return (int)e;
-    }
-    if (K::PIPE) {
-      int dev = 0, sms = 0, occ = 0;
-      cudaError_t e = cudaGetDevice(&dev);
-      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_kernel<K, RB>, K::NT, K::SMEM);
-      if (e != cudaSuccess) return (int)e;
-      resident = (unsigned long long)sms * (unsigned long long)(occ < 1 ? 1 : occ);
-    }
-    configured = true;
-  }
+  static std::mutex mu;
+  static std::map<int, unsigned long long> done;
+  unsigned long long resident = 0;  // CTAs the device holds at once (persistent kernels)
+  if (int rc = configure_kernel(fft_kernel<K, RB>, K::NT, K::SMEM, K::PIPE, mu, done, &resident)) return rc;
   unsigned long long nblk = K::blocks(p);
   if (nblk == 0) return 0;
   if (nblk > 2147483647ull) return -2;
@@ -41,14 +62,10 @@ int launch_k(const typename K::Params& p, cudaStream_t st) {
 template <class K>
 int launch_cluster_k(const typename K::Params& p, cudaStream_t st) {
   if (K::SMEM > SMEM_LIMIT) return -1;
-  static bool configured = false;
-  if (!configured) {
-    if (K::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(fft_cluster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
-      if (e != cudaSuccess) return (int)e;
-    }
-    configured = true;
-  }
+  static std::mutex mu;
+  static std::map<int, unsigned long long> done;
+  unsigned long long unused = 0;
+  if (int rc = configure_kernel(fft_cluster_kernel<K>, K::NT, K::SMEM, false, mu, done, &unused)) return rc;
   const unsigned long long nblk = K::blocks(p);
   if (nblk == 0) return 0;
   if (nblk > 2147483647ull) return -2;
@@ -73,21 +90,10 @@ int launch_fused_pair(const typename KA::Params& pa, const typename KB::Params& 
   if (groups + 1 > FUSE_CTL_WORDS || c.a.n == 0 || c.b.n == 0 || c.a.upg < c.a.upb || c.b.upg < c.b.upb ||
       (unsigned long long)c.a.n + c.b.n > 2147483647ull)
     return -3;
-  static bool configured = false;
-  static unsigned long long resident = 0;
-  if (!configured) {
-    if (F::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(fused_pair_kernel<KA, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
-      if (e != cudaSuccess) return (int)e;
-    }
-    int dev = 0, sms = 0, occ = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pair_kernel<KA, KB>, F::NT, F::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    resident = (unsigned long long)sms * (unsigned long long)(occ < 1 ? 1 : occ);
-    configured = true;
-  }
+  static std::mutex mu;
+  static std::map<int, unsigned long long> done;
+  unsigned long long resident = 0;
+  if (int rc = configure_kernel(fused_pair_kernel<KA, KB>, F::NT, F::SMEM, true, mu, done, &resident)) return rc;
   cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(unsigned) * (size_t)(1 + groups), st);
   if (e != cudaSuccess) return (int)e;
   c.ctr = ctl;
