@@ -467,7 +467,8 @@ def run_ours(args):
     # opt-in kernels / schedules that were active (environment switches): a line measured
     # with any of them says so
     tuning = {k: os.environ[k] for k in ("B200FFT_VARIANT", "B200FFT_L2_PLANES", "B200FFT_L2_MODE", "B200FFT_TRANSPORT",
-                                          "B200FFT_PIPELINE", "B200FFT_CHUNKS") if os.environ.get(k)}
+                                          "B200FFT_PIPELINE", "B200FFT_CHUNKS", "B200FFT_KZ_BLOCK", "B200FFT_COPY_STREAMS")
+              if os.environ.get(k)}
     if tuning:
         cfg["tuning"] = tuning
     if P > 1:

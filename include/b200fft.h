@@ -193,6 +193,9 @@ typedef struct {
   int kz_block;    /* single-rank slab plans: > 0 keeps the array between the passes kz-blocked,
                       [kz block of this many entries][x][y][.], so that the x pass has only one far-strided
                       side (the caller's array) and the y pass none; at most 16 blocks; 0 = natural layout */
+  int copy_streams;/* copy-engine transport: 1 = one copy stream per peer, so that the per-copy issue latency
+                      (~25 us) of the pushes to different peers overlaps instead of adding up (8 GPUs: 7 peers
+                      per exchange step); 0 = all pushes in order on the communication stream */
   int l2_mode;     /* how the groups of an L2-blocked single-rank plan are issued: 0 / 1 = launches on one
                       stream; 2 = the two passes of a group on two streams, so that the next group's first
                       pass overlaps this group's second (at most two groups in flight); 3 = ONE persistent

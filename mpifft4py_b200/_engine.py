@@ -69,6 +69,8 @@ class Transform(object):
         d.l2_mode = int(getattr(self, "l2_mode", 0) or os.environ.get("B200FFT_L2_MODE", "0"))
         # single-rank slab plans: kz-blocked intermediate array (only one far-strided side left in the x pass)
         d.kz_block = int(getattr(self, "kz_block", 0) or os.environ.get("B200FFT_KZ_BLOCK", "0"))
+        # copy-engine transport: one copy stream per peer (overlaps the per-copy issue latency)
+        d.copy_streams = int(getattr(self, "copy_streams", 0) or os.environ.get("B200FFT_COPY_STREAMS", "0"))
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
         # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
         # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree

@@ -17,6 +17,11 @@ for w in slab1024_f64 slab1024_f64_32; do
   run nccl x 0 $w; run p2p x 0 $w; run store x 1 $w
   for c in 2 4 8; do run nccl kz $c $w; run p2p kz $c $w; run store kz $c $w; done
 done
+# copy-engine transport with one copy stream per peer
+for c in 0 4 8; do
+  B200FFT_COPY_STREAMS=1 run p2p x $c slab1024_f64
+  mv $O/bench_slab1024_f64_p2p_x_c$c.json $O/bench_slab1024_f64_p2p_x_c${c}_cs.json
+done
 # fused z+y kernel through L2 inside each exchange chunk (groups of 4 / 8 planes), best transports
 for g in 4 8; do
   for t in p2p store; do

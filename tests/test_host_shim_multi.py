@@ -270,3 +270,40 @@ def test_c2c_single_precision_ranks_as_threads(transport, pipeline, chunks):
             L.b200fft_comm_destroy(c)
 
     R.run(rank)
+
+
+@pytest.mark.parametrize("kind,P,P1,P2", [(D.SLAB, 4, 1, 1), (D.PENCIL_X, 8, 4, 2), (D.LINE, 4, 1, 1)])
+def test_copy_engine_with_one_stream_per_peer(kind, P, P1, P2):
+    """plan option copy_streams: the pushes of an exchange step are issued on per-peer streams forked from and
+    joined into the communication stream; same results, flags and credits as with one stream."""
+    L = host_shim_util.load()
+    if kind == D.LINE:
+        N = (32, 64)
+        g = oracle.line.Geometry(N, P)
+        fwd = lambda u: oracle.line.fft2(u, N, P)
+        cshape = [g.complex_shape(r) for r in range(P)]
+    elif kind == D.SLAB:
+        N = (16, 16, 32)
+        g = oracle.slab.Geometry(N, P)
+        fwd = lambda u: oracle.slab.fftn(u, N, P)
+        cshape = [g.complex_shape()] * P
+    else:
+        N = (16, 16, 32)
+        g = oracle.pencil.Geometry(N, P, "X", P1, "Alltoallw")
+        fwd = lambda u: oracle.pencil.fftn(u, N, P, alignment="X", P1=P1, communication="Alltoallw")
+        cshape = [g.complex_shape(r) for r in range(P)]
+    A = np.random.default_rng(11).random(N)
+    u = [np.ascontiguousarray(A[g.real_local_slice(r)]) for r in range(P)]
+    ref = fwd(u)
+    R = Ranks(P)
+
+    def rank(r):
+        h, _ = _make_plan(L, R, r, kind, N, P, D.TRANSPORT_P2P, P1=P1, P2=P2, copy_streams=1, chunks=2)
+        for rep in range(3):
+            c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(cshape[r], np.nan, dtype=np.complex128))
+            assert oracle.rel_l2(c, ref[r]) <= TOL
+            assert oracle.rel_l2(_exec(L, h, 1, D.DEALIAS_NONE, c, np.full(g.real_shape(), np.nan)), u[r]) <= TOL
+        R.bar.wait()
+        assert L.b200fft_plan_destroy(h) == 0
+
+    R.run(rank)
