@@ -7,6 +7,10 @@ mkdir -p $O
 B200FFT_EXPERIMENTAL=1 timeout 2400 python -m pytest tests/test_gpu_multi.py tests/test_zz_gpu_transports.py -m gpu -q -rxXs \
     -k "test_multi_gpu_parity[$N] or test_slab_transport_parity[$N-" > $O/pytest.log 2>&1
 tail -25 $O/pytest.log
+# parity of the copy-engine transport with one copy stream per peer (slab, pencil, line)
+B200FFT_COPY_STREAMS=1 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port $((29500 + RANDOM % 500)) tests/gpu_dist_worker.py --transport p2p x > $O/parity_copy_streams.log 2>&1
+echo "copy-streams parity rc=$? ($(grep -c GPU_WORKER_OK $O/parity_copy_streams.log) of $N ranks ok)"
 run() {  # transport pipeline chunks workload
   B200FFT_TRANSPORT=$1 B200FFT_PIPELINE=$2 B200FFT_CHUNKS=$3 timeout 300 python -m torch.distributed.run --nnodes=1 \
       --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) bench.py --gpus $N --steps 10 --warmup 3 \
