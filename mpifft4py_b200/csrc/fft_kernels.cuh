@@ -623,7 +623,8 @@ struct RowParams {
 // takes as many rows as fit a ~32 KB buffer (<= 256 threads).  Row kernels are persistent and
 // double-buffered: while a CTA transforms one group of rows, the asynchronous loads of its next
 // group are in flight, so every resident CTA always has a buffer's worth of HBM reads outstanding.
-template <class real, class P>
+// CAPV > 0 overrides the resident-CTA target that sets the register budget (see MINB_CAP)
+template <class real, class P, int CAPV = 0>
 struct RowCfg {
   static constexpr int CB = (int)sizeof(cx<real>);
   static constexpr int H = P::N;
@@ -660,17 +661,17 @@ struct RowCfg {
   static constexpr int SMEM = PIPE ? 2 * SMEM1 : SMEM1;
   static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
   // register budget: double-precision radix-16 butterflies need ~128 registers, radix-12 ~96
-  static constexpr int MINB_CAP = (P::RMAX >= 16 && CB == 16) ? 2 : (P::RMAX >= 12 ? 3 : 4);
+  static constexpr int MINB_CAP = CAPV > 0 ? CAPV : (P::RMAX >= 16 && CB == 16) ? 2 : (P::RMAX >= 12 ? 3 : 4);
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > MINB_CAP ? MINB_CAP : MINB_);
 };
 
-template <class real, class P, bool STREAM_LD = false>
+template <class real, class P, bool STREAM_LD = false, int CAPV = 0>
 struct R2CK {  // forward: real rows -> complex rows
   static constexpr int GROUP = RowCfg<real, P>::TC;
   // Stage 0 loads its butterfly inputs straight from HBM into registers (coalesced 16-byte loads,
   // all issued before the first use): staging the row through shared memory first, as C2R does,
   // measured 20% slower here because the kernel is bound by LSU wavefronts, not by load latency.
-  using Cfg = RowCfg<real, P>;
+  using Cfg = RowCfg<real, P, CAPV>;
   using C = cx<real>;
   using Params = RowParams<real>;
   static constexpr int NPHASE = P::S + 1;
@@ -745,10 +746,10 @@ struct R2CK {  // forward: real rows -> complex rows
   }
 };
 
-template <class real, class P, bool STREAM_ST = false>
+template <class real, class P, bool STREAM_ST = false, int CAPV = 0>
 struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's scale carries 1/n)
   static constexpr int GROUP = RowCfg<real, P>::TC;
-  using Cfg = RowCfg<real, P>;
+  using Cfg = RowCfg<real, P, CAPV>;
   using C = cx<real>;
   using Params = RowParams<real>;
   static constexpr int NPHASE = P::S + 2;
