@@ -51,7 +51,7 @@ B200FFT_API int b200fft_supported_length(int n);
 /* Tuning switch for A/B measurements (same as the B200FFT_VARIANT environment variable): selects an
  * alternative kernel or radix plan where one is compiled; 0 = the defaults.  Returns the old value.
  * 20: strided passes with rows >= 1 MB apart run on 2-CTA clusters (128-byte rows split over
- * distributed shared memory); 22: also near-stride passes of n >= 2048, with 64-byte rows; 21 / 23: all
+ * distributed shared memory); 22: also near-stride passes of n >= 1536, with 64-byte rows; 21 / 23: all
  * strided passes that have a cluster plan do (128- / 64-byte rows; testing aids); 31: register-staged
  * C2R kernel (loads its spectrum pairs straight into registers, like the R2C kernel, no staging copy);
  * 32: the 3/2-rule row kernels (last radix 12) compiled for four resident CTAs per SM instead of three;
