@@ -32,7 +32,9 @@ for g in (2, 3, 4, 6):
 for g in (2, 3, 4, 6, 8, 12, 16):
     CONFIGS += [("l2_fused_g%d" % g, 0, {"l2_planes": g, "l2_mode": 3})]
 CONFIGS += [("cluster_x+row_barriers(105)", 105, {}), ("cluster_x+c2r_direct(109)", 109, {}), ("rows_4_ctas(32)", 32, {}),
-            ("rows_4_ctas+row_barriers(120)", 120, {})]
+            ("rows_4_ctas+row_barriers(120)", 120, {}),
+            ("cluster_x+long+rows_4_ctas(119)", 119, {}), ("cluster_x+long+rows_4_ctas+row_barriers(123)", 123, {}),
+            ("all_switches(127)", 127, {})]
 CONFIGS += [("kz_block48", 0, {"kz_block": 48}), ("kz_block64", 0, {"kz_block": 64}),
             ("kz_block48+l2_two_streams_g4", 0, {"kz_block": 48, "l2_planes": 4, "l2_mode": 2})]
 for g in (4, 8):
