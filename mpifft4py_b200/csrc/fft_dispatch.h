@@ -26,7 +26,7 @@ bool plan_exists(int n);
 // tuning switch (B200FFT_VARIANT environment variable, b200fft_set_variant): 0 = default kernels
 int kernel_variant();
 // switches that combine: variant = 100 + bits
-enum { VAR_CLUSTER_FAR = 1, VAR_CLUSTER_LONG = 2, VAR_ROW_BARRIERS = 4, VAR_C2R_DIRECT = 8, VAR_ROW_OCC4 = 16 };
+enum { VAR_CLUSTER_FAR = 1, VAR_CLUSTER_LONG = 2, VAR_ROW_BARRIERS = 4, VAR_C2R_DIRECT = 8, VAR_ROW_OCC4 = 16, VAR_R2C_PAIRED = 32 };
 inline bool variant_has(int flag) {
   const int v = kernel_variant();
   return v >= 100 && v < 200 && ((v - 100) & flag) != 0;

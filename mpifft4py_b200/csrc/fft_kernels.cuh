@@ -746,6 +746,97 @@ struct R2CK {  // forward: real rows -> complex rows
   }
 };
 
+// R2C with the split step folded into the last stage ("paired" form, B200FFT_VARIANT=33).  R2CK writes the
+// half-length spectrum F to shared memory after its last stage only to read F[k] and F[H-k] back in the split
+// step.  The last-stage butterfly u holds the frequencies u + c*NB, their mirrors H - (u + c*NB) sit in
+// butterfly NB - u at slot R-1-c: a thread that runs BOTH butterflies has every pair in registers and stores
+// X[k], X[H-k] straight to HBM.  That removes one shared-memory write and one read of the whole row (a third
+// of the shared-memory traffic of an LSU-bound kernel, ncu r01c) and one barrier; the price is 2R values in
+// registers and half the threads idle in the last phase.  Plans with at least two stages.
+template <class real, class P>
+struct R2CPK {
+  static_assert(P::S >= 2, "the paired form needs a last stage that reads shared memory");
+  using Cfg = RowCfg<real, P, (sizeof(real) == 8 ? 3 : 0)>;  // double: 2R = 16..24 complex values live -> three-CTA register budget
+  static constexpr int GROUP = Cfg::TC;
+  using C = cx<real>;
+  using Params = RowParams<real>;
+  static constexpr int NPHASE = P::S;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM1;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = false;
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > Cfg::MINB_CAP ? Cfg::MINB_CAP : MINB_);
+  B2_HD static unsigned long long blocks(const Params& p) { return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC); }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int H = Cfg::H, TC = Cfg::TC;
+    constexpr int M0 = P::template M<0>;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.rows;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
+    if constexpr (s < P::S - 1) {
+      const C* src = reinterpret_cast<const C*>(reinterpret_cast<const real*>(p.rin) + row * p.rpitch);
+      auto in = [&](int i) -> C { return live ? src[i] : C{0, 0}; };
+      auto out = [](int, C) {};
+      fft_stage<real, P, s, TC, 1, Cfg::SW, (s == 0), false>(t, sm, p.tw, 2 * p.tws, in, out, 0);
+    } else {
+      if (!live) return;
+      constexpr int R = P::template R<P::S - 1>;
+      constexpr int NB = H / R;
+      constexpr int ITEMS = NB / 2 + 1;
+      constexpr int ROUNDS = (ITEMS + TC - 1) / TC;
+      const Side& o = p.cside;
+      auto store = [&](int k, C v) {
+        if (k >= p.nk) return;  // z truncation of the 3/2-rule (slab.py:535)
+        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+        C* ptr = reinterpret_cast<C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk);
+        *ptr = (p.scale != (real)1) ? cscale(v, p.scale) : v;
+      };
+      // X[k] = E + W_n^k O, X[H-k] = conj(E - W_n^k O) from a = F[k], b = F[H-k]   (0 < k < H, k != H-k handled by caller)
+      auto split = [&](int k, C a, C bq) {
+        const C e = C{(real)0.5 * (a.x + bq.x), (real)0.5 * (a.y - bq.y)};
+        const C d = C{(real)0.5 * (a.x - bq.x), (real)0.5 * (a.y + bq.y)};
+        const C wo = cmul(p.tw[k * p.tws], mul_mi(d));
+        store(k, cadd(e, wo));
+        if (k != H - k) store(H - k, cconj(csub(e, wo)));
+      };
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int it = t + rr * TC;
+        if (it >= ITEMS) break;
+        const int u1 = it, u2 = (NB - it) % NB;
+        C v1[R], v2[R];
+        const int B1 = P::template pos<0>(u1), B2 = P::template pos<0>(u2);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v1[r] = sm[swz<M0, Cfg::SW>(B1 + r)];
+        Dft<R>::template run<1>(v1);
+        if (u2 != u1) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) v2[r] = sm[swz<M0, Cfg::SW>(B2 + r)];
+          Dft<R>::template run<1>(v2);
+#pragma unroll
+          for (int c = 0; c < R; ++c) split(u1 + c * NB, v1[c], v2[R - 1 - c]);
+        } else if (u1 == 0) {  // frequencies c*NB: mirror (R-c)*NB in the same butterfly; k = 0 carries X[0] and X[H]
+          store(0, C{v1[0].x + v1[0].y, 0});
+          store(H, C{v1[0].x - v1[0].y, 0});
+#pragma unroll
+          for (int c = 1; c <= R / 2; ++c) split(c * NB, v1[c], v1[R - c]);
+        } else {  // u = NB/2: frequencies NB/2 + c*NB, mirror at slot R-1-c of the same butterfly
+#pragma unroll
+          for (int c = 0; c < (R + 1) / 2; ++c) split(u1 + c * NB, v1[c], v1[R - 1 - c]);
+        }
+      }
+    }
+  }
+};
+
 template <class real, class P, bool STREAM_ST = false, int CAPV = 0>
 struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's scale carries 1/n)
   static constexpr int GROUP = RowCfg<real, P>::TC;

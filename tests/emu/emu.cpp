@@ -178,6 +178,9 @@ static int rows(const b200fft_rows_desc_t& d) {
   switch (d.n / 2) {
 #define X(n, ...)                                                     \
   case n:                                                             \
+    if (FWD && g_emu_variant == 33) {                                 \
+      if constexpr (Plan<__VA_ARGS__>::S >= 2) return emulate<R2CPK<real, Plan<__VA_ARGS__>>>(p); \
+    }                                                                 \
     if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);        \
     else if (g_emu_variant == 31) return emulate<C2RDK<real, Plan<__VA_ARGS__>>>(p); \
     else return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);

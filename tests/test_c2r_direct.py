@@ -28,3 +28,27 @@ def test_c2r_direct_zero_pad(be31, N):
 
 def test_c2r_direct_uneven_kz_chunks(be31):
     tp.test_rows_uneven_kz_chunks(be31)
+
+
+@pytest.fixture(scope="module")
+def be33():
+    """variant 33: R2C with the split step folded into a paired last stage (R2CPK)"""
+    lib = emu_util.load()
+    old = lib.emu_set_variant(33)
+    yield tp._Emu()
+    lib.emu_set_variant(old)
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+@pytest.mark.parametrize("h", [2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 256, 384, 512, 768, 1024, 1536, 2048, 8192])
+def test_r2c_paired_all_plans(be33, h, prec):
+    tp.test_rows_r2c_c2r(be33, h, prec)
+
+
+@pytest.mark.parametrize("N", [8, 32, 256, 1024])
+def test_r2c_paired_truncation(be33, N):
+    tp.test_rows_truncate_and_zero_pad(be33, N)
+
+
+def test_r2c_paired_uneven_kz_chunks(be33):
+    tp.test_rows_uneven_kz_chunks(be33)
