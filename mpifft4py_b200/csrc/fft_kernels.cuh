@@ -1002,6 +1002,122 @@ struct C2RDK {
   }
 };
 
+// C2R with the merge step folded into the first stage ("paired" form, B200FFT_VARIANT=34) -- the mirror image
+// of R2CPK.  The first-stage butterfly q reads G[q + r*M]; G[k] needs X[k] and X[H-k], and H - (q + r*M) sits in
+// butterfly M - q at slot R-1-r: a thread that runs BOTH butterflies loads their 2R spectrum entries straight
+// from HBM (coalesced in q), merges the pairs in registers, runs the two butterflies and writes the stage's
+// result to shared memory.  Against C2RK: no staging copy, no separate merge pass (two shared-memory round
+// trips and two barriers less); against C2RDK one more round trip less.  Plans with a first radix <= 8, at
+// least two stages and an even first stride (the 1024- and 1536-point benchmark rows).
+template <class real, class P>
+struct C2RPK {
+  static constexpr int R0 = P::template R<0>;
+  static constexpr int M = P::template M<0>;
+  static_assert(P::S >= 2 && R0 <= 8 && M % 2 == 0, "paired C2R: first radix <= 8, two or more stages, even first stride");
+  using Cfg = RowCfg<real, P, (sizeof(real) == 8 ? 3 : 0)>;
+  static constexpr int GROUP = Cfg::TC;
+  using C = cx<real>;
+  using Params = RowParams<real>;
+  static constexpr int NPHASE = P::S;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM1;
+  static constexpr int SMEM1 = Cfg::SMEM1;
+  static constexpr bool PIPE = false;
+  static constexpr int MINB_ = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > Cfg::MINB_CAP ? Cfg::MINB_CAP : MINB_);
+  B2_HD static unsigned long long blocks(const Params& p) { return (unsigned long long)((p.rows + Cfg::RPC - 1) / Cfg::RPC); }
+  B2_HD static void decode(const Params&, unsigned blk, int& bx, int& by) {
+    bx = (int)blk;
+    by = 0;
+  }
+
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int) {
+    constexpr int H = Cfg::H, TC = Cfg::TC;
+    const int rl = tid / TC, t = tid % TC;
+    const long long row = (long long)bx * Cfg::RPC + rl;
+    const bool live = row < p.rows;
+    C* sm = reinterpret_cast<C*>(smraw) + rl * Cfg::SROW;
+    if constexpr (s == 0) {
+      const Side& o = p.cside;
+      auto load = [&](int k) -> C {  // X[k], 0 in the z zero pad (slab.py:524-525) and for rows past the end
+        if (!live || k >= p.nk) return C{0, 0};
+        const int pc = (o.nchunk > 1) ? chunk_of(k, o.chunk, o.nchunk) : 0;
+        return *(reinterpret_cast<const C*>(o.base[pc]) + row * o.sb[pc] + (k - pc * o.chunk));
+      };
+      // G[k], G[H-k] (stored swapped: inverse by swapping) from a = X[k], b = X[H-k], 0 < k < H
+      auto merge = [&](int k, C a, C bq, C& gk, C& ghk) {
+        const C e = C{a.x + bq.x, a.y - bq.y};
+        const C d = C{a.x - bq.x, a.y + bq.y};
+        const C o2 = cmul(cconj(p.tw[k * p.tws]), d);
+        gk = cswap(cadd(e, mul_pi(o2)));
+        ghk = cswap(cadd(cconj(e), mul_pi(cconj(o2))));
+      };
+      // one first-stage butterfly on G values in registers: DFT, twiddles W_H^(q*c), result to shared memory
+      auto butterfly = [&](int q, C* v) {
+        Dft<R0>::template run<1>(v);
+        C w[R0];
+        twiddle_powers<R0>(w, p.tw, q * 2 * p.tws);  // W_H^q = W_n^(2q)
+        sm[swz<M, Cfg::SW>(q)] = v[0];
+#pragma unroll
+        for (int c = 1; c < R0; ++c) sm[swz<M, Cfg::SW>(q + c * M)] = cmul(v[c], w[c]);
+      };
+      constexpr int ITEMS = M / 2 + 1;
+      constexpr int ROUNDS = (ITEMS + TC - 1) / TC;
+#pragma unroll
+      for (int rr = 0; rr < ROUNDS; ++rr) {
+        const int it = t + rr * TC;
+        if (it >= ITEMS) break;
+        const int q1 = it, q2 = (M - it) % M;
+        C v1[R0], v2[R0];
+#pragma unroll
+        for (int r = 0; r < R0; ++r) v1[r] = load(q1 + r * M);
+        if (q2 != q1) {
+#pragma unroll
+          for (int r = 0; r < R0; ++r) v2[r] = load(q2 + r * M);
+#pragma unroll
+          for (int r = 0; r < R0; ++r) {  // pair (k, H-k) = (q1 + r*M, q2 + (R0-1-r)*M)
+            C gk, ghk;
+            merge(q1 + r * M, v1[r], v2[R0 - 1 - r], gk, ghk);
+            v1[r] = gk;
+            v2[R0 - 1 - r] = ghk;
+          }
+          butterfly(q1, v1);
+          butterfly(q2, v2);
+        } else if (q1 == 0) {  // entries r*M: mirror (R0-r)*M in the same butterfly; k = 0 pairs with X[H]
+          const C xh = load(H);
+          v2[0] = cswap(C{v1[0].x + xh.x, v1[0].x - xh.x});  // imaginary parts of DC / Nyquist ignored (C2R)
+#pragma unroll
+          for (int r = 1; r <= R0 / 2; ++r) {
+            C gk, ghk;
+            merge(r * M, v1[r], v1[R0 - r], gk, ghk);
+            v2[r] = gk;
+            if (r != R0 - r) v2[R0 - r] = ghk;
+          }
+          butterfly(0, v2);
+        } else {  // q = M/2: entries M/2 + r*M, mirror at slot R0-1-r of the same butterfly
+#pragma unroll
+          for (int r = 0; r < (R0 + 1) / 2; ++r) {
+            C gk, ghk;
+            merge(q1 + r * M, v1[r], v1[R0 - 1 - r], gk, ghk);
+            v2[r] = gk;
+            if (r != R0 - 1 - r) v2[R0 - 1 - r] = ghk;
+          }
+          butterfly(q1, v2);
+        }
+      }
+    } else {
+      real* dst = reinterpret_cast<real*>(p.rout) + row * p.rpitch;
+      auto in = [](int) -> C { return C{0, 0}; };
+      auto out = [&](int m, C v) {
+        if (!live) return;
+        *reinterpret_cast<C*>(dst + 2 * (long long)m) = C{v.y * p.scale, v.x * p.scale};
+      };
+      fft_stage<real, P, s, TC, 1, Cfg::SW, false, (s == P::S - 1)>(t, sm, p.tw, 2 * p.tws, in, out, 0);
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // contiguous-row C2C pass (the z pass of slab.C2C, slab.py:538-825): the strided pass's index maps
 // (zero pad on load, truncate / fold on store, reversed output index for the inverse, scale) on

@@ -183,6 +183,11 @@ static int rows(const b200fft_rows_desc_t& d) {
     }                                                                 \
     if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);        \
     else if (g_emu_variant == 31) return emulate<C2RDK<real, Plan<__VA_ARGS__>>>(p); \
+    else if (g_emu_variant == 34) {                                    \
+      using PP = Plan<__VA_ARGS__>;                                    \
+      if constexpr (PP::S >= 2 && PP::template R<0> <= 8 && (PP::template M<0> % 2) == 0) return emulate<C2RPK<real, PP>>(p); \
+      else return emulate<C2RK<real, PP>>(p);                          \
+    }                                                                  \
     else return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);
     B200FFT_ROW_PLANS(X)
 #undef X

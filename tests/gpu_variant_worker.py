@@ -66,7 +66,7 @@ def rowbar():
     """Row-kernel variants: 30 = the rows of a CTA synchronise on their own named barrier (many more rows
     than one wave of persistent CTAs, so that rows really run out of step); 31 = register-staged C2R."""
     be = tp._Gpu()
-    for variant in (30, 31, 32, 33):  # 32: radix-12 row kernels at four resident CTAs; 33: paired R2C
+    for variant in (30, 31, 32, 33, 34):  # 32: radix-12 row kernels at four resident CTAs; 33 / 34: paired R2C / C2R
         _rows_checks(be, variant)
     be.L.b200fft_set_variant(0)
 

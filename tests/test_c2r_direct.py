@@ -52,3 +52,29 @@ def test_r2c_paired_truncation(be33, N):
 
 def test_r2c_paired_uneven_kz_chunks(be33):
     tp.test_rows_uneven_kz_chunks(be33)
+
+
+@pytest.fixture(scope="module")
+def be34():
+    """variant 34: C2R with the merge step folded into a paired first stage (C2RPK; plans with a first radix <= 8)"""
+    lib = emu_util.load()
+    old = lib.emu_set_variant(34)
+    yield tp._Emu()
+    lib.emu_set_variant(old)
+
+
+@pytest.mark.parametrize("prec", ["d", "s"])
+@pytest.mark.parametrize("h", [32, 48, 64, 96, 384, 512, 768, 6144, 8, 256, 1024])
+def test_c2r_paired_all_plans(be34, h, prec):
+    # 32 = (4,8), 48 = (4,12), 64 = (8,8), 96 = (8,12), 384 = (4,8,12), 512, 768, 6144 = (8,8,8,12): paired form;
+    # 8 (one stage), 256 = (16,16), 1024 = (16,8,8): fall back to C2RK
+    tp.test_rows_r2c_c2r(be34, h, prec)
+
+
+@pytest.mark.parametrize("N", [32, 256, 1024])
+def test_c2r_paired_zero_pad(be34, N):
+    tp.test_rows_truncate_and_zero_pad(be34, N)
+
+
+def test_c2r_paired_uneven_kz_chunks(be34):
+    tp.test_rows_uneven_kz_chunks(be34)
