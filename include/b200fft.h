@@ -57,7 +57,8 @@ B200FFT_API int b200fft_supported_length(int n);
  * 32: the 3/2-rule row kernels (last radix 12) compiled for four resident CTAs per SM instead of three;
  * 33: R2C kernel with the split step folded into a paired last stage (one shared-memory round trip less);
  * 34: C2R kernel with the merge step folded into a paired first stage (loads from HBM into registers);
- * 100 + bits combines switches (1: as 20, 2: the n >= 2048 part of 22, 4: as 30, 8: as 31, 16: as 32, 32: as 33, 64: as 34); 30: the threads of a
+ * 35: strided pass whose first stage loads straight from HBM into registers (no staging copy of the tile);
+ * 100 + bits combines switches (1: as 20, 2: the n >= 2048 part of 22, 4: as 30, 8: as 31, 16: as 32, 32: as 33, 64: as 34, 128: as 35); 30: the threads of a
  * row of the R2C / C2R passes synchronise on a named barrier of their own instead of the CTA's. */
 B200FFT_API int b200fft_set_variant(int v);
 

@@ -26,8 +26,8 @@ bool plan_exists(int n);
 // tuning switch (B200FFT_VARIANT environment variable, b200fft_set_variant): 0 = default kernels
 int kernel_variant();
 // switches that combine: variant = 100 + bits
-enum { VAR_CLUSTER_FAR = 1, VAR_CLUSTER_LONG = 2, VAR_ROW_BARRIERS = 4, VAR_C2R_DIRECT = 8, VAR_ROW_OCC4 = 16, VAR_R2C_PAIRED = 32, VAR_C2R_PAIRED = 64 };
-inline bool variant_in_range(int v) { return v >= 100 && v < 228; }
+enum { VAR_CLUSTER_FAR = 1, VAR_CLUSTER_LONG = 2, VAR_ROW_BARRIERS = 4, VAR_C2R_DIRECT = 8, VAR_ROW_OCC4 = 16, VAR_R2C_PAIRED = 32, VAR_C2R_PAIRED = 64, VAR_STRIDED_DIRECT = 128 };
+inline bool variant_in_range(int v) { return v >= 100 && v < 356; }
 inline bool variant_has(int flag) {
   const int v = kernel_variant();
   return variant_in_range(v) && ((v - 100) & flag) != 0;

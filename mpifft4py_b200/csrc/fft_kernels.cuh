@@ -499,6 +499,78 @@ struct StridedK {
 };
 
 
+// Strided pass with its first stage fed straight from HBM ("direct" form, B200FFT_VARIANT=35).  StridedK
+// stages the whole tile in shared memory with asynchronous copies before the first butterflies read it
+// back; ncu r01c shows the pass bound by LSU wavefronts (77 %), two of whose six shared-memory accesses
+// per element are that staging.  Here a thread loads the R inputs of its first-stage butterflies from
+// the row-address table straight into registers (all loads issued before the first use: 16 x 16 bytes
+// per thread in flight for a radix-16 stage), so the tile makes its first trip through shared memory as
+// the first stage's OUTPUT.  Same tile geometry, index maps and later stages; one barrier less.
+template <class real, class P, int MB = 0, int RB = 0>
+struct StridedDK {
+  using SK = StridedK<real, P, MB, RB>;
+  using Cfg = typename SK::Cfg;
+  using C = cx<real>;
+  using Params = StridedParams<real>;
+  static_assert(Cfg::TAB, "the direct form keeps its row-address table in shared memory");
+  static_assert(P::S >= 2, "the direct form needs a later stage to store from");
+  static constexpr int NPHASE = P::S + 2;
+  static constexpr int NT = Cfg::NT;
+  static constexpr int SMEM = Cfg::SMEM;
+  static constexpr int SMEM1 = Cfg::SMEM;
+  static constexpr bool PIPE = false;
+  static constexpr int MINB = Cfg::MINB;
+  B2_HD static unsigned long long blocks(const Params& p) { return SK::blocks(p); }
+  B2_HD static void decode(const Params& p, unsigned blk, int& bx, int& by) { SK::decode(p, blk, bx, by); }
+
+  // phases: 0 load-row table; 1 stage 0 (HBM -> registers -> shared); 2 store-row table; 3.. stages 1..S-1.
+  // Plans with at least two stages (a single stage would have to store from phase 1).
+  template <int s>
+  B2_HD static void phase(const Params& p, void* smraw, int tid, int bx, int by) {
+    constexpr int T = Cfg::T, n = P::N, CB = Cfg::CB;
+    const int c = tid % T;
+    const int t = tid / T;
+    const int j0 = bx * T;
+    const long long b = by;
+    const bool live = j0 + c < p.J;
+    addr_t* tab = reinterpret_cast<addr_t*>(reinterpret_cast<unsigned char*>(smraw) + Cfg::TILE);
+    C* sm = reinterpret_cast<C*>(smraw) + c;
+    auto no_in = [](int) -> C { return C{0, 0}; };
+    auto no_out = [](int, C) {};
+    auto store = [&](int k, C v) {
+      if (!live) return;
+      const addr_t a = tab[k];
+      if (a == 0) return;
+      if (p.scale != (real)1) v = cscale(v, p.scale);
+      *reinterpret_cast<C*>(a + (addr_t)c * CB) = v;
+    };
+    const int fold = (p.inverse && p.fold_mode == 2) ? 3 : p.fold_mode;
+    if constexpr (s == 0) {
+      for (int i = tid; i < n; i += Cfg::NT) tab[i] = SK::in_row(p, b, i, j0);
+    } else if constexpr (s == 1) {
+      bool colzero = !live;
+      if (p.mask.on && live) {
+        const Mask& m = p.mask;
+        const int j = j0 + c;
+        const int bb = (int)b + m.b_off, jq = j / m.jdiv + m.jq_off, jr = j % m.jdiv + m.jr_off;
+        if ((bb >= m.b_lo && bb <= m.b_hi) || (jq >= m.jq_lo && jq <= m.jq_hi) || (jr >= m.jr_lo && jr <= m.jr_hi))
+          colzero = true;
+      }
+      auto in = [&](int i) -> C {  // pad rows, masked rows / columns and dead lanes read as zero
+        const addr_t a = tab[i];
+        return (a != 0 && !colzero) ? *reinterpret_cast<const C*>(a + (addr_t)c * CB) : C{0, 0};
+      };
+      // (a single-stage plan would need the store table here: such lengths stay with StridedK, see dispatch)
+      fft_stage<real, P, 0, Cfg::TC, T, Cfg::SW, true, false>(t, sm, p.tw, p.tws, in, no_out, 0);
+    } else if constexpr (s == 2) {
+      for (int k = tid; k < n; k += Cfg::NT) tab[k] = SK::out_row(p, b, k, j0);
+    } else {
+      constexpr int st = s - 2;
+      fft_stage<real, P, st, Cfg::TC, T, Cfg::SW, false, (st == P::S - 1)>(t, sm, p.tw, p.tws, no_in, store, fold);
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // strided C2C pass on a 2-CTA cluster ("far" strides: the x pass of a slab)
 // ------------------------------------------------------------------------------------------

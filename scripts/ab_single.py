@@ -31,7 +31,8 @@ for g in (2, 3, 4, 6):
     CONFIGS += [("l2_two_streams_g%d" % g, 0, {"l2_planes": g, "l2_mode": 2})]
 for g in (2, 3, 4, 6, 8, 12, 16):
     CONFIGS += [("l2_fused_g%d" % g, 0, {"l2_planes": g, "l2_mode": 3})]
-CONFIGS += [("cluster_x+row_barriers(105)", 105, {}), ("cluster_x+c2r_direct(109)", 109, {}), ("rows_4_ctas(32)", 32, {}), ("r2c_paired(33)", 33, {}), ("c2r_paired(34)", 34, {}), ("r2c+c2r_paired(196)", 196, {}),
+CONFIGS += [("cluster_x+row_barriers(105)", 105, {}), ("cluster_x+c2r_direct(109)", 109, {}), ("rows_4_ctas(32)", 32, {}), ("strided_direct(35)", 35, {}), ("strided_direct+r2c+c2r_paired(324)", 324, {}),
+            ("cluster_x+strided_direct+r2c+c2r_paired(325)", 325, {}), ("r2c_paired(33)", 33, {}), ("c2r_paired(34)", 34, {}), ("r2c+c2r_paired(196)", 196, {}),
             ("cluster_x+r2c+c2r_paired(197)", 197, {}), ("cluster_x+long+r2c+c2r_paired(199)", 199, {}),
             ("r2c_paired+c2r_direct(140)", 140, {}), ("cluster_x+r2c_paired+c2r_direct(141)", 141, {}),
             ("rows_4_ctas+row_barriers(120)", 120, {}),

@@ -19,7 +19,7 @@ timeout 1500 python scripts/ab_single.py --steps 5 > $O/ab_single.jsonl 2> $O/ab
 # 2. cluster strided pass (variant 20: far launches only), per-row barriers in the row kernels (30),
 #    register-staged C2R (31)
 #    against the default, plain and 3/2-rule
-for v in 0 20 30 31 32 33 34; do
+for v in 0 20 30 31 32 33 34 35; do
   for w in slab1024_f64 slab1024_f64_32; do
     B200FFT_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --workload $w \
         > $O/bench_${w}_v$v.json 2> $O/bench_${w}_v$v.err

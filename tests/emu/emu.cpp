@@ -150,6 +150,19 @@ static int strided(const b200fft_strided_desc_t& d) {
     B200FFT_CLUSTER_PLANS(X)
 #undef X
   }
+  if (g_emu_variant == 35) {  // first stage fed straight from memory (plans with two or more stages)
+    switch (d.n) {
+#define X(n, ...)                                                                            \
+  case n:                                                                                    \
+    if constexpr (Plan<__VA_ARGS__>::S >= 2 && StridedCfg<real, Plan<__VA_ARGS__>>::TAB)     \
+      return emulate<StridedDK<real, Plan<__VA_ARGS__>>>(p);                                 \
+    break;
+      B200FFT_PLANS(X)
+#undef X
+      default:
+        break;
+    }
+  }
   if (d.in.jc > 0 || d.out.jc > 0) {  // blocked column layouts: the JS form of the kernel (every length here)
     switch (d.n) {
 #define X(n, ...) \

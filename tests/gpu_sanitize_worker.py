@@ -25,7 +25,7 @@ def main():
     assert torch.cuda.is_available()
     be = tp._Gpu()
     L3 = np.array([2 * np.pi] * 3)
-    for variant in (0, 21, 23, 30, 31, 32, 33, 34):
+    for variant in (0, 21, 23, 30, 31, 32, 33, 34, 35):
         be.L.b200fft_set_variant(variant)
         for prec in "ds":
             for n in (64, 1024, 1536):

@@ -27,6 +27,8 @@ def cluster():
     import mpifft4py_b200 as m
     from mpifft4py_b200.comm import SelfComm
     be = tp._Gpu()
+    be.L.b200fft_set_variant(35)  # (not a cluster kernel: the strided pass with its first stage fed from HBM)
+    cc.run_all(be)
     be.L.b200fft_set_variant(23)  # 64-byte tile rows
     cc.run_all(be)
     be.L.b200fft_set_variant(21)  # every strided pass whose length has a cluster plan, 128-byte rows
