@@ -561,3 +561,51 @@ def test_kz_block_needs_at_most_16_blocks():
     ip = (C.c_void_p * 1)(A.ctypes.data)
     op = (C.c_void_p * 1)(out.ctypes.data)
     assert lib.emu_plan_run(C.byref(d), 0, D.DEALIAS_NONE, ip, op) == D.ERR_ARG
+
+
+@pytest.mark.parametrize("N,variants", [((8, 16, 32), [dict(l2_planes=2, l2_mode=1), dict(l2_planes=3, l2_mode=2)]),
+                                        ((8, 512, 512), [dict(l2_planes=2, l2_mode=3), dict(l2_planes=3, l2_mode=3)])])
+def test_schedule_only_options_do_not_change_a_single_bit(N, variants):
+    """L2 grouping, the two-stream schedule and the fused launch run the same kernels on the same data in a
+    different order: the results must equal the default plan's bit for bit (forward, inverse, 3/2-rule)."""
+    prec = "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, 1)
+    rng = np.random.default_rng(21)
+    u = [rng.random(g.real_shape()).astype(rt)]
+    fu = [_rand_c(rng, g.complex_shape(), ct)]
+    base = _desc(D.SLAB, N, 1, prec)
+    ref_f = run_plan(base, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)[0]
+    ref_i = run_plan(base, 1, D.DEALIAS_NONE, fu, [g.real_shape()], rt)[0]
+    ref_p = run_plan(base, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)[0] if N[1] < 512 else None
+    for kw in variants:
+        d = _desc(D.SLAB, N, 1, prec, **kw)
+        assert np.array_equal(run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)[0], ref_f), kw
+        assert np.array_equal(run_plan(d, 1, D.DEALIAS_NONE, fu, [g.real_shape()], rt)[0], ref_i), kw
+        if ref_p is not None:
+            assert np.array_equal(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)[0], ref_p), kw
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_transports_and_pipelines_do_not_change_a_single_bit(P):
+    """NCCL, copy engines and fused stores, x-plane and kz pipelines, any chunk count: same kernels, same
+    arithmetic -- identical bits on every rank."""
+    N, prec = (16, 16, 64), "double"
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.slab.Geometry(N, P)
+    rng = np.random.default_rng(22)
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    fu = [_rand_c(rng, g.complex_shape(), ct) for _ in range(P)]
+    base = _desc(D.SLAB, N, P, prec, chunks=1)
+    ref_f = run_plan(base, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
+    ref_p = run_plan(base, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, rt)
+    for transport in (D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE):
+        for pipeline in (D.PIPELINE_X, D.PIPELINE_KZ):
+            for chunks in (0, 2, 3):
+                d = _desc(D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport)
+                got_f = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
+                got_p = run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()] * P, rt)
+                for r in range(P):
+                    assert np.array_equal(got_f[r], ref_f[r]), (transport, pipeline, chunks, r)
+                    assert np.array_equal(got_p[r], ref_p[r]), (transport, pipeline, chunks, r)
