@@ -1,0 +1,119 @@
+"""On-device selection of the opt-in kernels and schedules -- the role FFTW's planner plays behind the
+reference's ``planner_effort`` argument (``pyfftw_fft.py:26-203`` forwards it to ``pyfftw.builders``):
+measure candidate configurations of a transform object on the device it runs on, check each against the
+default configuration's result, and keep the fastest.
+
+    import mpifft4py_b200 as m
+    F = m.Slab_R2C(N, L, comm, "double")
+    report = m.tune.autotune(F)            # times the candidates, installs the best one into F
+    report = m.tune.autotune(F, dealias="3/2-rule", candidates=m.tune.CANDIDATES["patient"])
+
+A candidate is ``(name, kernel_variant, {plan attribute: value})`` (DESIGN.md section 8 lists the switches).
+The kernel variant is a process-wide switch of the library (``b200fft_set_variant``); the plan attributes are
+read when a plan is created, so installing a candidate drops the object's device plan and lets the next
+transform build it again.  Every rank of a multi-rank object must call ``autotune`` collectively; the
+slowest rank's time decides (``comm.allgather``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+PLAN_ATTRS = ("transport", "exchange_chunks", "exchange_pipeline", "copy_streams", "l2_planes", "l2_mode", "kz_block")
+
+CANDIDATES = {
+    # kernel forms that replace a default kernel one to one
+    "measure": [("default", 0, {}), ("cluster_x", 20, {}), ("row_barriers", 30, {}), ("c2r_direct", 31, {}),
+                ("rows_4_ctas", 32, {}), ("r2c_paired", 33, {}), ("c2r_paired", 34, {}), ("strided_direct", 35, {})],
+}
+CANDIDATES["patient"] = CANDIDATES["measure"] + [
+    ("paired_rows+strided_direct", 100 + 32 + 64 + 128, {}), ("cluster_x+paired_rows+strided_direct", 100 + 1 + 32 + 64 + 128, {}),
+    ("l2_fused_g4", 0, {"l2_planes": 4, "l2_mode": 3}), ("l2_fused_g8", 0, {"l2_planes": 8, "l2_mode": 3}),
+    ("l2_two_streams_g4", 0, {"l2_planes": 4, "l2_mode": 2}), ("kz_block48", 0, {"kz_block": 48}),
+]
+
+
+def _install(F, variant, attrs, set_variant):
+    """Make ``F`` use a candidate: plan attributes on the object, the kernel variant in the library, and a
+    fresh device plan at the next transform."""
+    for a in PLAN_ATTRS:
+        if hasattr(F, a) and a not in attrs:
+            try:
+                delattr(F, a)
+            except AttributeError:  # class attribute: leave it
+                pass
+    for a, v in attrs.items():
+        setattr(F, a, v)
+    set_variant(variant)
+    if getattr(F, "_plan", None) is not None:
+        _lib.lib().b200fft_plan_destroy(F._plan)
+        F._plan = None
+
+
+def select(candidates, measure, tol, reduce_max=lambda x: x):
+    """Core of the tuner, free of device code: ``measure(candidate) -> (seconds, error vs the default result)``
+    (may raise: the candidate is then skipped and reported); a candidate qualifies when its error is within
+    ``tol``; the fastest qualifying one wins, ties and failures fall back to the first candidate (the default).
+    Returns ``(best, report)`` with ``report`` a list of dicts."""
+    report, best, best_t = [], None, None
+    for cand in candidates:
+        name = cand[0]
+        try:
+            t, err = measure(cand)
+            t = reduce_max(t)
+            ok = bool(err <= tol)
+            report.append({"name": name, "seconds": t, "error": float(err), "ok": ok})
+            if ok and (best_t is None or t < best_t):
+                best, best_t = cand, t
+        except Exception as e:  # noqa: BLE001 - an opt-in kernel that fails must not take the application down
+            report.append({"name": name, "seconds": None, "error": None, "ok": False, "exception": repr(e)[:200]})
+    if best is None:
+        best = candidates[0]
+    return best, report
+
+
+def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
+    """Time ``fftn`` + ``ifftn`` (``fft2`` + ``ifft2`` for line objects) of ``F`` for every candidate on random
+    data, keep the fastest whose forward result matches the default configuration's, install it into ``F`` and
+    return the report.  Device memory: one real and one complex array of the object's local shapes, twice."""
+    import torch
+    L = _lib.lib()
+    L.b200fft_set_variant.restype = C.c_int
+    candidates = list(candidates if candidates is not None else CANDIDATES["measure"])
+    double = F.float is np.float64
+    tol = tol if tol is not None else (1e-12 if double else 1e-5)
+    fwd, inv = (F.fft2, F.ifft2) if hasattr(F, "fft2") else (F.fftn, F.ifftn)
+    rshape = tuple(int(s) for s in (F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()))
+    cshape = tuple(int(s) for s in F.complex_shape())
+    rdt, cdt = (torch.float64, torch.complex128) if double else (torch.float32, torch.complex64)
+    u = torch.rand(rshape, dtype=rdt, device="cuda")
+    fu = torch.empty(cshape, dtype=cdt, device="cuda")
+    u2 = torch.empty_like(u)
+    ref = {}
+    comm = getattr(F, "comm", None)
+    many = comm is not None and getattr(F, "num_processes", 1) > 1
+
+    def measure(cand):
+        _install(F, cand[1], cand[2], L.b200fft_set_variant)
+        fwd(u, fu, dealias)
+        inv(fu, u2, dealias)  # warm-up: plan creation, kernel set-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fwd(u, fu, dealias)
+            inv(fu, u2, dealias)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd(u, fu, dealias)
+        if "fu" not in ref:
+            ref["fu"] = fu.clone()
+        err = float(torch.linalg.vector_norm(fu - ref["fu"]) / torch.linalg.vector_norm(ref["fu"]))
+        return e0.elapsed_time(e1) * 1e-3 / reps, err
+
+    best, report = select(candidates, measure, tol, (lambda t: max(comm.allgather(t))) if many else (lambda t: t))
+    if many:  # every rank must install the same candidate: rank 0's choice (they agree unless times tie)
+        best = candidates[[c[0] for c in candidates].index(comm.bcast(best[0], root=0))]
+    _install(F, best[1], best[2], L.b200fft_set_variant)
+    return {"chosen": best[0], "candidates": report}

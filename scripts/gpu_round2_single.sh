@@ -16,6 +16,10 @@ for tool in racecheck synccheck memcheck; do
 done
 # 2a. everything below in one process first (one import, one set of arrays): the quick overall picture
 timeout 1500 python scripts/ab_single.py --steps 5 > $O/ab_single.jsonl 2> $O/ab_single.txt; tail -80 $O/ab_single.txt
+# 2a'. the tuner's own view (same candidates through mpifft4py_b200.tune.autotune)
+for w in slab1024_f64 slab1024_f64_32; do
+  timeout 900 python scripts/tune_single.py $w patient > $O/tune_$w.json 2> $O/tune_$w.err; tail -3 $O/tune_$w.err; grep chosen $O/tune_$w.json
+done
 # 2. cluster strided pass (variant 20: far launches only), per-row barriers in the row kernels (30),
 #    register-staged C2R (31)
 #    against the default, plain and 3/2-rule

@@ -1,0 +1,42 @@
+"""Selection logic of mpifft4py_b200.tune (the device-free core: measure -> qualify -> pick)."""
+import mpifft4py_b200 as m
+from mpifft4py_b200 import tune
+
+
+def test_fastest_qualifying_candidate_wins_and_failures_are_reported():
+    cands = [("default", 0, {}), ("fast_but_wrong", 1, {}), ("fast", 2, {}), ("crashes", 3, {}), ("slow", 4, {})]
+    times = {"default": (1.0, 0.0), "fast_but_wrong": (0.1, 1e-3), "fast": (0.5, 1e-15), "slow": (2.0, 0.0)}
+
+    def measure(c):
+        if c[0] == "crashes":
+            raise RuntimeError("launch failed")
+        return times[c[0]]
+
+    best, report = tune.select(cands, measure, 1e-12)
+    assert best[0] == "fast"
+    by = {r["name"]: r for r in report}
+    assert by["fast_but_wrong"]["ok"] is False and by["crashes"]["ok"] is False and "launch failed" in by["crashes"]["exception"]
+    assert by["fast"]["ok"] and by["default"]["ok"]
+
+
+def test_default_is_kept_when_nothing_qualifies_and_slowest_rank_decides():
+    cands = [("default", 0, {}), ("a", 1, {})]
+    best, _ = tune.select(cands, lambda c: (1.0, 1.0), 1e-12)
+    assert best[0] == "default"
+    # reduce_max models the allgather over ranks: candidate "a" is fast here but slow on another rank
+    best, rep = tune.select(cands, lambda c: ((1.0, 0.0) if c[0] == "default" else (0.5, 0.0)), 1e-12,
+                            reduce_max=lambda t: t if t == 1.0 else 3.0)
+    assert best[0] == "default" and rep[1]["seconds"] == 3.0
+
+
+def test_install_sets_and_clears_plan_attributes():
+    class F(object):
+        _plan = None
+    f = F()
+    seen = []
+    tune._install(f, 20, {"l2_planes": 4, "l2_mode": 3}, seen.append)
+    assert (f.l2_planes, f.l2_mode, seen) == (4, 3, [20])
+    tune._install(f, 0, {"kz_block": 48}, seen.append)
+    assert not hasattr(f, "l2_planes") and f.kz_block == 48 and seen == [20, 0]
+    assert set(c[0] for c in tune.CANDIDATES["measure"]) <= set(c[0] for c in tune.CANDIDATES["patient"])
+    assert m.tune is tune
