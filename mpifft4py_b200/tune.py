@@ -34,17 +34,17 @@ CANDIDATES["patient"] = CANDIDATES["measure"] + [
 ]
 
 
-def _install(F, variant, attrs, set_variant):
-    """Make ``F`` use a candidate: plan attributes on the object, the kernel variant in the library, and a
-    fresh device plan at the next transform."""
+def _install(F, variant, attrs, set_variant, base=None):
+    """Make ``F`` use a candidate: the caller's own plan attributes (``base``) overlaid with the candidate's,
+    the kernel variant in the library, and a fresh device plan at the next transform."""
+    base = base or {}
     for a in PLAN_ATTRS:
-        if hasattr(F, a) and a not in attrs:
-            try:
-                delattr(F, a)
-            except AttributeError:  # class attribute: leave it
-                pass
-    for a, v in attrs.items():
-        setattr(F, a, v)
+        if a in attrs:
+            setattr(F, a, attrs[a])
+        elif a in base:
+            setattr(F, a, base[a])
+        elif a in getattr(F, "__dict__", {}):
+            delattr(F, a)
     set_variant(variant)
     if getattr(F, "_plan", None) is not None:
         _lib.lib().b200fft_plan_destroy(F._plan)
@@ -93,9 +93,10 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
     ref = {}
     comm = getattr(F, "comm", None)
     many = comm is not None and getattr(F, "num_processes", 1) > 1
+    base = {a: F.__dict__[a] for a in PLAN_ATTRS if a in F.__dict__}  # what the caller chose stays unless a candidate overrides it
 
     def measure(cand):
-        _install(F, cand[1], cand[2], L.b200fft_set_variant)
+        _install(F, cand[1], cand[2], L.b200fft_set_variant, base)
         fwd(u, fu, dealias)
         inv(fu, u2, dealias)  # warm-up: plan creation, kernel set-up
         torch.cuda.synchronize()
@@ -115,5 +116,5 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
     best, report = select(candidates, measure, tol, (lambda t: max(comm.allgather(t))) if many else (lambda t: t))
     if many:  # every rank must install the same candidate: rank 0's choice (they agree unless times tie)
         best = candidates[[c[0] for c in candidates].index(comm.bcast(best[0], root=0))]
-    _install(F, best[1], best[2], L.b200fft_set_variant)
+    _install(F, best[1], best[2], L.b200fft_set_variant, base)
     return {"chosen": best[0], "candidates": report}

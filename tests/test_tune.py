@@ -36,7 +36,7 @@ def test_install_sets_and_clears_plan_attributes():
     seen = []
     tune._install(f, 20, {"l2_planes": 4, "l2_mode": 3}, seen.append)
     assert (f.l2_planes, f.l2_mode, seen) == (4, 3, [20])
-    tune._install(f, 0, {"kz_block": 48}, seen.append)
-    assert not hasattr(f, "l2_planes") and f.kz_block == 48 and seen == [20, 0]
+    tune._install(f, 0, {"kz_block": 48}, seen.append, base={"transport": "nccl"})
+    assert not hasattr(f, "l2_planes") and f.kz_block == 48 and f.transport == "nccl" and seen == [20, 0]
     assert set(c[0] for c in tune.CANDIDATES["measure"]) <= set(c[0] for c in tune.CANDIDATES["patient"])
     assert m.tune is tune
