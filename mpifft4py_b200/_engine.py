@@ -108,7 +108,8 @@ class Transform(object):
                 h = None
         if h is None:
             d.transport = D.TRANSPORT_NCCL
-            d.comm = _comm.nccl_handle(comm) if comm is not None else None
+            # (pencil plans exchange within comm0 / comm1 only; their world comm is for the peer-mapped handshake)
+            d.comm = _comm.nccl_handle(comm) if (comm is not None and comm0 is None and comm1 is None) else None
             d.comm0 = _comm.nccl_handle(comm0) if comm0 is not None else None
             d.comm1 = _comm.nccl_handle(comm1) if comm1 is not None else None
             h = C.c_void_p()
