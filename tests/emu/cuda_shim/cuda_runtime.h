@@ -11,7 +11,10 @@
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorNotSupported = 801 };
 typedef struct shim_stream* cudaStream_t;
-struct shim_event { double t; };
+struct shim_event { double t; long epoch; };
+// One epoch per transform call of a rank (a thread): tests bump it through shim_next_epoch() before each call,
+// and an event only counts as recorded within the call that waits for it.
+inline long& shim_epoch() { static thread_local long e = 1; return e; }
 typedef shim_event* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
@@ -31,12 +34,15 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = reinterpret_cast<cudaStream_t>(std::malloc(1)); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
-inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) { return e ? cudaSuccess : 1; }
-inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new shim_event{0}; return cudaSuccess; }
+// On the device a wait for an event that was never recorded is a silent no-op, i.e. a missing dependency:
+// here it is an error, so that the host-shim tests catch it.
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) { return (e && e->epoch == shim_epoch()) ? cudaSuccess : 1; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new shim_event{0, 0}; return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
   if (!e) return 1;
+  e->epoch = shim_epoch();
   e->t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   return cudaSuccess;
 }

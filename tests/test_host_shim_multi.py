@@ -91,6 +91,7 @@ def _make_plan(L, R, r, kind, N, P, transport, P1=1, P2=1, drop=0, **kw):
 
 def _exec(L, h, inverse, mode, src, dst):
     fn = L.b200fft_exec_inverse if inverse else L.b200fft_exec_forward
+    L.shim_next_epoch()  # an event recorded by an earlier call must not satisfy a wait of this one
     rc = fn(h, C.c_void_p(src.ctypes.data), C.c_void_p(dst.ctypes.data), mode, None)
     assert rc == 0, (rc, L.b200fft_last_error())
     return dst
