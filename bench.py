@@ -301,6 +301,10 @@ def run_ours(args):
     name = args.workload
     kind, N, prec, dealias, kw = WORKLOADS[name]
     F = make_transform(m, comm, name)
+    tuned = None
+    if args.tune:  # let the planner pick among the opt-in kernels / schedules first (reported in config.tuning)
+        tuned = m.tune.autotune(F, dealias=dealias, candidates=m.tune.CANDIDATES[args.tune])
+        torch.cuda.empty_cache()
     fwd, inv = (F.fft2, F.ifft2) if kind == "line" else (F.fftn, F.ifftn)
     rshape = tuple(int(s) for s in (F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()))
     cshape = tuple(int(s) for s in F.complex_shape())
@@ -469,6 +473,9 @@ def run_ours(args):
     tuning = {k: os.environ[k] for k in ("B200FFT_VARIANT", "B200FFT_L2_PLANES", "B200FFT_L2_MODE", "B200FFT_TRANSPORT",
                                           "B200FFT_PIPELINE", "B200FFT_CHUNKS", "B200FFT_KZ_BLOCK", "B200FFT_COPY_STREAMS")
               if os.environ.get(k)}
+    if tuned is not None:
+        tuning["planner"] = {"effort": args.tune, "chosen": tuned["chosen"],
+                             "candidates": [{k: c.get(k) for k in ("name", "seconds", "ok")} for c in tuned["candidates"]]}
     if tuning:
         cfg["tuning"] = tuning
     if P > 1:
@@ -499,6 +506,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tune", default=None, choices=["measure", "patient"],
+                    help="run mpifft4py_b200.tune.autotune on the workload first (default: the library's defaults)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
