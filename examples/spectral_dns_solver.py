@@ -36,16 +36,22 @@ def solve(FFT, xp, to_xp, N, nu=0.000625, T=0.1, dt=0.01, dealias="3/2-rule"):
     rshape = tuple(int(s) for s in FFT.real_shape())
     cshape = tuple(int(s) for s in FFT.complex_shape())
     wshape = tuple(int(s) for s in FFT.work_shape(dealias))
-    rdt, cdt = xp.float64, xp.complex128
-    U = xp.zeros((3,) + rshape, dtype=rdt)
-    U_hat = xp.zeros((3,) + cshape, dtype=cdt)
-    U_hat0 = xp.zeros((3,) + cshape, dtype=cdt)
-    U_hat1 = xp.zeros((3,) + cshape, dtype=cdt)
-    dU = xp.zeros((3,) + cshape, dtype=cdt)
-    U_d = xp.zeros((3,) + wshape, dtype=rdt)
-    curl_d = xp.zeros((3,) + wshape, dtype=rdt)
-    tmp_r = xp.zeros(wshape, dtype=rdt)
-    tmp_c = xp.zeros(cshape, dtype=cdt)
+    rdt, cdt = np.float64, np.complex128
+
+    def zeros(shape, dtype):
+        # every state array goes through to_xp, so it lives where the transform's arrays live (a bare
+        # xp.zeros under torch would be a CPU tensor, which the engine refuses)
+        return to_xp(np.zeros(shape, dtype=dtype))
+
+    U = zeros((3,) + rshape, rdt)
+    U_hat = zeros((3,) + cshape, cdt)
+    U_hat0 = zeros((3,) + cshape, cdt)
+    U_hat1 = zeros((3,) + cshape, cdt)
+    dU = zeros((3,) + cshape, cdt)
+    U_d = zeros((3,) + wshape, rdt)
+    curl_d = zeros((3,) + wshape, rdt)
+    tmp_r = zeros(wshape, rdt)
+    tmp_c = zeros(cshape, cdt)
     X = [to_xp(np.ascontiguousarray(np.broadcast_to(x, rshape))) for x in FFT.get_local_mesh()]
     K = [to_xp(np.ascontiguousarray(np.broadcast_to(np.asarray(k, dtype=np.float64), cshape)))
          for k in FFT.get_local_wavenumbermesh(scaled=True)]

@@ -47,6 +47,38 @@ def test_taylor_green_known_answer_oracle():
     assert round(k - sds.KNOWN_ANSWER, 7) == 0, k
 
 
+def test_solver_keeps_every_array_on_the_transform_device():
+    """The solver under torch, on the CPU: to_xp tags its tensors (a Tensor subclass stands in for
+    "lives on the engine's device"); every array handed to fftn / ifftn must carry the tag.  A bare
+    xp.zeros(...) would produce an untagged (CPU) tensor -- the round-1 bug that the engine's
+    `assert src.is_cuda` only caught on a GPU box."""
+    import torch
+
+    class OnDevice(torch.Tensor):
+        pass
+
+    def to_xp(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).as_subclass(OnDevice)
+
+    seen = []
+
+    class Checked(_OracleSlab):
+        def fftn(self, u, fu, dealias=None):
+            seen.append((type(u), type(fu)))
+            assert isinstance(u, OnDevice) and isinstance(fu, OnDevice)
+            fu[...] = torch.from_numpy(oracle.slab.fftn([u.as_subclass(torch.Tensor).numpy()], self.Nt, 1, dealias=dealias)[0])
+            return fu
+
+        def ifftn(self, fu, u, dealias=None):
+            seen.append((type(fu), type(u)))
+            assert isinstance(u, OnDevice) and isinstance(fu, OnDevice)
+            u[...] = torch.from_numpy(oracle.slab.ifftn([fu.as_subclass(torch.Tensor).numpy()], self.Nt, 1, dealias=dealias)[0])
+            return u
+
+    k = sds.solve(Checked(), torch, to_xp, N, T=0.02)
+    assert len(seen) > 20 and np.isfinite(k)
+
+
 @pytest.mark.gpu
 def test_taylor_green_known_answer_gpu():
     import torch
