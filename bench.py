@@ -143,8 +143,9 @@ def _load_reference():
     return load_reference
 
 
-def reference_roundtrip(lr, kind, N, prec, dealias, kw, P, reps):
-    """min over `reps` of (max over ranks of) one fftn+ifftn of the unmodified reference."""
+def reference_roundtrip(lr, kind, N, prec, dealias, kw, P, reps, warmup=1):
+    """Per-step seconds (max over ranks; `reps` timed fftn+ifftn round trips after `warmup` untimed ones) of the
+    unmodified reference; the transform object and its arrays are built once."""
     from mpi4py import MPI  # the refshim's in-process stand-in
 
     def body():
@@ -165,20 +166,21 @@ def reference_roundtrip(lr, kind, N, prec, dealias, kw, P, reps):
         u = np.random.default_rng(1234 + comm.Get_rank()).random(rshape).astype(F.float)
         fu = np.zeros(F.complex_shape(), dtype=F.complex)
         u2 = np.zeros_like(u)
-        fwd(u, fu, dealias)
-        inv(fu, u2, dealias)  # warm-up: work arrays, subarray types
-        best = None
+        for _ in range(max(1, warmup)):  # work arrays, subarray types
+            fwd(u, fu, dealias)
+            inv(fu, u2, dealias)
+        ts = []
         for _ in range(reps):
             comm.barrier()
             t0 = time.perf_counter()
             fwd(u, fu, dealias)
             inv(fu, u2, dealias)
             comm.barrier()
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        return best
+            ts.append(time.perf_counter() - t0)
+        return ts
 
-    return max(lr.run_ranks(P, body))
+    per_rank = lr.run_ranks(P, body)
+    return [max(t) for t in zip(*per_rank)]
 
 
 def port_roundtrip(kind, N, prec, dealias, workers):
@@ -197,27 +199,30 @@ def port_roundtrip(kind, N, prec, dealias, workers):
     return time.perf_counter() - t0
 
 
-def cpu_time(name, Ns, reps):
-    """(seconds per round trip, descriptor) of the CPU reference on mesh Ns."""
+def reference_ranks(name, Ns):
+    """Rank count of the reference arm: as many thread-ranks as the host has cores, within what the class accepts."""
+    kind = WORKLOADS[name][0]
+    cores = os.cpu_count() or 1
+    if kind == "pencil":
+        return 8 if cores >= 8 else 4
+    return max(1, min(_pow2_floor(cores), 32, Ns[0] // 2))
+
+
+def cpu_time(name, Ns, reps, warmup=1):
+    """(list of `reps` seconds per round trip, descriptor) of the CPU reference on mesh Ns."""
     kind, N, prec, dealias, kw = WORKLOADS[name]
     cores = os.cpu_count() or 1
     lr = _load_reference()
-    if lr is not None and kind in ("slab", "line"):
-        P = min(_pow2_floor(cores), 32, Ns[0] // 2)
-        t = reference_roundtrip(lr, kind, Ns, prec, dealias, kw, P, reps)
-        return t, {"kind": "reference", "cores": P,
-                   "how": "unmodified mpiFFT4py %s.R2C (baseline/_ref) under oracle/refshim: %d ranks as threads, "
-                          "numpy.fft backend, memcpy collectives" % (kind, P)}
-    if lr is not None and kind == "pencil":
-        P = 8 if cores >= 8 else 4
-        t = reference_roundtrip(lr, kind, Ns, prec, dealias, kw, P, reps)
-        return t, {"kind": "reference", "cores": P,
-                   "how": "unmodified mpiFFT4py pencil.R2C (baseline/_ref) under oracle/refshim: %d ranks as threads, "
-                          "numpy.fft backend, memcpy collectives" % P}
+    if lr is not None:
+        P = reference_ranks(name, Ns)
+        ts = reference_roundtrip(lr, kind, Ns, prec, dealias, kw, P, reps, warmup)
+        return ts, {"kind": "reference", "cores": P, "ranks": P,
+                    "how": "unmodified mpiFFT4py %s.R2C (baseline/_ref) under oracle/refshim: %d ranks as threads, "
+                           "numpy.fft backend, memcpy collectives" % (kind, P)}
     port_roundtrip(kind, tuple(max(32, n // 4) for n in Ns), prec, dealias, cores)  # warm-up
-    t = min(port_roundtrip(kind, Ns, prec, dealias, cores) for _ in range(reps))
-    return t, {"kind": "port", "cores": cores,
-               "how": "oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d)" % (kind, cores)}
+    ts = [port_roundtrip(kind, Ns, prec, dealias, cores) for _ in range(reps)]
+    return ts, {"kind": "port", "cores": cores, "ranks": 1,
+                "how": "oracle port of the reference algorithm (%s P=1, pocketfft via scipy.fft workers=%d)" % (kind, cores)}
 
 
 def global_real_shape(Ns, dealias):
@@ -228,13 +233,40 @@ def cpu_baseline(name):
     """About 10-30 s of host work on a bounded sample of the workload."""
     kind, N, prec, dealias, kw = WORKLOADS[name]
     Ns = cpu_sample(name)
-    t, d = cpu_time(name, Ns, 1)
-    if kind != "line" and t < 1.5 and Ns[0] < N[0]:
+    ts, d = cpu_time(name, Ns, 1)
+    if kind != "line" and min(ts) < 1.5 and Ns[0] < N[0]:
         Ns = tuple(2 * n for n in Ns)
-        t, d = cpu_time(name, Ns, 2)
+        ts, d = cpu_time(name, Ns, 2)
+    t = min(ts)
     return {"value": flops_roundtrip(global_real_shape(Ns, dealias)) / t / 1e9, "unit": UNIT, "cores": d["cores"],
             "kind": d["kind"], "sample": "%s; %s %s round trip (dealias=%s), %.2f s" % (d["how"], "x".join(map(str, Ns)), prec, dealias, t),
             "seconds": t, "N": list(Ns), "host_cores": os.cpu_count()}
+
+
+def _host_bytes_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def reference_mesh(name, steps, warmup, budget_s=420.0):
+    """The mesh the reference arm is timed on: the workload's own if the host can hold it and `steps + warmup`
+    round trips fit the time budget, else the largest halving that does.  A probe on a small mesh gives the rate."""
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    Ns = cpu_sample(name)
+    ts, d = cpu_time(name, Ns, 1)
+    rate = flops_roundtrip(global_real_shape(Ns, dealias)) / min(ts)
+    word = 8 if prec == "double" else 4
+    cand = tuple(N)
+    while True:
+        pts = float(np.prod(global_real_shape(cand, dealias)))
+        need = pts * word * 8  # u, fu, u2, the class's work arrays and transients of numpy.fft
+        est = flops_roundtrip(global_real_shape(cand, dealias)) / rate * (steps + warmup) * 1.3 + pts * 2e-8
+        if (need < 0.6 * _host_bytes_available() and est < budget_s) or cand[0] <= Ns[0]:
+            return cand
+        cand = tuple(n // 2 for n in cand)
 
 
 def run_reference(args):
@@ -243,23 +275,26 @@ def run_reference(args):
         return 0
     name = args.workload
     kind, N, prec, dealias, kw = WORKLOADS[name]
-    Ns = cpu_sample(name)
-    t, d = cpu_time(name, Ns, 1)
-    if kind != "line" and t * 8 * (args.steps + args.warmup) < 150.0 and Ns[0] < N[0]:
-        Ns = tuple(2 * n for n in Ns)
-    for _ in range(args.warmup):
-        cpu_time(name, Ns, 1)
-    t0 = time.perf_counter()
-    ts = [cpu_time(name, Ns, 1)[0] for _ in range(args.steps)]
-    wall = (time.perf_counter() - t0) / args.steps
+    Ns = reference_mesh(name, args.steps, args.warmup)
+    ts, d = cpu_time(name, Ns, args.steps, max(1, args.warmup))
     dt = float(np.mean(ts))
     val = flops_roundtrip(global_real_shape(Ns, dealias)) / dt / 1e9
-    cfg = describe(name, 1)
-    sample = "%s on a bounded sample %s %s of the %s workload (setup %.2f s per step excluded)" % (
-        d["how"], "x".join(map(str, Ns)), prec, "x".join(map(str, N)), wall - dt)
+    # config describes what was TIMED: the mesh of this run and the reference's rank count on the host cores
+    cfg = describe(name, d["ranks"])
+    cfg["N"] = list(Ns)
+    cfg["workload"] = "%s.R2C N=%s %s fftn+ifftn round trip, dealias=%s" % (kind, "x".join(map(str, Ns)), prec, dealias)
+    cfg["decomposition"] = "%s P=%d CPU thread-ranks" % (kind, d["ranks"])
+    cfg["l2"] = "host run"
+    full = tuple(Ns) == tuple(N)
+    if not full:
+        cfg["sampled_from"] = {"N": list(N), "why": "host memory / time budget", "compare_as": "GFLOP/s rate, not ms_per_step"}
+    sample = "%s on %s %s %s (%d timed round trips, mean)" % (
+        d["how"], "the full mesh" if full else "a bounded sample of the %s workload:" % "x".join(map(str, N)),
+        "x".join(map(str, Ns)), prec, args.steps)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": cfg,
+           "same_mesh_as_b200_arm": full,
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": d["cores"], "kind": d["kind"], "sample": sample,
                             "host_cores": os.cpu_count()},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -279,6 +314,72 @@ def make_transform(m, comm, name):
     if kind == "pencil":
         return m.Pencil_R2C(Nn, L, comm, prec, **kw)
     return m.Line_R2C(Nn, L, comm, prec)
+
+
+def separable_vectors(N, dealias):
+    pad = 1.5 if dealias == "3/2-rule" else 1
+    rng = np.random.default_rng(4321)
+    return [rng.random(int(pad * n)) + 0.25 for n in N]
+
+
+def separable_spectra(vec, N, dealias, single):
+    """1D spectra whose outer product is the transform of the separable field (see forward_parity)."""
+    padded = dealias == "3/2-rule"
+    pad = 1.5 if padded else 1
+    out = []
+    for ax, (v, n) in enumerate(zip(vec, N)):
+        v = v.astype(np.float32).astype(np.float64) if single else v  # the real array holds v rounded to its precision
+        last = ax == len(N) - 1
+        f = np.fft.rfft(v) if last else np.fft.fft(v)
+        if padded:
+            h = n // 2
+            if last:
+                f = f[:h + 1].copy()
+            else:
+                t = np.zeros(n, dtype=np.complex128)
+                t[:h + 1] = f[:h + 1]
+                t[h:] += f[-h:]
+                f = t
+            f = f / pad
+        out.append(f)
+    return out
+
+
+def forward_parity(F, kind, N, dealias, fwd, u, fu, torch):
+    """rel. L2 error of THIS rank's forward result against the closed form for a separable field
+    u = a(x) b(y) c(z): its transform is the outer product of the three 1D transforms (for the 3/2-rule: each
+    padded-length 1D spectrum truncated with the Nyquist fold of slab.py:529-533 and divided by padsize),
+    cut by complex_local_slice().  One extra transform; works at every rank count and decomposition, so the
+    scaling runs carry forward parity for P > 1 (a round trip alone would also close under a self-inverse
+    permutation mistake).  numpy's 1D FFTs of three vectors are the reference here, nothing from oracle/."""
+    padded = dealias == "3/2-rule"
+    pad = 1.5 if padded else 1
+    dims = len(N)
+    vec = separable_vectors(N, dealias)
+    rs = F.real_local_slice(padsize=pad) if padded else F.real_local_slice()
+    cs = F.complex_local_slice()
+    dev = u.device
+    loc = [torch.from_numpy(np.ascontiguousarray(v[sl])).to(dev).to(u.dtype) for v, sl in zip(vec, rs)]
+    if dims == 3:
+        torch.mul(loc[0][:, None, None] * loc[1][None, :, None], loc[2][None, None, :], out=u)
+    else:
+        torch.mul(loc[0][:, None], loc[1][None, :], out=u)
+    fwd(u, fu, dealias)
+    spec = [torch.from_numpy(np.ascontiguousarray(f[cs[ax]])).to(dev)
+            for ax, f in enumerate(separable_spectra(vec, N, dealias, u.dtype == torch.float32))]
+    num = torch.zeros((), dtype=torch.float64, device=dev)
+    den = torch.zeros((), dtype=torch.float64, device=dev)
+    rows = max(1, (256 << 20) // max(1, fu[0].numel() * 16))
+    for i0 in range(0, fu.shape[0], rows):
+        i1 = min(fu.shape[0], i0 + rows)
+        if dims == 3:
+            ref = spec[0][i0:i1, None, None] * spec[1][None, :, None] * spec[2][None, None, :]
+        else:
+            ref = spec[0][i0:i1, None] * spec[1][None, :]
+        d = fu[i0:i1].to(torch.complex128) - ref
+        num += (d.real ** 2 + d.imag ** 2).sum()
+        den += (ref.real ** 2 + ref.imag ** 2).sum()
+    return float(torch.sqrt(num / den).item())
 
 
 def run_ours(args):
@@ -323,6 +424,15 @@ def run_ours(args):
         if P > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # forward parity at this rank count (max over ranks), before the timed part; u is refilled afterwards
+    fwd_err = None
+    if dealias in (None, "3/2-rule") and not (kind == "line" and dealias):
+        fe = torch.tensor([forward_parity(F, kind, N, dealias, fwd, u, fu, torch)], dtype=torch.float64, device="cuda")
+        if P > 1:
+            dist.all_reduce(fe, op=dist.ReduceOp.MAX)
+        fwd_err = float(fe.item())
+        u.copy_(torch.rand(rshape, dtype=rdt, device="cuda", generator=g))
 
     def step():
         fwd(u, fu, dealias)
@@ -439,7 +549,7 @@ def run_ours(args):
             hu = m.empty(rshape, dtype=rnp)
             hf = m.empty(cshape, dtype=cnp)
             hu[...] = np.random.default_rng(1234 + rank).random(rshape[-1], dtype=np.float64).astype(rnp)  # broadcast rows
-            nst = max(1, min(args.steps, args.e2e_steps))
+            nst = max(1, args.e2e_steps or args.steps)
             fwd(hu, hf, dealias)
             inv(hf, hu, dealias)  # warm-up (allocates the staging buffers)
             barrier()
@@ -486,7 +596,9 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64" if prec == "double" else "f32", "data": "synthetic", "config": cfg,
-               "roundtrip_rel_l2": err, "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
+               "roundtrip_rel_l2": err, "forward_rel_l2": fwd_err,
+               "forward_parity": "separable field a(x)b(y)c(z) vs the outer product of numpy 1D FFTs cut by complex_local_slice(), max over ranks",
+               "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
                "kernels_per_transform": int(k1), "nccl_groups_per_transform": int(x1),
                "roofline": roofline, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
                "workspace_bytes": F.workspace_bytes()}
@@ -503,7 +615,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="slab1024_f64", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tune", default=None, choices=["measure", "patient"],
