@@ -22,6 +22,8 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200fft.h"
@@ -357,10 +359,18 @@ int ensure_program(b200fft_plan* pl, int inverse, int dealias) {
   for (int w = 0; w < NWORK; ++w) {
     const size_t need = (size_t)pg.need[BUF_W0 + w] * csz;
     if (need > pl->wbytes[w]) {
-      if (pl->p2p.connected) return fail(B200FFT_ERR_NOMEM, "P2P plans size their buffers at connect time (need %zu > %zu)", need, pl->wbytes[w]);
+      // (every early return below leaves the program unbuilt, so that a later call cannot run it with
+      // undersized work buffers)
+      if (pl->p2p.connected) {
+        pg.built = false;
+        return fail(B200FFT_ERR_NOMEM, "P2P plans size their buffers at connect time (need %zu > %zu)", need, pl->wbytes[w]);
+      }
       if (pl->ws[w]) {
         cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+        if (e != cudaSuccess) {
+          pg.built = false;
+          return cuda_fail(e, "cudaDeviceSynchronize");
+        }
         cudaFree(pl->ws[w]);
         pl->ws[w] = nullptr;
         pl->wbytes[w] = 0;
@@ -821,12 +831,23 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
 int b200fft_plan_destroy(b200fft_plan_t plan) {
   if (!plan) return 0;
   cudaDeviceSynchronize();
-  for (int w = 0; w < NWORK; ++w)
-    if (plan->ws[w]) cudaFree(plan->ws[w]);
-  for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
   if (plan->p2p.connected) {
+    // Peer-mapped plans: a slower peer's last write into THIS rank's exported memory is the credit word of the
+    // last transform (posted by its last reader, after every push and arrival flag).  Freeing the flags or the
+    // work buffers before it landed would let the peer's DMA hit freed memory, so wait (bounded: a peer that
+    // died never posts) until every peer's credit shows the last call, then drop the imported mappings BEFORE
+    // the exported allocations go.
+    if (plan->p2p.calls > 0 && plan->p2p.flags) {
+      unsigned host[2 * B200FFT_MAXP];
+      for (int spin = 0; spin < 20000; ++spin) {
+        if (cudaMemcpy(host, plan->p2p.flags, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        bool all = true;
+        for (int q = 0; q < plan->d.nranks; ++q)
+          if (q != plan->d.rank && (int)(host[B200FFT_MAXP + q] - plan->p2p.calls) < 0) all = false;
+        if (all) break;
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+      }
+    }
     for (int q = 0; q < plan->d.nranks; ++q) {
       if (q == plan->d.rank) continue;
       for (int w = 0; w < NPEERBUF; ++w)
@@ -834,6 +855,11 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
       if (plan->p2p.peer_flags[q]) cudaIpcCloseMemHandle(plan->p2p.peer_flags[q]);
     }
   }
+  for (int w = 0; w < NWORK; ++w)
+    if (plan->ws[w]) cudaFree(plan->ws[w]);
+  for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
   if (plan->fuse_ctl) cudaFree(plan->fuse_ctl);
   if (plan->p2p.flags) cudaFree(plan->p2p.flags);
   if (plan->p2p.wait_stream) cudaStreamDestroy(plan->p2p.wait_stream);

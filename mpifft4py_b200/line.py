@@ -107,33 +107,11 @@ class R2C(Transform):
     def real_shape_padded(self):
         return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]))
 
-    def complex_padded_xy(self):
-        return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]/2+1))
-
-    def complex_shape_padded_01(self):
-        return (int(self.padsize*self.Np[0]), self.Nf)
-
-    def complex_padded_x(self):
-        return (int(self.padsize*self.N[0]), self.Npf)
-
     def work_shape(self, dealias):
         if dealias == '3/2-rule':
             return self.real_shape_padded()
         else:
             return self.real_shape()
-
-    def copy_to_padded_x(self, fu, fp):
-        fp[:self.N[0]//2] = fu[:self.N[0]//2]
-        fp[-(self.N[0]//2):] = fu[self.N[0]//2:]
-        return fp
-
-    def copy_to_padded_y(self, fu, fp):
-        fp[:, :self.Nf] = fu[:]
-        return fp
-
-    def copy_from_padded_y(self, fp, fu):
-        fu[:] = fp[:, :self.Nf]
-        return fu
 
     def fft2(self, u, fu, dealias=None):
         """Forward 2D transform (``line.py:179-260``)."""

@@ -171,36 +171,7 @@ class R2CY(Transform):
                            (abs(K[2]) < kmax[2]), dtype=np.uint8)
         return dealias
 
-    # host helpers kept for API parity (pencil.py:351-379); fused into the FFT passes by the engine
-    def copy_to_padded_x(self, fu, fp):
-        fp[:self.N[0]//2] = fu[:self.N[0]//2]
-        fp[-(self.N[0]//2):] = fu[self.N[0]//2:]
-        return fp
-
-    def copy_to_padded_y(self, fu, fp):
-        fp[:, :self.N[1]//2] = fu[:, :self.N[1]//2]
-        fp[:, -(self.N[1]//2):] = fu[:, self.N[1]//2:]
-        return fp
-
-    def copy_to_padded_z(self, fu, fp):
-        fp[:, :, :self.Nf] = fu[:]
-        return fp
-
-    def copy_from_padded_z(self, fp, fu):
-        fu[:] = fp[:, :, :self.Nf]
-        return fu
-
-    def copy_from_padded_x(self, fp, fu):
-        fu.fill(0)
-        fu[:self.N[0]//2+1] = fp[:self.N[0]//2+1]
-        fu[self.N[0]//2:] += fp[-self.N[0]//2:]
-        return fu
-
-    def copy_from_padded_y(self, fp, fu):
-        fu.fill(0)
-        fu[:, :self.N[1]//2+1] = fp[:, :self.N[1]//2+1]
-        fu[:, self.N[1]//2:] += fp[:, -self.N[1]//2:]
-        return fu
+    # (copy_to_padded_* / copy_from_padded_* of pencil.py:351-379: index maps inside the FFT passes here)
 
     def global_complex_shape(self, padsize=1.0):
         """Global size of problem in complex wavenumber space"""

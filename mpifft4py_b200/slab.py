@@ -168,54 +168,9 @@ class R2C(Transform):
         """The local shape of the real data"""
         return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]), int(self.padsize*self.N[2]))
 
-    def complex_shape_padded_0(self):
-        """Padding in x-direction"""
-        return (int(self.padsize*self.N[0]), self.Np[1], self.Nf)
-
-    def complex_shape_padded_0_I(self):
-        """Padding in x-direction - reshaped for MPI communications"""
-        return (self.num_processes, int(self.padsize*self.Np[0]), self.Np[1], self.Nf)
-
-    def complex_shape_padded_1(self):
-        """Transpose of complex_shape_padded_0"""
-        return (int(self.padsize*self.Np[0]), self.N[1], self.Nf)
-
-    def complex_shape_padded_2(self):
-        """Padding in x and y-directions"""
-        return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]), self.Nf)
-
-    def complex_shape_padded_3(self):
-        """Padding in all directions."""
-        return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]), self.Nfp)
-
-    def complex_shape_padded_I(self):
-        """A local intermediate shape of the complex data"""
-        return (int(self.padsize*self.Np[0]), self.num_processes, self.Np[1], self.Nf)
-
-    @staticmethod
-    def copy_to_padded(fu, fp, N, axis=0):
-        """Host helper kept for API parity (``slab.py:516-526``); the engine fuses this copy into
-        the load of the following FFT pass."""
-        if axis == 0:
-            fp[:N[0]//2] = fu[:N[0]//2]
-            fp[-N[0]//2:] = fu[N[0]//2:]
-        elif axis == 1:
-            fp[:, :N[1]//2] = fu[:, :N[1]//2]
-            fp[:, -N[1]//2:] = fu[:, N[1]//2:]
-        elif axis == 2:
-            fp[:, :, :(N[2]//2+1)] = fu[:]
-        return fp
-
-    @staticmethod
-    def copy_from_padded(fp, fu, N, axis=0):
-        """Host helper kept for API parity (``slab.py:528-536``); fused into FFT stores by the engine."""
-        if axis == 1:
-            fu.fill(0)
-            fu[:, :N[1]//2+1] = fp[:, :N[1]//2+1, :(N[2]//2+1)]
-            fu[:, N[1]//2:] += fp[:, -N[1]//2:, :(N[2]//2+1)]
-        elif axis == 2:
-            fu[:] = fp[:, :, :(N[2]//2+1)]
-        return fu
+    # The reference's intermediate shapes (complex_shape_padded_0 ... _I) and its copy_to_padded /
+    # copy_from_padded helpers (slab.py:491-536) have no counterpart here: the pad / truncate copies are index
+    # maps inside the FFT passes and the intermediates live in the plan's work buffers.
 
 
 class C2C(R2C):
@@ -276,28 +231,3 @@ class C2C(R2C):
         assert dealias in ('3/2-rule', '2/3-rule', 'None', None)
         ushape = self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
         return self._run(0, u, fu, dealias, ushape, self.complex, self.complex_shape(), self.complex)
-
-    @staticmethod
-    def copy_to_padded(fu, fp, N, axis=0):
-        """Host helper kept for API parity (``slab.py:802-813``)."""
-        if axis == 0:
-            fp[:N[0]//2] = fu[:N[0]//2]
-            fp[-N[0]//2:] = fu[N[0]//2:]
-        elif axis == 1:
-            fp[:, :N[1]//2] = fu[:, :N[1]//2]
-            fp[:, -N[1]//2:] = fu[:, N[1]//2:]
-        elif axis == 2:
-            fp[:, :, :N[2]//2] = fu[:, :, :N[2]//2]
-            fp[:, :, -N[2]//2:] = fu[:, :, N[2]//2:]
-        return fp
-
-    @staticmethod
-    def copy_from_padded(fp, fu, N, axis=0):
-        """Host helper kept for API parity (``slab.py:815-825``)."""
-        if axis == 1:
-            fu.fill(0)
-            fu[:, :N[1]//2+1, :N[2]//2+1] = fp[:, :N[1]//2+1, :N[2]//2+1]
-            fu[:, :N[1]//2+1, N[2]//2:] += fp[:, :N[1]//2+1, -N[2]//2:]
-            fu[:, N[1]//2:, :N[2]//2+1] += fp[:, -N[1]//2:, :N[2]//2+1]
-            fu[:, N[1]//2:, N[2]//2:] += fp[:, -N[1]//2:, -N[2]//2:]
-        return fu

@@ -51,23 +51,34 @@ def _install(F, variant, attrs, set_variant, base=None):
         F._plan = None
 
 
-def select(candidates, measure, tol, reduce_max=lambda x: x):
+def select(candidates, measure, tol, gather=None):
     """Core of the tuner, free of device code: ``measure(candidate) -> (seconds, error vs the default result)``
     (may raise: the candidate is then skipped and reported); a candidate qualifies when its error is within
-    ``tol``; the fastest qualifying one wins, ties and failures fall back to the first candidate (the default).
-    Returns ``(best, report)`` with ``report`` a list of dicts."""
+    ``tol`` ON EVERY RANK; the fastest qualifying one (slowest rank's time) wins, ties and failures fall back to
+    the first candidate (the default).  ``gather(x) -> [x of every rank]`` is called exactly once per candidate,
+    also when ``measure`` raised on this rank, so the ranks of a multi-rank object stay in step and a candidate
+    that is wrong or fails on any one rank is rejected everywhere.  Returns ``(best, report)``."""
+    gather = gather or (lambda x: [x])
     report, best, best_t = [], None, None
     for cand in candidates:
         name = cand[0]
+        mine = (None, None, None)
         try:
             t, err = measure(cand)
-            t = reduce_max(t)
-            ok = bool(err <= tol)
-            report.append({"name": name, "seconds": t, "error": float(err), "ok": ok})
-            if ok and (best_t is None or t < best_t):
-                best, best_t = cand, t
+            mine = (float(t), float(err), None)
         except Exception as e:  # noqa: BLE001 - an opt-in kernel that fails must not take the application down
-            report.append({"name": name, "seconds": None, "error": None, "ok": False, "exception": repr(e)[:200]})
+            mine = (None, None, repr(e)[:200])
+        everyone = gather(mine)
+        failed = [x[2] for x in everyone if x[2] is not None]
+        if failed:
+            report.append({"name": name, "seconds": None, "error": None, "ok": False, "exception": failed[0]})
+            continue
+        t = max(x[0] for x in everyone)
+        err = max(x[1] for x in everyone)
+        ok = bool(err <= tol)
+        report.append({"name": name, "seconds": t, "error": err, "ok": ok})
+        if ok and (best_t is None or t < best_t):
+            best, best_t = cand, t
     if best is None:
         best = candidates[0]
     return best, report
@@ -113,8 +124,7 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
         err = float(torch.linalg.vector_norm(fu - ref["fu"]) / torch.linalg.vector_norm(ref["fu"]))
         return e0.elapsed_time(e1) * 1e-3 / reps, err
 
-    best, report = select(candidates, measure, tol, (lambda t: max(comm.allgather(t))) if many else (lambda t: t))
-    if many:  # every rank must install the same candidate: rank 0's choice (they agree unless times tie)
-        best = candidates[[c[0] for c in candidates].index(comm.bcast(best[0], root=0))]
+    # (every rank sees the same gathered (time, error, failure) triples, so every rank picks the same candidate)
+    best, report = select(candidates, measure, tol, comm.allgather if many else None)
     _install(F, best[1], best[2], L.b200fft_set_variant, base)
     return {"chosen": best[0], "candidates": report}

@@ -23,10 +23,30 @@ def test_default_is_kept_when_nothing_qualifies_and_slowest_rank_decides():
     cands = [("default", 0, {}), ("a", 1, {})]
     best, _ = tune.select(cands, lambda c: (1.0, 1.0), 1e-12)
     assert best[0] == "default"
-    # reduce_max models the allgather over ranks: candidate "a" is fast here but slow on another rank
+    # gather models the allgather over ranks: candidate "a" is fast here but slow on another rank
     best, rep = tune.select(cands, lambda c: ((1.0, 0.0) if c[0] == "default" else (0.5, 0.0)), 1e-12,
-                            reduce_max=lambda t: t if t == 1.0 else 3.0)
+                            gather=lambda x: [x, (x[0] if x[0] == 1.0 else 3.0, x[1], None)])
     assert best[0] == "default" and rep[1]["seconds"] == 3.0
+
+
+def test_a_candidate_wrong_or_failing_on_another_rank_is_rejected_and_the_gather_is_always_called():
+    cands = [("default", 0, {}), ("wrong_elsewhere", 1, {}), ("fails_elsewhere", 2, {}), ("fails_here", 3, {})]
+    calls = []
+
+    def measure(c):
+        if c[0] == "fails_here":
+            raise RuntimeError("boom")
+        return (1.0, 0.0) if c[0] == "default" else (0.1, 0.0)
+
+    def gather(x):
+        calls.append(x)
+        other = {1: (0.1, 1e-3, None), 2: (None, None, "RuntimeError('peer')")}.get(len(calls) - 1, x)
+        return [x, other]
+
+    best, rep = tune.select(cands, measure, 1e-12, gather=gather)
+    assert best[0] == "default" and len(calls) == len(cands)  # one collective per candidate, failures included
+    assert [r["ok"] for r in rep] == [True, False, False, False]
+    assert rep[1]["error"] == 1e-3 and "peer" in rep[2]["exception"] and "boom" in rep[3]["exception"]
 
 
 def test_install_sets_and_clears_plan_attributes():
