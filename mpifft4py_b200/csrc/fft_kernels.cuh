@@ -195,16 +195,26 @@ B2_HD addr_t side_addr(const Side& sd, long long b, int r, long long j) {
 
 // 16 / 8-byte asynchronous global -> shared copy (LDGSTS): no registers hold the data, so a CTA
 // keeps its whole tile in flight; src_bytes == 0 zero-fills (pad rows, masked entries, dead lanes).
+// l2hint: L2 prefetch size of the copy (cp.async ... .L2::128B / .L2::256B): a miss brings the whole 128- /
+// 256-byte chunk around the source into L2, so that the neighbouring column tiles (other CTAs, moments
+// later) hit in L2 and DRAM sees one wide read per row instead of one per tile.
 template <int BYTES>
-B2_HD void async_copy(void* dst_smem, addr_t src, bool valid) {
+B2_HD void async_copy(void* dst_smem, addr_t src, bool valid, int l2hint = 0) {
 #if defined(__CUDA_ARCH__)
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
   const int nb = valid ? BYTES : 0;
-  if constexpr (BYTES == 16)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
-  else
+  if constexpr (BYTES == 16) {
+    if (l2hint == 0)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+    else if (l2hint == 1)
+      asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+    else
+      asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+  } else {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(nb) : "memory");
+  }
 #else
+  (void)l2hint;
   unsigned char* d = reinterpret_cast<unsigned char*>(dst_smem);
   const unsigned char* g = reinterpret_cast<const unsigned char*>(src);
   for (int i = 0; i < BYTES; ++i) d[i] = valid ? g[i] : (unsigned char)0;
@@ -334,6 +344,7 @@ struct StridedParams {
   Mask mask;
   const cx<real>* tw;
   int tws;  // table length / n
+  int l2hint;  // L2 prefetch size of the tile loads: 0 none, 1 = 128 bytes, 2 = 256 bytes
 };
 
 // Tile geometry.  A CTA owns T adjacent columns (ROWB = T*sizeof(complex) contiguous bytes per
@@ -471,7 +482,7 @@ struct StridedK {
         if constexpr (Cfg::TAB) a = tab[i];
         else a = in_row(p, b, i, jin);
         const bool ok = (a != 0) && !colzero;
-        async_copy<CB>(sm + swz<M0, Cfg::SW>(i) * T, ok ? a + (addr_t)(cin * CB) : fallback, ok);
+        async_copy<CB>(sm + swz<M0, Cfg::SW>(i) * T, ok ? a + (addr_t)(cin * CB) : fallback, ok, p.l2hint);
       }
     } else if constexpr (s == 2) {  // store-row address table (overlaps the loads in flight)
       if constexpr (Cfg::TAB)

@@ -50,7 +50,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--workloads", default="slab1024_f64,slab1024_f64_32")
     ap.add_argument("--only", default="")
+    ap.add_argument("--variants", default="", help="comma-separated kernel variants to run instead of the built-in list")
     args = ap.parse_args()
+    global CONFIGS
+    if args.variants:
+        CONFIGS = [("default", 0, {})] + [("variant(%s)" % v, int(v), {}) for v in args.variants.split(",") if int(v) != 0]
     L = _lib.lib()
     peak = 6554.9
     try:
