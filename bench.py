@@ -578,11 +578,9 @@ def run_ours(args):
     if P > 1:
         dist.barrier()
     cfg = describe(name, P)
-    # opt-in kernels / schedules that were active (environment switches): a line measured
-    # with any of them says so
-    tuning = {k: os.environ[k] for k in ("B200FFT_VARIANT", "B200FFT_L2_PLANES", "B200FFT_L2_MODE", "B200FFT_TRANSPORT",
-                                          "B200FFT_PIPELINE", "B200FFT_CHUNKS", "B200FFT_KZ_BLOCK", "B200FFT_COPY_STREAMS")
-              if os.environ.get(k)}
+    # plan options set through the environment: a line measured with any of them says so
+    tuning = {k: os.environ[k] for k in ("B200FFT_LAYOUT", "B200FFT_TRANSPORT", "B200FFT_PIPELINE", "B200FFT_CHUNKS",
+                                          "B200FFT_COPY_STREAMS") if os.environ.get(k)}
     if tuned is not None:
         tuning["planner"] = {"effort": args.tune, "chosen": tuned["chosen"],
                              "candidates": [{k: c.get(k) for k in ("name", "seconds", "ok")} for c in tuned["candidates"]]}

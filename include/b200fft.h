@@ -31,6 +31,7 @@ enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LIN
        B200FFT_SLAB_C2C = 4 /* slab.C2C, slab.py:538-825: u and fu are both complex */ };
 enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
 enum { B200FFT_PIPELINE_X = 0, B200FFT_PIPELINE_KZ = 1 };
+enum { B200FFT_LAYOUT_YBLOCK = 0, B200FFT_LAYOUT_NATURAL = 1 };
 enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1,
        B200FFT_TRANSPORT_STORE = 2 /* fused: the producing FFT pass stores into the peers' buffers */ };
 
@@ -48,19 +49,6 @@ B200FFT_API int b200fft_version(void);
 B200FFT_API const char* b200fft_last_error(void);
 /* 1 if complex length n has a kernel plan (n = 2^k or 3*2^k within the supported range) */
 B200FFT_API int b200fft_supported_length(int n);
-/* Tuning switch for A/B measurements (same as the B200FFT_VARIANT environment variable): selects an
- * alternative kernel or radix plan where one is compiled; 0 = the defaults.  Returns the old value.
- * 20: strided passes with rows >= 1 MB apart run on 2-CTA clusters (128-byte rows split over
- * distributed shared memory); 22: also near-stride passes of n >= 1536, with 64-byte rows; 21 / 23: all
- * strided passes that have a cluster plan do (128- / 64-byte rows; testing aids); 31: register-staged
- * C2R kernel (loads its spectrum pairs straight into registers, like the R2C kernel, no staging copy);
- * 32: the 3/2-rule row kernels (last radix 12) compiled for four resident CTAs per SM instead of three;
- * 33: R2C kernel with the split step folded into a paired last stage (one shared-memory round trip less);
- * 34: C2R kernel with the merge step folded into a paired first stage (loads from HBM into registers);
- * 35: strided pass whose first stage loads straight from HBM into registers (no staging copy of the tile);
- * 100 + bits combines switches (1: as 20, 2: the n >= 2048 part of 22, 4: as 30, 8: as 31, 16: as 32, 32: as 33, 64: as 34, 128: as 35); 30: the threads of a
- * row of the R2C / C2R passes synchronise on a named barrier of their own instead of the CTA's. */
-B200FFT_API int b200fft_set_variant(int v);
 
 /* ---------------------------------------------------------------------------------------------
  * Low level: one fused FFT pass.  These are what serialFFT.fft/ifft/rfft/irfft (and the copies
@@ -80,11 +68,6 @@ typedef struct {
   int chunk;
   int nchunk;
   int nphys; /* physical extent along the FFT axis; < n means zero-pad (load) / truncate (store) */
-  /* optional blocking of the contiguous index j (strided passes): jc > 0 places column j at
-   * (j / jc) * sj + (j % jc) instead of j -- a kz-blocked intermediate array [block][...][jc] whose rows
-   * along the transformed axis are closer together than in the natural layout.  0 = plain. */
-  int jc;
-  long long sj;
 } b200fft_side_t;
 
 /* 2/3-rule mask folded into a load (dealias_filter maths.pyx:9-19; get_dealias_filter
@@ -130,6 +113,13 @@ typedef struct {
   void* real_base;
   long long rpitch;
   b200fft_side_t cside;
+  /* optional permutation of the rows on the complex side ("y-blocked" intermediate of single-rank slab plans):
+   * with rm_block > 0 real row r = x * rm_period + y has its spectrum at complex row
+   *     ((y / rm_block) * rm_planes + x) * rm_block + y % rm_block
+   * i.e. the array [x][y][k] is kept as [y block][x][y in block][k].  A pass along x then finds its rows
+   * rm_block * (row length) apart instead of rm_period * (row length), and a pass along y reads whole
+   * contiguous blocks.  rm_block == 0: row r at complex row r. */
+  long long rm_period, rm_block, rm_planes;
 } b200fft_rows_desc_t;
 
 /* Stream-ordered copy with cudaMemcpyDefault (either side may be host memory; pinned host memory
@@ -141,18 +131,6 @@ B200FFT_API int b200fft_stream_sync(void* stream);
 B200FFT_API int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
-/* The z and y passes of a single-rank slab transform (rfft2 / irfft2 of slab.py:366-370,247-268) as ONE
- * persistent kernel that keeps the intermediate in L2: the planes (batch entries of `cols`) are cut into
- * groups of `planes_per_group` and the blocks of both passes are pulled from one queue ordered so that
- * the second pass of a group runs right after the first (held back by a counter until it is complete).
- * `rows` is the R2C (forward) or C2R (inverse_order != 0) pass over rows = planes * rows-per-plane,
- * `cols` the strided pass along y with B = planes; forward runs rows then cols, inverse cols then rows.
- * `ctl` is device scratch of 4097 32-bit words.  Returns B200FFT_ERR_UNSUPPORTED when no fused kernel
- * exists for the size pair or there would be more than 4096 groups (callers then run the two passes
- * separately). */
-B200FFT_API int b200fft_exec_fused_zy(const b200fft_rows_desc_t* rows, const b200fft_strided_desc_t* cols, int inverse_order,
-                                      int planes_per_group, void* ctl, void* stream);
-
 /* ---------------------------------------------------------------------------------------------
  * Communicators: replace the mpi4py communicator (comm.Alltoall / Alltoallw / Sendrecv_replace /
  * Scatter / Send / Recv call sites listed in SURVEY.md section 2 row 7) by NCCL over NVLink.
@@ -189,22 +167,12 @@ typedef struct {
                       planes -- z(c), y(c) | exchange(c), then one x pass; B200FFT_PIPELINE_KZ by kz
                       ranges -- one z pass, then y(c) | exchange(c) | x(c), so the exchange overlaps
                       FFT passes on BOTH sides (three-stage pipeline; receive layout is chunk-major) */
-  int l2_planes;   /* slab plans: > 0 runs the z and y passes per group of this many local x planes
-                      (z(g), y(g), z(g+1), ...) so that the y pass finds the z pass's output -- and the
-                      inverse z pass the y pass's -- still in the 126 MB L2: the intermediate
-                      (rfft2 / irfft2 of slab.py:366-370,247-268) then costs no HBM round trip.
-                      0 = one launch per pass */
-  int kz_block;    /* single-rank slab plans: > 0 keeps the array between the passes kz-blocked,
-                      [kz block of this many entries][x][y][.], so that the x pass has only one far-strided
-                      side (the caller's array) and the y pass none; at most 16 blocks; 0 = natural layout */
   int copy_streams;/* copy-engine transport: 1 = one copy stream per peer, so that the per-copy issue latency
                       (~25 us) of the pushes to different peers overlaps instead of adding up (8 GPUs: 7 peers
                       per exchange step); 0 = all pushes in order on the communication stream */
-  int l2_mode;     /* how the groups of an L2-blocked single-rank plan are issued: 0 / 1 = launches on one
-                      stream; 2 = the two passes of a group on two streams, so that the next group's first
-                      pass overlaps this group's second (at most two groups in flight); 3 = ONE persistent
-                      kernel that pulls the blocks of both passes from a queue in dependency order
-                      (b200fft_exec_fused_zy): no launch gaps, no partly empty last waves */
+  int layout;      /* single-rank slab.R2C plans: B200FFT_LAYOUT_YBLOCK (0, default) keeps the array between the
+                      passes y-blocked and runs z, x, y (inverse y, x, z) so that no pass has rows megabytes apart;
+                      B200FFT_LAYOUT_NATURAL runs z, y, x on [x][y][kz] like slab.py:366-370 (A/B measurements) */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

@@ -7,13 +7,14 @@ SLAB, PENCIL_X, PENCIL_Y, LINE, SLAB_C2C = 0, 1, 2, 3, 4
 DEALIAS_NONE, DEALIAS_3_2, DEALIAS_2_3 = 0, 1, 2
 TRANSPORT_NCCL, TRANSPORT_P2P, TRANSPORT_STORE = 0, 1, 2
 PIPELINE_X, PIPELINE_KZ = 0, 1
+LAYOUT_YBLOCK, LAYOUT_NATURAL = 0, 1
 
 ERR_ARG, ERR_RANKS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = 1, 2, 3, 4, 5, 6
 
 
 class Side(C.Structure):
     _fields_ = [("base", C.c_void_p * MAXP), ("sb", C.c_longlong * MAXP), ("si", C.c_longlong * MAXP),
-                ("chunk", C.c_int), ("nchunk", C.c_int), ("nphys", C.c_int), ("jc", C.c_int), ("sj", C.c_longlong)]
+                ("chunk", C.c_int), ("nchunk", C.c_int), ("nphys", C.c_int)]
 
 
 class Mask(C.Structure):
@@ -34,7 +35,7 @@ class StridedDesc(C.Structure):
 class RowsDesc(C.Structure):
     _fields_ = [("precision", C.c_int), ("n", C.c_int), ("rows", C.c_longlong), ("nk", C.c_int),
                 ("scale", C.c_double), ("real_base", C.c_void_p), ("rpitch", C.c_longlong),
-                ("cside", Side)]
+                ("cside", Side), ("rm_period", C.c_longlong), ("rm_block", C.c_longlong), ("rm_planes", C.c_longlong)]
 
 
 class PlanDesc(C.Structure):
@@ -42,8 +43,7 @@ class PlanDesc(C.Structure):
                 ("nranks", C.c_int), ("rank", C.c_int), ("P1", C.c_int), ("P2", C.c_int),
                 ("padsize", C.c_double), ("drop_nyquist", C.c_int), ("transport", C.c_int),
                 ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int),
-                ("l2_planes", C.c_int), ("kz_block", C.c_int), ("copy_streams", C.c_int),
-                ("l2_mode", C.c_int)]
+                ("copy_streams", C.c_int), ("layout", C.c_int)]
 
 
 def no_mask():

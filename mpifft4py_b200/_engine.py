@@ -63,12 +63,11 @@ class Transform(object):
         pipe = str(getattr(self, "exchange_pipeline", None) or os.environ.get("B200FFT_PIPELINE", "x")).lower()
         assert pipe in ("x", "kz"), "exchange_pipeline must be 'x' or 'kz'"
         d.pipeline = D.PIPELINE_KZ if pipe == "kz" else D.PIPELINE_X
-        # L2 blocking of the z and y passes of slab plans: run them per group of this many x planes so
-        # that the y pass reads what the z pass just wrote from L2 instead of HBM (0 = whole array)
-        d.l2_planes = int(getattr(self, "l2_planes", 0) or os.environ.get("B200FFT_L2_PLANES", "0"))
-        d.l2_mode = int(getattr(self, "l2_mode", 0) or os.environ.get("B200FFT_L2_MODE", "0"))
-        # single-rank slab plans: kz-blocked intermediate array (only one far-strided side left in the x pass)
-        d.kz_block = int(getattr(self, "kz_block", 0) or os.environ.get("B200FFT_KZ_BLOCK", "0"))
+        # single-rank slab.R2C plans keep the array between the passes y-blocked (no pass with rows megabytes
+        # apart); "natural" runs z, y, x on [x][y][kz] as the reference does (A/B measurements)
+        lay = str(getattr(self, "layout", None) or os.environ.get("B200FFT_LAYOUT", "yblock")).lower()
+        assert lay in ("yblock", "natural"), "layout must be 'yblock' or 'natural'"
+        d.layout = D.LAYOUT_NATURAL if lay == "natural" else D.LAYOUT_YBLOCK
         # copy-engine transport: one copy stream per peer (overlaps the per-copy issue latency)
         d.copy_streams = int(getattr(self, "copy_streams", 0) or os.environ.get("B200FFT_COPY_STREAMS", "0"))
         # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do

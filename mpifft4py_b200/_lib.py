@@ -18,8 +18,7 @@ SYMBOLS = [
     "b200fft_plan_create", "b200fft_plan_destroy", "b200fft_plan_workspace_bytes",
     "b200fft_exec_forward", "b200fft_exec_inverse", "b200fft_plan_last_launches",
     "b200fft_plan_set_timing", "b200fft_plan_last_phase_ms", "b200fft_plan_last_steps",
-    "b200fft_plan_p2p_handles", "b200fft_plan_p2p_connect", "b200fft_set_variant",
-    "b200fft_exec_fused_zy",
+    "b200fft_plan_p2p_handles", "b200fft_plan_p2p_connect",
 ]
 
 
@@ -32,14 +31,11 @@ def declare(L):
     L.b200fft_version.restype = C.c_int
     L.b200fft_last_error.restype = C.c_char_p
     L.b200fft_supported_length.argtypes = [C.c_int]
-    L.b200fft_set_variant.argtypes = [C.c_int]
     L.b200fft_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.b200fft_stream_sync.argtypes = [C.c_void_p]
     L.b200fft_exec_strided.argtypes = [C.POINTER(D.StridedDesc), C.c_void_p]
     L.b200fft_exec_r2c.argtypes = [C.POINTER(D.RowsDesc), C.c_void_p]
     L.b200fft_exec_c2r.argtypes = [C.POINTER(D.RowsDesc), C.c_void_p]
-    L.b200fft_exec_fused_zy.argtypes = [C.POINTER(D.RowsDesc), C.POINTER(D.StridedDesc), C.c_int, C.c_int, C.c_void_p,
-                                        C.c_void_p]
     L.b200fft_comm_unique_id.argtypes = [C.c_void_p]
     L.b200fft_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
     L.b200fft_comm_destroy.argtypes = [C.c_void_p]

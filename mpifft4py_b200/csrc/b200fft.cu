@@ -45,17 +45,6 @@ bool plan_exists(int n) {
       return false;
   }
 }
-static std::atomic<int> g_variant{-1};
-int kernel_variant() {
-  int v = g_variant.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = std::getenv("B200FFT_VARIANT");
-    v = e ? std::atoi(e) : 0;
-    if (v < 0) v = 0;
-    g_variant.store(v, std::memory_order_relaxed);
-  }
-  return v;
-}
 }  // namespace b200fft
 
 namespace {
@@ -132,34 +121,6 @@ int exec_rows(const b200fft_rows_desc_t& d, bool fwd, cudaStream_t st) {
     rc = fwd ? launch_r2c_f32(h, p, st) : launch_c2r_f32(h, p, st);
   }
   return map_launch_rc(rc, fwd ? "R2C pass" : "C2R pass", d.n);
-}
-
-// z + y passes as one persistent kernel through L2; B200FFT_ERR_UNSUPPORTED (without touching memory) when
-// there is no fused kernel for the pair or the grids do not split into `groups`
-int exec_fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg, void* ctl,
-                  cudaStream_t st) {
-  if (const char* e = check_rows(r)) return fail(B200FFT_ERR_ARG, "fused row pass: %s", e);
-  if (const char* e = check_strided(c)) return fail(B200FFT_ERR_ARG, "fused strided pass: %s", e);
-  if (r.precision != c.precision || !ctl || ppg < 1 || c.B < 1 || r.rows % c.B)
-    return fail(B200FFT_ERR_ARG, "fused passes: bad arguments (rows must be a whole number per plane)");
-  if (contiguous_rows(c)) return fail(B200FFT_ERR_UNSUPPORTED, "fused passes: the column pass must be strided");
-  if (c.in.jc > 0 || c.out.jc > 0) return fail(B200FFT_ERR_UNSUPPORTED, "fused passes: no kernel for blocked column layouts");
-  int rc;
-  if (r.precision == B200FFT_DOUBLE) {
-    const cx<double>*twr, *twc;
-    if (int e = get_tw<double>(r.n, &twr)) return e;
-    if (int e = get_tw<double>(c.n, &twc)) return e;
-    rc = launch_fused_zy_f64(r.n / 2, c.n, convert_rows<double>(r, twr, 1, !inverse_order), convert_strided<double>(c, twc, 1),
-                             inverse_order, ppg, (unsigned*)ctl, st);
-  } else {
-    const cx<float>*twr, *twc;
-    if (int e = get_tw<float>(r.n, &twr)) return e;
-    if (int e = get_tw<float>(c.n, &twc)) return e;
-    rc = launch_fused_zy_f32(r.n / 2, c.n, convert_rows<float>(r, twr, 1, !inverse_order), convert_strided<float>(c, twc, 1),
-                             inverse_order, ppg, (unsigned*)ctl, st);
-  }
-  if (rc == -1 || rc == -3) return fail(B200FFT_ERR_UNSUPPORTED, "no fused z+y kernel for rows of %d and columns of %d, %d planes per group", r.n, c.n, ppg);
-  return map_launch_rc(rc, "fused z+y passes", c.n);
 }
 
 // ---- NCCL through dlopen: the library loads (and does P == 1 work) without NCCL ---------------
@@ -260,7 +221,6 @@ struct b200fft_plan {
     unsigned seq = 0;                        // exchange steps executed so far (identical on all ranks)
     unsigned calls = 0;                      // transforms with exchanges executed so far
   } p2p;
-  unsigned* fuse_ctl = nullptr;         // queue head + per-group counters of fused z+y launches
   cudaStream_t comm_stream = nullptr;   // exchanges of pipelined programs run here
   std::vector<cudaEvent_t> sched_ev;    // ordering events between the two streams
   std::vector<cudaEvent_t> ev;  // timing events, two per step (grown on demand)
@@ -408,8 +368,6 @@ void fill_side(const b200fft_plan* pl, const SideT& s, b200fft_side_t& o, const 
   o.chunk = s.chunk;
   o.nchunk = s.nchunk;
   o.nphys = s.nphys;
-  o.jc = s.jc;
-  o.sj = s.sj;
 }
 
 int run_exchange(b200fft_plan* pl, const Step& s, const void* in, void* out, size_t csz, cudaStream_t st) {
@@ -561,6 +519,9 @@ b200fft_rows_desc_t rows_desc(const b200fft_plan* pl, const Step& s, const void*
   d.real_base = resolve(pl, s.real, in, out, csz / 2);
   d.rpitch = s.rpitch;
   fill_side(pl, s.cside, d.cside, in, out, csz);
+  d.rm_period = s.rm_period;
+  d.rm_block = s.rm_block;
+  d.rm_planes = s.rm_planes;
   return d;
 }
 
@@ -632,37 +593,7 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       if (int rc = wait_credits(pl, st)) return rc;
     if (pl->timing) cudaEventRecord(pl->ev[(size_t)evi], st);
     int rc = 0;
-    bool fused = false;
-    if (s.fuse_planes > 0 && si + 1 < pg.steps.size() && pg.steps[si + 1].stream == s.stream) {
-      // z + y (inverse: y + z) as one persistent kernel through L2; two launches if no such kernel exists
-      const Step& t = pg.steps[si + 1];
-      const Step& rs = (s.type == ST_STRIDED) ? t : s;
-      const Step& cs = (s.type == ST_STRIDED) ? s : t;
-      // the second pass's own preconditions hold for the whole launch
-      if (t.wait_ev >= 0) {
-        cudaError_t e = cudaStreamWaitEvent(st, pl->sched_ev[(size_t)t.wait_ev], 0);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-      }
-      if (use_p2p && t.wait_credits)
-        if (int rc2 = wait_credits(pl, st)) return rc2;
-      if (!pl->fuse_ctl) {
-        cudaError_t e = cudaMalloc(&pl->fuse_ctl, sizeof(unsigned) * FUSE_CTL_WORDS);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fuse control words)");
-      }
-      if (cs.type == ST_STRIDED && (rs.type == ST_R2C || rs.type == ST_C2R)) {
-        rc = exec_fused_zy(rows_desc(pl, rs, in, out, csz), strided_desc(pl, cs, in, out, csz), s.type == ST_STRIDED, s.fuse_planes,
-                           pl->fuse_ctl, st);
-        if (rc == 0) {
-          fused = true;
-          pl->last_kernels++;
-        } else if (rc == B200FFT_ERR_UNSUPPORTED) {
-          rc = 0;
-        }
-      }
-    }
-    if (rc || fused) {
-      // error, or both steps done by the fused launch
-    } else if (s.type == ST_STRIDED) {
+    if (s.type == ST_STRIDED) {
       rc = exec_strided(strided_desc(pl, s, in, out, csz), st);
       pl->last_kernels++;
     } else if (s.type == ST_R2C || s.type == ST_C2R) {
@@ -679,8 +610,7 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
     pl->st_type.push_back((int)s.type);
     pl->st_len.push_back(s.type == ST_EXCH ? s.npeers : s.n);
     pl->st_pass.push_back(s.pass);
-    // (a fused launch is reported as its first pass, with the bytes of both)
-    pl->st_bytes.push_back(step_bytes(s, csz) + (fused ? step_bytes(pg.steps[si + 1], csz) : 0.0));
+    pl->st_bytes.push_back(step_bytes(s, csz));
     if (pl->timing) {
       cudaEventRecord(pl->ev[(size_t)evi + 1], st);
       pl->ev_marks.emplace_back(evi, s.type == ST_EXCH ? 1 : 0);
@@ -692,15 +622,7 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
       cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)s.rec_ev], st);
       if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
     }
-    bool last_reader = s.last_reader != 0;
-    if (fused) {  // the next step ran inside the fused launch: its event and credits follow the launch
-      const Step& t = pg.steps[++si];
-      if (t.rec_ev >= 0) {
-        cudaError_t e = cudaEventRecord(pl->sched_ev[(size_t)t.rec_ev], st);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-      }
-      last_reader = last_reader || t.last_reader != 0;
-    }
+    const bool last_reader = s.last_reader != 0;
     if (use_p2p && last_reader) {  // hand the receive buffers back to the peers
       for (int q = 0; q < pl->d.nranks; ++q)
         if (q != pl->d.rank)
@@ -723,12 +645,6 @@ int b200fft_version(void) { return 100; }
 const char* b200fft_last_error(void) { return g_err.c_str(); }
 
 int b200fft_supported_length(int n) { return plan_exists(n) ? 1 : 0; }
-
-int b200fft_set_variant(int v) {
-  const int old = b200fft::kernel_variant();
-  b200fft::g_variant.store(v < 0 ? 0 : v, std::memory_order_relaxed);
-  return old;
-}
 
 int b200fft_copy(void* dst, const void* src, size_t bytes, void* stream) {
   if (bytes == 0) return 0;
@@ -757,12 +673,6 @@ int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream) {
 int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream) {
   if (!d) return fail(B200FFT_ERR_ARG, "null descriptor");
   return exec_rows(*d, false, (cudaStream_t)stream);
-}
-
-int b200fft_exec_fused_zy(const b200fft_rows_desc_t* rows, const b200fft_strided_desc_t* cols, int inverse_order, int planes_per_group,
-                          void* ctl, void* stream) {
-  if (!rows || !cols) return fail(B200FFT_ERR_ARG, "null descriptor");
-  return exec_fused_zy(*rows, *cols, inverse_order, planes_per_group, ctl, (cudaStream_t)stream);
 }
 
 int b200fft_comm_unique_id(void* id128) {
@@ -860,7 +770,6 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
   for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->sched_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
-  if (plan->fuse_ctl) cudaFree(plan->fuse_ctl);
   if (plan->p2p.flags) cudaFree(plan->p2p.flags);
   if (plan->p2p.wait_stream) cudaStreamDestroy(plan->p2p.wait_stream);
   for (int q = 0; q < B200FFT_MAXP; ++q) {

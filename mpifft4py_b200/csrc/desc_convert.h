@@ -85,6 +85,9 @@ RowParams<real> convert_rows(const b200fft_rows_desc_t& d, const cx<real>* tw, i
   p.scale = (real)d.scale;
   p.tw = tw;
   p.tws = tws;
+  p.rm_period = d.rm_period;
+  p.rm_block = d.rm_block;
+  p.rm_planes = d.rm_planes;
   return p;
 }
 
@@ -96,8 +99,7 @@ inline const char* check_side(const b200fft_side_t& s, int n, bool strided) {
   if (s.nchunk > 1 && (long long)s.chunk * (s.nchunk - 1) >= s.nphys) return "side chunks exceed extent";
   for (int p = 0; p < s.nchunk; ++p)
     if (!s.base[p]) return "side.base is null";
-  if (s.jc < 0 || (s.jc > 0 && s.sj <= 0)) return "side.jc / side.sj out of range";
-  if (s.jc > 0 && !strided) return "blocked columns are for strided passes";
+  (void)strided;
   return nullptr;
 }
 
@@ -118,8 +120,7 @@ inline const char* check_strided(const b200fft_strided_desc_t& d) {
 
 // a strided pass whose "columns" are single elements of contiguous rows: served by the row C2C kernel
 inline bool contiguous_rows(const b200fft_strided_desc_t& d) {
-  return d.J == 1 && d.in.nchunk == 1 && d.out.nchunk == 1 && d.in.si[0] == 1 && d.out.si[0] == 1 && !d.mask.on &&
-         d.in.jc == 0 && d.out.jc == 0;
+  return d.J == 1 && d.in.nchunk == 1 && d.out.nchunk == 1 && d.in.si[0] == 1 && d.out.si[0] == 1 && !d.mask.on;
 }
 
 inline const char* check_rows(const b200fft_rows_desc_t& d) {
@@ -132,7 +133,8 @@ inline const char* check_rows(const b200fft_rows_desc_t& d) {
   if (s.nchunk < 1 || s.nchunk > B200FFT_MAXP) return "cside.nchunk out of range";
   for (int p = 0; p < s.nchunk; ++p)
     if (!s.base[p]) return "cside.base is null";
-  if (s.jc != 0) return "blocked columns are for strided passes";
+  if (d.rm_block < 0 || (d.rm_block > 0 && (d.rm_period < 1 || d.rm_planes < 1 || d.rm_period % d.rm_block || d.rows > d.rm_period * d.rm_planes)))
+    return "bad row map (rm_block must divide rm_period; rows <= rm_period * rm_planes)";
   return nullptr;
 }
 

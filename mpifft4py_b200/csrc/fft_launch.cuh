@@ -42,67 +42,18 @@ int configure_kernel(Kernel kernel, int threads, int smem, bool want_resident, s
   return 0;
 }
 
-template <class K, bool RB = false>
+template <class K>
 int launch_k(const typename K::Params& p, cudaStream_t st) {
   if (K::SMEM > SMEM_LIMIT) return -1;
   static std::mutex mu;
   static std::map<int, unsigned long long> done;
   unsigned long long resident = 0;  // CTAs the device holds at once (persistent kernels)
-  if (int rc = configure_kernel(fft_kernel<K, RB>, K::NT, K::SMEM, K::PIPE, mu, done, &resident)) return rc;
+  if (int rc = configure_kernel(fft_kernel<K>, K::NT, K::SMEM, K::PIPE, mu, done, &resident)) return rc;
   unsigned long long nblk = K::blocks(p);
   if (nblk == 0) return 0;
   if (nblk > 2147483647ull) return -2;
   if (K::PIPE && nblk > resident) nblk = resident;
-  fft_kernel<K, RB><<<(unsigned)nblk, K::NT, K::SMEM, st>>>(p);
-  return (int)cudaGetLastError();
-}
-
-// 2-CTA cluster kernels (ClusterStridedK): the cluster shape is a compile-time attribute of the kernel,
-// the grid holds two CTAs per column tile
-template <class K>
-int launch_cluster_k(const typename K::Params& p, cudaStream_t st) {
-  if (K::SMEM > SMEM_LIMIT) return -1;
-  static std::mutex mu;
-  static std::map<int, unsigned long long> done;
-  unsigned long long unused = 0;
-  if (int rc = configure_kernel(fft_cluster_kernel<K>, K::NT, K::SMEM, false, mu, done, &unused)) return rc;
-  const unsigned long long nblk = K::blocks(p);
-  if (nblk == 0) return 0;
-  if (nblk > 2147483647ull) return -2;
-  fft_cluster_kernel<K><<<(unsigned)nblk, K::NT, K::SMEM, st>>>(p);
-  return (int)cudaGetLastError();
-}
-
-// Fused pair of passes (fused_pair_kernel) over `planes` planes in groups of `planes_per_group`.  `ctl`
-// points at FUSE_CTL_WORDS words of device memory (queue head + per-group counters); -3 when there would
-// be more groups than that or a group smaller than one block.
-
-template <class KA, class KB>
-int launch_fused_pair(const typename KA::Params& pa, const typename KB::Params& pb, long long planes, long long planes_per_group,
-                      unsigned* ctl, cudaStream_t st) {
-  using F = FusePair<KA, KB>;
-  if (F::SMEM > SMEM_LIMIT) return -1;
-  if (planes < 1 || planes_per_group < 1) return -3;
-  const long long groups = (planes + planes_per_group - 1) / planes_per_group;
-  FuseCtl c;
-  c.a = KA::fuse_side(pa, planes, planes_per_group);
-  c.b = KB::fuse_side(pb, planes, planes_per_group);
-  if (groups + 1 > FUSE_CTL_WORDS || c.a.n == 0 || c.b.n == 0 || c.a.upg < c.a.upb || c.b.upg < c.b.upb ||
-      (unsigned long long)c.a.n + c.b.n > 2147483647ull)
-    return -3;
-  static std::mutex mu;
-  static std::map<int, unsigned long long> done;
-  unsigned long long resident = 0;
-  if (int rc = configure_kernel(fused_pair_kernel<KA, KB>, F::NT, F::SMEM, true, mu, done, &resident)) return rc;
-  cudaError_t e = cudaMemsetAsync(ctl, 0, sizeof(unsigned) * (size_t)(1 + groups), st);
-  if (e != cudaSuccess) return (int)e;
-  c.ctr = ctl;
-  c.done = ctl + 1;
-  c.G = (unsigned)groups;
-  // every CTA of the grid must be resident (a waiting block relies on the blocks before it making progress)
-  const unsigned long long total = (unsigned long long)c.a.n + c.b.n;
-  const unsigned long long grid = total < resident ? total : resident;
-  fused_pair_kernel<KA, KB><<<(unsigned)grid, F::NT, F::SMEM, st>>>(pa, pb, c);
+  fft_kernel<K><<<(unsigned)nblk, K::NT, K::SMEM, st>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -51,8 +51,6 @@ struct SideT {
   long long sb[PMAXP] = {0};
   long long si[PMAXP] = {0};
   int chunk = 1, nchunk = 1, nphys = 1;
-  int jc = 0;        // > 0: blocked column map, column j at (j / jc) * sj + (j % jc)
-  long long sj = 0;
 };
 
 enum StepType { ST_STRIDED, ST_R2C, ST_C2R, ST_EXCH };
@@ -73,15 +71,12 @@ struct Step {
   Ref real;
   long long rpitch = 0;
   SideT cside;
+  long long rm_period = 0, rm_block = 0, rm_planes = 0;  // complex-side row permutation (b200fft_rows_desc_t)
   // scheduling: stream 0 = the caller's stream (FFT passes), 1 = the plan's communication stream;
   // wait_ev: event the step's stream waits for before the step (-1 none); rec_ev: event recorded
   // after it.  Lets the exchange of one chunk overlap the FFT passes of the next.
   int stream = 0, wait_ev = -1, wait_ev2 = -1, rec_ev = -1;
   int pass = 0;  // logical pass of the transform this step belongs to (chunks of one pass share it)
-  // > 0: this step and the next (a row pass and a strided pass over the same planes) run as ONE persistent
-  // kernel that keeps the intermediate in L2, the planes cut into groups of this many (l2_mode 3); the
-  // executor falls back to two launches when no fused kernel exists for the sizes
-  int fuse_planes = 0;
   // exchange
   int comm = 0;  // 0: world, 1: comm0, 2: comm1
   int npeers = 0, me = 0;
@@ -274,40 +269,6 @@ inline int finish_peer_mapped(const b200fft_plan_desc_t& d, Program& pg) {
   return 0;
 }
 
-// Two-stream schedule of an L2-blocked single-rank program (d.l2_mode == 2).  On one stream every
-// small launch drains before the next starts; here the first pass of a group runs on the caller's
-// stream and the second on the plan's second stream, so group g+1's first pass fills the SMs that
-// group g's second pass leaves idle.  At most two groups are in flight (the first pass of group g+2
-// waits for the second pass of group g), which bounds the L2 footprint.
-//   forward  [z0 y0 z1 y1 ... x]:  z on stream 0, y on stream 1, x after the last y
-//   inverse  [x y0 z0 y1 z1 ...]:  y on stream 1, z on stream 0
-inline void two_stream_groups(Program& pg, int inverse) {
-  const int n = (int)pg.steps.size(), G = (n - 1) / 2;
-  if (G < 2 || n != 2 * G + 1) return;
-  std::vector<int> first_ev((size_t)G), second_ev((size_t)G);
-  for (int g = 0; g < G; ++g) {
-    first_ev[(size_t)g] = pg.nevents++;
-    second_ev[(size_t)g] = pg.nevents++;
-  }
-  const int base = inverse ? 1 : 0;
-  int x_ev = -1;
-  if (inverse) x_ev = pg.steps[0].rec_ev = pg.nevents++;
-  for (int g = 0; g < G; ++g) {
-    Step& a = pg.steps[(size_t)(base + 2 * g)];      // first pass of the group  (forward z, inverse y)
-    Step& c = pg.steps[(size_t)(base + 2 * g + 1)];  // second pass              (forward y, inverse z)
-    a.rec_ev = first_ev[(size_t)g];
-    c.wait_ev = first_ev[(size_t)g];
-    c.rec_ev = second_ev[(size_t)g];
-    if (g >= 2) a.wait_ev = second_ev[(size_t)g - 2];
-    (inverse ? a : c).stream = 1;
-    if (inverse && g == 0) a.wait_ev = x_ev;
-  }
-  if (!inverse) pg.steps[(size_t)n - 1].wait_ev = second_ev[(size_t)G - 1];
-}
-
-// ------------------------------------------------------------------------------------------------
-// slab.R2C / slab.C2C programs (slab.py:214-485, 538-825)
-// ------------------------------------------------------------------------------------------------
 inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Program& pg) {
   Builder b(pg);
   const bool padded = dealias == B200FFT_DEALIAS_3_2;
@@ -351,72 +312,67 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
     z.real.off = row0 * pN2;
     return z;
   };
-  // L2 blocking (d.l2_planes > 0): the z and y passes over local x planes [x0, x0 + xn) run as
-  // z(g), y(g), z(g+1), ... per group of l2_planes planes, so the second pass of a group reads the
-  // first one's output from L2.  `zy(x0, xn, emit)` calls emit(first plane, plane count) per group.
-  const bool fused_zy = d.l2_mode == 3 && d.l2_planes > 0 && !c2c;
-  auto zy_groups = [&](long long x0, long long xn, auto&& emit) {
-    const long long gsz = (d.l2_planes > 0 && d.l2_planes < xn && !fused_zy) ? d.l2_planes : xn;
-    for (long long g0 = 0; g0 < xn; g0 += gsz) emit(x0 + g0, (g0 + gsz <= xn) ? gsz : xn - g0);
-  };
-  if (d.kz_block > 0 && P == 1 && !c2c) {
-    // kz-blocked intermediate (single rank): the array between the passes is [kz block][x][y][jc] instead of
-    // [x][y][Nf].  Along x its rows are N1*jc elements apart instead of N1*Nf (tens of KB instead of 8 MB
-    // at 1024^3), so the x pass -- whose other side is the caller's array and cannot move -- has only ONE
-    // far-strided side left; along y they are jc apart.  The row passes address the blocks as chunks of
-    // their complex side (hence at most 16 blocks), the strided passes through Side::jc.
-    const long long jc = d.kz_block;
-    const int nblk = (int)((Nf + jc - 1) / jc);
-    if (nblk > PMAXP) return fail(B200FFT_ERR_ARG, "kz_block: at most %d blocks (kz_block >= %lld here)", PMAXP, (Nf + PMAXP - 1) / PMAXP);
-    auto rows_side = [&](int buf, long long ROWS, long long row0) {  // complex side of a row pass over rows [row0, ...)
-      SideT sd;
-      sd.chunk = (int)jc; sd.nchunk = nblk; sd.nphys = (int)Nf;
-      for (int c = 0; c < nblk; ++c) { sd.base[c].buf = buf; sd.base[c].off = (long long)c * ROWS * jc + row0 * jc; sd.sb[c] = jc; sd.si[c] = 1; }
-      return sd;
+  // (`zy_groups(x0, xn, emit)` calls emit(first plane, plane count) for the z and y passes over local x planes
+  // [x0, x0 + xn): one group.  Cutting them into L2-sized groups -- z(g), y(g), z(g+1), ... -- was measured in
+  // round 2 and lost in every form, profiles/r02_single/ab_single.txt: the small launches cost more than the
+  // L2 hits save.)
+  auto zy_groups = [&](long long x0, long long xn, auto&& emit) { emit(x0, xn); };
+  // Single-rank R2C plans: "y-blocked" intermediate.  In the natural layout [x][y][kz] the x pass works on rows
+  // N1*Nf elements apart (8.4 MB at 1024^3 double): one 2 MB page per row segment on BOTH of its sides, 0.57 of
+  // the HBM figure where the near-stride y pass reaches 0.76 (profiles/r01c, r02_single).  Nothing forces that
+  // layout between the passes.  The z pass writes (forward) / reads (inverse) the intermediate as
+  //     W0 = [y block c][x][y in block][kz],   NC = at most 16 blocks of YB = pN1 / NC rows  (row map of the row kernels)
+  // the x pass runs IN PLACE on it with B = NC, J = YB*Nf -- rows YB*Nf elements apart (525 KB at 1024^3) --
+  // and the y pass, now last (forward) / first (inverse), gathers its column from the NC blocks (the per-chunk
+  // bases every exchange layout already uses) and has the caller's array [x][y][kz] on its other side, where
+  // rows along y are Nf elements apart.  No pass has a far side; the order of the x and y passes is free
+  // because the truncations / pads of the 3/2-rule act per axis.  One work buffer instead of two for the 3/2-rule.
+  const bool yblock = P == 1 && !c2c && d.layout != B200FFT_LAYOUT_NATURAL;
+  if (yblock) {
+    int NC = 1;
+    while (NC < PMAXP && NC * 2 <= PMAXP && pN1 % (NC * 2) == 0) NC *= 2;
+    const long long YB = pN1 / NC;
+    const long long blkc = (long long)pN0 * YB * Nf;  // one y block: [x][y in block][kz]
+    b.use(BUF_W0, NC * blkc);
+    SideT yside;  // a y column of the intermediate for batch entry b = x: chunk c at c*blkc + b*YB*Nf + (y - c*YB)*Nf
+    yside.chunk = (int)YB;
+    yside.nchunk = NC;
+    yside.nphys = pN1;
+    for (int c = 0; c < NC; ++c) {
+      yside.base[c].buf = BUF_W0;
+      yside.base[c].off = c * blkc;
+      yside.sb[c] = YB * Nf;
+      yside.si[c] = Nf;
+    }
+    auto rowmap = [&](Step& z) {
+      z.rm_period = pN1;
+      z.rm_block = YB;
+      z.rm_planes = pN0;
     };
-    auto cols_side = [&](int buf, long long ROWS, long long row0, long long sb_rows, long long si_rows, int nphys) {
-      SideT sd = nat(buf, row0 * jc, sb_rows * jc, si_rows * jc, nphys);
-      sd.jc = (int)jc;
-      sd.sj = ROWS * jc;
-      return sd;
-    };
-    const long long R0 = (long long)pN0 * pN1, R1 = (long long)pN0 * N1;  // rows of the array before / after the y truncation
-    const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
-    if (!inverse) {
-      b.use(BUF_W0, (long long)nblk * R0 * jc);
-      if (padded) b.use(BUF_W1, (long long)nblk * R1 * jc);
-      const int ybuf = padded ? BUF_W1 : BUF_W0;
-      zy_groups(0, pN0, [&](long long g0, long long gn) {
-        b.fixed = 0;
-        Step& z = b.rows(true, gn * pN1, pN2, (int)Nf, BUF_IN, rows_side(BUF_W0, R0, g0 * pN1));
-        z.real.off = g0 * pN1 * pN2;
-        b.fixed = 1;
-        b.strided(pN1, gn, Nf, 0, cols_side(BUF_W0, R0, g0 * pN1, pN1, 1, pN1), cols_side(ybuf, R1, g0 * N1, N1, 1, (int)N1), yfold);
-      });
-      b.fixed = 2;
-      b.strided(pN0, N1, Nf, 0, cols_side(ybuf, R1, 0, 1, N1, pN0), nat(BUF_OUT, 0, Nf, N1 * Nf, (int)N0), xfold, padded ? 1.0 / p3 : 1.0);
-      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 0);
-    } else {
-      b.use(BUF_W0, (long long)nblk * R1 * jc);
-      if (padded) b.use(BUF_W1, (long long)nblk * R0 * jc);
-      const int zbuf = padded ? BUF_W1 : BUF_W0;
+    if (!inverse) {  // slab.py:366-387
       b.fixed = 0;
-      Step& sx = b.strided(pN0, N1, Nf, 1, nat(BUF_IN, 0, Nf, N1 * Nf, (int)N0), cols_side(BUF_W0, R1, 0, 1, N1, pN0));
-      if (masked) {  // batch index = ky, column index = kz
-        sx.mask.on = 1;
-        sx.mask.jdiv = 0x3fffffff;
-        band(N0, false, sx.mask.i_lo, sx.mask.i_hi);
-        band(N1, false, sx.mask.b_lo, sx.mask.b_hi);
-        band(N2, true, sx.mask.jr_lo, sx.mask.jr_hi);
+      Step& z = b.rows(true, (long long)pN0 * pN1, pN2, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
+      rowmap(z);
+      b.fixed = 1;
+      b.strided(pN0, NC, YB * Nf, 0, nat(BUF_W0, 0, blkc, YB * Nf, pN0), nat(BUF_W0, 0, blkc, YB * Nf, (int)N0), xfold);
+      b.fixed = 2;
+      b.strided(pN1, N0, Nf, 0, yside, nat(BUF_OUT, 0, N1 * Nf, Nf, (int)N1), yfold, padded ? 1.0 / p3 : 1.0);
+    } else {  // slab.py:247-268
+      const double scale = (padded ? p3 : 1.0) / ((double)pN0 * (double)pN1 * (double)pN2);
+      b.fixed = 0;
+      Step& sy = b.strided(pN1, N0, Nf, 1, nat(BUF_IN, 0, N1 * Nf, Nf, (int)N1), yside);
+      if (masked) {  // rows = ky, batch entries = kx, columns = kz
+        sy.mask.on = 1;
+        sy.mask.jdiv = 0x3fffffff;
+        band(N1, false, sy.mask.i_lo, sy.mask.i_hi);
+        band(N0, false, sy.mask.b_lo, sy.mask.b_hi);
+        band(N2, true, sy.mask.jr_lo, sy.mask.jr_hi);
       }
-      zy_groups(0, pN0, [&](long long g0, long long gn) {
-        b.fixed = 1;
-        b.strided(pN1, gn, Nf, 1, cols_side(BUF_W0, R1, g0 * N1, N1, 1, (int)N1), cols_side(zbuf, R0, g0 * pN1, pN1, 1, pN1));
-        b.fixed = 2;
-        Step& z = b.rows(false, gn * pN1, pN2, (int)Nf, BUF_OUT, rows_side(zbuf, R0, g0 * pN1), scale);
-        z.real.off = g0 * pN1 * pN2;
-      });
-      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 1);
+      b.fixed = 1;
+      b.strided(pN0, NC, YB * Nf, 1, nat(BUF_W0, 0, blkc, YB * Nf, (int)N0), nat(BUF_W0, 0, blkc, YB * Nf, pN0));
+      b.fixed = 2;
+      Step& z = b.rows(false, (long long)pN0 * pN1, pN2, (int)Nf, BUF_OUT, nat(BUF_W0, 0, Nf, 1, (int)Nf), scale);
+      rowmap(z);
     }
     return 0;
   }
@@ -429,7 +385,6 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 1;
           b.strided((int)N1, gn, Nf, 0, nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), nat(BUF_OUT, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1));
         });
-        if (fused_zy) pg.steps[0].fuse_planes = d.l2_planes;
         b.fixed = 2;
         b.strided((int)N0, 1, N1 * Nf, 0, nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0));
       } else {  // slab.py:371-387
@@ -441,11 +396,9 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 1;
           b.strided(pN1, gn, Nf, 0, nat(BUF_W0, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1), nat(BUF_W1, g0 * N1 * Nf, N1 * Nf, Nf, (int)N1), yfold);
         });
-        if (fused_zy) pg.steps[0].fuse_planes = d.l2_planes;
         b.fixed = 2;
         b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
       }
-      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 0);
     } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
       // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
       // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
@@ -536,7 +489,6 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 0;
           const size_t zi = pg.steps.size();
           zfwd(gn * pN1, g0 * pN1, BUF_W0, g0 * pN1 * Nf);
-          if (fused_zy) pg.steps[zi].fuse_planes = d.l2_planes;  // z(c) + y(c) as one kernel through L2
           SideT o;
           o.chunk = (int)Np1;
           o.nchunk = P;
@@ -605,8 +557,6 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
         });
       }
-      if (fused_zy) pg.steps[1].fuse_planes = d.l2_planes;
-      if (d.l2_planes > 0 && d.l2_mode == 2) two_stream_groups(pg, 1);
     } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
       // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
       const int C = kz_chunks(d.chunks, Nf);
@@ -757,7 +707,6 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           b.fixed = 2;
           Step& y = b.strided(pN1, gn, Nf, 1, g, nat(ybuf, g0 * pN1 * Nf, pN1 * Nf, Nf, pN1));
           if (g0 == x0) y.wait_ev = xev[(size_t)c];
-          if (fused_zy) y.fuse_planes = d.l2_planes;  // y(c) + z(c) as one kernel through L2
           b.fixed = 3;
           Step& z = zinv(gn * pN1, g0 * pN1, ybuf, g0 * pN1 * Nf, scale);
           // credits go back after the last z pass, not the last y pass: W2 (this program's y output)

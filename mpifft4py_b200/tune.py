@@ -8,35 +8,38 @@ default configuration's result, and keep the fastest.
     report = m.tune.autotune(F)            # times the candidates, installs the best one into F
     report = m.tune.autotune(F, dealias="3/2-rule", candidates=m.tune.CANDIDATES["patient"])
 
-A candidate is ``(name, kernel_variant, {plan attribute: value})`` (DESIGN.md section 8 lists the switches).
-The kernel variant is a process-wide switch of the library (``b200fft_set_variant``); the plan attributes are
-read when a plan is created, so installing a candidate drops the object's device plan and lets the next
-transform build it again.  Every rank of a multi-rank object must call ``autotune`` collectively; the
-slowest rank's time decides (``comm.allgather``).
-"""
-import ctypes as C
+A candidate is ``(name, {plan attribute: value})``.  The plan attributes are read when a plan is created, so
+installing a candidate drops the object's device plan and lets the next transform build it again.  Every rank of a
+multi-rank object must call ``autotune`` collectively; the slowest rank's time decides and a candidate that is wrong
+or fails on any rank is rejected on all of them (one ``comm.allgather`` per candidate).
 
+The kernel-level switches round 1 left open were decided by measurement in round 2 and are no longer options
+(profiles/r02_single/ab_single.txt); what remains to choose per machine and mesh is the exchange: transport,
+pipeline depth and direction, copy streams -- and, for single-rank slab plans, the intermediate layout.
+"""
 import numpy as np
 
 from . import _lib
 
-PLAN_ATTRS = ("transport", "exchange_chunks", "exchange_pipeline", "copy_streams", "l2_planes", "l2_mode", "kz_block")
+PLAN_ATTRS = ("transport", "exchange_chunks", "exchange_pipeline", "copy_streams", "layout")
 
 CANDIDATES = {
-    # kernel forms that replace a default kernel one to one
-    "measure": [("default", 0, {}), ("cluster_x", 20, {}), ("row_barriers", 30, {}), ("c2r_direct", 31, {}),
-                ("rows_4_ctas", 32, {}), ("r2c_paired", 33, {}), ("c2r_paired", 34, {}), ("strided_direct", 35, {})],
+    "measure": [("default", {}), ("p2p_c2", {"transport": "p2p", "exchange_chunks": 2}),
+                ("p2p_c4", {"transport": "p2p", "exchange_chunks": 4}), ("p2p_c8", {"transport": "p2p", "exchange_chunks": 8}),
+                ("nccl_c1", {"transport": "nccl", "exchange_chunks": 1}), ("nccl_c2", {"transport": "nccl", "exchange_chunks": 2})],
 }
 CANDIDATES["patient"] = CANDIDATES["measure"] + [
-    ("paired_rows+strided_direct", 100 + 32 + 64 + 128, {}), ("cluster_x+paired_rows+strided_direct", 100 + 1 + 32 + 64 + 128, {}),
-    ("l2_fused_g4", 0, {"l2_planes": 4, "l2_mode": 3}), ("l2_fused_g8", 0, {"l2_planes": 8, "l2_mode": 3}),
-    ("l2_two_streams_g4", 0, {"l2_planes": 4, "l2_mode": 2}), ("kz_block48", 0, {"kz_block": 48}),
+    ("p2p_c4_copy_streams", {"transport": "p2p", "exchange_chunks": 4, "copy_streams": 1}),
+    ("p2p_kz2", {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 2}),
+    ("p2p_kz4", {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 4}),
+    ("store_c1", {"transport": "store", "exchange_chunks": 1}),
+    ("natural_layout", {"layout": "natural"}),
 ]
 
 
-def _install(F, variant, attrs, set_variant, base=None):
-    """Make ``F`` use a candidate: the caller's own plan attributes (``base``) overlaid with the candidate's,
-    the kernel variant in the library, and a fresh device plan at the next transform."""
+def _install(F, attrs, base=None):
+    """Make ``F`` use a candidate: the caller's own plan attributes (``base``) overlaid with the candidate's, and a
+    fresh device plan at the next transform."""
     base = base or {}
     for a in PLAN_ATTRS:
         if a in attrs:
@@ -45,7 +48,6 @@ def _install(F, variant, attrs, set_variant, base=None):
             setattr(F, a, base[a])
         elif a in getattr(F, "__dict__", {}):
             delattr(F, a)
-    set_variant(variant)
     if getattr(F, "_plan", None) is not None:
         _lib.lib().b200fft_plan_destroy(F._plan)
         F._plan = None
@@ -89,8 +91,6 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
     data, keep the fastest whose forward result matches the default configuration's, install it into ``F`` and
     return the report.  Device memory: one real and one complex array of the object's local shapes, twice."""
     import torch
-    L = _lib.lib()
-    L.b200fft_set_variant.restype = C.c_int
     candidates = list(candidates if candidates is not None else CANDIDATES["measure"])
     double = F.float is np.float64
     tol = tol if tol is not None else (1e-12 if double else 1e-5)
@@ -104,10 +104,12 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
     ref = {}
     comm = getattr(F, "comm", None)
     many = comm is not None and getattr(F, "num_processes", 1) > 1
+    if not many:  # exchange options mean nothing to a single rank
+        candidates = [c for c in candidates if not (set(c[1]) - {"layout"})] or [("default", {})]
     base = {a: F.__dict__[a] for a in PLAN_ATTRS if a in F.__dict__}  # what the caller chose stays unless a candidate overrides it
 
     def measure(cand):
-        _install(F, cand[1], cand[2], L.b200fft_set_variant, base)
+        _install(F, cand[1], base)
         fwd(u, fu, dealias)
         inv(fu, u2, dealias)  # warm-up: plan creation, kernel set-up
         torch.cuda.synchronize()
@@ -126,5 +128,5 @@ def autotune(F, dealias=None, candidates=None, reps=3, tol=None):
 
     # (every rank sees the same gathered (time, error, failure) triples, so every rank picks the same candidate)
     best, report = select(candidates, measure, tol, comm.allgather if many else None)
-    _install(F, best[1], best[2], L.b200fft_set_variant, base)
+    _install(F, best[1], base)
     return {"chosen": best[0], "candidates": report}

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the opt-in kernels and schedules on ONE GPU in ONE process (one torch import, one set of
+"""A/B of plan options on ONE GPU in ONE process (one torch import, one set of
 arrays): for every (workload, configuration) a fresh plan object, warm-up, K timed round trips with CUDA
 events, the per-pass table and a parity check (round-trip rel. L2; forward result against the default
 configuration's, which the parity suite pins to the oracle).  One JSON line per case on stdout, a table
@@ -22,27 +22,8 @@ import mpifft4py_b200 as m  # noqa: E402
 from mpifft4py_b200 import _lib  # noqa: E402
 from mpifft4py_b200.comm import SelfComm  # noqa: E402
 
-# name -> (kernel variant, plan attributes)
-CONFIGS = [("default", 0, {})]
-CONFIGS += [("cluster_x(20)", 20, {}), ("cluster_x+long(22)", 22, {}), ("row_barriers(30)", 30, {}), ("c2r_direct(31)", 31, {})]
-for g in (2, 3, 4, 6, 8, 12, 16):
-    CONFIGS += [("l2_launches_g%d" % g, 0, {"l2_planes": g, "l2_mode": 1})]
-for g in (2, 3, 4, 6):
-    CONFIGS += [("l2_two_streams_g%d" % g, 0, {"l2_planes": g, "l2_mode": 2})]
-for g in (2, 3, 4, 6, 8, 12, 16):
-    CONFIGS += [("l2_fused_g%d" % g, 0, {"l2_planes": g, "l2_mode": 3})]
-CONFIGS += [("cluster_x+row_barriers(105)", 105, {}), ("cluster_x+c2r_direct(109)", 109, {}), ("rows_4_ctas(32)", 32, {}), ("strided_direct(35)", 35, {}), ("strided_direct+r2c+c2r_paired(324)", 324, {}),
-            ("cluster_x+strided_direct+r2c+c2r_paired(325)", 325, {}), ("r2c_paired(33)", 33, {}), ("c2r_paired(34)", 34, {}), ("r2c+c2r_paired(196)", 196, {}),
-            ("cluster_x+r2c+c2r_paired(197)", 197, {}), ("cluster_x+long+r2c+c2r_paired(199)", 199, {}),
-            ("r2c_paired+c2r_direct(140)", 140, {}), ("cluster_x+r2c_paired+c2r_direct(141)", 141, {}),
-            ("rows_4_ctas+row_barriers(120)", 120, {}),
-            ("cluster_x+long+rows_4_ctas(119)", 119, {}), ("cluster_x+long+rows_4_ctas+row_barriers(123)", 123, {}),
-            ("all_switches(127)", 127, {})]
-CONFIGS += [("kz_block48", 0, {"kz_block": 48}), ("kz_block64", 0, {"kz_block": 64}),
-            ("kz_block48+l2_two_streams_g4", 0, {"kz_block": 48, "l2_planes": 4, "l2_mode": 2})]
-for g in (4, 8):
-    CONFIGS += [("l2_fused_g%d+cluster_x" % g, 101, {"l2_planes": g, "l2_mode": 3}),
-                ("l2_fused_g%d+cluster_x+c2r_direct" % g, 109, {"l2_planes": g, "l2_mode": 3})]
+# name -> plan attributes
+CONFIGS = [("yblock (default)", {}), ("natural", {"layout": "natural"})]
 
 
 def main():
@@ -50,11 +31,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--workloads", default="slab1024_f64,slab1024_f64_32")
     ap.add_argument("--only", default="")
-    ap.add_argument("--variants", default="", help="comma-separated kernel variants to run instead of the built-in list")
     args = ap.parse_args()
-    global CONFIGS
-    if args.variants:
-        CONFIGS = [("default", 0, {})] + [("variant(%s)" % v, int(v), {}) for v in args.variants.split(",") if int(v) != 0]
     L = _lib.lib()
     peak = 6554.9
     try:
@@ -75,10 +52,9 @@ def main():
         ref = None
         flops = bench.flops_roundtrip(tuple(int(1.5 * n) if dealias == "3/2-rule" else n for n in N))
         del F0
-        for cname, variant, attrs in CONFIGS:
-            if args.only and args.only not in cname and cname != "default":
+        for cname, attrs in CONFIGS:
+            if args.only and args.only not in cname and not cname.endswith("(default)"):
                 continue
-            L.b200fft_set_variant(variant)  # (100 + bits combines switches, include/b200fft.h)
             F = bench.make_transform(m, SelfComm(), name)
             for k, v in attrs.items():
                 if not k.startswith("_"):
@@ -114,7 +90,7 @@ def main():
                 passes = [{"dir": d, "pass": i, "type": t, "ms": round(v[0], 3), "GBps": round(v[1] / v[0] / 1e6, 0) if v[0] > 0 else None}
                           for (d, i, t), v in sorted(acc.items())]
                 k, _ = F.last_launches()
-                out = {"workload": name, "config": cname, "variant": variant, "attrs": attrs, "ms_per_round_trip": round(ms, 3),
+                out = {"workload": name, "config": cname, "attrs": attrs, "ms_per_round_trip": round(ms, 3),
                        "GFLOPs": round(flops / ms / 1e6), "roundtrip_rel_l2": rt, "forward_vs_default_rel_l2": dev,
                        "kernels_last_transform": k, "passes": passes, "hbm_peak": peak}
             except Exception as e:  # noqa: BLE001
@@ -127,7 +103,6 @@ def main():
                     name, cname, ms, rt, dev, " ".join("%s%d:%.2f" % (p["dir"][0], p["pass"], p["ms"]) for p in passes)))
             del F
             torch.cuda.empty_cache()
-        L.b200fft_set_variant(0)
         del u, fu, u2, ref
         torch.cuda.empty_cache()
 

@@ -5,7 +5,7 @@ Same transform length, same bytes, only the distance between consecutive rows of
 axis changes -- separates HBM/L2 effects from address-translation effects of the long-stride x pass.
 Prints one line per case: GB/s of algorithmic bytes (read once + written once).
 
-    B200FFT_VARIANT=k python scripts/microbench_strided.py [n] [precision d|s]
+    python scripts/microbench_strided.py [n] [precision d|s]
 """
 import ctypes as C
 import os
@@ -85,7 +85,7 @@ def main():
     prec = sys.argv[2] if len(sys.argv) > 2 else "d"
     esz = 16 if prec == "d" else 8
     total = (4 << 30) // esz // n  # B*J for 4 GiB
-    print("variant", os.environ.get("B200FFT_VARIANT", "0"), "n", n, prec)
+    print("n", n, prec)
     for J in (512, 513, 4096, 32768, 131072, 131072 + 8, 524288, total):
         B = max(1, total // J)
         for inplace in (True, False):

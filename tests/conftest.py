@@ -21,10 +21,10 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:  # noqa: BLE001
         has_gpu = False
-    # hot path first (SURVEY.md section 8 rows a, e), the "next" rows (f) and opt-in variants after it, so that
+    # hot path first (SURVEY.md section 8 rows a, e), the "next" rows (f) after it, so that
     # `pytest -x` can never again stop in an optional row before the kernels' own parity tests ran
-    first = ("test_passes.py", "test_gpu_transforms.py", "test_gpu_multi.py", "test_c2r_direct.py",
-             "test_strided_direct.py", "test_cluster_pass.py", "test_c2c.py")
+    first = ("test_passes.py", "test_gpu_transforms.py", "test_gpu_multi.py", "test_c2r_staging.py",
+             "test_c2c.py")
     items.sort(key=lambda it: (first.index(it.fspath.basename) if it.fspath.basename in first else len(first)))
     if has_gpu:
         return

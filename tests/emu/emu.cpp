@@ -35,86 +35,7 @@ static int emulate(const typename K::Params& p) {
   return 0;
 }
 
-// 2-CTA cluster kernels: both CTAs of a cluster are stepped through phase s (each seeing the other's
-// shared memory as `peer`) before either starts phase s+1 -- at least as strict as the cluster barriers
-// around the cross stage and the CTA barriers elsewhere.
-template <class K, int s>
-static void emu_cluster_phases(const typename K::Params& p, std::vector<unsigned char>* sm, int bx, int by) {
-  for (int rank = 0; rank < 2; ++rank)
-    for (int tid = 0; tid < K::NT; ++tid) K::template phase<s>(p, sm[rank].data(), sm[rank ^ 1].data(), tid, rank, bx, by);
-  if constexpr (s + 1 < K::NPHASE) emu_cluster_phases<K, s + 1>(p, sm, bx, by);
-}
-
-template <class K>
-static int emulate_cluster(const typename K::Params& p) {
-  const unsigned long long nblk = K::blocks(p);
-  std::vector<unsigned char> sm[2];
-  for (auto& v : sm) v.resize((size_t)K::SMEM + 256);
-  for (unsigned long long b = 0; b < nblk; b += 2) {
-    int bx, by, bx1, by1;
-    K::decode(p, (unsigned)b, bx, by);
-    K::decode(p, (unsigned)b + 1, bx1, by1);
-    if (bx != bx1 || by != by1) return 95;  // both CTAs of a cluster work on the same tile
-    for (auto& v : sm)
-      for (auto& c : v) c = 0x7f;
-    emu_cluster_phases<K, 0>(p, sm, bx, by);
-  }
-  return 0;
-}
-
-// Fused pair of passes (fused_pair_kernel): the queue is walked in index order by ONE worker, which is a
-// legal schedule of the persistent kernel; on the way it checks what the device relies on -- the decode
-// visits every block of both grids exactly once, and every block of pass B finds the pass-A counters of
-// the groups it reads complete (i.e. all blocks it would wait for have a smaller queue index).
-template <class KA, class KB>
-static int emulate_fused_pair(const typename KA::Params& pa, const typename KB::Params& pb, long long planes, long long ppg) {
-  if (planes < 1 || ppg < 1) return -3;
-  FuseCtl c;
-  c.ctr = nullptr;
-  c.done = nullptr;
-  c.G = (unsigned)((planes + ppg - 1) / ppg);
-  c.a = KA::fuse_side(pa, planes, ppg);
-  c.b = KB::fuse_side(pb, planes, ppg);
-  if (c.G + 1 > 4097 || c.a.n == 0 || c.b.n == 0 || c.a.upg < c.a.upb || c.b.upg < c.b.upb) return -3;
-  std::vector<unsigned> done(c.G, 0);
-  std::vector<char> seenA(c.a.n, 0), seenB(c.b.n, 0);
-  const size_t smem = (size_t)(KA::SMEM1 > KB::SMEM1 ? KA::SMEM1 : KB::SMEM1) + 256;
-  std::vector<unsigned char> sm(smem);
-  for (unsigned i = 0; i < c.a.n + c.b.n; ++i) {
-    bool isB;
-    unsigned blk, g1, g2, u1, u2;
-    fuse_decode(c, i, isB, blk);
-    for (auto& x : sm) x = 0x7f;
-    int bx, by;
-    if (!isB) {
-      if (blk >= c.a.n || seenA[blk]++) return 97;
-      KA::decode(pa, blk, bx, by);
-      emu_phases<KA, 0>(pa, sm, bx, by);
-      c.a.groups(blk, g1, g2, u1, u2);
-      if (g2 >= c.G || g2 > g1 + 1) return 94;
-      done[g1] += u1;
-      if (g2 != g1) done[g2] += u2;
-    } else {
-      if (blk >= c.b.n || seenB[blk]++) return 98;
-      c.b.groups(blk, g1, g2, u1, u2);
-      if (g2 >= c.G) return 95;
-      for (unsigned g = g1; g <= g2; ++g)
-        if (done[g] != c.a.need(g)) return 96;  // the device would wait for a block that is queued later: deadlock
-      KB::decode(pb, blk, bx, by);
-      emu_phases<KB, 0>(pb, sm, bx, by);
-    }
-  }
-  for (char x : seenA) if (!x) return 99;
-  for (char x : seenB) if (!x) return 99;
-  for (unsigned g = 0; g < c.G; ++g) if (done[g] != c.a.need(g)) return 93;
-  return 0;
-}
-
-template <class real>
-static int fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg);
-
-static int g_emu_variant = 0;
-static int g_emu_fused_runs = 0;  // fused launches executed by emu_plan_run (tests check the path was taken)
+static int g_emu_c2r_staging = 0;  // tests: 1 = the staging C2R kernel (C2RK) for every length
 
 template <class real>
 static const cx<real>* table(int len) {
@@ -138,42 +59,6 @@ static int strided(const b200fft_strided_desc_t& d) {
         return -1;
     }
   }
-  if (g_emu_variant == 21) {
-#define X(nn, ...) \
-  if (d.n == nn) return emulate_cluster<ClusterStridedK<real, Plan<__VA_ARGS__>>>(p);
-    B200FFT_CLUSTER_PLANS(X)
-#undef X
-  }
-  if (g_emu_variant == 23) {  // 64-byte rows
-#define X(nn, ...) \
-  if (d.n == nn) return emulate_cluster<ClusterStridedK<real, Plan<__VA_ARGS__>, 64>>(p);
-    B200FFT_CLUSTER_PLANS(X)
-#undef X
-  }
-  if (g_emu_variant == 35) {  // first stage fed straight from memory (plans with two or more stages)
-    switch (d.n) {
-#define X(n, ...)                                                                            \
-  case n:                                                                                    \
-    if constexpr (Plan<__VA_ARGS__>::S >= 2 && StridedCfg<real, Plan<__VA_ARGS__>>::TAB)     \
-      return emulate<StridedDK<real, Plan<__VA_ARGS__>>>(p);                                 \
-    break;
-      B200FFT_PLANS(X)
-#undef X
-      default:
-        break;
-    }
-  }
-  if (d.in.jc > 0 || d.out.jc > 0) {  // blocked column layouts: the JS form of the kernel (every length here)
-    switch (d.n) {
-#define X(n, ...) \
-  case n:         \
-    return emulate<StridedK<real, Plan<__VA_ARGS__>, 0, 0, false, true>>(p);
-      B200FFT_PLANS(X)
-#undef X
-      default:
-        return -1;
-    }
-  }
   switch (d.n) {
 #define X(n, ...) \
   case n:         \
@@ -185,23 +70,17 @@ static int strided(const b200fft_strided_desc_t& d) {
   }
 }
 
+// the same kernel choice as csrc/k_rows.inc: four-CTA register budget for the 3/2-rule R2C lengths (no effect on the
+// emulated arithmetic), the register-staged C2R kernel for half-lengths 256 ... 1536 and the staging kernel elsewhere
 template <class real, bool FWD>
 static int rows(const b200fft_rows_desc_t& d) {
   auto p = convert_rows<real>(d, table<real>(d.n), 1, FWD);
   switch (d.n / 2) {
-#define X(n, ...)                                                     \
-  case n:                                                             \
-    if (FWD && g_emu_variant == 33) {                                 \
-      if constexpr (Plan<__VA_ARGS__>::S >= 2) return emulate<R2CPK<real, Plan<__VA_ARGS__>>>(p); \
-    }                                                                 \
-    if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);        \
-    else if (g_emu_variant == 31) return emulate<C2RDK<real, Plan<__VA_ARGS__>>>(p); \
-    else if (g_emu_variant == 34) {                                    \
-      using PP = Plan<__VA_ARGS__>;                                    \
-      if constexpr (PP::S >= 2 && PP::template R<0> <= 8 && (PP::template M<0> % 2) == 0) return emulate<C2RPK<real, PP>>(p); \
-      else return emulate<C2RK<real, PP>>(p);                          \
-    }                                                                  \
-    else return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);
+#define X(n, ...)                                                                                            \
+  case n:                                                                                                    \
+    if (FWD) return emulate<R2CK<real, Plan<__VA_ARGS__>>>(p);                                               \
+    else if (g_emu_c2r_staging || n < 256 || n > 1536) return emulate<C2RK<real, Plan<__VA_ARGS__>>>(p);     \
+    else return emulate<C2RDK<real, Plan<__VA_ARGS__>>>(p);
     B200FFT_ROW_PLANS(X)
 #undef X
     default:
@@ -209,68 +88,10 @@ static int rows(const b200fft_rows_desc_t& d) {
   }
 }
 
-template <class real>
-static int fused_zy(const b200fft_rows_desc_t& r, const b200fft_strided_desc_t& c, int inverse_order, int ppg) {
-  if (contiguous_rows(c) || c.B < 1 || r.rows % c.B || c.in.jc > 0 || c.out.jc > 0) return -1;
-  auto pr = convert_rows<real>(r, table<real>(r.n), 1, !inverse_order);
-  auto pc = convert_strided<real>(c, table<real>(c.n), 1);
-#define X(h, ny, PR, PC)                                                                                  \
-  if (r.n / 2 == h && c.n == ny)                                                                          \
-    return inverse_order ? emulate_fused_pair<StridedK<real, PC>, C2RK<real, PR>>(pc, pr, c.B, ppg)       \
-                         : emulate_fused_pair<R2CK<real, PR>, StridedK<real, PC>>(pr, pc, c.B, ppg);
-  B200FFT_FUSED_PAIRS(X)
-#undef X
-  return -1;
-}
-
 extern "C" {
-// -1: no fused kernel for the size pair, -3: too many / too small groups (callers fall back)
-int emu_exec_fused_zy(const b200fft_rows_desc_t* r, const b200fft_strided_desc_t* c, int inverse_order, int ppg) {
-  if (const char* e = check_rows(*r)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
-  if (const char* e = check_strided(*c)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
-  return r->precision == B200FFT_DOUBLE ? fused_zy<double>(*r, *c, inverse_order, ppg) : fused_zy<float>(*r, *c, inverse_order, ppg);
-}
-int emu_fused_runs() { return g_emu_fused_runs; }
-// Queue of the fused pair kernel without running any FFT: rows * planes rows in blocks of `rpc` rows next to
-// `tiles` column tiles per plane, groups of `ppg` planes, either order.  Checks that the queue visits every
-// block of both passes once and that no block of the second pass precedes a block it waits for.
-int emu_check_fuse_queue(long long rows_per_plane, int rpc, long long planes, long long ppg, int tiles, int rows_first) {
-  FuseCtl c;
-  c.ctr = c.done = nullptr;
-  c.G = (unsigned)((planes + ppg - 1) / ppg);
-  const long long rows = rows_per_plane * planes;
-  const FuseSide r{(unsigned)((rows + rpc - 1) / rpc), (unsigned)rpc, (unsigned)(ppg * rows_per_plane), (unsigned)rows};
-  const FuseSide t{(unsigned)(planes * tiles), 1u, (unsigned)(ppg * tiles), (unsigned)(planes * tiles)};
-  c.a = rows_first ? r : t;
-  c.b = rows_first ? t : r;
-  if (c.a.upg < c.a.upb || c.b.upg < c.b.upb) return -3;
-  std::vector<unsigned> done(c.G, 0);
-  std::vector<char> seenA(c.a.n, 0), seenB(c.b.n, 0);
-  for (unsigned i = 0; i < c.a.n + c.b.n; ++i) {
-    bool isB;
-    unsigned blk, g1, g2, u1, u2;
-    fuse_decode(c, i, isB, blk);
-    if (!isB) {
-      if (blk >= c.a.n || seenA[blk]++) return 97;
-      c.a.groups(blk, g1, g2, u1, u2);
-      if (g2 >= c.G || g2 > g1 + 1) return 94;
-      done[g1] += u1;
-      if (g2 != g1) done[g2] += u2;
-    } else {
-      if (blk >= c.b.n || seenB[blk]++) return 98;
-      c.b.groups(blk, g1, g2, u1, u2);
-      if (g2 >= c.G) return 95;
-      for (unsigned g = g1; g <= g2; ++g)
-        if (done[g] != c.a.need(g)) return 96;
-    }
-  }
-  for (char x : seenA) if (!x) return 99;
-  for (char x : seenB) if (!x) return 99;
-  return 0;
-}
-int emu_set_variant(int v) {  // 21: lengths with a cluster plan run the 2-CTA cluster kernel
-  const int old = g_emu_variant;
-  g_emu_variant = v;
+int emu_set_c2r_staging(int v) {
+  const int old = g_emu_c2r_staging;
+  g_emu_c2r_staging = v;
   return old;
 }
 int emu_exec_strided(const b200fft_strided_desc_t* d) {
@@ -284,6 +105,30 @@ int emu_exec_r2c(const b200fft_rows_desc_t* d) {
 int emu_exec_c2r(const b200fft_rows_desc_t* d) {
   if (const char* e = check_rows(*d)) { std::fprintf(stderr, "emu: %s\n", e); return 1; }
   return d->precision == B200FFT_DOUBLE ? rows<double, false>(*d) : rows<float, false>(*d);
+}
+// Step list of rank 0's program for tests: per step (type: 0 strided / 1 R2C / 2 C2R / 3 exchange, n, B or rows, J,
+// row stride of the load side, of the store side, chunks of the load side, of the store side).  Returns the step
+// count (and fills `out` when it has room for `cap` steps), negative on a build error.
+int emu_plan_steps(const b200fft_plan_desc_t* d, int inverse, int dealias, long long* out, int cap) {
+  Program pg;
+  if (int rc = build_program(*d, inverse, dealias, pg)) return -rc;
+  const int n = (int)pg.steps.size();
+  if (out && cap >= n) {
+    for (int i = 0; i < n; ++i) {
+      const Step& s = pg.steps[(size_t)i];
+      long long* o = out + 8 * i;
+      const bool rows = s.type == ST_R2C || s.type == ST_C2R;
+      o[0] = (long long)s.type;
+      o[1] = s.n;
+      o[2] = rows ? s.rows : s.B;
+      o[3] = rows ? s.nk : s.J;
+      o[4] = rows ? s.cside.sb[0] : s.in.si[0];
+      o[5] = rows ? s.cside.sb[0] : s.out.si[0];
+      o[6] = rows ? s.cside.nchunk : s.in.nchunk;
+      o[7] = rows ? s.cside.nchunk : s.out.nchunk;
+    }
+  }
+  return n;
 }
 // Run one distributed transform for ALL ranks in lockstep: the same plan programs as
 // libb200fft.so (plan_program.h), kernels emulated on the CPU, exchanges done by memcpy.
@@ -313,48 +158,12 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
     b200fft_side_t o;
     std::memset(&o, 0, sizeof(o));
     for (int q = 0; q < s.nchunk; ++q) { o.base[q] = resolve(r, s.base[q], csz); o.sb[q] = s.sb[q]; o.si[q] = s.si[q]; }
-    o.chunk = s.chunk; o.nchunk = s.nchunk; o.nphys = s.nphys; o.jc = s.jc; o.sj = s.sj;
+    o.chunk = s.chunk; o.nchunk = s.nchunk; o.nphys = s.nphys;
     return o;
   };
   const size_t nsteps = pg[0].steps.size();
   for (int r = 1; r < P; ++r) if (pg[r].steps.size() != nsteps) return 90;
-  auto strided_of = [&](int r, const Step& s) {
-    b200fft_strided_desc_t d;
-    std::memset(&d, 0, sizeof(d));
-    d.precision = d0->precision; d.n = s.n; d.B = s.B; d.J = s.J; d.inverse = s.inverse;
-    d.fold_mode = s.fold; d.scale = s.scale; d.in = side(r, s.in); d.out = side(r, s.out); d.mask = s.mask;
-    return d;
-  };
-  auto rows_of = [&](int r, const Step& s) {
-    b200fft_rows_desc_t d;
-    std::memset(&d, 0, sizeof(d));
-    d.precision = d0->precision; d.n = s.n; d.rows = s.rows; d.nk = s.nk; d.scale = s.scale;
-    d.real_base = resolve(r, s.real, csz / 2); d.rpitch = s.rpitch; d.cside = side(r, s.cside);
-    return d;
-  };
   for (size_t si = 0; si < nsteps; ++si) {
-    if (pg[0].steps[si].fuse_planes > 0 && si + 1 < nsteps) {  // as b200fft.cu: fused launch, else two passes
-      bool all = true;
-      for (int r = 0; r < P && all; ++r) {  // (the same sizes on every rank: all fuse or none does)
-        const Step& s = pg[r].steps[si];
-        const Step& t = pg[r].steps[si + 1];
-        const Step& rs = (s.type == ST_STRIDED) ? t : s;
-        const Step& cs = (s.type == ST_STRIDED) ? s : t;
-        if (cs.type != ST_STRIDED || (rs.type != ST_R2C && rs.type != ST_C2R)) { all = false; break; }
-        auto rd = rows_of(r, rs);
-        auto cd = strided_of(r, cs);
-        const int rc = emu_exec_fused_zy(&rd, &cd, s.type == ST_STRIDED, s.fuse_planes);
-        if (rc == -1 || rc == -3) {
-          if (r != 0) return 92;
-          all = false;
-        } else if (rc) {
-          return rc;
-        } else {
-          ++g_emu_fused_runs;
-        }
-      }
-      if (all) { ++si; continue; }
-    }
     for (int r = 0; r < P; ++r) {
       const Step& s = pg[r].steps[si];
       int rc = 0;
@@ -369,6 +178,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
         std::memset(&d, 0, sizeof(d));
         d.precision = d0->precision; d.n = s.n; d.rows = s.rows; d.nk = s.nk; d.scale = s.scale;
         d.real_base = resolve(r, s.real, csz / 2); d.rpitch = s.rpitch; d.cside = side(r, s.cside);
+        d.rm_period = s.rm_period; d.rm_block = s.rm_block; d.rm_planes = s.rm_planes;
         rc = s.type == ST_R2C ? emu_exec_r2c(&d) : emu_exec_c2r(&d);
       } else {
         for (int q = 0; q < s.npeers; ++q) {
@@ -428,15 +238,14 @@ int emu_check_p2p(const b200fft_plan_desc_t* d0, int inverse, int dealias, int* 
           if (o.base[q].peer != w || w == r || o.nchunk != x.npeers) return 111;
           const Step& t = pg[w].steps[sx];
           if (!x.fused || t.type != ST_EXCH || !t.fused || t.comm != x.comm) return 114;
-          // it must lie inside the block peer w receives from this rank (member x.me of the communicator);
-          // all of it, when the pass is not one of several L2 groups of the chunk
+          // it must be exactly the block peer w receives from this rank (member x.me of the communicator)
           const long long rows_q = (q == o.nchunk - 1) ? o.nphys - (long long)q * o.chunk : o.chunk;
           const long long nb = s.type == ST_STRIDED ? s.B : s.rows, nj = s.type == ST_STRIDED ? s.J : 1;
           const long long ext = (nb - 1) * o.sb[q] + (rows_q - 1) * o.si[q] + nj;
           if (o.base[q].buf != t.recv[x.me].buf || o.base[q].off < t.recv[x.me].off ||
               o.base[q].off + ext > t.recv[x.me].off + t.rcnt[x.me])
             return 115;
-          if (d0->l2_planes <= 0 && (o.base[q].off != t.recv[x.me].off || ext != t.rcnt[x.me])) return 120;
+          if (o.base[q].off != t.recv[x.me].off || ext != t.rcnt[x.me]) return 120;
           if (o.base[q].buf < BUF_W0 || o.base[q].buf > BUF_W2 || t.recv[x.me].off + t.rcnt[x.me] > pg[w].need[t.recv[x.me].buf]) return 116;
         }
         continue;
@@ -483,14 +292,6 @@ void side_regions(const SideT& s, long long nb, long long nj, bool write, long l
   for (int q = 0; q < s.nchunk; ++q) {
     if (s.base[q].peer >= 0) continue;
     const long long rows_q = (q == s.nchunk - 1) ? s.nphys - (long long)q * s.chunk : s.chunk;
-    if (s.jc > 0) {  // blocked columns: one interval per block (the blocks of one pass are sj apart)
-      for (long long c = 0; c * s.jc < nj; ++c) {
-        const long long w = (nj - c * s.jc < s.jc) ? nj - c * s.jc : s.jc;
-        const long long lo = s.base[q].off + c * s.sj, ext = (nb - 1) * s.sb[q] + (rows_q - 1) * s.si[q] + w;
-        out.push_back(Region{s.base[q].buf, lo * unit, (lo + ext) * unit, write});
-      }
-      continue;
-    }
     const long long ext = (nb - 1) * s.sb[q] + (rows_q - 1) * s.si[q] + nj;
     out.push_back(Region{s.base[q].buf, s.base[q].off * unit, (s.base[q].off + ext) * unit, write});
   }

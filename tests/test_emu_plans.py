@@ -15,7 +15,7 @@ from mpifft4py_b200 import _cdefs as D
 TOL = {"double": 5e-14, "single": 5e-6}
 
 
-def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0, l2_planes=0, kz_block=0, l2_mode=0):
+def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=0, layout=0):
     d = D.PlanDesc()
     d.kind = kind
     d.precision = D.DOUBLE if prec == "double" else D.SINGLE
@@ -29,9 +29,7 @@ def _desc(kind, N, P, prec, P1=1, P2=1, drop=0, chunks=0, pipeline=0, transport=
     d.transport = transport
     d.chunks = chunks
     d.pipeline = pipeline
-    d.l2_planes = l2_planes
-    d.kz_block = kz_block
-    d.l2_mode = l2_mode
+    d.layout = layout
     return d
 
 
@@ -357,104 +355,67 @@ def test_slab_kz_pipeline_runs_in_emulator(kind, N, P, chunks, transport):
                 assert 1 <= n.value <= max(chunks, 4)
 
 
-@pytest.mark.parametrize("l2_planes", [1, 3, 4])
-@pytest.mark.parametrize("kind", ["r2c", "c2c"])
-def test_slab_single_rank_l2_groups(kind, l2_planes):
-    """P = 1 with the z and y passes run per group of x planes (L2 blocking): same results; the step list
-    alternates z(g), y(g) and keeps one x pass."""
-    N, P, prec = (16, 8, 32), 1, "double"
-    rt, ct = oracle.common.dtypes(prec)
-    g = oracle.slab.Geometry(N, P)
-    rng = np.random.default_rng(5)
-    c2c = kind == "c2c"
-    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, l2_planes=l2_planes)
-    if c2c:
-        cs, it = tuple(N), ct
-        new_in = lambda shape: _rand_c(rng, shape, ct)
-        fwd = lambda u, **k: oracle.slab.c2c_fftn(u, N, P, precision=prec, **k)
-        inv = lambda fu, **k: oracle.slab.c2c_ifftn(fu, N, P, precision=prec, **k)
-    else:
-        cs, it = g.complex_shape(), rt
-        new_in = lambda shape: rng.random(shape).astype(rt)
-        fwd = lambda u, **k: oracle.slab.fftn(u, N, P, precision=prec, **k)
-        inv = lambda fu, **k: oracle.slab.ifftn(fu, N, P, precision=prec, **k)
-    u = [new_in(g.real_shape())]
-    _check(run_plan(d, 0, D.DEALIAS_NONE, u, [cs], ct), fwd(u), TOL[prec])
-    fu = [_rand_c(rng, cs, ct)]
-    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
-        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
-        _check(run_plan(d, 1, mode, fu, [shp], it), inv(fu, dealias=name), TOL[prec])
-    up = [new_in(g.real_shape_padded())]
-    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [cs], ct), fwd(up, dealias="3/2-rule"), TOL[prec])
-
-
-@pytest.mark.parametrize("N,l2_planes,prec", [((8, 512, 512), 2, "double"), ((8, 512, 512), 4, "single"),
-                                              ((4, 1024, 1024), 1, "double"), ((6, 512, 512), 4, "double")])
-def test_slab_single_rank_fused_zy(N, l2_planes, prec):
-    """l2_mode 3: the z and y passes as one persistent kernel (queue order A(0) | A(1) B(0) | ...); the
-    emulator walks the queue in order and checks that every block runs once and never ahead of the blocks
-    it depends on.  Row blocks of RPC rows straddle plane groups (1024-point rows: 3 per block; 6 planes in
-    groups of 4 leave a short last group): such blocks credit / wait for two groups."""
+@pytest.mark.parametrize("layout", [D.LAYOUT_YBLOCK, D.LAYOUT_NATURAL])
+@pytest.mark.parametrize("N,prec", [((16, 8, 32), "double"), ((8, 32, 16), "single"), ((4, 64, 8), "double"), ((32, 4, 16), "double"),
+                                    ((8, 6, 16), "double"), ((6, 48, 8), "double"), ((2, 2, 4), "double")])
+def test_slab_single_rank_layouts(N, prec, layout):
+    """P = 1, slab.R2C: the y-blocked intermediate (default: z, x, y over [y block][x][y in block][kz], the row
+    kernels' row map, an in-place x pass with near rows, the y pass gathering from <= 16 blocks) and the natural
+    layout (z, y, x on [x][y][kz], slab.py:366-370) against the oracle -- forward, inverse, 2/3-rule, 3/2-rule both
+    ways; y extents that give 16, 8, 4, 2 blocks and a single block (N1 = 6 -> padded 9 rows: odd)."""
     rt, ct = oracle.common.dtypes(prec)
     g = oracle.slab.Geometry(N, 1)
-    rng = np.random.default_rng(12)
-    d = _desc(D.SLAB, N, 1, prec, l2_planes=l2_planes)
-    d.l2_mode = 3
-    lib = emu_util.load()
-    before = lib.emu_fused_runs()
+    rng = np.random.default_rng(sum(N) + layout)
+    d = _desc(D.SLAB, N, 1, prec, layout=layout)
+    tol = TOL[prec]
     u = [rng.random(g.real_shape()).astype(rt)]
-    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)
-    _check(c, oracle.slab.fftn(u, N, 1, precision=prec), TOL[prec])
-    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()], rt), u, TOL[prec])
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct), oracle.slab.fftn(u, N, 1, precision=prec), tol)
     fu = [_rand_c(rng, g.complex_shape(), ct)]
-    _check(run_plan(d, 1, D.DEALIAS_2_3, fu, [g.real_shape()], rt), oracle.slab.ifftn(fu, N, 1, dealias="2/3-rule", precision=prec),
-           TOL[prec])
-    assert lib.emu_fused_runs() - before == 3
-    assert lib.emu_check_schedule(C.byref(d), 0, D.DEALIAS_NONE) == 0 and lib.emu_check_schedule(C.byref(d), 1, D.DEALIAS_NONE) == 0
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule")):
+        _check(run_plan(d, 1, mode, fu, [g.real_shape()], rt), oracle.slab.ifftn(fu, N, 1, dealias=name, precision=prec), tol)
+    def ok(m):  # lengths with a radix plan: 2^k and 3 * 2^k
+        while m % 2 == 0:
+            m //= 2
+        return m in (1, 3)
+
+    if all(n % 2 == 0 and ok(3 * n // 2) for n in N):
+        _check(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt),
+               oracle.slab.ifftn(fu, N, 1, dealias="3/2-rule", precision=prec), tol)
+        up = [rng.random(g.real_shape_padded()).astype(rt)]
+        _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct),
+               oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec), tol)
 
 
-def test_slab_single_rank_fused_zy_padded():
-    """3/2-rule: rows of 1536 reals next to columns of 1536 points (the (768, 1536) fused pair), 3 plane groups"""
-    N, prec = (2, 1024, 1024), "double"
+def test_slab_single_rank_c2c_keeps_the_natural_layout():
+    """slab.C2C at P = 1 (rows of the z pass are complex: no row map) runs z, y, x whatever `layout` says."""
+    N, prec = (16, 8, 32), "double"
     rt, ct = oracle.common.dtypes(prec)
-    g = oracle.slab.Geometry(N, 1)
-    rng = np.random.default_rng(13)
-    d = _desc(D.SLAB, N, 1, prec, l2_planes=1)
-    d.l2_mode = 3
-    lib = emu_util.load()
-    before = lib.emu_fused_runs()
-    fu = [_rand_c(rng, g.complex_shape(), ct)]
-    up = run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)
-    _check(up, oracle.slab.ifftn(fu, N, 1, dealias="3/2-rule", precision=prec), TOL[prec])
-    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct), oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec),
-           TOL[prec])
-    assert lib.emu_fused_runs() - before == 2
+    rng = np.random.default_rng(5)
+    u = [_rand_c(rng, N, ct)]
+    ref = oracle.slab.c2c_fftn(u, N, 1, precision=prec)
+    for layout in (D.LAYOUT_YBLOCK, D.LAYOUT_NATURAL):
+        _check(run_plan(_desc(D.SLAB_C2C, N, 1, prec, layout=layout), 0, D.DEALIAS_NONE, u, [tuple(N)], ct), ref, TOL[prec])
 
 
-@pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_STORE])
-def test_slab_multi_rank_fused_zy(transport):
-    """P = 2: inside each exchange chunk the z and y passes run as one fused kernel (the y pass storing
-    into the per-peer blocks, or straight into the peer's buffer with the fused transport)."""
-    N, P, prec = (16, 512, 512), 2, "double"
-    rt, ct = oracle.common.dtypes(prec)
-    g = oracle.slab.Geometry(N, P)
-    rng = np.random.default_rng(14)
-    d = _desc(D.SLAB, N, P, prec, chunks=2, transport=transport, l2_planes=2)
-    d.l2_mode = 3
+def test_y_blocked_program_has_no_far_pass():
+    """The point of the layout, checked on the step list of the 1024^3 plan: three passes, the x pass in place
+    with rows 16 x fewer elements apart than N1*Nf, the y pass reading 16 chunks and writing rows Nf apart."""
     lib = emu_util.load()
-    before = lib.emu_fused_runs()
-    A = rng.random(N).astype(rt)
-    u = [A[g.real_local_slice(r)] for r in range(P)]
-    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()] * P, ct)
-    _check(c, oracle.slab.fftn(u, N, P, precision=prec), TOL[prec])
-    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()] * P, rt), u, TOL[prec])
-    # forward: two chunks; inverse: two chunks, or one with the fused transport (its x pass moves everything at once)
-    assert lib.emu_fused_runs() - before == (2 + (1 if transport == D.TRANSPORT_STORE else 2)) * P
+    N = (1024, 1024, 1024)
+    Nf = 513
     for inverse in (0, 1):
-        assert lib.emu_check_schedule(C.byref(d), inverse, D.DEALIAS_NONE) == 0
-        if transport != D.TRANSPORT_NCCL:
-            n = C.c_int()
-            assert lib.emu_check_p2p(C.byref(d), inverse, D.DEALIAS_NONE, C.byref(n)) == 0
+        d = _desc(D.SLAB, N, 1, "double")
+        n = lib.emu_plan_steps(C.byref(d), inverse, D.DEALIAS_NONE, None, 0)
+        buf = (C.c_longlong * (8 * n))()
+        assert lib.emu_plan_steps(C.byref(d), inverse, D.DEALIAS_NONE, buf, n) == n == 3
+        steps = [tuple(buf[8 * i:8 * i + 8]) for i in range(n)]  # (type, n, B, J, in stride, out stride, in chunks, out chunks)
+        order = [st[0] for st in steps]
+        assert order == ([1, 0, 0] if not inverse else [0, 0, 2])  # 0 strided, 1 R2C, 2 C2R
+        x = steps[1]
+        assert (x[1], x[2], x[3]) == (1024, 16, 64 * Nf) and x[4] == x[5] == 64 * Nf
+        y = steps[2] if not inverse else steps[0]
+        assert (y[1], y[2], y[3]) == (1024, 1024, Nf) and y[4] == y[5] == Nf
+        assert (y[6], y[7]) == ((16, 1) if not inverse else (1, 16))
 
 
 @pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P])
@@ -523,67 +484,6 @@ def test_line_pipelined(P, chunks, transport):
                 n = C.c_int()
                 assert lib.emu_check_p2p(C.byref(d), inverse, mode, C.byref(n)) == 0
                 assert n.value >= 2
-
-
-@pytest.mark.parametrize("l2", [(0, 0), (2, 1), (3, 2), (2, 3)])
-@pytest.mark.parametrize("kz_block,N", [(16, (8, 16, 64)), (8, (16, 8, 32)), (48, (4, 8, 128))])
-@pytest.mark.parametrize("prec", ["double", "single"])
-def test_slab_single_rank_kz_blocked_intermediate(prec, kz_block, N, l2):
-    """kz_block: the array between the passes is [kz block][x][y][jc]; row passes address the blocks as
-    chunks, strided passes through Side::jc; every dealias mode, with and without L2 grouping (mode 3 has
-    no fused kernel for blocked layouts and must fall back to two launches)."""
-    rt, ct = oracle.common.dtypes(prec)
-    g = oracle.slab.Geometry(N, 1)
-    rng = np.random.default_rng(kz_block + N[0])
-    d = _desc(D.SLAB, N, 1, prec, kz_block=kz_block, l2_planes=l2[0], l2_mode=l2[1])
-    u = [rng.random(g.real_shape()).astype(rt)]
-    c = run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)
-    _check(c, oracle.slab.fftn(u, N, 1, precision=prec), TOL[prec])
-    _check(run_plan(d, 1, D.DEALIAS_NONE, c, [g.real_shape()], rt), u, TOL[prec])
-    fu = [_rand_c(rng, g.complex_shape(), ct)]
-    for mode, name in ((D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
-        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
-        _check(run_plan(d, 1, mode, fu, [shp], rt), oracle.slab.ifftn(fu, N, 1, dealias=name, precision=prec), TOL[prec])
-    up = [rng.random(g.real_shape_padded()).astype(rt)]
-    _check(run_plan(d, 0, D.DEALIAS_3_2, up, [g.complex_shape()], ct), oracle.slab.fftn(up, N, 1, dealias="3/2-rule", precision=prec),
-           TOL[prec])
-    lib = emu_util.load()
-    for inverse in (0, 1):
-        for mode in (D.DEALIAS_NONE, D.DEALIAS_3_2, D.DEALIAS_2_3):
-            assert lib.emu_check_schedule(C.byref(d), inverse, mode) == 0
-
-
-def test_kz_block_needs_at_most_16_blocks():
-    d = _desc(D.SLAB, (8, 8, 1024), 1, "double", kz_block=16)  # 513 entries in blocks of 16: 33 blocks
-    lib = emu_util.load()
-    A = np.zeros((8, 8, 1024))
-    out = np.zeros((8, 8, 513), dtype=np.complex128)
-    ip = (C.c_void_p * 1)(A.ctypes.data)
-    op = (C.c_void_p * 1)(out.ctypes.data)
-    assert lib.emu_plan_run(C.byref(d), 0, D.DEALIAS_NONE, ip, op) == D.ERR_ARG
-
-
-@pytest.mark.parametrize("N,variants", [((8, 16, 32), [dict(l2_planes=2, l2_mode=1), dict(l2_planes=3, l2_mode=2)]),
-                                        ((8, 512, 512), [dict(l2_planes=2, l2_mode=3), dict(l2_planes=3, l2_mode=3)])])
-def test_schedule_only_options_do_not_change_a_single_bit(N, variants):
-    """L2 grouping, the two-stream schedule and the fused launch run the same kernels on the same data in a
-    different order: the results must equal the default plan's bit for bit (forward, inverse, 3/2-rule)."""
-    prec = "double"
-    rt, ct = oracle.common.dtypes(prec)
-    g = oracle.slab.Geometry(N, 1)
-    rng = np.random.default_rng(21)
-    u = [rng.random(g.real_shape()).astype(rt)]
-    fu = [_rand_c(rng, g.complex_shape(), ct)]
-    base = _desc(D.SLAB, N, 1, prec)
-    ref_f = run_plan(base, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)[0]
-    ref_i = run_plan(base, 1, D.DEALIAS_NONE, fu, [g.real_shape()], rt)[0]
-    ref_p = run_plan(base, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)[0] if N[1] < 512 else None
-    for kw in variants:
-        d = _desc(D.SLAB, N, 1, prec, **kw)
-        assert np.array_equal(run_plan(d, 0, D.DEALIAS_NONE, u, [g.complex_shape()], ct)[0], ref_f), kw
-        assert np.array_equal(run_plan(d, 1, D.DEALIAS_NONE, fu, [g.real_shape()], rt)[0], ref_i), kw
-        if ref_p is not None:
-            assert np.array_equal(run_plan(d, 1, D.DEALIAS_3_2, fu, [g.real_shape_padded()], rt)[0], ref_p), kw
 
 
 @pytest.mark.parametrize("P", [2, 4])

@@ -28,8 +28,7 @@ def _cases(count, seed):
         chunks = int(rng.choice([0, 1, 2, 3, 4, 5]))
         kind = str(rng.choice(["r2c", "c2c"]))
         prec = "double" if rng.random() < 0.75 else "single"
-        l2 = int(rng.choice([0, 0, 1, 2, 3]))
-        out.append((N, P, transport, pipeline, chunks, kind, prec, l2))
+        out.append((N, P, transport, pipeline, chunks, kind, prec))
     return out
 
 
@@ -39,15 +38,14 @@ def _supported(n):
     return n in (1, 3)
 
 
-@pytest.mark.parametrize("N,P,transport,pipeline,chunks,kind,prec,l2", _cases(60, 2026),
+@pytest.mark.parametrize("N,P,transport,pipeline,chunks,kind,prec", _cases(60, 2026),
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
-def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec, l2):
+def test_random_slab_plan(N, P, transport, pipeline, chunks, kind, prec):
     rt, ct = oracle.common.dtypes(prec)
     c2c = kind == "c2c"
     g = oracle.slab.Geometry(N, P)
     rng = np.random.default_rng(sum(N) * P + chunks)
-    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport,
-              l2_planes=l2)
+    d = _desc(D.SLAB_C2C if c2c else D.SLAB, N, P, prec, chunks=chunks, pipeline=pipeline, transport=transport)
     tol = TOL[prec]
     if c2c:
         cs, it = (N[0], N[1] // P, N[2]), ct

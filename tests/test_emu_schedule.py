@@ -22,30 +22,24 @@ def _check(d):
             assert lib.emu_check_schedule(C.byref(d), inverse, m) == 0, (inverse, m)
 
 
-@pytest.mark.parametrize("l2,streams", [(0, 0), (2, 1), (2, 2), (3, 2)])
 @pytest.mark.parametrize("chunks", [0, 1, 2, 4])
 @pytest.mark.parametrize("pipeline", [D.PIPELINE_X, D.PIPELINE_KZ])
 @pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE])
 @pytest.mark.parametrize("P", [1, 2, 4])
 @pytest.mark.parametrize("kind", [D.SLAB, D.SLAB_C2C])
-def test_slab_schedules(kind, P, transport, pipeline, chunks, l2, streams):
+def test_slab_schedules(kind, P, transport, pipeline, chunks):
     if P == 1 and (transport or pipeline or chunks):
         pytest.skip("single rank: no exchange")
-    d = _desc(kind, (32, 16, 64), P, "double", chunks=chunks, pipeline=pipeline, transport=transport, l2_planes=l2)
-    d.l2_mode = streams
-    _check(d)
+    for layout in ((D.LAYOUT_YBLOCK, D.LAYOUT_NATURAL) if P == 1 else (D.LAYOUT_YBLOCK,)):
+        _check(_desc(kind, (32, 16, 64), P, "double", chunks=chunks, pipeline=pipeline, transport=transport, layout=layout))
 
 
 def test_headline_sizes():
-    for P, transport, pipeline, chunks, l2, streams in itertools.product(
-            (1, 2, 8), (D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE), (D.PIPELINE_X, D.PIPELINE_KZ), (0, 8),
-            (0, 4), (0, 2)):
+    for P, transport, pipeline, chunks in itertools.product(
+            (1, 2, 8), (D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE), (D.PIPELINE_X, D.PIPELINE_KZ), (0, 8)):
         if P == 1 and (transport or pipeline or chunks):
             continue
-        d = _desc(D.SLAB, (1024, 1024, 1024), P, "double", chunks=chunks, pipeline=pipeline, transport=transport,
-                  l2_planes=l2)
-        d.l2_mode = streams
-        _check(d)
+        _check(_desc(D.SLAB, (1024, 1024, 1024), P, "double", chunks=chunks, pipeline=pipeline, transport=transport))
 
 
 @pytest.mark.parametrize("transport", [D.TRANSPORT_NCCL, D.TRANSPORT_P2P, D.TRANSPORT_STORE])

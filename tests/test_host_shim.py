@@ -1,5 +1,5 @@
 """The product's C-ABI layer (csrc/b200fft.cu: plan objects, the program execution loop with its
-descriptor construction, fused-launch fallback, event bookkeeping, timing / step records, error codes)
+descriptor construction, event bookkeeping, timing / step records, error codes)
 executed on the CPU: built with g++ against an inert CUDA runtime stand-in, kernels bound to the emulator
 (tests/host_shim_util.py).  The emulator tests run the plan PROGRAMS; these run the code that executes
 them on the device, through the same entry points the Python classes call."""
@@ -46,15 +46,15 @@ def _steps(L, h):
     return [(ty[i], ms[i], by[i], ln[i], ps[i]) for i in range(n.value)]
 
 
-@pytest.mark.parametrize("l2", [(0, 0), (2, 1), (2, 2), (3, 3), (8, 3)])
+@pytest.mark.parametrize("layout", [D.LAYOUT_YBLOCK, D.LAYOUT_NATURAL])
 @pytest.mark.parametrize("prec", ["double", "single"])
-def test_slab_single_rank_through_the_c_abi(prec, l2):
-    """fftn / ifftn of every dealias mode through b200fft_exec_forward / _inverse, default and L2-blocked
-    (grouped launches, two streams, the fused launch with its fallback), with timing records on."""
+def test_slab_single_rank_through_the_c_abi(prec, layout):
+    """fftn / ifftn of every dealias mode through b200fft_exec_forward / _inverse, y-blocked (default) and natural
+    intermediate layout, with timing records on."""
     L = host_shim_util.load()
-    N = (8, 512, 512) if l2[1] == 3 else (8, 16, 32)
+    N = (8, 16, 32)
     rt, ct = oracle.common.dtypes(prec)
-    rc, h = _plan(L, D.SLAB, N, prec, l2_planes=l2[0], l2_mode=l2[1])
+    rc, h = _plan(L, D.SLAB, N, prec, layout=layout)
     assert rc == 0, L.b200fft_last_error()
     assert L.b200fft_plan_set_timing(h, 1) == 0
     rng = np.random.default_rng(3)
@@ -64,45 +64,28 @@ def test_slab_single_rank_through_the_c_abi(prec, l2):
     assert oracle.rel_l2(c, oracle.slab.fftn([A], N, 1, precision=prec)[0]) <= TOL[prec]
     k, x = C.c_int(), C.c_int()
     assert L.b200fft_plan_last_launches(h, C.byref(k), C.byref(x)) == 0
-    groups = -(-N[0] // l2[0]) if l2[0] else 1
-    expected = {0: 3, 1: 2 * groups + 1, 2: 2 * groups + 1, 3: 2}[l2[1]]
-    assert (k.value, x.value) == (expected, 0)
+    assert (k.value, x.value) == (3, 0)
     st = _steps(L, h)
-    assert len(st) == expected and all(s[1] >= 0 for s in st)
-    # the records carry the algorithmic bytes of the whole transform whatever the grouping
+    assert len(st) == 3 and all(s[1] >= 0 for s in st)
+    # the records carry the algorithmic bytes of the whole transform whatever the layout
     csz, rsz = np.dtype(ct).itemsize, np.dtype(rt).itemsize
     Nf = N[2] // 2 + 1
     total = N[0] * N[1] * (N[2] * rsz + Nf * csz) + 2 * 2 * N[0] * N[1] * Nf * csz
     assert sum(s[2] for s in st) == pytest.approx(total)
     back = _run(L, h, 1, D.DEALIAS_NONE, c, np.full(N, np.nan, dtype=rt))
     assert oracle.rel_l2(back, A) <= TOL[prec]
-    if l2[1] != 3:  # (the padded sizes of the large mesh are not needed to cover the fused path again)
-        fu = (rng.standard_normal(g.complex_shape()) + 1j * rng.standard_normal(g.complex_shape())).astype(ct)
-        for mode, name in ((D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
-            shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
-            got = _run(L, h, 1, mode, fu, np.full(shp, np.nan, dtype=rt))
-            assert oracle.rel_l2(got, oracle.slab.ifftn([fu], N, 1, dealias=name, precision=prec)[0]) <= TOL[prec]
-        up = rng.random(g.real_shape_padded()).astype(rt)
-        got = _run(L, h, 0, D.DEALIAS_3_2, up, np.full(g.complex_shape(), np.nan, dtype=ct))
-        assert oracle.rel_l2(got, oracle.slab.fftn([up], N, 1, dealias="3/2-rule", precision=prec)[0]) <= TOL[prec]
-        assert L.b200fft_plan_workspace_bytes(h) > 0
+    fu = (rng.standard_normal(g.complex_shape()) + 1j * rng.standard_normal(g.complex_shape())).astype(ct)
+    for mode, name in ((D.DEALIAS_2_3, "2/3-rule"), (D.DEALIAS_3_2, "3/2-rule")):
+        shp = g.real_shape_padded() if name == "3/2-rule" else g.real_shape()
+        got = _run(L, h, 1, mode, fu, np.full(shp, np.nan, dtype=rt))
+        assert oracle.rel_l2(got, oracle.slab.ifftn([fu], N, 1, dealias=name, precision=prec)[0]) <= TOL[prec]
+    up = rng.random(g.real_shape_padded()).astype(rt)
+    got = _run(L, h, 0, D.DEALIAS_3_2, up, np.full(g.complex_shape(), np.nan, dtype=ct))
+    assert oracle.rel_l2(got, oracle.slab.fftn([up], N, 1, dealias="3/2-rule", precision=prec)[0]) <= TOL[prec]
+    assert L.b200fft_plan_workspace_bytes(h) > 0
     f, xms = C.c_float(), C.c_float()
     assert L.b200fft_plan_last_phase_ms(h, C.byref(f), C.byref(xms)) == 0 and f.value >= 0
     assert L.b200fft_plan_destroy(h) == 0
-
-
-def test_fused_launch_falls_back_when_no_kernel_pair_exists():
-    L = host_shim_util.load()
-    N = (8, 16, 32)  # rows of 32 reals next to columns of 16: no fused pair compiled -> two launches per pair
-    rc, h = _plan(L, D.SLAB, N, "double", l2_planes=2, l2_mode=3)
-    assert rc == 0
-    A = np.random.default_rng(1).random(N)
-    c = _run(L, h, 0, D.DEALIAS_NONE, A, np.zeros((8, 16, 17), dtype=np.complex128))
-    assert oracle.rel_l2(c, np.fft.rfftn(A)) <= 5e-14
-    k, x = C.c_int(), C.c_int()
-    L.b200fft_plan_last_launches(h, C.byref(k), C.byref(x))
-    assert k.value == 3
-    L.b200fft_plan_destroy(h)
 
 
 def test_c2c_and_line_plans_and_error_codes():
@@ -136,23 +119,4 @@ def test_c2c_and_line_plans_and_error_codes():
     A = rng.random((8, 16, 32))
     assert L.b200fft_exec_forward(h, C.c_void_p(A.ctypes.data), None, 0, None) == D.ERR_ARG
     assert L.b200fft_exec_forward(h, C.c_void_p(A.ctypes.data), C.c_void_p(A.ctypes.data), 9, None) == D.ERR_ARG
-    L.b200fft_plan_destroy(h)
-
-
-@pytest.mark.parametrize("l2", [(0, 0), (2, 2)])
-def test_kz_blocked_plan_through_the_c_abi(l2):
-    L = host_shim_util.load()
-    N = (8, 16, 64)
-    rc, h = _plan(L, D.SLAB, N, "double", kz_block=16, l2_planes=l2[0], l2_mode=l2[1])
-    assert rc == 0, L.b200fft_last_error()
-    rng = np.random.default_rng(4)
-    A = rng.random(N)
-    g = oracle.slab.Geometry(N, 1)
-    c = _run(L, h, 0, D.DEALIAS_NONE, A, np.full(g.complex_shape(), np.nan, dtype=np.complex128))
-    assert oracle.rel_l2(c, np.fft.rfftn(A)) <= 5e-14
-    assert oracle.rel_l2(_run(L, h, 1, D.DEALIAS_NONE, c, np.full(N, np.nan)), A) <= 5e-14
-    up = _run(L, h, 1, D.DEALIAS_3_2, c, np.full(g.real_shape_padded(), np.nan))
-    assert oracle.rel_l2(up, oracle.slab.ifftn([c], N, 1, dealias="3/2-rule")[0]) <= 5e-14
-    back = _run(L, h, 0, D.DEALIAS_3_2, up, np.full(g.complex_shape(), np.nan, dtype=np.complex128))
-    assert oracle.rel_l2(back, oracle.slab.fftn([up], N, 1, dealias="3/2-rule")[0]) <= 5e-13
     L.b200fft_plan_destroy(h)

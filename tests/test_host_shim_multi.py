@@ -97,17 +97,16 @@ def _exec(L, h, inverse, mode, src, dst):
     return dst
 
 
-SLAB_CASES = [(D.TRANSPORT_NCCL, D.PIPELINE_X, 0, 0, 0), (D.TRANSPORT_NCCL, D.PIPELINE_X, 2, 0, 0),
-              (D.TRANSPORT_P2P, D.PIPELINE_X, 0, 0, 0), (D.TRANSPORT_P2P, D.PIPELINE_X, 4, 0, 0),
-              (D.TRANSPORT_STORE, D.PIPELINE_X, 0, 0, 0), (D.TRANSPORT_STORE, D.PIPELINE_X, 2, 0, 0),
-              (D.TRANSPORT_NCCL, D.PIPELINE_KZ, 3, 0, 0), (D.TRANSPORT_P2P, D.PIPELINE_KZ, 2, 0, 0),
-              (D.TRANSPORT_STORE, D.PIPELINE_KZ, 2, 0, 0), (D.TRANSPORT_P2P, D.PIPELINE_X, 2, 2, 1),
-              (D.TRANSPORT_STORE, D.PIPELINE_X, 0, 2, 1)]
+SLAB_CASES = [(D.TRANSPORT_NCCL, D.PIPELINE_X, 0), (D.TRANSPORT_NCCL, D.PIPELINE_X, 2),
+              (D.TRANSPORT_P2P, D.PIPELINE_X, 0), (D.TRANSPORT_P2P, D.PIPELINE_X, 4),
+              (D.TRANSPORT_STORE, D.PIPELINE_X, 0), (D.TRANSPORT_STORE, D.PIPELINE_X, 2),
+              (D.TRANSPORT_NCCL, D.PIPELINE_KZ, 3), (D.TRANSPORT_P2P, D.PIPELINE_KZ, 2),
+              (D.TRANSPORT_STORE, D.PIPELINE_KZ, 2)]
 
 
-@pytest.mark.parametrize("transport,pipeline,chunks,l2_planes,l2_mode", SLAB_CASES)
+@pytest.mark.parametrize("transport,pipeline,chunks", SLAB_CASES)
 @pytest.mark.parametrize("P", [2, 4])
-def test_slab_ranks_as_threads(P, transport, pipeline, chunks, l2_planes, l2_mode):
+def test_slab_ranks_as_threads(P, transport, pipeline, chunks):
     L = host_shim_util.load()
     N = (16, 16, 32)
     g = oracle.slab.Geometry(N, P)
@@ -120,8 +119,7 @@ def test_slab_ranks_as_threads(P, transport, pipeline, chunks, l2_planes, l2_mod
     R = Ranks(P)
 
     def rank(r):
-        h, comms = _make_plan(L, R, r, D.SLAB, N, P, transport, pipeline=pipeline, chunks=chunks, l2_planes=l2_planes,
-                              l2_mode=l2_mode)
+        h, comms = _make_plan(L, R, r, D.SLAB, N, P, transport, pipeline=pipeline, chunks=chunks)
         for rep in range(3):  # back to back: sequence numbers and credits carry over from call to call
             c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(g.complex_shape(), np.nan, dtype=np.complex128))
             assert oracle.rel_l2(c, ref[r]) <= TOL, (r, rep)

@@ -233,8 +233,10 @@ def test_mask_bands(be):
     assert _rel(out, ref) < 1e-14
 
 
-def run_rows(be, fn, real, cplx_side, n, rows, nk, prec, scale=1.0):
+def run_rows(be, fn, real, cplx_side, n, rows, nk, prec, scale=1.0, rowmap=None):
     d = D.RowsDesc()
+    if rowmap is not None:
+        d.rm_period, d.rm_block, d.rm_planes = rowmap
     d.precision = prec
     d.n = n
     d.rows = rows
@@ -353,34 +355,24 @@ def test_rows_c2c_pad_truncate_fold(be, N):
     assert _rel(got2, ref2) < 1e-14
 
 
-@pytest.mark.parametrize("n,prec", [(16, "d"), (96, "d"), (1024, "d"), (1024, "s"), (1536, "d"), (512, "s")])
-def test_blocked_column_layout(be, n, prec, request):
-    """Side::jc -- a kz-blocked array [block][b][n][jc] on either side of a strided pass: natural -> blocked on
-    the store side, blocked -> natural on the load side, and blocked in place.  (The device library compiles
-    this form for n = 512, 1024, 1536; the emulator for every length.)"""
-    if be.name == "gpu" and n not in (512, 1024, 1536):
-        pytest.skip("blocked column layouts are compiled for the benchmark lengths on the device")
-    if be.name == "gpu":  # written after round 1's GPU minutes were spent: emulator-checked only so far
-        request.applymarker(pytest.mark.xfail(strict=False, reason="opt-in kernel form; first device run pending"))
-    ct = np.complex128 if prec == "d" else np.complex64
-    tol = 2e-15 * np.log2(n) if prec == "d" else 6e-7 * np.log2(n)
-    rng = np.random.default_rng(n)
-    B, J, jc = 2, 37, 16
-    nb = -(-J // jc)
-    x = be.arr(_cplx(rng, (B, n, J), ct))
-    X = np.fft.fft(x.astype(np.complex128), axis=1)
-    blk = be.zeros((nb, B, n, jc), ct)
-    side_b = D.plain_side(_ptr(blk), n * jc, jc, n)
-    side_b.jc, side_b.sj = jc, B * n * jc
-    run_strided(be, x, n, None, out_side=side_b)
-    for c in range(nb):
-        w = min(jc, J - c * jc)
-        assert _rel(blk[c, :, :, :w], X[:, :, c * jc:c * jc + w]) < tol
-    back = be.zeros(x.shape, x.dtype)
-    run_strided(be, None, n, back, inverse=1, scale=1.0 / n, in_side=side_b, B=B, J=J, prec=D.DOUBLE if prec == "d" else D.SINGLE)
-    assert _rel(back, x) < 2 * tol
-    run_strided(be, None, n, None, inverse=1, scale=1.0 / n, in_side=side_b, out_side=side_b, B=B, J=J,
-                prec=D.DOUBLE if prec == "d" else D.SINGLE)
-    for c in range(nb):
-        w = min(jc, J - c * jc)
-        assert _rel(blk[c, :, :, :w], x[:, :, c * jc:c * jc + w]) < 2 * tol
+@pytest.mark.parametrize("h,prec", [(8, "d"), (48, "d"), (128, "s"), (512, "d"), (768, "d"), (2048, "s")])
+def test_rows_row_map(be, h, prec):
+    """Row map of the row kernels (b200fft_rows_desc_t::rm_*): the spectrum of real row r = x * period + y lands at
+    complex row ((y / block) * planes + x) * block + y % block -- the y-blocked intermediate [y block][x][y in block][k]
+    of single-rank slab plans -- for the R2C store and both C2R kernels' loads (h = 2048: the staging kernel)."""
+    n = 2 * h
+    rt, ct = (np.float64, np.complex128) if prec == "d" else (np.float32, np.complex64)
+    pr = D.DOUBLE if prec == "d" else D.SINGLE
+    tol = 3e-15 * np.log2(n) if prec == "d" else 8e-7 * np.log2(n)
+    rng = np.random.default_rng(h)
+    planes, period, block = 3, 6, 2
+    rows = planes * period
+    x = be.arr(rng.standard_normal((rows, n)).astype(rt))
+    X = be.zeros((period // block, planes, block, h + 1), ct)
+    run_rows(be, "exec_r2c", x, D.plain_side(_ptr(X), h + 1, 1, h + 1), n, rows, h + 1, pr, rowmap=(period, block, planes))
+    ref = np.fft.rfft(x.astype(np.float64), axis=1).reshape(planes, period // block, block, h + 1).transpose(1, 0, 2, 3)
+    assert _rel(X, ref) < tol
+    y = be.zeros((rows, n), rt)
+    run_rows(be, "exec_c2r", y, D.plain_side(_ptr(X), h + 1, 1, h + 1), n, rows, h + 1, pr, scale=1.0 / n,
+             rowmap=(period, block, planes))
+    assert _rel(y, x) < 3 * tol

@@ -4,7 +4,7 @@ from mpifft4py_b200 import tune
 
 
 def test_fastest_qualifying_candidate_wins_and_failures_are_reported():
-    cands = [("default", 0, {}), ("fast_but_wrong", 1, {}), ("fast", 2, {}), ("crashes", 3, {}), ("slow", 4, {})]
+    cands = [("default", {}), ("fast_but_wrong", {}), ("fast", {}), ("crashes", {}), ("slow", {})]
     times = {"default": (1.0, 0.0), "fast_but_wrong": (0.1, 1e-3), "fast": (0.5, 1e-15), "slow": (2.0, 0.0)}
 
     def measure(c):
@@ -20,7 +20,7 @@ def test_fastest_qualifying_candidate_wins_and_failures_are_reported():
 
 
 def test_default_is_kept_when_nothing_qualifies_and_slowest_rank_decides():
-    cands = [("default", 0, {}), ("a", 1, {})]
+    cands = [("default", {}), ("a", {})]
     best, _ = tune.select(cands, lambda c: (1.0, 1.0), 1e-12)
     assert best[0] == "default"
     # gather models the allgather over ranks: candidate "a" is fast here but slow on another rank
@@ -30,7 +30,7 @@ def test_default_is_kept_when_nothing_qualifies_and_slowest_rank_decides():
 
 
 def test_a_candidate_wrong_or_failing_on_another_rank_is_rejected_and_the_gather_is_always_called():
-    cands = [("default", 0, {}), ("wrong_elsewhere", 1, {}), ("fails_elsewhere", 2, {}), ("fails_here", 3, {})]
+    cands = [("default", {}), ("wrong_elsewhere", {}), ("fails_elsewhere", {}), ("fails_here", {})]
     calls = []
 
     def measure(c):
@@ -53,10 +53,9 @@ def test_install_sets_and_clears_plan_attributes():
     class F(object):
         _plan = None
     f = F()
-    seen = []
-    tune._install(f, 20, {"l2_planes": 4, "l2_mode": 3}, seen.append)
-    assert (f.l2_planes, f.l2_mode, seen) == (4, 3, [20])
-    tune._install(f, 0, {"kz_block": 48}, seen.append, base={"transport": "nccl"})
-    assert not hasattr(f, "l2_planes") and f.kz_block == 48 and f.transport == "nccl" and seen == [20, 0]
+    tune._install(f, {"exchange_chunks": 4, "transport": "p2p"})
+    assert (f.exchange_chunks, f.transport) == (4, "p2p")
+    tune._install(f, {"layout": "natural"}, base={"transport": "nccl"})
+    assert not hasattr(f, "exchange_chunks") and f.layout == "natural" and f.transport == "nccl"
     assert set(c[0] for c in tune.CANDIDATES["measure"]) <= set(c[0] for c in tune.CANDIDATES["patient"])
     assert m.tune is tune
