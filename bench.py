@@ -487,12 +487,20 @@ def run_ours(args):
             if rep == 0:
                 a[1] += s[2]
 
+    # Each timed transform is the last of a run of back-to-back round trips without host synchronisation, so it is
+    # measured at the clocks the timed K-step region saw (a transform timed alone after a synchronize runs at boost
+    # clocks: round 1's per-pass sum was 6 % under its step time for exactly that reason -- sw_power_cap, BENCH_r01).
+    lead = 0 if flush is not None else 3
     for rep in range(reps):
+        for _ in range(lead):
+            step()
         if flush is not None:
             flush.fill_(1)
         fwd(u, fu, dealias)
         torch.cuda.synchronize()
         record("fwd", rep)
+        for _ in range(lead):
+            step()
         if flush is not None:
             flush.fill_(1)
         inv(fu, u2, dealias)
@@ -523,6 +531,7 @@ def run_ours(args):
                 "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(dom["GBps"] / hbm_peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": dom["bytes"], "ms": dom["ms"],
                 "passes": passes,
+                "pass_timing": "CUDA events around each pass of a transform that ends a run of %d back-to-back round trips" % lead,
                 "sum_fft_ms": round(sum(p["ms"] for p in ffts), 4),
                 "sum_exchange_ms": round(sum(p["ms"] for p in passes if p["type"] == "exchange"), 4)}
     # whole-step roofline: time the algorithmic bytes need at the HBM figure plus the

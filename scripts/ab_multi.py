@@ -34,6 +34,7 @@ CONFIGS = {
     "p2p_c2": {"transport": "p2p", "exchange_chunks": 2},
     "p2p_c4": {"transport": "p2p", "exchange_chunks": 4},
     "p2p_c8": {"transport": "p2p", "exchange_chunks": 8},
+    "p2p_c2_cs": {"transport": "p2p", "exchange_chunks": 2, "copy_streams": 1},
     "p2p_c4_cs": {"transport": "p2p", "exchange_chunks": 4, "copy_streams": 1},
     "p2p_c8_cs": {"transport": "p2p", "exchange_chunks": 8, "copy_streams": 1},
     "store_c1": {"transport": "store", "exchange_chunks": 1},
