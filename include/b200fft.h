@@ -132,6 +132,29 @@ B200FFT_API int b200fft_exec_strided(const b200fft_strided_desc_t* d, void* stre
 B200FFT_API int b200fft_exec_r2c(const b200fft_rows_desc_t* d, void* stream);
 B200FFT_API int b200fft_exec_c2r(const b200fft_rows_desc_t* d, void* stream);
 /* ---------------------------------------------------------------------------------------------
+ * The caller of the transforms: pointwise operations of a pseudo-spectral
+ * Navier-Stokes right-hand side, /root/reference/demo/spectral_dns_solver.py:53-77,87-98.  Vector fields
+ * are [3][n] arrays (component-major, like the demo's U_hat / U / dU); wavenumbers come from three 1D device
+ * vectors through the point's linear index, so no wavenumber mesh is read from HBM.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int precision;
+  long long n0, n1, n2;       /* local complex shape (complex_shape()), C order */
+  const void *kx, *ky, *kz;   /* device vectors of n0, n1, n2 reals: this rank's (scaled) wavenumbers
+                                 (get_local_wavenumbermesh(scaled=True), slab.py:160-189) */
+} b200fft_ns_mesh_t;
+/* curl_hat = i K x u_hat  (demo :60-64) */
+B200FFT_API int b200fft_ns_curl(const b200fft_ns_mesh_t* m, const void* u_hat, void* curl_hat, void* stream);
+/* out = a x b on [3][npoints] real arrays (demo :53-58, before the forward transforms) */
+B200FFT_API int b200fft_ns_cross(int precision, long long npoints, const void* a, const void* b, void* out, void* stream);
+/* du (the transformed cross product) -> right-hand side: pressure projection and viscous term (demo :72-76);
+ * with u_hat0 / u_hat1 given also the Runge-Kutta bookkeeping of the stage (demo :91-97) in the same pass:
+ * u_hat1 += a_dt * rhs;  u_hat = last ? u_hat1 : u_hat0 + b_dt * rhs.  With u_hat0 == u_hat1 == NULL the
+ * right-hand side is written back to du. */
+B200FFT_API int b200fft_ns_rhs(const b200fft_ns_mesh_t* m, double nu, void* du, void* u_hat, const void* u_hat0, void* u_hat1,
+                               double a_dt, double b_dt, int last, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Communicators: replace the mpi4py communicator (comm.Alltoall / Alltoallw / Sendrecv_replace /
  * Scatter / Send / Recv call sites listed in SURVEY.md section 2 row 7) by NCCL over NVLink.
  * The caller distributes the 128-byte unique id (host memory) out of band (torch.distributed,

@@ -13,6 +13,7 @@ from .serialFFT import dct, fft, ifft, rfft, irfft, rfft2, irfft2, rfftn, irfftn
 from numpy.fft import fftfreq, rfftfreq
 from . import comm
 from . import device  # device-resident mesh / wavenumber / mask helpers and work arrays
-from . import tune    # on-device selection of the opt-in kernels / schedules (the planner_effort of this engine)
+from . import tune    # on-device selection of exchange transport / pipeline depth (the planner_effort of this engine)
+from . import ns      # Navier-Stokes right-hand side around the transforms (elementwise kernels of the library)
 
 __version__ = '0.1.0'

@@ -46,6 +46,11 @@ class PlanDesc(C.Structure):
                 ("copy_streams", C.c_int), ("layout", C.c_int)]
 
 
+class NsMesh(C.Structure):
+    _fields_ = [("precision", C.c_int), ("n0", C.c_longlong), ("n1", C.c_longlong), ("n2", C.c_longlong),
+                ("kx", C.c_void_p), ("ky", C.c_void_p), ("kz", C.c_void_p)]
+
+
 def no_mask():
     m = Mask()
     m.on = 0

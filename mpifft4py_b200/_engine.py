@@ -70,18 +70,16 @@ class Transform(object):
         d.layout = D.LAYOUT_NATURAL if lay == "natural" else D.LAYOUT_YBLOCK
         # copy-engine transport: one copy stream per peer (overlaps the per-copy issue latency)
         d.copy_streams = int(getattr(self, "copy_streams", 0) or os.environ.get("B200FFT_COPY_STREAMS", "0"))
-        # slab exchanges default to the copy-engine (P2P) transport: DMA pushes over NVLink that do
-        # not occupy SMs, pipelined against the FFT passes.  B200FFT_TRANSPORT=nccl (or
-        # obj.transport = "nccl") selects the NCCL send/recv path; it is also what all ranks agree
-        # to use if any of them cannot map its peers' buffers (no IPC / no peer access).
-        # "store" is the fused transport: same peer mappings, but the y (forward) / x (inverse) FFT
-        # pass stores each peer's block straight into that peer's receive buffer over NVLink, so no
-        # copy step, send buffer or per-copy launch cost remains (include/b200fft.h).
-        # Pencil and line plans use NCCL unless a peer-mapped transport is asked for (they address their
-        # sub-communicators' peers through the same world-wide mappings).
-        slab = kind in (D.SLAB, D.SLAB_C2C)
-        choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT") or
-                     ("p2p" if slab else "nccl")).lower()
+        # Exchanges default to the copy-engine (P2P) transport for every class: DMA pushes over NVLink that do not
+        # occupy SMs, pipelined against the FFT passes (8 GPUs, profiles/r02_multi_8: slab 1024^3 5.4 ms against
+        # 5.7 over NCCL send/recv, pencil X 5.9 against 7.7, pencil Y 2048^3 single 27.0 against 33.6).
+        # B200FFT_TRANSPORT=nccl (or obj.transport = "nccl") selects the NCCL send/recv path; it is also what all
+        # ranks agree to use if any of them cannot map its peers' buffers (no IPC / no peer access).
+        # "store" is the fused transport: same peer mappings, but the FFT pass in front of an exchange stores each
+        # peer's block straight into that peer's receive buffer over NVLink (one kernel does the FFT, the pack and
+        # the transfer; measured slower than the copy engines on NVSwitch boxes because the storing pass then runs at
+        # link speed -- 6.2 ms against 5.4 at 8 GPUs -- kept for machines without peer DMA overlap).
+        choice = str(getattr(self, "transport", None) or os.environ.get("B200FFT_TRANSPORT") or "p2p").lower()
         assert choice in ("p2p", "nccl", "store"), "transport must be 'p2p', 'store' or 'nccl'"
         h = None
         if int(nranks) > 1 and choice in ("p2p", "store"):

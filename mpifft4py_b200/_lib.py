@@ -18,7 +18,7 @@ SYMBOLS = [
     "b200fft_plan_create", "b200fft_plan_destroy", "b200fft_plan_workspace_bytes",
     "b200fft_exec_forward", "b200fft_exec_inverse", "b200fft_plan_last_launches",
     "b200fft_plan_set_timing", "b200fft_plan_last_phase_ms", "b200fft_plan_last_steps",
-    "b200fft_plan_p2p_handles", "b200fft_plan_p2p_connect",
+    "b200fft_plan_p2p_handles", "b200fft_plan_p2p_connect", "b200fft_ns_curl", "b200fft_ns_cross", "b200fft_ns_rhs",
 ]
 
 
@@ -33,6 +33,10 @@ def declare(L):
     L.b200fft_supported_length.argtypes = [C.c_int]
     L.b200fft_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.b200fft_stream_sync.argtypes = [C.c_void_p]
+    L.b200fft_ns_curl.argtypes = [C.POINTER(D.NsMesh), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200fft_ns_cross.argtypes = [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200fft_ns_rhs.argtypes = [C.POINTER(D.NsMesh), C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_double, C.c_double, C.c_int, C.c_void_p]
     L.b200fft_exec_strided.argtypes = [C.POINTER(D.StridedDesc), C.c_void_p]
     L.b200fft_exec_r2c.argtypes = [C.POINTER(D.RowsDesc), C.c_void_p]
     L.b200fft_exec_c2r.argtypes = [C.POINTER(D.RowsDesc), C.c_void_p]

@@ -118,13 +118,20 @@ class TorchComm(object):
         groups = {}
         for c, k, r in info:
             groups.setdefault(c, []).append((k, r))
-        mine = None
-        for c in sorted(groups):
-            ranks = [r for _, r in sorted(groups[c])]
-            g = dist.new_group(ranks=ranks)
-            if dist.get_rank() in ranks:
-                mine = g
-        return TorchComm(mine)
+        # the same partition again (every pencil object splits the world the same two ways) returns the communicator
+        # made the first time: no new process groups, no new NCCL communicators behind them
+        part = tuple(tuple(r for _, r in sorted(groups[c])) for c in sorted(groups))
+        mine = _split_cache.get(part)
+        if mine is None:
+            for ranks in part:
+                g = dist.new_group(ranks=list(ranks))
+                if dist.get_rank() in ranks:
+                    mine = TorchComm(g)
+            _split_cache[part] = mine
+        return mine
+
+
+_split_cache = {}
 
 
 def world():

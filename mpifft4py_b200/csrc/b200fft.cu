@@ -45,6 +45,7 @@ bool plan_exists(int n) {
       return false;
   }
 }
+int ns_fail(int code, const char* msg) { return fail(code, "%s", msg); }  // ns_kernels.cu
 }  // namespace b200fft
 
 namespace {

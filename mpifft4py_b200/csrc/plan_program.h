@@ -217,6 +217,18 @@ inline int pick_chunks(int requested, long long ext, long long peer_msg_bytes, b
   return 1;
 }
 
+// Pipeline depth of pencil and line plans when the caller leaves it open (d.chunks == 0): two chunks with the
+// copy-engine transport once a rank exchanges 256 MB or more per step, else one.  8 GPUs, profiles/r02_multi_8:
+// pencil X 1024^3 double (1.07 GB per rank) 6.76 / 5.86 / 6.44 ms at 1 / 2 / 4 chunks, pencil Y 2048^3 single
+// (4.3 GB) 32.0 / 27.0 / 27.1, pencil X 512^3 double (134 MB) 1.19 / 1.20 / 1.33, line 16384^2 single (134 MB)
+// 1.78 / 1.89 / 2.20; NCCL exchanges lose with any chunking there (7.68 / 8.70 / 9.25 ms).
+inline int grid_chunks(const b200fft_plan_desc_t& d, long long local_complex_elems) {
+  if (d.transport == B200FFT_TRANSPORT_STORE) return 1;
+  if (d.chunks > 0) return d.chunks;
+  const long long csz = d.precision == B200FFT_DOUBLE ? 16 : 8;
+  return (d.transport == B200FFT_TRANSPORT_P2P && local_complex_elems * csz >= (256ll << 20)) ? 2 : 1;
+}
+
 // kz pipeline: number of kz ranges (each at least 8 entries wide so that tiles stay full)
 inline int kz_chunks(int requested, long long Nf) {
   long long c = requested > 0 ? requested : 4;
@@ -784,7 +796,7 @@ inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, 
     // e2(c) then one x pass, inverse one x pass then e2(c) | y(c) | e1(c) | z(c) -- so each exchange
     // overlaps the FFT passes of the neighbouring chunks.  The send buffer of the second exchange of a
     // direction must not alias the first one's any more (W3 where W2 is taken).
-    int CH = (d.chunks > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+    int CH = grid_chunks(d, N0 * N1 * (N2 / 2 + 1) / P);
     while (CH > 1 && pa % CH) --CH;
     const long long xc = pa / CH;
     // kz-chunked side of the z pass restricted to local planes [x0, x0 + xc)
@@ -1004,7 +1016,7 @@ inline int build_pencil(const b200fft_plan_desc_t& d, int inverse, int dealias, 
     // message contiguous.  forward: z | ea(c) | x(c) | eb(c) | y(c);  inverse: y(c) | eb(c) | x(c) | ea(c) | z:
     // a three-stage pipeline on both sides of the x pass.  The z pass addresses the P1*CH kz chunks of
     // its complex side directly (hence P1*CH <= 16).
-    int CH = (d.chunks > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+    int CH = grid_chunks(d, N0 * N1 * (N2 / 2 + 1) / P);
     while (CH > 1 && (C % CH || (long long)P1 * CH > PMAXP)) --CH;
     const long long kzc = C / CH;
     auto kq = [&](int c, int q) { return kzc + ((c == CH - 1) ? zc[q] - C : 0); };   // width of sub-range c on rank q
@@ -1259,7 +1271,7 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   if (padded && (long long)pNp0 * P != pN0) return fail(B200FFT_ERR_ARG, "3/2-rule: padsize * N[0] / ranks must be an integer");
   // pipelined programs (d.chunks > 1; NCCL and copy-engine transports): the local rows are cut into CH
   // chunks whose exchange runs on the second stream beside the z pass of the next chunk
-  int CH = (d.chunks > 1 && P > 1 && d.transport != B200FFT_TRANSPORT_STORE) ? d.chunks : 1;
+  int CH = P > 1 ? grid_chunks(d, N0 * (N1 / 2 + 1) / P) : 1;
   while (CH > 1 && pNp0 % CH) --CH;
   const long long rc = pNp0 / CH;
   const double p2 = p * p;

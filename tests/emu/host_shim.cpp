@@ -171,3 +171,44 @@ static void* sym(void* h, const char* name) {
 
 // test hook: start a new epoch for this rank's events (see cuda_shim/cuda_runtime.h)
 extern "C" void shim_next_epoch() { ++shim_epoch(); }
+
+// ---- the Navier-Stokes pointwise operations (csrc/ns_ops.cuh) as plain host loops behind the product's entry points ----
+#include "../../mpifft4py_b200/csrc/ns_ops.cuh"
+namespace {
+template <class real>
+b200fft::NsMesh<real> shim_mesh(const b200fft_ns_mesh_t& m) {
+  return b200fft::NsMesh<real>{m.n0, m.n1, m.n2, (const real*)m.kx, (const real*)m.ky, (const real*)m.kz};
+}
+}  // namespace
+extern "C" {
+int b200fft_ns_curl(const b200fft_ns_mesh_t* m, const void* u, void* c, void*) {
+  using namespace b200fft;
+  const long long n = m->n0 * m->n1 * m->n2;
+  for (long long i = 0; i < n; ++i) {
+    if (m->precision == B200FFT_DOUBLE) ns_curl_point(shim_mesh<double>(*m), n, i, (const cx<double>*)u, (cx<double>*)c);
+    else ns_curl_point(shim_mesh<float>(*m), n, i, (const cx<float>*)u, (cx<float>*)c);
+  }
+  return 0;
+}
+int b200fft_ns_cross(int precision, long long n, const void* a, const void* b, void* w, void*) {
+  using namespace b200fft;
+  for (long long i = 0; i < n; ++i) {
+    if (precision == B200FFT_DOUBLE) ns_cross_point(n, i, (const double*)a, (const double*)b, (double*)w);
+    else ns_cross_point(n, i, (const float*)a, (const float*)b, (float*)w);
+  }
+  return 0;
+}
+int b200fft_ns_rhs(const b200fft_ns_mesh_t* m, double nu, void* du, void* u, const void* u0, void* u1, double a_dt, double b_dt, int last,
+                   void*) {
+  using namespace b200fft;
+  const long long n = m->n0 * m->n1 * m->n2;
+  for (long long i = 0; i < n; ++i) {
+    if (m->precision == B200FFT_DOUBLE)
+      ns_rhs_point(shim_mesh<double>(*m), n, i, nu, (cx<double>*)du, (cx<double>*)u, (const cx<double>*)u0, (cx<double>*)u1, a_dt, b_dt, last);
+    else
+      ns_rhs_point(shim_mesh<float>(*m), n, i, (float)nu, (cx<float>*)du, (cx<float>*)u, (const cx<float>*)u0, (cx<float>*)u1, (float)a_dt,
+                   (float)b_dt, last);
+  }
+  return 0;
+}
+}

@@ -31,8 +31,22 @@ def check(name, got, ref, tol, rank):
         raise SystemExit("rank %d: %s: rel L2 %.3e > %.1e (shapes %r %r)" % (rank, name, err, tol, got.shape, ref.shape))
 
 
+_T0 = [None]
+
+
+def note(comm, msg):
+    """progress line of rank 0 (a run that is cut off by a timeout still shows how far it got)"""
+    import time
+    if _T0[0] is None:
+        _T0[0] = time.time()
+    if comm.Get_rank() == 0:
+        print("[%6.1f s] %s" % (time.time() - _T0[0], msg), flush=True)
+
+
 def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, transport=None, pipeline=None, chunks=0):
     P, r = comm.Get_size(), comm.Get_rank()
+    note(comm, "run_3d %s %s P1=%s %s %s transport=%s pipeline=%s chunks=%s" % (kind, alignment, P1, communication, prec, transport,
+                                                                            pipeline, chunks))
     rt, ct = oracle.common.dtypes(prec)
     tol = TOL[prec]
     rng = np.random.default_rng(99)  # same stream on every rank: global arrays are identical
@@ -198,6 +212,24 @@ def run_known_answer(comm):
         raise SystemExit("Taylor-Green known answer: got %.12f, expected %.12f" % (k, sds.KNOWN_ANSWER))
 
 
+def run_known_answer_kernels(comm):
+    """The same known answer through mpifft4py_b200.ns.Solver: the library's three elementwise kernels per RK stage
+    around the distributed transforms (each rank holds its own wavenumber vectors)."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import spectral_dns_solver as sds
+    N = np.array([32, 32, 32], dtype=int)
+    F = m.Slab_R2C(N, L3, comm, "double")
+    S = m.ns.Solver(F, nu=0.000625, dt=0.01)
+    X = [torch.from_numpy(np.ascontiguousarray(np.broadcast_to(x, F.real_shape()))).cuda() for x in F.get_local_mesh()]
+    S.set_velocity(torch.stack([torch.sin(X[0]) * torch.cos(X[1]) * torch.cos(X[2]),
+                                -torch.cos(X[0]) * torch.sin(X[1]) * torch.cos(X[2]), torch.zeros_like(X[0])]))
+    for _ in range(10):
+        S.step()
+    k = comm.reduce(S.kinetic_energy())
+    if comm.Get_rank() == 0 and round(k - sds.KNOWN_ANSWER, 7) != 0:
+        raise SystemExit("Taylor-Green known answer (kernels): got %.12f, expected %.12f" % (k, sds.KNOWN_ANSWER))
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -236,6 +268,7 @@ def main():
         dist.destroy_process_group()
         print("GPU_WORKER_OK", local)
         return
+    # defaults (copy-engine transport for every class) ...
     for prec in ("double", "single"):
         run_3d(comm, "slab", N, prec)
         run_line(comm, (64, 128), prec)
@@ -249,8 +282,18 @@ def main():
                 for cm in ("Alltoall", "Alltoallw", "AlltoallN"):
                     run_3d(comm, "pencil", N, "double", al, P1, cm)
             run_3d(comm, "pencil", N, "single", al, None, "Alltoall")
+    # ... and NCCL send / recv for one object of each class
+    run_3d(comm, "slab", N, "double", transport="nccl")
+    run_line(comm, (64, 128), "double", transport="nccl")
+    if P >= 4:
+        for al in "XY":
+            run_3d(comm, "pencil", N, "double", al, None, "Alltoallw", transport="nccl")
+    note(comm, "goldens")
     run_golden(comm)
+    note(comm, "known answer")
     run_known_answer(comm)
+    run_known_answer_kernels(comm)
+    note(comm, "done")
     comm.barrier()
     dist.destroy_process_group()
     print("GPU_WORKER_OK", comm.Get_rank() if False else local)

@@ -17,7 +17,7 @@ CS = os.path.join(ROOT, "mpifft4py_b200", "csrc")
 DEPS = [SRC, os.path.join(HERE, "emu", "emu.cpp")] + \
        [os.path.join(HERE, "emu", "cuda_shim", f) for f in ("cuda_runtime.h", "cuda.h", "nccl.h")] + \
        [os.path.join(CS, f) for f in ("b200fft.cu", "fft_kernels.cuh", "fft_radix.cuh", "fft_plans.h", "fft_dispatch.h",
-                                      "desc_convert.h", "plan_program.h")] + [os.path.join(ROOT, "include", "b200fft.h")]
+                                      "desc_convert.h", "plan_program.h", "ns_ops.cuh")] + [os.path.join(ROOT, "include", "b200fft.h")]
 
 _shim = None
 

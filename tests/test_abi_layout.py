@@ -9,7 +9,7 @@ import tempfile
 from mpifft4py_b200 import _cdefs as D
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PAIRS = [("b200fft_side_t", D.Side, {}), ("b200fft_mask_t", D.Mask, {}),
+PAIRS = [("b200fft_ns_mesh_t", D.NsMesh, {}), ("b200fft_side_t", D.Side, {}), ("b200fft_mask_t", D.Mask, {}),
          ("b200fft_strided_desc_t", D.StridedDesc, {"inp": "in"}), ("b200fft_rows_desc_t", D.RowsDesc, {}),
          ("b200fft_plan_desc_t", D.PlanDesc, {})]
 
