@@ -253,6 +253,8 @@ struct StridedCfg {
   static constexpr int NBMIN = P::N / P::RMAX;
   static constexpr int pow2floor(int x) { int p = 1; while (2 * p <= x) p *= 2; return p; }
   static constexpr int TC_ = pow2floor(NBMIN) < (256 / T0) ? pow2floor(NBMIN) : (256 / T0);
+  // (96 threads per column for the 1536-point double-precision columns -- one full round of first-stage radix-16
+  // butterflies, 24 warps per SM instead of 16 at 80 registers -- measured 3-6 % SLOWER than 64, round 2.)
   static constexpr int TC = TC_ < 1 ? 1 : TC_;
   static constexpr int T = (T0 * TC >= 128) ? T0 : (128 / TC);
   static constexpr int NT = T * TC;
@@ -615,9 +617,9 @@ struct C2RK {  // inverse: complex rows -> real rows (unnormalised; caller's sca
 // asynchronous double buffer and relies on CTA residency for overlap, exactly like R2CK (which reaches
 // 0.84 of the HBM figure where C2RK reaches 0.67).  Measured 3.31 ms against 3.93 ms at 1024^3 double
 // (profiles/r02_single/ab_single.txt): the default for rows of 512 ... 3072 reals (k_rows.inc).
-template <class real, class P>
+template <class real, class P, int CAPV = 0>
 struct C2RDK {
-  using Cfg = RowCfg<real, P>;
+  using Cfg = RowCfg<real, P, CAPV>;
   using C = cx<real>;
   using Params = RowParams<real>;
   static constexpr int NPHASE = P::S + 1;
