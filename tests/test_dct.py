@@ -31,9 +31,7 @@ def test_dct_type_errors():
         serialFFT._dct_core(torch.zeros(8, dtype=torch.complex128), 1, 0, _torch_fft)
 
 
-# (written after round 1's GPU minutes were spent: the reordering is checked above, the device call is pending)
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first device run pending")
 @pytest.mark.parametrize("type", [2, 3])
 @pytest.mark.parametrize("prec", ["double", "single"])
 def test_dct_on_device(prec, type):
