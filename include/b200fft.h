@@ -97,6 +97,11 @@ typedef struct {
   double scale;
   b200fft_side_t in, out;
   b200fft_mask_t mask;
+  /* cross twiddle of a two-launch ("four-step") transform of a long axis, N = n1 * n2: the first launch (n = n1
+   * over rows n2 apart, the n2 interleaved sub-columns side by side as J' = n2 * J columns) multiplies its output
+   * k1 of sub-column x2 = column / cross_div by W_N^(x2 * k1) (conjugated for the inverse) with N = cross_n;
+   * the second launch (n = n2, B = n1) needs nothing.  cross_n == 0: none. */
+  int cross_n, cross_div;
 } b200fft_strided_desc_t;
 
 /* Batched real<->complex FFT along contiguous rows (serialFFT rfft/irfft axis -1:
@@ -195,7 +200,9 @@ typedef struct {
                       per exchange step); 0 = all pushes in order on the communication stream */
   int layout;      /* single-rank slab.R2C plans: B200FFT_LAYOUT_YBLOCK (0, default) keeps the array between the
                       passes y-blocked and runs z, x, y (inverse y, x, z) so that no pass has rows megabytes apart;
-                      B200FFT_LAYOUT_NATURAL runs z, y, x on [x][y][kz] like slab.py:366-370 (A/B measurements) */
+                      B200FFT_LAYOUT_NATURAL runs z, y, x on [x][y][kz] like slab.py:366-370 (A/B measurements).
+                      line.R2C plans: NATURAL also keeps columns of >= 128 KB in one launch instead of the two-launch
+                      (four-step) form */
 } b200fft_plan_desc_t;
 
 typedef struct b200fft_plan* b200fft_plan_t;

@@ -29,7 +29,7 @@ class Mask(C.Structure):
 class StridedDesc(C.Structure):
     _fields_ = [("precision", C.c_int), ("n", C.c_int), ("B", C.c_longlong), ("J", C.c_int),
                 ("inverse", C.c_int), ("fold_mode", C.c_int), ("scale", C.c_double),
-                ("inp", Side), ("out", Side), ("mask", Mask)]
+                ("inp", Side), ("out", Side), ("mask", Mask), ("cross_n", C.c_int), ("cross_div", C.c_int)]
 
 
 class RowsDesc(C.Structure):

@@ -97,11 +97,19 @@ int exec_strided(const b200fft_strided_desc_t& d, cudaStream_t st) {
     const cx<double>* tw;
     if (int rc = get_tw<double>(d.n, &tw)) return rc;
     auto p = convert_strided<double>(d, tw, 1);
+    if (d.cross_n > 0) {
+      if (int rc = get_tw<double>(d.cross_n, &p.tw2)) return rc;
+      p.tw2_div = d.cross_div;
+    }
     return map_launch_rc(rows ? launch_rowc2c_f64(d.n, p, st) : launch_strided_f64(d.n, p, st), "strided pass", d.n);
   }
   const cx<float>* tw;
   if (int rc = get_tw<float>(d.n, &tw)) return rc;
   auto p = convert_strided<float>(d, tw, 1);
+  if (d.cross_n > 0) {
+    if (int rc = get_tw<float>(d.cross_n, &p.tw2)) return rc;
+    p.tw2_div = d.cross_div;
+  }
   return map_launch_rc(rows ? launch_rowc2c_f32(d.n, p, st) : launch_strided_f32(d.n, p, st), "strided pass", d.n);
 }
 
@@ -506,6 +514,8 @@ b200fft_strided_desc_t strided_desc(const b200fft_plan* pl, const Step& s, const
   fill_side(pl, s.in, d.in, in, out, csz);
   fill_side(pl, s.out, d.out, in, out, csz);
   d.mask = s.mask;
+  d.cross_n = s.cross_n;
+  d.cross_div = s.cross_div;
   return d;
 }
 
@@ -527,6 +537,7 @@ b200fft_rows_desc_t rows_desc(const b200fft_plan* pl, const Step& s, const void*
 }
 
 double step_bytes(const Step& s, size_t csz) {  // algorithmic bytes: operand read once, result written once
+  if (s.type == ST_STRIDED && s.cross_n > 0) return 0.0;  // first launch of a four-step pass: the pass's algorithmic bytes are counted once, on the second
   if (s.type == ST_STRIDED) return (double)s.B * s.J * ((double)s.in.nphys + (double)s.out.nphys) * (double)csz;
   if (s.type == ST_R2C || s.type == ST_C2R) return (double)s.rows * ((double)s.n * (csz / 2) + (double)s.nk * csz);
   double b = 0;

@@ -115,12 +115,15 @@ inline const char* check_strided(const b200fft_strided_desc_t& d) {
     if (d.out.nphys % 2) return "odd truncated extent";
   }
   if (d.in.nphys < d.n && d.in.nphys % 2) return "odd padded extent";
+  if (d.cross_n < 0 || (d.cross_n > 0 && (d.cross_div < 1 || d.cross_n % d.n || (long long)(d.J / d.cross_div + (d.J % d.cross_div != 0)) * d.n > d.cross_n ||
+                                          d.in.nphys != d.n || d.out.nphys != d.n || d.fold_mode != 0)))
+    return "bad cross twiddle (cross_n = n * sub-columns, no pad / truncation in a four-step launch)";
   return nullptr;
 }
 
 // a strided pass whose "columns" are single elements of contiguous rows: served by the row C2C kernel
 inline bool contiguous_rows(const b200fft_strided_desc_t& d) {
-  return d.J == 1 && d.in.nchunk == 1 && d.out.nchunk == 1 && d.in.si[0] == 1 && d.out.si[0] == 1 && !d.mask.on;
+  return d.J == 1 && d.in.nchunk == 1 && d.out.nchunk == 1 && d.in.si[0] == 1 && d.out.si[0] == 1 && !d.mask.on && d.cross_n == 0;
 }
 
 inline const char* check_rows(const b200fft_rows_desc_t& d) {

@@ -228,6 +228,8 @@ struct StridedParams {
   Mask mask;
   const cx<real>* tw;
   int tws;  // table length / n
+  const cx<real>* tw2;  // cross twiddles W_N^j of a four-step transform (b200fft_strided_desc_t::cross_n), or null
+  int tw2_div;          // sub-column of a column: column / tw2_div
 };
 
 // Tile geometry.  A CTA owns T adjacent columns (ROWB = T*sizeof(complex) contiguous bytes per
@@ -375,6 +377,11 @@ struct StridedK {
         else a = out_row(p, b, k, jout);
         if (a == 0) return;
         if (p.scale != (real)1) v = cscale(v, p.scale);
+        if (p.tw2 != nullptr) {  // four-step: W_N^(x2 * k1), k1 = the frequency this slot really holds
+          const int k1 = p.inverse ? (k == 0 ? 0 : n - k) : k;
+          const C w = p.tw2[(long long)((j0 + c) / p.tw2_div) * k1];
+          v = cmul(v, p.inverse ? cconj(w) : w);
+        }
         *reinterpret_cast<C*>(a + (addr_t)(cout * CB)) = v;
       };
       // reversed output index: the slot that survives a "keep -N/2" truncation is the other one

@@ -65,6 +65,7 @@ struct Step {
   double scale = 1.0;
   SideT in, out;
   b200fft_mask_t mask;
+  int cross_n = 0, cross_div = 1;  // four-step cross twiddle (b200fft_strided_desc_t)
   // rows
   long long rows = 0;
   int nk = 0;
@@ -1276,11 +1277,64 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   const long long rc = pNp0 / CH;
   const double p2 = p * p;
   const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
+  // The pass along x.  A column that needs 128 KB or more of shared memory on its own (16384 points in single
+  // precision -- BASELINE config 5a -- 8192 in double) would leave tiles one column wide: 8- or 16-byte row
+  // segments, a quarter / half of every 32-byte sector.  Such a transform runs as TWO launches instead
+  // ("four-step", N = n1 * n2): A) n1-point transforms over rows n2 apart -- the n2 interleaved sub-columns side by
+  // side as n2 * J columns, i.e. full-width tiles -- times the cross twiddles W_N^(x2 * k1) on store;
+  // B) n2-point transforms over the n2 consecutive rows of each k1, output k2 scattered to row k1 + n1 * k2 (for
+  // the inverse: to its peer's send block).  Twice the HBM traffic of one pass at full sector use instead of four
+  // times.  Plain and 2^k lengths only: padded / masked / 3 * 2^k transforms keep the single launch.
+  const long long csz_line = d.precision == B200FFT_DOUBLE ? 16 : 8;
+  auto xpass = [&](int inv, long long J, const SideT& in, const SideT& out, int fold, double scale, int tmpbuf,
+                   Step** first, Step** last) {
+    const long long n = pN0;
+    const bool pow2 = n > 0 && (n & (n - 1)) == 0;
+    bool split = !padded && !masked && pow2 && n * csz_line >= (128ll << 10) && in.nchunk == 1 && in.si[0] == J && fold == 0 &&
+                 d.layout != B200FFT_LAYOUT_NATURAL;  // ("natural": the single launch, for A/B runs)
+    long long n1 = 1;
+    while (n1 * n1 < n) n1 *= 2;
+    const long long n2 = n / n1;
+    if (split && out.nchunk > 1 && out.chunk % n1) split = false;
+    if (split && out.nchunk == 1 && out.si[0] != J) split = false;
+    if (!split) {
+      Step& s1 = b.strided((int)n, 1, J, inv, in, out, fold, scale);
+      *first = *last = &s1;
+      return;
+    }
+    const bool inplace = in.base[0].buf != BUF_IN && in.base[0].buf != BUF_OUT;
+    const int abuf = inplace ? in.base[0].buf : tmpbuf;
+    const long long aoff = inplace ? in.base[0].off : 0;
+    if (!inplace) b.use(tmpbuf, n * J);
+    const int pid = b.fixed;
+    if (b.fixed < 0) b.fixed = b.next_pass++;  // both launches are one logical pass
+    Step& sa = b.strided((int)n1, 1, n2 * J, inv, nat(in.base[0].buf, in.base[0].off, 0, n2 * J, (int)n1), nat(abuf, aoff, 0, n2 * J, (int)n1));
+    sa.cross_n = (int)n;
+    sa.cross_div = (int)J;
+    SideT o2 = out;
+    o2.nphys = (int)n2;
+    if (out.nchunk == 1) {
+      o2.chunk = (int)n2;
+      o2.sb[0] = out.si[0];
+      o2.si[0] = n1 * out.si[0];
+    } else {
+      o2.chunk = (int)(out.chunk / n1);
+      for (int q = 0; q < out.nchunk; ++q) {
+        o2.sb[q] = out.si[q];
+        o2.si[q] = n1 * out.si[q];
+      }
+    }
+    Step& sb2 = b.strided((int)n2, n1, J, inv, nat(abuf, aoff, n2 * J, J, (int)n2), o2, 0, scale);
+    b.fixed = pid;
+    *first = &sa;
+    *last = &sb2;
+  };
+  Step *xs0 = nullptr, *xs1 = nullptr;
   if (!inverse) {
     if (P == 1) {  // line.py:182-191
       if (!padded) {
         b.rows(true, N0, (int)N1, (int)Nf, BUF_IN, nat(BUF_OUT, 0, Nf, 1, (int)Nf));
-        b.strided((int)N0, 1, Nf, 0, nat(BUF_OUT, 0, 0, Nf, (int)N0), nat(BUF_OUT, 0, 0, Nf, (int)N0));
+        xpass(0, Nf, nat(BUF_OUT, 0, 0, Nf, (int)N0), nat(BUF_OUT, 0, 0, Nf, (int)N0), 0, 1.0, BUF_W0, &xs0, &xs1);
       } else {
         b.rows(true, pN0, pN1, (int)Nf, BUF_IN, nat(BUF_W0, 0, Nf, 1, (int)Nf));
         b.use(BUF_W0, (long long)pN0 * Nf);
@@ -1316,9 +1370,9 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         }
       }
       b.fixed = 2;
-      Step& fx = b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
-                           padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
-      fx.wait_ev = last_ev;
+      xpass(0, Npf, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0), padded ? 1 : 0, padded ? 1.0 / p2 : 1.0, BUF_W2,
+            &xs0, &xs1);
+      xs0->wait_ev = last_ev;
     } else {  // line.py:193-258
       const int recvbuf = (padded || peer_mapped) ? BUF_W1 : BUF_OUT;
       SideT o;
@@ -1337,12 +1391,13 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         x.recv[q].buf = recvbuf; x.recv[q].off = (long long)q * pNp0 * Npf; x.rcnt[q] = (long long)pNp0 * Npf;
         x.rpeer[q].buf = recvbuf; x.rpeer[q].off = (long long)me * pNp0 * kcl[q];
       }
-      b.strided(pN0, 1, Npf, 0, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0),
-                padded ? 1 : 0, padded ? 1.0 / p2 : 1.0);
+      xpass(0, Npf, nat(recvbuf, 0, 0, Npf, pN0), nat(BUF_OUT, 0, 0, Npf, (int)N0), padded ? 1 : 0, padded ? 1.0 / p2 : 1.0, BUF_W2,
+            &xs0, &xs1);
     }
   } else {
     if (P == 1) {  // line.py:274-283
-      Step& sx = b.strided(pN0, 1, Nf, 1, nat(BUF_IN, 0, 0, Nf, (int)N0), nat(BUF_W0, 0, 0, Nf, pN0));
+      xpass(1, Nf, nat(BUF_IN, 0, 0, Nf, (int)N0), nat(BUF_W0, 0, 0, Nf, pN0), 0, 1.0, BUF_W1, &xs0, &xs1);
+      Step& sx = *xs0;
       b.use(BUF_W0, (long long)pN0 * Nf);
       if (masked) {
         sx.mask.on = 1;
@@ -1361,7 +1416,8 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         o.sb[q] = 0; o.si[q] = Npf;
       }
       b.fixed = 0;
-      Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
+      xpass(1, Npf, nat(BUF_IN, 0, 0, Npf, (int)N0), o, 0, 1.0, BUF_W2, &xs0, &xs1);
+      Step& sx = *xs0;
       if (masked) {
         sx.mask.on = 1;
         sx.mask.jdiv = 0x3fffffff;
@@ -1369,7 +1425,7 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         band(N1, true, sx.mask.jr_lo, sx.mask.jr_hi);
         sx.mask.jr_off = (int)(me * kc);
       }
-      const int xev = sx.rec_ev = pg.nevents++;
+      const int xev = xs1->rec_ev = pg.nevents++;
       b.use(BUF_W0, P * blk);
       b.use(BUF_W1, (long long)pNp0 * Nf);
       std::vector<int> eev((size_t)CH);
@@ -1405,7 +1461,8 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         o.base[q].off = (q == me) ? (long long)pNp0 * koff[me] : q * blk;
         o.sb[q] = 0; o.si[q] = Npf;
       }
-      Step& sx = b.strided(pN0, 1, Npf, 1, nat(BUF_IN, 0, 0, Npf, (int)N0), o);
+      xpass(1, Npf, nat(BUF_IN, 0, 0, Npf, (int)N0), o, 0, 1.0, BUF_W2, &xs0, &xs1);
+      Step& sx = *xs0;
       if (masked) {
         sx.mask.on = 1;
         sx.mask.jdiv = 0x3fffffff;

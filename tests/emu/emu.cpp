@@ -48,6 +48,10 @@ static const cx<real>* table(int len) {
 template <class real>
 static int strided(const b200fft_strided_desc_t& d) {
   auto p = convert_strided<real>(d, table<real>(d.n), 1);
+  if (d.cross_n > 0) {
+    p.tw2 = table<real>(d.cross_n);
+    p.tw2_div = d.cross_div;
+  }
   if (contiguous_rows(d)) {
     switch (d.n) {
 #define X(n, ...) \
@@ -172,6 +176,7 @@ int emu_plan_run(const b200fft_plan_desc_t* d0, int inverse, int dealias, void**
         std::memset(&d, 0, sizeof(d));
         d.precision = d0->precision; d.n = s.n; d.B = s.B; d.J = s.J; d.inverse = s.inverse;
         d.fold_mode = s.fold; d.scale = s.scale; d.in = side(r, s.in); d.out = side(r, s.out); d.mask = s.mask;
+        d.cross_n = s.cross_n; d.cross_div = s.cross_div;
         rc = emu_exec_strided(&d);
       } else if (s.type == ST_R2C || s.type == ST_C2R) {
         b200fft_rows_desc_t d;

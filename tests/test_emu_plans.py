@@ -175,6 +175,38 @@ def test_line_peer_mapped_transports(P, transport):
     _line_body((64, 32), P, "double", transport)
 
 
+@pytest.mark.parametrize("N,prec,P,transport,chunks", [
+    ((16384, 16), "single", 1, D.TRANSPORT_NCCL, 0), ((16384, 16), "single", 2, D.TRANSPORT_P2P, 0),
+    ((16384, 32), "single", 4, D.TRANSPORT_NCCL, 2), ((16384, 32), "single", 4, D.TRANSPORT_STORE, 0),
+    ((8192, 16), "double", 2, D.TRANSPORT_P2P, 2), ((8192, 8), "double", 1, D.TRANSPORT_NCCL, 0)])
+def test_line_long_axis_four_step(N, prec, P, transport, chunks):
+    """BASELINE config 5a shape class: columns of 16384 single / 8192 double points run as two launches (four-step:
+    n1-point transforms over interleaved sub-columns with cross twiddles, then n2-point transforms with a scattering
+    store -- into the peers' send blocks for the inverse).  fft2 / ifft2 against the oracle; the 2/3-rule inverse
+    (masked first pass) keeps the single launch.  Also: the program really has the extra step, peer invariants hold."""
+    rt, ct = oracle.common.dtypes(prec)
+    g = oracle.line.Geometry(N, P)
+    rng = np.random.default_rng(N[0] + P)
+    d = _desc(D.LINE, N, P, prec, transport=transport if P > 1 else 0, chunks=chunks)
+    lib = emu_util.load()
+    nsteps = lib.emu_plan_steps(C.byref(d), 0, D.DEALIAS_NONE, None, 0)
+    d1 = _desc(D.LINE, (N[0] // 4, N[1]), P, prec, transport=transport if P > 1 else 0, chunks=chunks)
+    assert nsteps == lib.emu_plan_steps(C.byref(d1), 0, D.DEALIAS_NONE, None, 0) + 1
+    assert lib.emu_plan_steps(C.byref(d), 1, D.DEALIAS_2_3, None, 0) == lib.emu_plan_steps(C.byref(d1), 1, D.DEALIAS_2_3, None, 0)
+    if transport != D.TRANSPORT_NCCL and P > 1:
+        _check_peer_mapped(d, (D.DEALIAS_NONE, D.DEALIAS_2_3))
+    for inverse in (0, 1):
+        assert lib.emu_check_schedule(C.byref(d), inverse, D.DEALIAS_NONE) == 0
+    tol = 2 * TOL[prec]
+    A = rng.random(N).astype(rt)
+    u = [A[g.real_local_slice(r)] for r in range(P)]
+    cshape = [g.complex_shape(r) for r in range(P)]
+    _check(run_plan(d, 0, D.DEALIAS_NONE, u, cshape, ct), oracle.line.fft2(u, N, P, precision=prec), tol)
+    fu = [_rand_c(rng, s_, ct) for s_ in cshape]
+    for mode, name in ((D.DEALIAS_NONE, None), (D.DEALIAS_2_3, "2/3-rule")):
+        _check(run_plan(d, 1, mode, fu, [g.real_shape()] * P, rt), oracle.line.ifft2(fu, N, P, dealias=name, precision=prec), tol)
+
+
 def _line_body(N, P, prec, transport):
     if N[1] % (2 * P) or N[0] % P:
         pytest.skip("illegal decomposition")

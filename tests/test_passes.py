@@ -78,8 +78,10 @@ def _cplx(rng, shape, ct):
 
 
 def run_strided(be, x, n, out, inverse=0, scale=1.0, in_side=None, out_side=None, fold=0, mask=None,
-                B=None, J=None, prec=None):
+                B=None, J=None, prec=None, cross=None):
     d = D.StridedDesc()
+    if cross is not None:
+        d.cross_n, d.cross_div = cross
     ref = x if x is not None else out
     if prec is None:
         prec = D.DOUBLE if (ref is None or ref.dtype == np.complex128) else D.SINGLE
@@ -376,3 +378,29 @@ def test_rows_row_map(be, h, prec):
     run_rows(be, "exec_c2r", y, D.plain_side(_ptr(X), h + 1, 1, h + 1), n, rows, h + 1, pr, scale=1.0 / n,
              rowmap=(period, block, planes))
     assert _rel(y, x) < 3 * tol
+
+
+@pytest.mark.parametrize("n1,n2,prec", [(8, 8, "d"), (16, 8, "d"), (4, 32, "s"), (128, 128, "s"), (128, 64, "d")])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_four_step_long_axis(be, n1, n2, prec, inverse):
+    """A transform of length N = n1 * n2 along the strided axis as TWO launches (columns too long for a tile of
+    useful width): launch A runs n1-point transforms over rows n2 apart, the n2 interleaved sub-columns side by side
+    as n2 * J columns, and multiplies by the cross twiddles W_N^(x2 * k1) on store; launch B runs n2-point transforms
+    over the n2 consecutive rows of each k1 and scatters output k2 to row k1 + n1 * k2."""
+    ct = np.complex128 if prec == "d" else np.complex64
+    pr = D.DOUBLE if prec == "d" else D.SINGLE
+    N = n1 * n2
+    tol = 3e-15 * np.log2(N) if prec == "d" else 8e-7 * np.log2(N)
+    rng = np.random.default_rng(N + inverse)
+    J = 5
+    x = be.arr(_cplx(rng, (1, N, J), ct))
+    ref = (np.fft.ifft if inverse else np.fft.fft)(x.astype(np.complex128), axis=1)
+    w = be.arr(x.copy())
+    # A: in place; row i of the launch = rows [i * n2, (i + 1) * n2) of the array = n2 * J columns
+    side = D.plain_side(_ptr(w), N * J, n2 * J, n1)
+    run_strided(be, None, n1, None, inverse=inverse, in_side=side, out_side=side, B=1, J=n2 * J, prec=pr, cross=(N, J))
+    # B: batch entry k1 = n2 consecutive rows; output k2 -> row k1 + n1 * k2
+    out = be.zeros((1, N, J), ct)
+    run_strided(be, None, n2, None, inverse=inverse, scale=(1.0 / N if inverse else 1.0),
+                in_side=D.plain_side(_ptr(w), n2 * J, J, n2), out_side=D.plain_side(_ptr(out), J, n1 * J, n2), B=n1, J=J, prec=pr)
+    assert _rel(out, ref) < tol
