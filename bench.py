@@ -34,6 +34,9 @@ WORKLOADS = {
     "pencilX512_f64": ("pencil", (512, 512, 512), "double", None, dict(alignment="X", P1=2, communication="Alltoallw")),
     "pencilX1024_f64": ("pencil", (1024, 1024, 1024), "double", None, dict(alignment="X", P1=None, communication="Alltoallw")),
     "pencilY2048_f32": ("pencil", (2048, 2048, 2048), "single", None, dict(alignment="Y", P1=None, communication="Alltoallw")),
+    "line4096_f32": ("line", (4096, 4096), "single", None, {}),
+    "line4096_f64": ("line", (4096, 4096), "double", None, {}),
+    "line2048_f64": ("line", (2048, 2048), "double", None, {}),
     "line8192_f32": ("line", (8192, 8192), "single", None, {}),
     "line16384_f32": ("line", (16384, 16384), "single", None, {}),
 }

@@ -1277,20 +1277,22 @@ inline int build_line(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   const long long rc = pNp0 / CH;
   const double p2 = p * p;
   const double iscale = (padded ? p2 : 1.0) / ((double)pN0 * (double)pN1);
-  // The pass along x.  A column that needs 128 KB or more of shared memory on its own (16384 points in single
-  // precision -- BASELINE config 5a -- 8192 in double) would leave tiles one column wide: 8- or 16-byte row
+  // The pass along x.  A column that needs 64 KB or more of shared memory (8192 points in single precision, 4096 in
+  // double; BASELINE config 5a has 16384 single = 128 KB) leaves tiles one or two columns wide: 8- / 16-byte row
   // segments, a quarter / half of every 32-byte sector.  Such a transform runs as TWO launches instead
   // ("four-step", N = n1 * n2): A) n1-point transforms over rows n2 apart -- the n2 interleaved sub-columns side by
   // side as n2 * J columns, i.e. full-width tiles -- times the cross twiddles W_N^(x2 * k1) on store;
   // B) n2-point transforms over the n2 consecutive rows of each k1, output k2 scattered to row k1 + n1 * k2 (for
   // the inverse: to its peer's send block).  Twice the HBM traffic of one pass at full sector use instead of four
-  // times.  Plain and 2^k lengths only: padded / masked / 3 * 2^k transforms keep the single launch.
+  // times.  One GPU, x pass of line 16384^2 single: 2.75 -> 0.99 ms (round trip 7.16 -> 3.61); 8192^2: 0.45 -> 0.26
+  // (1.22 -> 0.83); at 32 KB columns it no longer pays (2048^2 double 0.095 -> 0.105 ms), profiles/r02_fourstep.
+  // Plain and 2^k lengths only: padded / masked / 3 * 2^k transforms keep the single launch.
   const long long csz_line = d.precision == B200FFT_DOUBLE ? 16 : 8;
   auto xpass = [&](int inv, long long J, const SideT& in, const SideT& out, int fold, double scale, int tmpbuf,
                    Step** first, Step** last) {
     const long long n = pN0;
     const bool pow2 = n > 0 && (n & (n - 1)) == 0;
-    bool split = !padded && !masked && pow2 && n * csz_line >= (128ll << 10) && in.nchunk == 1 && in.si[0] == J && fold == 0 &&
+    bool split = !padded && !masked && pow2 && n * csz_line >= (64ll << 10) && in.nchunk == 1 && in.si[0] == J && fold == 0 &&
                  d.layout != B200FFT_LAYOUT_NATURAL;  // ("natural": the single launch, for A/B runs)
     long long n1 = 1;
     while (n1 * n1 < n) n1 *= 2;
