@@ -548,8 +548,12 @@ def run_ours(args):
                               "link_peak_GBps_per_direction": 770.0}
     xs = [p for p in passes if p["type"] == "exchange" and p["ms"] > 0]
     if xs:
-        roofline["nvlink"] = {"achieved_GBps_per_direction": round(sum(p["bytes"] for p in xs) / sum(p["ms"] for p in xs) / 1e6, 1),
-                              "peak": 770.0, "unit": "GB/s", "peak_source": "measured peer copy (B200_PROFILING.md)"}
+        ach = sum(p["bytes"] for p in xs) / sum(p["ms"] for p in xs) / 1e6
+        roofline["nvlink"] = {"achieved_GBps_per_direction": round(ach, 1), "peak": 770.0, "unit": "GB/s",
+                              "frac": round(ach / 770.0, 3), "frac_of_nominal_900": round(ach / 900.0, 3),
+                              "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md); nominal NVLink 5: 900",
+                              "note": "exchange steps are timed on the communication stream while FFT passes of the "
+                                      "neighbouring chunks run beside them (they share HBM)"}
 
     # ---- e2e: numpy API, pinned host buffers, H2D + D2H inside the timed region -------------------
     e2e = None

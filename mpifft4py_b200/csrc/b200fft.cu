@@ -411,6 +411,21 @@ int post_flag(b200fft_plan* pl, cudaStream_t st, void* peer_word, unsigned value
   return 0;
 }
 
+// The same for several peers at once: one single-warp kernel (p2p_kernels.cu) instead of two stream operations per
+// peer.  B200FFT_FLAG_DMA=1 keeps the per-peer DMA form (A/B runs; also what machines without kernel access to
+// peer memory would need).
+int post_flags(b200fft_plan* pl, cudaStream_t st, unsigned* const* words, int n, unsigned value) {
+  static const bool dma = [] { const char* e = std::getenv("B200FFT_FLAG_DMA"); return e && e[0] == '1'; }();
+  if (dma) {
+    for (int i = 0; i < n; ++i)
+      if (int rc = post_flag(pl, st, words[i], value)) return rc;
+    return 0;
+  }
+  const int rc = b200fft::launch_post_flags(words, n, value, st);
+  if (rc) return fail(B200FFT_ERR_CUDA, "flag kernel launch failed (%d)", rc);
+  return 0;
+}
+
 // Block `st` until every peer has handed this rank's blocks of the previous transform back (its last
 // reader of received data has run): only then may this rank write into the peers' buffers again.
 int wait_credits(b200fft_plan* pl, cudaStream_t st) {
@@ -472,10 +487,11 @@ int run_exchange_p2p(b200fft_plan* pl, const Step& s, const void* in, void* out,
     cudaError_t e = cudaMemcpyAsync(dst, resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, cudaMemcpyDeviceToDevice, s1);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(peer)");
   }
+  unsigned* words[B200FFT_MAXP];
+  int nw = 0;
   for (int q = 0; q < s.npeers; ++q)
-    if (q != s.me)
-      if (int rc = post_flag(pl, s1, (unsigned*)pp.peer_flags[world_rank(pl->d, s.comm, me_w, q)] + me_w, seq)) return rc;
-  return 0;
+    if (q != s.me) words[nw++] = (unsigned*)pp.peer_flags[world_rank(pl->d, s.comm, me_w, q)] + me_w;
+  return post_flags(pl, s1, words, nw, seq);
 }
 
 // wait-stream half of a P2P exchange step: own sends done + all peers' blocks arrived -> rec_ev
@@ -636,9 +652,11 @@ int run_program(b200fft_plan* pl, int inverse, int dealias, const void* in, void
     }
     const bool last_reader = s.last_reader != 0;
     if (use_p2p && last_reader) {  // hand the receive buffers back to the peers
+      unsigned* words[B200FFT_MAXP];
+      int nw = 0;
       for (int q = 0; q < pl->d.nranks; ++q)
-        if (q != pl->d.rank)
-          if (int rc2 = post_flag(pl, st, (unsigned*)pl->p2p.peer_flags[q] + B200FFT_MAXP + pl->d.rank, pl->p2p.calls + 1)) return rc2;
+        if (q != pl->d.rank) words[nw++] = (unsigned*)pl->p2p.peer_flags[q] + B200FFT_MAXP + pl->d.rank;
+      if (int rc2 = post_flags(pl, st, words, nw, pl->p2p.calls + 1)) return rc2;
     }
   }
   if (use_p2p) pl->p2p.calls++;

@@ -13,6 +13,8 @@ int launch_r2c_f64(int h, const RowParams<double>& p, cudaStream_t st);
 int launch_r2c_f32(int h, const RowParams<float>& p, cudaStream_t st);
 int launch_c2r_f64(int h, const RowParams<double>& p, cudaStream_t st);
 int launch_c2r_f32(int h, const RowParams<float>& p, cudaStream_t st);
+// peer-mapped transports: write `value` into n (<= 16) flag words (peer-mapped device memory) from one tiny kernel
+int launch_post_flags(unsigned* const* words, int n, unsigned value, cudaStream_t st);
 // does the last stage of the plan for complex length n hold the factor 3 (fold-capable)?
 bool plan_exists(int n);
 }  // namespace b200fft

@@ -46,6 +46,11 @@ static int h_rows(int h, const RowParams<real>& p) {
       return -1;
   }
 }
+// (the flag kernel of the peer-mapped transports: plain stores; the waits of the stand-in poll the same words)
+int launch_post_flags(unsigned* const* words, int n, unsigned value, cudaStream_t) {
+  for (int i = 0; i < n; ++i) __atomic_store_n(words[i], value, __ATOMIC_RELEASE);
+  return 0;
+}
 int launch_strided_f64(int n, const StridedParams<double>& p, cudaStream_t) { return h_strided<double>(n, p); }
 int launch_strided_f32(int n, const StridedParams<float>& p, cudaStream_t) { return h_strided<float>(n, p); }
 int launch_rowc2c_f64(int n, const StridedParams<double>& p, cudaStream_t) { return h_rowc2c<double>(n, p); }
