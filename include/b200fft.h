@@ -30,7 +30,7 @@ enum { B200FFT_SINGLE = 0, B200FFT_DOUBLE = 1 };              /* mpibase.py:133-
 enum { B200FFT_SLAB = 0, B200FFT_PENCIL_X = 1, B200FFT_PENCIL_Y = 2, B200FFT_LINE = 3,
        B200FFT_SLAB_C2C = 4 /* slab.C2C, slab.py:538-825: u and fu are both complex */ };
 enum { B200FFT_DEALIAS_NONE = 0, B200FFT_DEALIAS_3_2 = 1, B200FFT_DEALIAS_2_3 = 2 };
-enum { B200FFT_PIPELINE_X = 0, B200FFT_PIPELINE_KZ = 1 };
+enum { B200FFT_PIPELINE_AUTO = 0, B200FFT_PIPELINE_X = 1, B200FFT_PIPELINE_KZ = 2 };
 enum { B200FFT_LAYOUT_YBLOCK = 0, B200FFT_LAYOUT_NATURAL = 1 };
 enum { B200FFT_TRANSPORT_NCCL = 0, B200FFT_TRANSPORT_P2P = 1,
        B200FFT_TRANSPORT_STORE = 2 /* fused: the producing FFT pass stores into the peers' buffers */ };
@@ -191,10 +191,12 @@ typedef struct {
   int chunks;      /* pipeline depth of the exchange (the MPI collectives of slab.py:281-332,406-471
                       cut into `chunks` pieces, each overlapped with the FFT passes of the next
                       piece on a second stream); 0 = automatic, 1 = no overlap */
-  int pipeline;    /* how a slab exchange is cut into pieces: B200FFT_PIPELINE_X (default) by local x
-                      planes -- z(c), y(c) | exchange(c), then one x pass; B200FFT_PIPELINE_KZ by kz
-                      ranges -- one z pass, then y(c) | exchange(c) | x(c), so the exchange overlaps
-                      FFT passes on BOTH sides (three-stage pipeline; receive layout is chunk-major) */
+  int pipeline;    /* how a slab exchange is cut into pieces: B200FFT_PIPELINE_X by local x planes -- z(c), y(c) |
+                      exchange(c), then one x pass; B200FFT_PIPELINE_KZ by kz ranges -- one z pass, then y(c) |
+                      exchange(c) | x(c), so the exchange overlaps FFT passes on BOTH sides (three-stage pipeline;
+                      receive layout is chunk-major); B200FFT_PIPELINE_AUTO (0, default): KZ for plain / 2/3-rule
+                      R2C transforms over the copy engines whose per-peer message is >= 96 MB (measured faster at
+                      2, 4 and 8 GPUs), X otherwise (3/2-rule, small meshes, NCCL, fused stores, C2C) */
   int copy_streams;/* copy-engine transport: 1 = one copy stream per peer, so that the per-copy issue latency
                       (~25 us) of the pushes to different peers overlaps instead of adding up (8 GPUs: 7 peers
                       per exchange step); 0 = all pushes in order on the communication stream */

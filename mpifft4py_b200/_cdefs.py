@@ -6,7 +6,7 @@ SINGLE, DOUBLE = 0, 1
 SLAB, PENCIL_X, PENCIL_Y, LINE, SLAB_C2C = 0, 1, 2, 3, 4
 DEALIAS_NONE, DEALIAS_3_2, DEALIAS_2_3 = 0, 1, 2
 TRANSPORT_NCCL, TRANSPORT_P2P, TRANSPORT_STORE = 0, 1, 2
-PIPELINE_X, PIPELINE_KZ = 0, 1
+PIPELINE_AUTO, PIPELINE_X, PIPELINE_KZ = 0, 1, 2
 LAYOUT_YBLOCK, LAYOUT_NATURAL = 0, 1
 
 ERR_ARG, ERR_RANKS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NOMEM = 1, 2, 3, 4, 5, 6

@@ -58,11 +58,12 @@ class Transform(object):
         d.drop_nyquist = int(drop_nyquist)
         d.transport = D.TRANSPORT_NCCL
         d.chunks = int(getattr(self, "exchange_chunks", 0) or os.environ.get("B200FFT_CHUNKS", "0"))
-        # slab exchanges are cut by local x planes ("x": z, y | exchange, then x) or by kz ranges ("kz":
-        # z, then y | exchange | x -- the exchange overlaps FFT passes on both sides)
-        pipe = str(getattr(self, "exchange_pipeline", None) or os.environ.get("B200FFT_PIPELINE", "x")).lower()
-        assert pipe in ("x", "kz"), "exchange_pipeline must be 'x' or 'kz'"
-        d.pipeline = D.PIPELINE_KZ if pipe == "kz" else D.PIPELINE_X
+        # slab exchanges are cut by local x planes ("x": z, y | exchange, then x) or by kz ranges ("kz": z, then
+        # y | exchange | x -- the exchange overlaps FFT passes on both sides); "auto" (default) lets the plan choose
+        # per transform (include/b200fft.h: kz for large plain transforms over the copy engines)
+        pipe = str(getattr(self, "exchange_pipeline", None) or os.environ.get("B200FFT_PIPELINE", "auto")).lower()
+        assert pipe in ("auto", "x", "kz"), "exchange_pipeline must be 'auto', 'x' or 'kz'"
+        d.pipeline = {"auto": D.PIPELINE_AUTO, "x": D.PIPELINE_X, "kz": D.PIPELINE_KZ}[pipe]
         # single-rank slab.R2C plans keep the array between the passes y-blocked (no pass with rows megabytes
         # apart); "natural" runs z, y, x on [x][y][kz] as the reference does (A/B measurements)
         lay = str(getattr(self, "layout", None) or os.environ.get("B200FFT_LAYOUT", "yblock")).lower()

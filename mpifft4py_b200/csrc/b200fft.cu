@@ -745,7 +745,7 @@ int b200fft_plan_create(b200fft_plan_t* plan, const b200fft_plan_desc_t* d) {
   const bool peer_mapped = d->transport == B200FFT_TRANSPORT_P2P || d->transport == B200FFT_TRANSPORT_STORE;
   if (d->transport != B200FFT_TRANSPORT_NCCL && !peer_mapped)
     return fail(B200FFT_ERR_ARG, "unknown transport %d", d->transport);
-  if (d->pipeline != B200FFT_PIPELINE_X && d->pipeline != B200FFT_PIPELINE_KZ)
+  if (d->pipeline != B200FFT_PIPELINE_AUTO && d->pipeline != B200FFT_PIPELINE_X && d->pipeline != B200FFT_PIPELINE_KZ)
     return fail(B200FFT_ERR_ARG, "unknown pipeline %d", d->pipeline);
   if (peer_mapped && d->nranks > B200FFT_MAXP)
     return fail(B200FFT_ERR_RANKS, "peer-mapped transports address at most %d ranks", B200FFT_MAXP);

@@ -306,6 +306,15 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
   // receive buffer -- exactly where the copy-engine transport's DMA would put it (`rpeer`)
   const bool store = d.transport == B200FFT_TRANSPORT_STORE && P > 1;
   const bool p2p = (d.transport == B200FFT_TRANSPORT_P2P || store) && P > 1;  // peers write into plan-owned buffers only
+  // Pipeline direction.  AUTO: kz ranges for plain / 2/3-rule R2C transforms over the copy engines once a per-peer
+  // message reaches 96 MB, in 4 chunks while a chunk's message stays >= 64 MB, else 2.  1024^3 double, round trip in
+  // ms, x planes (depth of pick_chunks) against kz ranges (profiles/r02_flags_2, r02_sweep_4, r02_final_8):
+  // 2 GPUs 13.07 / 12.88 (4), 4 GPUs 8.69 / 8.01 (4) / 8.45 (2), 8 GPUs 5.16 / 5.02 (2) / 5.67 (4); with the
+  // 3/2-rule the x-plane pipeline wins (4 GPUs 15.06 / 15.79, 8 GPUs 8.28 / 9.00) and keeps the default there.
+  const bool auto_kz = d.pipeline == B200FFT_PIPELINE_AUTO && P > 1 && !padded && !c2c && d.transport == B200FFT_TRANSPORT_P2P &&
+                       blk * csz >= (96ll << 20);
+  const bool use_kz = d.pipeline == B200FFT_PIPELINE_KZ || auto_kz;
+  const int kz_req = (auto_kz && d.chunks <= 0) ? ((blk * csz) / 4 >= (64ll << 20) ? 4 : 2) : d.chunks;
   const int yfold = !padded ? 0 : (c2c && P == 1) ? 2 : 1;
   const int xfold = !padded ? 0 : c2c ? 2 : 1;
   const int zfold = !padded ? 0 : (P == 1) ? 2 : 1;
@@ -412,14 +421,14 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
         b.fixed = 2;
         b.strided(pN0, 1, N1 * Nf, 0, nat(BUF_W1, 0, 0, N1 * Nf, pN0), nat(BUF_OUT, 0, 0, N1 * Nf, (int)N0), xfold, 1.0 / p3);
       }
-    } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:389-483, three-stage pipeline
+    } else if (use_kz) {  // slab.py:389-483, three-stage pipeline
       // one z pass; then per kz range c:  y(c) -> exchange(c) -> x(c).  Send and receive buffers are
       // chunk-major -- [c][peer q][x][y][kz in c] -- so every (chunk, peer) message is contiguous.
       // exchange(c) (second stream) overlaps y(c+1..) before it and x(..c-1) after it; with the fused
       // transport the y passes ARE the transfer (NVLink-bound) and run on the second stream beside the
       // HBM-bound x passes.
       const int recvbuf = BUF_W2;
-      const int C = kz_chunks(d.chunks, Nf);
+      const int C = kz_chunks(kz_req, Nf);
       const long long kc = Nf / C;
       b.use(BUF_W0, (long long)pNp0 * pN1 * Nf);
       if (!store) b.use(BUF_W1, P * blk);
@@ -570,9 +579,9 @@ inline int build_slab(const b200fft_plan_desc_t& d, int inverse, int dealias, Pr
           zinv(gn * pN1, g0 * pN1, BUF_W1, g0 * pN1 * Nf, scale);
         });
       }
-    } else if (d.pipeline == B200FFT_PIPELINE_KZ) {  // slab.py:270-345, three-stage pipeline
+    } else if (use_kz) {  // slab.py:270-345, three-stage pipeline
       // per kz range c:  x(c) -> exchange(c) -> y(c);  then one z pass (mirror of the forward program)
-      const int C = kz_chunks(d.chunks, Nf);
+      const int C = kz_chunks(kz_req, Nf);
       const long long kc = Nf / C;
       const int ybuf = BUF_W2;
       if (!store) b.use(BUF_W0, P * blk);

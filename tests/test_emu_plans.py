@@ -258,9 +258,15 @@ def test_slab_p2p_program_invariants(N, P, chunks):
             assert rc == 0, (rc, inverse, dealias)
             if chunks:
                 assert n.value == min(chunks, max(1, n.value))
-    # the automatic depth follows the measured cost model: 1024^3 double -> 8 chunks at P = 2, 4; 2 at P = 8
+    # the automatic pipeline follows the measurements (plan_program.h): 1024^3 double, plain transform -> kz ranges, 4
+    # chunks at P = 2, 4 and 2 at P = 8; 3/2-rule -> x planes, 8 chunks at P = 2, 4 and 4 at P = 8; an explicit "x" -> 8 / 8 / 2
     if N[0] == 1024 and chunks == 0:
         n = C.c_int()
+        assert lib.emu_check_p2p(C.byref(d), 0, D.DEALIAS_NONE, C.byref(n)) == 0
+        assert n.value == {2: 4, 4: 4, 8: 2}[P]
+        assert lib.emu_check_p2p(C.byref(d), 0, D.DEALIAS_3_2, C.byref(n)) == 0
+        assert n.value == {2: 8, 4: 8, 8: 4}[P]
+        d.pipeline = D.PIPELINE_X
         assert lib.emu_check_p2p(C.byref(d), 0, D.DEALIAS_NONE, C.byref(n)) == 0
         assert n.value == {2: 8, 4: 8, 8: 2}[P]
 
