@@ -35,7 +35,20 @@ def main():
     tp.test_rows_uneven_kz_chunks(be)
     tp.test_rows_row_map(be, 512, "d")
     tp.test_rows_c2c(be, 1024, "d")
+    for inverse in (0, 1):
+        tp.test_four_step_long_axis(be, 16, 8, "d", inverse)
+        tp.test_four_step_long_axis(be, 128, 128, "s", inverse)
     print("kernels ok", flush=True)
+    # Navier-Stokes elementwise kernels: one RK4 step of the 16^3 Taylor-Green problem
+    N16 = np.array([16, 16, 16])
+    FN = m.Slab_R2C(N16, L3, SelfComm(), "double")
+    S = m.ns.Solver(FN, nu=0.01, dt=0.01)
+    X = [torch.from_numpy(np.ascontiguousarray(np.broadcast_to(x, FN.real_shape()))).cuda() for x in FN.get_local_mesh()]
+    S.set_velocity(torch.stack([torch.sin(X[0]) * torch.cos(X[1]) * torch.cos(X[2]), -torch.cos(X[0]) * torch.sin(X[1]) * torch.cos(X[2]),
+                                torch.zeros_like(X[0])]))
+    S.step()
+    assert np.isfinite(S.kinetic_energy())
+    print("ns ok", flush=True)
     # whole transforms, y-blocked and natural intermediate
     N = (4, 512, 512)
     A = np.random.default_rng(0).random(N)
