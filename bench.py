@@ -596,7 +596,7 @@ def run_ours(args):
     cfg = describe(name, P)
     # plan options set through the environment: a line measured with any of them says so
     tuning = {k: os.environ[k] for k in ("B200FFT_LAYOUT", "B200FFT_TRANSPORT", "B200FFT_PIPELINE", "B200FFT_CHUNKS",
-                                          "B200FFT_COPY_STREAMS") if os.environ.get(k)}
+                                          "B200FFT_FLAG_DMA") if os.environ.get(k)}
     if tuned is not None:
         tuning["planner"] = {"effort": args.tune, "chosen": tuned["chosen"],
                              "candidates": [{k: c.get(k) for k in ("name", "seconds", "ok")} for c in tuned["candidates"]]}

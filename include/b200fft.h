@@ -197,9 +197,6 @@ typedef struct {
                       receive layout is chunk-major); B200FFT_PIPELINE_AUTO (0, default): KZ for plain / 2/3-rule
                       R2C transforms over the copy engines whose per-peer message is >= 96 MB (measured faster at
                       2, 4 and 8 GPUs), X otherwise (3/2-rule, small meshes, NCCL, fused stores, C2C) */
-  int copy_streams;/* copy-engine transport: 1 = one copy stream per peer, so that the per-copy issue latency
-                      (~25 us) of the pushes to different peers overlaps instead of adding up (8 GPUs: 7 peers
-                      per exchange step); 0 = all pushes in order on the communication stream */
   int layout;      /* single-rank slab.R2C plans: B200FFT_LAYOUT_YBLOCK (0, default) keeps the array between the
                       passes y-blocked and runs z, x, y (inverse y, x, z) so that no pass has rows megabytes apart;
                       B200FFT_LAYOUT_NATURAL runs z, y, x on [x][y][kz] like slab.py:366-370 (A/B measurements).

@@ -43,7 +43,7 @@ class PlanDesc(C.Structure):
                 ("nranks", C.c_int), ("rank", C.c_int), ("P1", C.c_int), ("P2", C.c_int),
                 ("padsize", C.c_double), ("drop_nyquist", C.c_int), ("transport", C.c_int),
                 ("comm", C.c_void_p), ("comm0", C.c_void_p), ("comm1", C.c_void_p), ("chunks", C.c_int), ("pipeline", C.c_int),
-                ("copy_streams", C.c_int), ("layout", C.c_int)]
+                ("layout", C.c_int)]
 
 
 class NsMesh(C.Structure):

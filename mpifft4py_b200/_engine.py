@@ -69,8 +69,6 @@ class Transform(object):
         lay = str(getattr(self, "layout", None) or os.environ.get("B200FFT_LAYOUT", "yblock")).lower()
         assert lay in ("yblock", "natural"), "layout must be 'yblock' or 'natural'"
         d.layout = D.LAYOUT_NATURAL if lay == "natural" else D.LAYOUT_YBLOCK
-        # copy-engine transport: one copy stream per peer (overlaps the per-copy issue latency)
-        d.copy_streams = int(getattr(self, "copy_streams", 0) or os.environ.get("B200FFT_COPY_STREAMS", "0"))
         # Exchanges default to the copy-engine (P2P) transport for every class: DMA pushes over NVLink that do not
         # occupy SMs, pipelined against the FFT passes (8 GPUs, profiles/r02_multi_8: slab 1024^3 5.4 ms against
         # 5.7 over NCCL send/recv, pencil X 5.9 against 7.7, pencil Y 2048^3 single 27.0 against 33.6).

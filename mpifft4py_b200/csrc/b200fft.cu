@@ -222,9 +222,6 @@ struct b200fft_plan {
     void* peer_ws[B200FFT_MAXP][NPEERBUF] = {};
     void* peer_flags[B200FFT_MAXP] = {};
     cudaStream_t wait_stream = nullptr;
-    cudaStream_t copy_stream[B200FFT_MAXP] = {};   // one per peer (plan option copy_streams)
-    cudaEvent_t copy_ev[B200FFT_MAXP] = {};
-    cudaEvent_t fork_ev = nullptr;
     std::vector<cudaEvent_t> send_ev;
     unsigned stage_slot = 0;                 // next staging word (flag values travel by 4-byte DMA)
     unsigned seq = 0;                        // exchange steps executed so far (identical on all ranks)
@@ -450,36 +447,8 @@ int run_exchange_p2p(b200fft_plan* pl, const Step& s, const void* in, void* out,
   // fused transport: the FFT pass this step waited for has stored the blocks already
   // peers are members q of the step's (sub)communicator; buffers and flags are indexed by world rank
   const int me_w = pl->d.rank;
-  if (pl->d.copy_streams && !s.fused && s.npeers > 2) {
-    // one stream per peer: every push (and its flag) is ordered behind the communication stream's earlier work
-    // (fork event) and the communication stream continues behind all of them (join), so the schedule seen by
-    // the rest of the program is unchanged while the pushes to different peers are issued side by side
-    if (!pp.fork_ev)
-      if (cudaError_t e = cudaEventCreateWithFlags(&pp.fork_ev, cudaEventDisableTiming)) return cuda_fail(e, "cudaEventCreate");
-    if (cudaError_t e = cudaEventRecord(pp.fork_ev, s1)) return cuda_fail(e, "cudaEventRecord(fork)");
-    for (int k = 1; k < s.npeers; ++k) {
-      const int q = (s.me + k) % s.npeers;
-      const int w = world_rank(pl->d, s.comm, me_w, q);
-      if (!pp.copy_stream[w]) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaError_t e = cudaStreamCreateWithPriority(&pp.copy_stream[w], cudaStreamNonBlocking, hi);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pp.copy_ev[w], cudaEventDisableTiming);
-        if (e != cudaSuccess) return cuda_fail(e, "copy stream");
-      }
-      cudaStream_t cs = pp.copy_stream[w];
-      cudaError_t e = cudaStreamWaitEvent(cs, pp.fork_ev, 0);
-      char* dst = (char*)pp.peer_ws[w][s.rpeer[q].buf - BUF_W0] + (size_t)s.rpeer[q].off * csz;
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(dst, resolve(pl, s.send[q], in, out, csz), (size_t)s.scnt[q] * csz, cudaMemcpyDeviceToDevice, cs);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(peer)");
-      if (int rc = post_flag(pl, cs, (unsigned*)pp.peer_flags[w] + me_w, seq)) return rc;
-      e = cudaEventRecord(pp.copy_ev[w], cs);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(s1, pp.copy_ev[w], 0);
-      if (e != cudaSuccess) return cuda_fail(e, "copy stream join");
-    }
-    return 0;
-  }
+  // (one copy stream per peer -- the pushes of a step issued side by side -- was measured at 8 GPUs and lost:
+  // 6.65 vs 5.47 ms, profiles/r02_multi_8; the pushes stay in order on the communication stream)
   for (int k = 1; k < s.npeers && !s.fused; ++k) {  // staggered peer order: no two ranks target the same GPU at once
     const int q = (s.me + k) % s.npeers;
     const int w = world_rank(pl->d, s.comm, me_w, q);
@@ -802,11 +771,6 @@ int b200fft_plan_destroy(b200fft_plan_t plan) {
   for (cudaEvent_t e : plan->p2p.send_ev) cudaEventDestroy(e);
   if (plan->p2p.flags) cudaFree(plan->p2p.flags);
   if (plan->p2p.wait_stream) cudaStreamDestroy(plan->p2p.wait_stream);
-  for (int q = 0; q < B200FFT_MAXP; ++q) {
-    if (plan->p2p.copy_stream[q]) cudaStreamDestroy(plan->p2p.copy_stream[q]);
-    if (plan->p2p.copy_ev[q]) cudaEventDestroy(plan->p2p.copy_ev[q]);
-  }
-  if (plan->p2p.fork_ev) cudaEventDestroy(plan->p2p.fork_ev);
   if (plan->comm_stream) cudaStreamDestroy(plan->comm_stream);
   delete plan;
   return 0;

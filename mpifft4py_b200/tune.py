@@ -15,13 +15,13 @@ or fails on any rank is rejected on all of them (one ``comm.allgather`` per cand
 
 The kernel-level switches round 1 left open were decided by measurement in round 2 and are no longer options
 (profiles/r02_single/ab_single.txt); what remains to choose per machine and mesh is the exchange: transport,
-pipeline depth and direction, copy streams -- and, for single-rank slab plans, the intermediate layout.
+pipeline depth and direction -- and, for single-rank slab plans, the intermediate layout.
 """
 import numpy as np
 
 from . import _lib
 
-PLAN_ATTRS = ("transport", "exchange_chunks", "exchange_pipeline", "copy_streams", "layout")
+PLAN_ATTRS = ("transport", "exchange_chunks", "exchange_pipeline", "layout")
 
 CANDIDATES = {
     "measure": [("default", {}), ("p2p_c2", {"transport": "p2p", "exchange_chunks": 2}),
@@ -29,7 +29,6 @@ CANDIDATES = {
                 ("nccl_c1", {"transport": "nccl", "exchange_chunks": 1}), ("nccl_c2", {"transport": "nccl", "exchange_chunks": 2})],
 }
 CANDIDATES["patient"] = CANDIDATES["measure"] + [
-    ("p2p_c4_copy_streams", {"transport": "p2p", "exchange_chunks": 4, "copy_streams": 1}),
     ("p2p_kz2", {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 2}),
     ("p2p_kz4", {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 4}),
     ("store_c1", {"transport": "store", "exchange_chunks": 1}),

@@ -24,7 +24,7 @@ import bench  # noqa: E402
 import mpifft4py_b200 as m  # noqa: E402
 from mpifft4py_b200.comm import world  # noqa: E402
 
-# name -> plan attributes (transport, exchange_pipeline, exchange_chunks, copy_streams)
+# name -> plan attributes (transport, exchange_pipeline, exchange_chunks)
 CONFIGS = {
     "default": {},
     "nccl_c1": {"transport": "nccl", "exchange_chunks": 1},
@@ -34,9 +34,6 @@ CONFIGS = {
     "p2p_c2": {"transport": "p2p", "exchange_chunks": 2},
     "p2p_c4": {"transport": "p2p", "exchange_chunks": 4},
     "p2p_c8": {"transport": "p2p", "exchange_chunks": 8},
-    "p2p_c2_cs": {"transport": "p2p", "exchange_chunks": 2, "copy_streams": 1},
-    "p2p_c4_cs": {"transport": "p2p", "exchange_chunks": 4, "copy_streams": 1},
-    "p2p_c8_cs": {"transport": "p2p", "exchange_chunks": 8, "copy_streams": 1},
     "store_c1": {"transport": "store", "exchange_chunks": 1},
     "store_c2": {"transport": "store", "exchange_chunks": 2},
     "store_c4": {"transport": "store", "exchange_chunks": 4},
@@ -44,14 +41,12 @@ CONFIGS = {
     "nccl_kz4": {"transport": "nccl", "exchange_pipeline": "kz", "exchange_chunks": 4},
     "p2p_kz2": {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 2},
     "p2p_kz4": {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 4},
-    "p2p_kz4_cs": {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 4, "copy_streams": 1},
-    "p2p_kz8_cs": {"transport": "p2p", "exchange_pipeline": "kz", "exchange_chunks": 8, "copy_streams": 1},
     "store_kz2": {"transport": "store", "exchange_pipeline": "kz", "exchange_chunks": 2},
     "store_kz4": {"transport": "store", "exchange_pipeline": "kz", "exchange_chunks": 4},
     "store_kz8": {"transport": "store", "exchange_pipeline": "kz", "exchange_chunks": 8},
 }
-SLAB_SET = ["default", "nccl_c1", "nccl_c2", "p2p_c1", "p2p_c2", "p2p_c4", "p2p_c4_cs", "p2p_c8_cs", "store_c1", "store_c2", "store_c4",
-            "nccl_kz2", "p2p_kz2", "p2p_kz4", "p2p_kz4_cs", "store_kz2", "store_kz4", "store_kz8"]
+SLAB_SET = ["default", "nccl_c1", "nccl_c2", "p2p_c1", "p2p_c2", "p2p_c4", "p2p_c8", "store_c1", "store_c2", "store_c4",
+            "nccl_kz2", "p2p_kz2", "p2p_kz4", "store_kz2", "store_kz4", "store_kz8"]
 OTHER_SET = ["default", "nccl_c1", "nccl_c2", "nccl_c4", "p2p_c1", "p2p_c2", "p2p_c4", "store_c1", "store_c2"]
 
 

@@ -272,9 +272,9 @@ def test_c2c_single_precision_ranks_as_threads(transport, pipeline, chunks):
 
 
 @pytest.mark.parametrize("kind,P,P1,P2", [(D.SLAB, 4, 1, 1), (D.PENCIL_X, 8, 4, 2), (D.LINE, 4, 1, 1)])
-def test_copy_engine_with_one_stream_per_peer(kind, P, P1, P2):
-    """plan option copy_streams: the pushes of an exchange step are issued on per-peer streams forked from and
-    joined into the communication stream; same results, flags and credits as with one stream."""
+def test_copy_engine_pipelined_for_every_class(kind, P, P1, P2):
+    """Copy-engine transport with two chunks for slab, pencil X (sub-communicators, world-rank flag indexing) and
+    line plans: three round trips back to back (flags posted by the flag kernel's host stand-in, credits carried over)."""
     L = host_shim_util.load()
     if kind == D.LINE:
         N = (32, 64)
@@ -297,7 +297,7 @@ def test_copy_engine_with_one_stream_per_peer(kind, P, P1, P2):
     R = Ranks(P)
 
     def rank(r):
-        h, _ = _make_plan(L, R, r, kind, N, P, D.TRANSPORT_P2P, P1=P1, P2=P2, copy_streams=1, chunks=2)
+        h, _ = _make_plan(L, R, r, kind, N, P, D.TRANSPORT_P2P, P1=P1, P2=P2, chunks=2)
         for rep in range(3):
             c = _exec(L, h, 0, D.DEALIAS_NONE, u[r], np.full(cshape[r], np.nan, dtype=np.complex128))
             assert oracle.rel_l2(c, ref[r]) <= TOL
