@@ -7,8 +7,10 @@ answer (kinetic energy 0.124953117517 after T = 0.1 at 32^3, ``:105``).  Everyth
 device: the transforms are mpifft4py_b200's kernels, called with CUDA tensors (zero copy); the
 cross / curl / projection arithmetic between them is plain tensor arithmetic of the caller.
 
-    python examples/spectral_dns_solver.py                 # 1 GPU
-    torchrun --nproc-per-node 4 examples/spectral_dns_solver.py
+    python examples/spectral_dns_solver.py                 # 1 GPU, the demo's array arithmetic between the transforms
+    python examples/spectral_dns_solver.py --kernels       # mpifft4py_b200.ns.Solver: three library kernels per RK stage
+    python examples/spectral_dns_solver.py --kernels --graph   # ... each time step replayed from a CUDA graph
+    torchrun --nproc-per-node 4 examples/spectral_dns_solver.py [--kernels]
 
 `solve` is written against a tiny array-module interface so that tests can also run it on the CPU
 oracle (numpy) and check the solver logic without a GPU.
@@ -121,7 +123,16 @@ def main():
     N = np.array([32, 32, 32], dtype=int)
     L = np.array([2 * np.pi] * 3)
     FFT = m.Slab_R2C(N, L, comm, "double")
-    k = solve(FFT, torch, lambda a: torch.from_numpy(a).cuda(), N)
+    if "--kernels" in sys.argv:
+        S = m.ns.Solver(FFT, nu=0.000625, dt=0.01, graph="--graph" in sys.argv)
+        X = [torch.from_numpy(np.ascontiguousarray(np.broadcast_to(x, FFT.real_shape()))).cuda() for x in FFT.get_local_mesh()]
+        S.set_velocity(torch.stack([torch.sin(X[0]) * torch.cos(X[1]) * torch.cos(X[2]),
+                                    -torch.cos(X[0]) * torch.sin(X[1]) * torch.cos(X[2]), torch.zeros_like(X[0])]))
+        for _ in range(10):
+            S.step()
+        k = S.kinetic_energy()
+    else:
+        k = solve(FFT, torch, lambda a: torch.from_numpy(a).cuda(), N)
     k = comm.reduce(k)
     if comm.Get_rank() == 0:
         print("kinetic energy %.12f (reference %.12f, difference %.2e)" % (k, KNOWN_ANSWER, k - KNOWN_ANSWER))

@@ -218,3 +218,49 @@ def test_3_2_rule_full_size_roundtrip():
     ref = u[::2, ::2, ::2]
     # interpolation is exact only without the Nyquist modes; compare through the spectrum instead
     assert sub.shape == ref.shape
+
+
+@pytest.mark.parametrize("dealias", [None, "2/3-rule", "3/2-rule"])
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("N", [(32, 64, 128), (64, 16, 32)])
+def test_slab_single_rank_natural_layout_vs_oracle(N, prec, dealias):
+    """layout="natural": z, y, x on [x][y][kz] like slab.py:366-370 (the y-blocked default is what every other test
+    runs); both directions of every dealias mode against the oracle, and bit-for-bit the same shapes."""
+    m = _mod()
+    rt, ct = oracle.common.dtypes(prec)
+    tol = TOL[prec]
+    F = m.Slab_R2C(np.array(N), L3, _self(), prec)
+    F.layout = "natural"
+    rng = np.random.default_rng(77)
+    fu = _rand_c(rng, F.complex_shape(), ct)
+    shp = F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()
+    u = F.ifftn(fu, np.zeros(shp, dtype=rt), dealias=dealias)
+    assert oracle.rel_l2(u, oracle.slab.ifftn([fu], N, 1, dealias=dealias, precision=prec)[0]) <= tol
+    fdeal = dealias if dealias == "3/2-rule" else None
+    a = rng.random(shp).astype(rt)
+    c = F.fftn(a, np.zeros(F.complex_shape(), dtype=ct), dealias=fdeal)
+    assert oracle.rel_l2(c, oracle.slab.fftn([a], N, 1, dealias=fdeal, precision=prec)[0]) <= tol
+    assert F.last_launches()[0] == 3
+
+
+@pytest.mark.parametrize("layout", ["yblock", "natural"])
+@pytest.mark.parametrize("N,prec", [((16384, 64), "single"), ((8192, 32), "double"), ((4096, 32), "double")])
+def test_line_long_columns_two_launches(N, prec, layout):
+    """line.R2C with columns of >= 64 KB (BASELINE config 5a shape class): the x pass runs as two launches (four-step)
+    by default, as one with layout="natural"; fft2 / ifft2 against numpy either way."""
+    m = _mod()
+    rt, ct = oracle.common.dtypes(prec)
+    tol = TOL[prec]
+    F = m.Line_R2C(np.array(N), L3[:2], _self(), prec)
+    F.layout = layout
+    rng = np.random.default_rng(N[0])
+    A = rng.random(N).astype(rt)
+    c = F.fft2(A, np.zeros(F.complex_shape(), dtype=ct))
+    assert oracle.rel_l2(c, np.fft.rfft2(A.astype(np.float64))) <= tol
+    split = layout == "yblock" and N[0] * np.dtype(ct).itemsize >= 64 * 1024
+    assert F.last_launches()[0] == (3 if split else 2)
+    a = F.ifft2(c, np.zeros(F.real_shape(), dtype=rt))
+    assert oracle.rel_l2(a, A) <= tol
+    fu = _rand_c(rng, F.complex_shape(), ct)
+    u = F.ifft2(fu, np.zeros(F.real_shape(), dtype=rt), dealias="2/3-rule")
+    assert oracle.rel_l2(u, oracle.line.ifft2([fu], N, 1, dealias="2/3-rule", precision=prec)[0]) <= tol
