@@ -31,6 +31,7 @@ WORKLOADS = {
     "slab1024_f64_32": ("slab", (1024, 1024, 1024), "double", "3/2-rule", {}),
     "slab512_f64": ("slab", (512, 512, 512), "double", None, {}),
     "slab256_f32": ("slab", (256, 256, 256), "single", None, {}),
+    "slab2048z_f32": ("slab", (256, 512, 2048), "single", None, {}),
     "pencilX512_f64": ("pencil", (512, 512, 512), "double", None, dict(alignment="X", P1=2, communication="Alltoallw")),
     "pencilX1024_f64": ("pencil", (1024, 1024, 1024), "double", None, dict(alignment="X", P1=None, communication="Alltoallw")),
     "pencilY2048_f32": ("pencil", (2048, 2048, 2048), "single", None, dict(alignment="Y", P1=None, communication="Alltoallw")),
