@@ -9,109 +9,91 @@ class where the pack trick itself is inexact upstream.
 from collections import defaultdict
 
 import numpy as np
-from numpy.fft import fftfreq, rfftfreq
+from numpy.fft import fftfreq
 
 from . import _cdefs as D
+from . import _geometry as G
 from ._engine import Transform
-from .mpibase import datatypes, work_arrays, zeros
+from .mpibase import datatypes, work_arrays
 
 
 class R2C(Transform):
-    """2D real-to-complex FFT (``fft2``/``ifft2``), row decomposition (``line.py:41-75``)."""
+    """2D real-to-complex FFT (``fft2``/``ifft2``), row decomposition (``line.py:41-75``): rank r owns rows
+    ``[r*Np0, (r+1)*Np0)`` of the real array and ``Npf`` columns of the half spectrum starting at ``r*Np1//2``."""
 
     def __init__(self, N, L, comm, precision, padsize=1.5, threads=1,
                  planner_effort=defaultdict(lambda: "FFTW_MEASURE")):
-        self.N = N
-        self.L = L
-        assert len(L) == 2
-        assert len(N) == 2
+        assert len(L) == 2 and len(N) == 2
+        self.N, self.L = N, L                      # (L keeps the caller's dtype here, line.py:57)
         self.comm = comm
         self.float, self.complex, self.mpitype = datatypes(precision)
-        self.num_processes = comm.Get_size()
-        self.rank = comm.Get_rank()
-        self.padsize = padsize
-        self.threads = threads
-        self.planner_effort = planner_effort
+        self.num_processes, self.rank = comm.Get_size(), comm.Get_rank()
+        self.padsize, self.threads, self.planner_effort = padsize, threads, planner_effort
         self.Np = N // self.num_processes
-        self.Nf = N[1]//2+1
-        self.Npf = self.Np[1]//2+1 if self.rank+1 == self.num_processes else self.Np[1]//2
-        self.Nfp = int(padsize*self.N[1]/2+1)
-        self.ks = (fftfreq(N[0])*N[0]).astype(int)
+        self.Nf = N[1] // 2 + 1
+        last = self.rank + 1 == self.num_processes
+        self.Npf = self.Np[1] // 2 + (1 if last else 0)   # the last rank also holds the Nyquist column
+        self.Nfp = int(padsize * self.N[1] / 2 + 1)
+        self.ks = (fftfreq(N[0]) * N[0]).astype(int)
         self.dealias = np.zeros(0)
         self.work_arrays = work_arrays()
         self._create_plan(D.LINE, N, self.num_processes, self.rank, comm=comm)
 
+    def get_N(self):
+        return self.N
+
+    # ---- shapes (line.py:77-103, 138-164)
     def real_shape(self):
-        """The local shape of the real data"""
         return (self.Np[0], self.N[1])
 
     def complex_shape(self):
-        """The local shape of the complex data"""
         return (self.N[0], self.Npf)
-
-    def global_complex_shape(self):
-        return (self.N[0], self.Nf)
 
     def global_real_shape(self):
         return (self.N[0], self.N[1])
 
-    def real_local_slice(self, padsize=1):
-        return (slice(int(padsize*self.rank*self.Np[0]),
-                      int(padsize*(self.rank+1)*self.Np[0]), 1),
-                slice(0, int(padsize*self.N[1])))
-
-    def complex_local_slice(self):
-        return (slice(0, self.N[0]),
-                slice(self.rank*self.Np[1]//2, self.rank*self.Np[1]//2+self.Npf, 1))
-
-    def get_N(self):
-        return self.N
-
-    def get_local_mesh(self):
-        X = np.mgrid[self.rank*self.Np[0]:(self.rank+1)*self.Np[0], :self.N[1]].astype(self.float)
-        X[0] *= self.L[0]/self.N[0]
-        X[1] *= self.L[1]/self.N[1]
-        return X
-
-    def get_local_wavenumbermesh(self, scaled=True, broadcast=False,
-                                 eliminate_highest_freq=False):
-        """``line.py:112-129`` (note scaled=True is the default here, unlike slab/pencil)."""
-        kx = fftfreq(self.N[0], 1./self.N[0])
-        ky = rfftfreq(self.N[1], 1./self.N[1])
-        if eliminate_highest_freq:
-            for i, k in enumerate((kx, ky)):
-                if self.N[i] % 2 == 0:
-                    k[self.N[i]//2] = 0
-
-        Ks = list(np.meshgrid(kx, ky[self.rank*self.Np[1]//2:(self.rank*self.Np[1]//2+self.Npf)], indexing='ij', sparse=True))
-        if scaled is True:
-            Lp = 2*np.pi/self.L
-            Ks[0] *= Lp[0]
-            Ks[1] *= Lp[1]
-        K = Ks
-        if broadcast is True:
-            K = [np.broadcast_to(k, self.complex_shape()) for k in Ks]
-        return K
-
-    def get_dealias_filter(self):
-        """``line.py:131-136``.  The engine's fused mask uses the unscaled wavenumbers, which is
-        the same thing for the 2*pi-periodic box the reference's mask assumes."""
-        K = self.get_local_wavenumbermesh()
-        kmax = 2./3.*(self.N//2+1)
-        dealias = np.array((abs(K[0]) < kmax[0])*(abs(K[1]) < kmax[1]), dtype=np.uint8)
-        return dealias
+    def global_complex_shape(self):
+        return (self.N[0], self.Nf)
 
     def global_complex_shape_padded(self):
-        return (int(self.padsize*self.N[0]), int(self.padsize*self.N[1]/2+1))
+        return (int(self.padsize * self.N[0]), int(self.padsize * self.N[1] / 2 + 1))
 
     def real_shape_padded(self):
-        return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]))
+        return G.padded(self.real_shape(), self.padsize)
 
     def work_shape(self, dealias):
-        if dealias == '3/2-rule':
-            return self.real_shape_padded()
-        else:
-            return self.real_shape()
+        return self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
+
+    # ---- slices (line.py:93-103: the slices over whole axes carry no step)
+    def real_local_slice(self, padsize=1):
+        return (G.block(self.Np[0], self.rank, padsize), G.whole(self.N[1], padsize, None))
+
+    def _ky_slice(self):
+        lo = self.rank * self.Np[1] // 2
+        return slice(lo, lo + self.Npf, 1)
+
+    def complex_local_slice(self):
+        return (G.whole(self.N[0], 1, None), self._ky_slice())
+
+    # ---- meshes (line.py:105-136)
+    def get_local_mesh(self):
+        return G.dense_physical_mesh((G.block(self.Np[0], self.rank), G.whole(self.N[1])), self.N, self.L, self.float)
+
+    def get_local_wavenumbermesh(self, scaled=True, broadcast=False, eliminate_highest_freq=False):
+        """Sparse wavenumber mesh of the local spectral block; scaled by 2 pi / L by DEFAULT here (unlike the 3D classes)."""
+        ks = [G.frequencies(self.N[0]), G.frequencies(self.N[1], half=True)]
+        if eliminate_highest_freq:
+            G.drop_nyquist(ks, self.N)
+        K = G.sparse_spectral_mesh((ks[0], ks[1][self._ky_slice()]))
+        if scaled is True:
+            for k, f in zip(K, 2 * np.pi / self.L):
+                k *= f
+        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
+
+    def get_dealias_filter(self):
+        """``line.py:131-136``: the mask tests the default (scaled) wavenumbers, i.e. assumes the 2 pi-periodic box; the
+        engine's fused mask uses the mode numbers, the same thing there."""
+        return G.two_thirds_mask(self.get_local_wavenumbermesh(), self.N)
 
     def fft2(self, u, fu, dealias=None):
         """Forward 2D transform (``line.py:179-260``)."""

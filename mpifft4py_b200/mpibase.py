@@ -40,29 +40,40 @@ def zeros(N, dtype=float, bytes=None):
     return a
 
 
-class work_array_dict(dict):
-    """Dictionary of work arrays indexed by their shape, type and an indicator i."""
-
-    def __missing__(self, key):
-        shape, dtype, i = key
-        a = np.zeros(shape, dtype=dtype)
-        self[key] = a
-        return self[key]
-
-
 class work_arrays(collections.abc.MutableMapping):
-    """Host work arrays keyed ``(shape, dtype, index[, fillzero])`` or ``(ndarray, index[, fillzero])``
-    (``mpibase.py:61-131``); fetched arrays are zeroed unless ``fillzero`` is False."""
+    """Host work arrays (``mpibase.py:53-131``), created on first use and handed out ZEROED on every fetch.
+
+    A key names an array by ``(shape, dtype, index)`` or by example, ``(ndarray, index)``; a trailing ``False``
+    (``fillzero``) keeps the content of an existing array.  The index tells apart arrays of equal shape and type."""
 
     def __init__(self):
-        self.store = work_array_dict()
+        self.store = {}
         self.fillzero = True
 
+    def __keytransform__(self, key):
+        like, rest = key[0], key[1:]
+        if isinstance(like, np.ndarray):
+            shape, dtype = like.shape, like.dtype
+        elif isinstance(like, tuple) and len(rest) in (2, 3):
+            shape, dtype, rest = like, rest[0], rest[1:]
+        else:
+            raise TypeError("Wrong type of key for work array")
+        if len(rest) not in (1, 2):
+            raise TypeError("Wrong type of key for work array")
+        index, zero = rest[0], (rest[1] if len(rest) == 2 else True)
+        assert isinstance(zero, bool)
+        assert isinstance(index, int)
+        self.fillzero = zero
+        return (tuple(int(s) for s in shape), np.dtype(dtype), index)
+
     def __getitem__(self, key):
-        val = self.store[self.__keytransform__(key)]
-        if self.fillzero is True:
-            val.fill(0)
-        return val
+        k = self.__keytransform__(key)
+        a = self.store.get(k)
+        if a is None:
+            a = self.store[k] = np.zeros(k[0], dtype=k[1])
+        elif self.fillzero is True:
+            a.fill(0)
+        return a
 
     def __setitem__(self, key, value):
         self.store[self.__keytransform__(key)] = value
@@ -78,27 +89,6 @@ class work_arrays(collections.abc.MutableMapping):
 
     def values(self):
         raise TypeError('Work arrays not iterable')
-
-    def __keytransform__(self, key):
-        if isinstance(key[0], np.ndarray):
-            shape = key[0].shape
-            dtype = key[0].dtype
-            i = key[1]
-            zero = True if len(key) == 2 else key[2]
-        elif isinstance(key[0], tuple):
-            if len(key) == 3:
-                shape, dtype, i = key
-                zero = True
-            elif len(key) == 4:
-                shape, dtype, i, zero = key
-            else:
-                raise TypeError("Wrong type of key for work array")
-        else:
-            raise TypeError("Wrong type of key for work array")
-        assert isinstance(zero, bool)
-        assert isinstance(i, int)
-        self.fillzero = zero
-        return (tuple(int(s) for s in shape), np.dtype(dtype), i)
 
 
 def datatypes(precision):

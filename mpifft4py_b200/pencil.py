@@ -12,172 +12,127 @@ Scatter/Send/Recv); 'AlltoallN' keeps its own layout with the Nyquist plane drop
 from collections import defaultdict
 
 import numpy as np
-from numpy.fft import fftfreq, rfftfreq
-
 from . import _cdefs as D
+from . import _geometry as G
 from ._engine import Transform
 from .mpibase import datatypes, work_arrays
 
 __all__ = ['R2C', 'R2CX', 'R2CY']
 
 
-def _compute_dims(P):
-    """MPI.Compute_dims(P, 2) (``pencil.py:185``): balanced factors, larger first (8 -> [4, 2])."""
-    best = (P, 1)
-    for a in range(1, int(P ** 0.5) + 1):
-        if P % a == 0:
-            best = (P // a, a)
-    return best
-
-
-def _subsize(N, size, rank):
-    return N // size + ((N % size) * (rank == size - 1))
-
-
 class R2CY(Transform):
-    """3D R2C FFT, pencil decomposition, final alignment in y (``pencil.py:145-216``)."""
+    """3D R2C FFT, pencil decomposition, final alignment in y (``pencil.py:145-216``).
+
+    Real space is cut along x by ``comm0`` (P1 ranks) and along y by ``comm1`` (P2 ranks); the spectral block holds
+    all of ky, the comm1-th part of kx and the comm0-th part of kz (the last part carrying the Nyquist plane)."""
 
     _kind = D.PENCIL_Y
 
     def __init__(self, N, L, comm, precision, P1=None, communication='Alltoallw', padsize=1.5, threads=1,
                  planner_effort=defaultdict(lambda: "FFTW_MEASURE")):
-        self.N = N
-        assert len(L) == 3
-        assert len(N) == 3
-        self.Nf = N[2]//2+1
-        self.comm = comm
+        assert len(L) == 3 and len(N) == 3
         self.float, self.complex, self.mpitype = datatypes(precision)
-        self.num_processes = comm.Get_size()
-        assert self.num_processes > 1
-        self.L = L.astype(self.float)   # pencil.py:173,177: `float` is rebound to the numpy type there
+        self.N, self.L = N, L.astype(self.float)
+        self.Nf = N[2] // 2 + 1
+        self.comm, self.communication = comm, communication
+        self.padsize, self.threads, self.planner_effort = padsize, threads, planner_effort
+        self.num_processes, self.rank = comm.Get_size(), comm.Get_rank()
+        assert self.num_processes > 1                                  # pencil.py:176
         self.dealias = np.zeros(0)
-        self.communication = communication
-        self.padsize = padsize
-        self.threads = threads
-        self.planner_effort = planner_effort
-        self.rank = comm.Get_rank()
-        if P1 is None:
-            P1, P2 = _compute_dims(self.num_processes)
-            self.P1, self.P2 = P1, P2
-        else:
-            self.P1 = P1
-            self.P2 = P2 = self.num_processes // P1
-        self.N1 = N // P1
-        self.N2 = N // P2
-        if not (self.num_processes % 2 == 0 or self.num_processes == 1):
+        self.P1, self.P2 = G.balanced_grid(self.num_processes) if P1 is None else (P1, self.num_processes // P1)
+        self.N1, self.N2 = N // self.P1, N // self.P2                  # points per rank of either grid direction
+        if self.num_processes % 2:                                     # pencil.py:201-205
             raise IOError("Number of cpus must be even")
-        if (P1 % 2 != 0) or (P2 % 2 != 0):
+        if self.P1 % 2 or self.P2 % 2:
             raise IOError("Number of cpus in each direction must be even power of 2")
-        self.comm0 = comm.Split(self.rank // P1)   # pencil.py:192 (true division upstream, Q4)
-        self.comm1 = comm.Split(self.rank % P1)
-        self.comm0_rank = self.comm0.Get_rank()
-        self.comm1_rank = self.comm1.Get_rank()
+        # grid: comm0 = P1 consecutive ranks (position rank % P1), comm1 = the P2 ranks with equal rank % P1
+        # (pencil.py:192-195; upstream passes rank / P1, a float under true division)
+        self.comm0 = comm.Split(self.rank // self.P1)
+        self.comm1 = comm.Split(self.rank % self.P1)
+        self.comm0_rank, self.comm1_rank = self.comm0.Get_rank(), self.comm1.Get_rank()
         self.work_arrays = work_arrays()
-        self.N1f = self.N1[2]//2 if self.comm0_rank < self.P1-1 else self.N1[2]//2+1
-        if self.communication == 'AlltoallN':
-            self.N1f = self.N1[2]//2
-        self._init_alignment()
+        drop = communication == 'AlltoallN'                            # that layout has no Nyquist plane at all
+        self.N1f = self._kz_count(self.N1, self.comm0_rank, self.P1, drop)
+        self._init_alignment(drop)
         self._create_plan(self._kind, N, self.num_processes, self.rank, P1=self.P1, P2=self.P2,
-                          drop_nyquist=int(self.communication == 'AlltoallN'),
-                          comm=comm, comm0=self.comm0, comm1=self.comm1)
+                          drop_nyquist=int(drop), comm=comm, comm0=self.comm0, comm1=self.comm1)
 
-    def _init_alignment(self):
+    @staticmethod
+    def _kz_count(Npart, idx, parts, drop):
+        """kz entries of part ``idx``: half the part's z extent, plus the Nyquist entry on the last part."""
+        return Npart[2] // 2 + (0 if (drop or idx < parts - 1) else 1)
+
+    def _init_alignment(self, drop):
         pass
 
-    def real_shape(self):
-        """The local shape of the real data"""
-        return (self.N1[0], self.N2[1], self.N[2])
-
-    def complex_shape(self):
-        """The local shape of the complex data"""
-        return (self.N2[0], self.N[1], self.N1f)
-
-    def real_shape_padded(self):
-        return (int(self.padsize*self.N1[0]), int(self.padsize*self.N2[1]), int(self.padsize*self.N[2]))
-
-    def work_shape(self, dealias):
-        if dealias == '3/2-rule':
-            return self.real_shape_padded()
-        else:
-            return self.real_shape()
-
-    def real_local_slice(self, padsize=1):
-        xzrank = self.comm0.Get_rank()
-        xyrank = self.comm1.Get_rank()
-        return (slice(int(padsize * xzrank * self.N1[0]), int(padsize * (xzrank+1) * self.N1[0]), 1),
-                slice(int(padsize * xyrank * self.N2[1]), int(padsize * (xyrank+1) * self.N2[1]), 1),
-                slice(0, int(padsize*self.N[2])))
-
-    def complex_local_slice(self):
-        xzrank = self.comm0.Get_rank()
-        xyrank = self.comm1.Get_rank()
-        return (slice(xyrank*self.N2[0], (xyrank+1)*self.N2[0], 1),
-                slice(0, self.N[1]),
-                slice(xzrank*self.N1[2]//2, xzrank*self.N1[2]//2 + self.N1f, 1))
-
-    def complex_local_wavenumbers(self):
-        s = self.complex_local_slice()
-        return (fftfreq(self.N[0], 1./self.N[0]).astype(int)[s[0]],
-                fftfreq(self.N[1], 1./self.N[1]).astype(int),
-                rfftfreq(self.N[2], 1./self.N[2]).astype(int)[s[2]])
+    # which block of x, y and kz this rank owns (alignment Y: kx by comm1, kz by comm0)
+    def _grid(self):
+        return self.comm0.Get_rank(), self.comm1.Get_rank()
 
     def get_P(self):
         return self.P1, self.P2
 
-    def get_local_mesh(self):
-        xzrank = self.comm0.Get_rank()
-        xyrank = self.comm1.Get_rank()
-        x1 = slice(xzrank * self.N1[0], (xzrank+1) * self.N1[0], 1)
-        x2 = slice(xyrank * self.N2[1], (xyrank+1) * self.N2[1], 1)
-        X = list(np.ogrid[x1, x2, :self.N[2]])
-        X[0] = (X[0]*self.L[0]/self.N[0]).astype(self.float)
-        X[1] = (X[1]*self.L[1]/self.N[1]).astype(self.float)
-        X[2] = (X[2]*self.L[2]/self.N[2]).astype(self.float)
-        X = [np.broadcast_to(x, self.real_shape()) for x in X]
-        return X
+    # ---- shapes
+    def real_shape(self):
+        return (self.N1[0], self.N2[1], self.N[2])
 
-    def get_local_wavenumbermesh(self, scaled=False, broadcast=False,
-                                 eliminate_highest_freq=False):
-        """``pencil.py:311-341``: integer wavenumbers unless scaled."""
-        s = self.complex_local_slice()
-        kx = fftfreq(self.N[0], 1./self.N[0]).astype(int)
-        ky = fftfreq(self.N[1], 1./self.N[1]).astype(int)
-        kz = rfftfreq(self.N[2], 1./self.N[2]).astype(int)
-        if eliminate_highest_freq:
-            for i, k in enumerate((kx, ky, kz)):
-                if self.N[i] % 2 == 0:
-                    k[self.N[i]//2] = 0
-        kx = kx[s[0]]
-        kz = kz[s[2]]
-        Ks = list(np.meshgrid(kx, ky, kz, indexing='ij', sparse=True))
-        if scaled is True:
-            Lp = 2*np.pi/self.L
-            for i in range(3):
-                Ks[i] = (Ks[i]*Lp[i]).astype(self.float)
-        K = Ks
-        if broadcast is True:
-            K = [np.broadcast_to(k, self.complex_shape()) for k in Ks]
-        return K
+    def complex_shape(self):
+        return (self.N2[0], self.N[1], self.N1f)
 
-    def get_dealias_filter(self):
-        """2/3-rule mask on the local spectral block (``pencil.py:343-349``)."""
-        s = self.complex_local_slice()
-        kx = fftfreq(self.N[0], 1./self.N[0]).astype(int)[s[0]]
-        ky = fftfreq(self.N[1], 1./self.N[1]).astype(int)[s[1]]
-        kz = rfftfreq(self.N[2], 1./self.N[2]).astype(int)[s[2]]
-        K = np.meshgrid(kx, ky, kz, indexing='ij', sparse=True)
-        kmax = 2./3.*(self.N//2+1)
-        dealias = np.array((abs(K[0]) < kmax[0])*(abs(K[1]) < kmax[1])*
-                           (abs(K[2]) < kmax[2]), dtype=np.uint8)
-        return dealias
+    def real_shape_padded(self):
+        return G.padded(self.real_shape(), self.padsize)
 
-    # (copy_to_padded_* / copy_from_padded_* of pencil.py:351-379: index maps inside the FFT passes here)
+    def work_shape(self, dealias):
+        return self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
 
     def global_complex_shape(self, padsize=1.0):
-        """Global size of problem in complex wavenumber space"""
-        return (int(padsize*self.N[0]), int(padsize*self.N[1]),
-                int(padsize*self.N[2]//2+1))
+        return (int(padsize * self.N[0]), int(padsize * self.N[1]), int(padsize * self.N[2] // 2 + 1))
 
+    # ---- slices (pencil.py:264-287; the z slice of the real block and the ky slice carry no step upstream)
+    def real_local_slice(self, padsize=1):
+        c0, c1 = self._grid()
+        return (G.block(self.N1[0], c0, padsize), G.block(self.N2[1], c1, padsize), G.whole(self.N[2], padsize, None))
+
+    def _kz_slice(self, Npart, idx, count):
+        lo = idx * Npart[2] // 2
+        return slice(lo, lo + count, 1)
+
+    def complex_local_slice(self):
+        c0, c1 = self._grid()
+        return (G.block(self.N2[0], c1), G.whole(self.N[1], 1, None), self._kz_slice(self.N1, c0, self.N1f))
+
+    # ---- meshes (pencil.py:289-349): integer wavenumbers unless scaled
+    def _k_axes(self):
+        return [G.frequencies(self.N[0]).astype(int), G.frequencies(self.N[1]).astype(int),
+                G.frequencies(self.N[2], half=True).astype(int)]
+
+    def complex_local_wavenumbers(self):
+        s = self.complex_local_slice()
+        kx, ky, kz = self._k_axes()
+        return (kx[s[0]], ky, kz[s[2]])
+
+    def get_local_mesh(self):
+        c0, c1 = self._grid()
+        sl = (G.block(self.N1[0], c0), G.block(self.N2[1], c1), G.whole(self.N[2]))
+        return G.sparse_physical_mesh(sl, self.N, self.L, self.float, self.real_shape())
+
+    def get_local_wavenumbermesh(self, scaled=False, broadcast=False, eliminate_highest_freq=False):
+        s = self.complex_local_slice()
+        ks = self._k_axes()
+        if eliminate_highest_freq:
+            G.drop_nyquist(ks, self.N)
+        K = G.sparse_spectral_mesh((ks[0][s[0]], ks[1], ks[2][s[2]]))
+        if scaled is True:
+            K = [(k * f).astype(self.float) for k, f in zip(K, 2 * np.pi / self.L)]
+        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
+
+    def get_dealias_filter(self):
+        """2/3-rule mask on the local spectral block (applied by the transforms inside their first inverse pass)."""
+        s = self.complex_local_slice()
+        K = G.sparse_spectral_mesh([k[sl] for k, sl in zip(self._k_axes(), s)])
+        return G.two_thirds_mask(K, self.N)
+
+    # ---- transforms
     def ifftn(self, fu, u, dealias=None):
         """Inverse transform (Y: ``pencil.py:386-632``; X: ``:1001-1226``).  fu is not modified.
         2/3-rule follows the slab/R2CY semantics for both alignments (the reference's R2CX variant
@@ -194,7 +149,8 @@ class R2CY(Transform):
 
 
 class R2CX(R2CY):
-    """3D R2C FFT, pencil decomposition, final alignment in x (``pencil.py:885-969``)."""
+    """3D R2C FFT, pencil decomposition, final alignment in x (``pencil.py:885-969``): the spectral block holds all of
+    kx, the comm0-th part of ky and the comm1-th part of kz."""
 
     _kind = D.PENCIL_X
 
@@ -204,54 +160,31 @@ class R2CX(R2CY):
         R2CY.__init__(self, N, L, comm, precision, P1=P1, communication=communication,
                       padsize=padsize, threads=threads, planner_effort=planner_effort)
 
-    def _init_alignment(self):
-        self.N2f = self.N2[2]//2 if self.comm1_rank < self.P2-1 else self.N2[2]//2+1
-        if self.communication == 'AlltoallN':
-            self.N2f = self.N2[2]//2
-        if self.communication == 'Alltoallw':
-            self.N2f = _subsize(self.Nf, self.P2, self.comm1_rank)
+    def _init_alignment(self, drop):
+        self.N2f = self._kz_count(self.N2, self.comm1_rank, self.P2, drop)
+        if self.communication == 'Alltoallw':   # pencil.py:911-913: remainder of Nf / P2 on the last rank (the same number)
+            self.N2f = self.Nf // self.P2 + (self.Nf % self.P2) * (self.comm1_rank == self.P2 - 1)
 
     def complex_shape(self):
-        """The local shape of the complex data"""
         return (self.N[0], self.N1[1], self.N2f)
 
-    def real_local_slice(self, padsize=1):
-        xyrank = self.comm0.Get_rank()
-        yzrank = self.comm1.Get_rank()
-        return (slice(int(padsize * xyrank * self.N1[0]), int(padsize * (xyrank+1) * self.N1[0]), 1),
-                slice(int(padsize * yzrank * self.N2[1]), int(padsize * (yzrank+1) * self.N2[1]), 1),
-                slice(0, int(padsize * self.N[2])))
-
     def complex_local_slice(self):
-        xyrank = self.comm0.Get_rank()
-        yzrank = self.comm1.Get_rank()
-        return (slice(0, self.N[0]),
-                slice(xyrank*self.N1[1], (xyrank+1)*self.N1[1], 1),
-                slice(yzrank*self.N2[2]//2, yzrank*self.N2[2]//2 + self.N2f, 1))
+        c0, c1 = self._grid()
+        return (G.whole(self.N[0], 1, None), G.block(self.N1[1], c0), self._kz_slice(self.N2, c1, self.N2f))
 
     def get_local_mesh(self):
-        xyrank = self.comm0.Get_rank()
-        yzrank = self.comm1.Get_rank()
-        x1 = slice(xyrank * self.N1[0], (xyrank+1) * self.N1[0], 1)
-        x2 = slice(yzrank * self.N2[1], (yzrank+1) * self.N2[1], 1)
-        X = np.mgrid[x1, x2, :self.N[2]].astype(self.float)
-        X[0] *= self.L[0]/self.N[0]
-        X[1] *= self.L[1]/self.N[1]
-        X[2] *= self.L[2]/self.N[2]
-        return X
+        """Dense (3, ...) coordinate array (``pencil.py:931-943``), unlike the sparse list of the Y alignment."""
+        c0, c1 = self._grid()
+        sl = (G.block(self.N1[0], c0), G.block(self.N2[1], c1), G.whole(self.N[2]))
+        return G.dense_physical_mesh(sl, self.N, self.L, self.float)
 
     def get_local_wavenumbermesh(self):
-        """Dense float mesh of shape (3, N0, N1[1], N2[2]//2) -- Nyquist plane excluded, exactly
-        as ``pencil.py:945-957``."""
-        xyrank = self.comm0.Get_rank()
-        yzrank = self.comm1.Get_rank()
-        kx = fftfreq(self.N[0], 1./self.N[0]).astype(int)
-        ky = fftfreq(self.N[1], 1./self.N[1]).astype(int)
-        kz = fftfreq(self.N[2], 1./self.N[2]).astype(int)
-        k2 = slice(xyrank*self.N1[1], (xyrank+1)*self.N1[1], 1)
-        k1 = slice(yzrank*self.N2[2]//2, (yzrank+1)*self.N2[2]//2, 1)
-        K = np.array(np.meshgrid(kx, ky[k2], kz[k1], indexing='ij'), dtype=self.float)
-        return K
+        """Dense float mesh of shape (3, N0, N1[1], N2[2]//2): the Nyquist plane is not part of it and kz is taken
+        from the full-axis frequency vector, exactly as ``pencil.py:945-957``."""
+        c0, c1 = self._grid()
+        kx, ky, kz = (G.frequencies(n).astype(int) for n in self.N)
+        kzs = slice(c1 * self.N2[2] // 2, (c1 + 1) * self.N2[2] // 2, 1)
+        return np.array(np.meshgrid(kx, ky[G.block(self.N1[1], c0)], kz[kzs], indexing='ij'), dtype=self.float)
 
 
 def R2C(N, L, comm, precision, P1=None, communication="Alltoall", padsize=1.5, threads=1,

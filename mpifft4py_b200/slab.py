@@ -7,9 +7,10 @@ x (``real_shape = (N0/P, N1, N2)``), wavenumber space along y (``complex_shape =
 from collections import defaultdict
 
 import numpy as np
-from numpy.fft import fftfreq, rfftfreq
+from numpy.fft import fftfreq
 
 from . import _cdefs as D
+from . import _geometry as G
 from ._engine import Transform
 from .mpibase import datatypes, work_arrays
 
@@ -19,7 +20,7 @@ class R2C(Transform):
 
     Args are the reference's: N, L (numpy arrays), comm, precision ("single"/"double"),
     communication ('Alltoall', 'Sendrecv_replace', 'Alltoallw' -- all three map onto the same
-    NCCL exchange and give identical results), padsize, threads and planner_effort (accepted,
+    exchange and give identical results), padsize, threads and planner_effort (accepted,
     meaningless on a GPU).
     """
 
@@ -30,115 +31,85 @@ class R2C(Transform):
                  padsize=1.5,
                  threads=1,
                  planner_effort=defaultdict(lambda: "FFTW_MEASURE")):
-        assert len(L) == 3
-        assert len(N) == 3
-        self.N = N
-        self.Nf = N[2]//2+1
-        self.Nfp = int(padsize*N[2]//2+1)
-        self.comm = comm
+        assert len(L) == 3 and len(N) == 3
         self.float, self.complex, self.mpitype = datatypes(precision)
-        self.communication = communication
-        self.num_processes = comm.Get_size()
-        self.rank = comm.Get_rank()
-        self.Np = N // self.num_processes
-        self.L = L.astype(self.float)
+        self.N, self.L = N, L.astype(self.float)
+        self.comm, self.communication = comm, communication
+        self.num_processes, self.rank = comm.Get_size(), comm.Get_rank()
+        self.padsize, self.threads, self.planner_effort = padsize, threads, planner_effort
+        self.Np = N // self.num_processes          # points per rank along every axis (x in real, y in spectral space)
+        self.Nf = N[2] // 2 + 1                    # kz entries of the half spectrum ...
+        self.Nfp = int(padsize * N[2] // 2 + 1)    # ... and of the padded one
         self.dealias = np.zeros(0)
-        self.padsize = padsize
-        self.threads = threads
-        self.planner_effort = planner_effort
         self.work_arrays = work_arrays()
-        if not self.num_processes in [2**i for i in range(int(np.log2(N[0]))+1)]:
-            raise IOError("Number of cpus must be in ",
-                          [2**i for i in range(int(np.log2(N[0]))+1)])
+        legal = [2 ** i for i in range(int(np.log2(N[0])) + 1)]
+        if self.num_processes not in legal:        # slab.py:89-91
+            raise IOError("Number of cpus must be in ", legal)
         self._create_plan(self._plan_kind, N, self.num_processes, self.rank, comm=comm)
 
+    # ---- shapes (slab.py:98-127, 487-489)
     def real_shape(self):
-        """The local shape of the real data"""
+        """Local real block: this rank's x planes, all of y and z."""
         return (self.Np[0], self.N[1], self.N[2])
 
     def complex_shape(self):
-        """The local shape of the complex data"""
+        """Local spectral block: all of kx, this rank's ky range, the half spectrum in kz."""
         return (self.N[0], self.Np[1], self.Nf)
 
     def complex_shape_T(self):
-        """The local transposed shape of the complex data"""
+        """The spectral block before the global transpose (x still local)."""
         return (self.Np[0], self.N[1], self.Nf)
 
     def global_real_shape(self):
-        """Global size of problem in real physical space"""
         return (self.N[0], self.N[1], self.N[2])
 
     def global_complex_shape(self, padsize=1.):
-        """Global size of problem in complex wavenumber space"""
-        return (int(padsize*self.N[0]), int(padsize*self.N[1]),
-                int(padsize*self.N[2]//2+1))
+        return (int(padsize * self.N[0]), int(padsize * self.N[1]), int(padsize * self.N[2] // 2 + 1))
+
+    def real_shape_padded(self):
+        return G.padded(self.real_shape(), self.padsize)
 
     def work_shape(self, dealias):
-        """Shape of work arrays used in convection with dealiasing (``slab.py:118-127``)."""
-        if dealias == '3/2-rule':
-            return self.real_shape_padded()
-        else:
-            return self.real_shape()
+        """Real-space shape a transform with this dealias mode works on."""
+        return self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
 
+    # ---- slices into the global arrays (slab.py:129-144): every step is 1
     def real_local_slice(self, padsize=1):
-        """Local slice in real space of the input array (``slab.py:129-138``)."""
-        return (slice(int(padsize*self.rank*self.Np[0]),
-                      int(padsize*(self.rank+1)*self.Np[0]), 1),
-                slice(0, int(padsize*self.N[1]), 1),
-                slice(0, int(padsize*self.N[2]), 1))
+        return (G.block(self.Np[0], self.rank, padsize), G.whole(self.N[1], padsize), G.whole(self.N[2], padsize))
 
     def complex_local_slice(self):
-        """Local slice of complex return array (``slab.py:140-144``)."""
-        return (slice(0, self.N[0], 1),
-                slice(self.rank*self.Np[1], (self.rank+1)*self.Np[1], 1),
-                slice(0, self.Nf, 1))
+        return (G.whole(self.N[0]), G.block(self.Np[1], self.rank), G.whole(self.Nf))
+
+    # ---- meshes (slab.py:146-197)
+    def _k_axes(self):
+        return [G.frequencies(self.N[0]), G.frequencies(self.N[1]), G.frequencies(self.N[2], half=True)]
 
     def complex_local_wavenumbers(self):
-        """Returns local wavenumbers of complex space"""
-        return (fftfreq(self.N[0], 1./self.N[0]).astype(self.float),
-                fftfreq(self.N[1], 1./self.N[1])[self.complex_local_slice()[1]].astype(self.float),
-                rfftfreq(self.N[2], 1./self.N[2]).astype(self.float))
+        kx, ky, kz = self._k_axes()
+        return (kx.astype(self.float), ky[self.complex_local_slice()[1]].astype(self.float), kz.astype(self.float))
 
     def get_local_mesh(self):
-        """Returns the local decomposed physical mesh (``slab.py:152-160``)."""
-        X = list(np.ogrid[self.rank*self.Np[0]:(self.rank+1)*self.Np[0],
-                          :self.N[1], :self.N[2]])
-        X[0] = (X[0]*self.L[0]/self.N[0]).astype(self.float)
-        X[1] = (X[1]*self.L[1]/self.N[1]).astype(self.float)
-        X[2] = (X[2]*self.L[2]/self.N[2]).astype(self.float)
-        X = [np.broadcast_to(x, self.real_shape()) for x in X]
-        return X
+        """Physical coordinates of the local block as three broadcast views."""
+        sl = (G.block(self.Np[0], self.rank), G.whole(self.N[1]), G.whole(self.N[2]))
+        return G.sparse_physical_mesh(sl, self.N, self.L, self.float, self.real_shape())
 
     def get_local_wavenumbermesh(self, scaled=False, broadcast=False, eliminate_highest_freq=False):
-        """Returns (scaled) local decomposed wavenumbermesh (``slab.py:162-189``)."""
+        """Sparse (or broadcast) wavenumber mesh of the local spectral block, optionally scaled by 2 pi / L."""
         kx, ky, kz = self.complex_local_wavenumbers()
         if eliminate_highest_freq:
-            ky = fftfreq(self.N[1], 1./self.N[1].astype(self.float))
-            for i, k in enumerate((kx, ky, kz)):
-                if self.N[i] % 2 == 0:
-                    k[self.N[i]//2] = 0
+            ky = G.frequencies(self.N[1])   # the whole axis: the Nyquist entry may lie outside this rank's range
+            G.drop_nyquist((kx, ky, kz), self.N)
             ky = ky[self.complex_local_slice()[1]]
-
-        Ks = list(np.meshgrid(kx, ky, kz, indexing='ij', sparse=True))
-        for i in range(3):
-            Ks[i] = Ks[i].astype(self.float)
+        K = [k.astype(self.float) for k in G.sparse_spectral_mesh((kx, ky, kz))]
         if scaled:
-            Lp = 2*np.pi/self.L
-            for i in range(3):
-                Ks[i] *= Lp[i]
-        K = Ks
-        if broadcast is True:
-            K = [np.broadcast_to(k, self.complex_shape()) for k in Ks]
-        return K
+            for k, f in zip(K, 2 * np.pi / self.L):
+                k *= f
+        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
 
     def get_dealias_filter(self):
-        """Filter for dealiasing nonlinear convection (``slab.py:191-197``).  The transforms apply
-        this mask inside the first inverse FFT pass; the array is returned for callers only."""
-        K = self.get_local_wavenumbermesh()
-        kmax = 2./3.*(self.N//2+1)
-        dealias = np.array((abs(K[0]) < kmax[0])*(abs(K[1]) < kmax[1])*
-                           (abs(K[2]) < kmax[2]), dtype=np.uint8)
-        return dealias
+        """2/3-rule mask on the local spectral block.  The transforms apply it inside the first inverse FFT
+        pass (mask bands of the load index map); the array is for callers that filter spectra themselves."""
+        return G.two_thirds_mask(self.get_local_wavenumbermesh(), self.N)
 
     def ifftn(self, fu, u, dealias=None):
         """Inverse transform (``slab.py:214-346``): fu of complex_shape() -> u of real_shape(), or
@@ -163,10 +134,6 @@ class R2C(Transform):
         else:
             ushape = self.real_shape()
         return self._run(0, u, fu, dealias, ushape, self.float, self.complex_shape(), self.complex)
-
-    def real_shape_padded(self):
-        """The local shape of the real data"""
-        return (int(self.padsize*self.Np[0]), int(self.padsize*self.N[1]), int(self.padsize*self.N[2]))
 
     # The reference's intermediate shapes (complex_shape_padded_0 ... _I) and its copy_to_padded /
     # copy_from_padded helpers (slab.py:491-536) have no counterpart here: the pad / truncate copies are index
@@ -209,15 +176,11 @@ class C2C(R2C):
         return (int(padsize*self.N[0]), int(padsize*self.N[1]), int(padsize*self.N[2]))
 
     def transformed_local_wavenumbers(self):
-        return (fftfreq(self.N[0], 1./self.N[0]),
-                fftfreq(self.N[1], 1./self.N[1])[self.transformed_local_slice()[1]],
-                fftfreq(self.N[2], 1./self.N[2]))
+        kx, ky, kz = (G.frequencies(n) for n in self.N)
+        return (kx, ky[self.transformed_local_slice()[1]], kz)
 
     def get_dealias_filter(self):
-        kx, ky, kz = self.transformed_local_wavenumbers()
-        K = np.meshgrid(kx, ky, kz, indexing='ij', sparse=True)
-        kmax = 2./3.*(self.N//2+1)
-        return np.array((abs(K[0]) < kmax[0])*(abs(K[1]) < kmax[1])*(abs(K[2]) < kmax[2]), dtype=np.uint8)
+        return G.two_thirds_mask(G.sparse_spectral_mesh(self.transformed_local_wavenumbers()), self.N)
 
     def ifftn(self, fu, u, dealias=None):
         """``slab.py:587-698``: fu of transformed_shape() -> u of original_shape() [3/2-rule:
