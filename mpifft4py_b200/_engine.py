@@ -97,6 +97,8 @@ class Transform(object):
                 ok = False
                 err = next(r[2] for r in replies if not r[0]) or err
             if not all(comm.allgather(ok)):
+                if os.environ.get("B200FFT_STRICT_TRANSPORT") == "1":  # tests: never trade the asked-for transport silently
+                    raise _lib.B200FFTError("peer-mapped transport '%s' unavailable: %s" % (choice, err))
                 import warnings
                 warnings.warn("mpifft4py_b200: copy-engine transport unavailable (%s); using NCCL send/recv" % err)
                 if h:

@@ -231,8 +231,50 @@ def run_known_answer_kernels(comm):
         raise SystemExit("Taylor-Green known answer (kernels): got %.12f, expected %.12f" % (k, sds.KNOWN_ANSWER))
 
 
+def shared_gpu(comm):
+    """All ranks on ONE GPU (tests/test_gpu_multi.py::test_multi_rank_shared_gpu): what a single-GPU box can say
+    about the distributed half of the path.  The ranks are separate processes with separate CUDA contexts on the same
+    device; the copy-engine and fused-store transports work unchanged there (CUDA IPC mappings of the peers' work
+    buffers and flag words, cudaMemcpyAsync pushes, stream memory operations) -- only NCCL refuses two ranks on one
+    device, so torch.distributed runs over gloo and the NCCL transport is left to the multi-GPU runs.  Plan programs,
+    per-peer chunk layouts, sub-communicator addressing, pipelines, sequence flags and credits are the very code an
+    8-GPU box executes; what this mode cannot show is NVLink."""
+    P = comm.Get_size()
+    N = (32, 64, 128)
+    for prec in ("double", "single"):
+        run_3d(comm, "slab", N, prec, transport="p2p")
+    run_3d(comm, "slab", N, "double", communication="Alltoall", transport="p2p", pipeline="kz")
+    run_3d(comm, "slab", (64, 64, 64), "double", transport="store")
+    run_line(comm, (64, 128), "double", transport="p2p")
+    run_line(comm, (64, 128), "single", transport="store")
+    run_c2c(comm, N, "double", transport="p2p")
+    if P >= 4:
+        grids = [None] + ([2] if P == 8 else [])
+        for al in "XY":
+            for P1 in grids:
+                for cm in ("Alltoall", "Alltoallw", "AlltoallN"):
+                    run_3d(comm, "pencil", N, "double", al, P1, cm, transport="p2p")
+            run_3d(comm, "pencil", N, "single", al, None, "Alltoall", transport="p2p", chunks=2)
+    note(comm, "goldens")
+    run_golden(comm)
+    note(comm, "known answer")
+    run_known_answer(comm)
+    run_known_answer_kernels(comm)
+    note(comm, "done")
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if "--share-gpu" in sys.argv:
+        os.environ["B200FFT_STRICT_TRANSPORT"] = "1"  # a transport that cannot be set up is an error, not an NCCL fallback
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+        comm = world()
+        shared_gpu(comm)
+        comm.barrier()
+        dist.destroy_process_group()
+        print("GPU_WORKER_OK", local)
+        return
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = world()

@@ -1,5 +1,7 @@
-"""Multi-GPU parity (NCCL, one process per GPU) -- runs where the box has >= 2 GPUs."""
+"""Multi-rank parity on the device: one process per GPU (copy engines + NCCL) where the box has >= 2 GPUs, and
+-- on ANY box with a GPU -- 2 / 4 / 8 rank processes sharing GPU 0 over the peer-mapped transports."""
 import os
+import signal
 import socket
 import subprocess
 import sys
@@ -29,4 +31,35 @@ def test_multi_gpu_parity(nproc):
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     text = out.stdout.decode("utf-8", "replace")
     assert out.returncode == 0, text[-6000:]
+    assert text.count("GPU_WORKER_OK") == nproc, text[-6000:]
+
+
+def run_group(cmd, timeout):
+    """Run a torchrun command in its own process group; on a timeout the whole group goes (a hung rank must not
+    keep the GPU busy behind the test's back).  Returns (returncode or None on timeout, output text)."""
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+        return proc.returncode, out.decode("utf-8", "replace")
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        out, _ = proc.communicate()
+        return None, out.decode("utf-8", "replace")
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_multi_rank_shared_gpu(nproc):
+    """The distributed transforms with all ranks on GPU 0 (separate processes, CUDA IPC between them): every class /
+    alignment / communication layout / dealias mode against the oracle, the goldens of the unmodified reference with
+    this rank count, both known answers -- through the copy-engine and fused-store transports (gpu_dist_worker.py:
+    shared_gpu).  Needs one GPU, so the single-GPU driver run covers slab P > 1, pencil and line too."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "gpu_dist_worker.py"), "--share-gpu"]
+    rc, text = run_group(cmd, 300)
+    assert rc is not None, "timed out:\n" + text[-6000:]
+    assert rc == 0, text[-6000:]
     assert text.count("GPU_WORKER_OK") == nproc, text[-6000:]
