@@ -241,13 +241,15 @@ def shared_gpu(comm):
     8-GPU box executes; what this mode cannot show is NVLink."""
     P = comm.Get_size()
     N = (32, 64, 128)
-    for prec in ("double", "single"):
-        run_3d(comm, "slab", N, prec, transport="p2p")
-    run_3d(comm, "slab", N, "double", communication="Alltoall", transport="p2p", pipeline="kz")
-    run_3d(comm, "slab", (64, 64, 64), "double", transport="store")
+    run_3d(comm, "slab", N, "double", transport="p2p")
     run_line(comm, (64, 128), "double", transport="p2p")
-    run_line(comm, (64, 128), "single", transport="store")
-    run_c2c(comm, N, "double", transport="p2p")
+    if P < 8:  # (eight contexts on one device take turns: the 8-rank run keeps to what only it can show -- the 4x2 and
+        #         2x4 pencil grids and the 8-rank goldens)
+        run_3d(comm, "slab", N, "single", transport="p2p")
+        run_3d(comm, "slab", N, "double", communication="Alltoall", transport="p2p", pipeline="kz")
+        run_3d(comm, "slab", (64, 64, 64), "double", transport="store")
+        run_line(comm, (64, 128), "single", transport="store")
+        run_c2c(comm, N, "double", transport="p2p")
     if P >= 4:
         grids = [None] + ([2] if P == 8 else [])
         for al in "XY":
@@ -258,7 +260,8 @@ def shared_gpu(comm):
     note(comm, "goldens")
     run_golden(comm)
     note(comm, "known answer")
-    run_known_answer(comm)
+    if P < 8:
+        run_known_answer(comm)
     run_known_answer_kernels(comm)
     note(comm, "done")
 

@@ -50,16 +50,21 @@ def run_group(cmd, timeout):
         return None, out.decode("utf-8", "replace")
 
 
-@pytest.mark.parametrize("nproc", [2, 4, 8])
+def shared_gpu_run(nproc, timeout=300):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "gpu_dist_worker.py"), "--share-gpu"]
+    rc, text = run_group(cmd, timeout)
+    assert rc is not None, "timed out:\n" + text[-6000:]
+    assert rc == 0, text[-6000:]
+    assert text.count("GPU_WORKER_OK") == nproc, text[-6000:]
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
 def test_multi_rank_shared_gpu(nproc):
     """The distributed transforms with all ranks on GPU 0 (separate processes, CUDA IPC between them): every class /
     alignment / communication layout / dealias mode against the oracle, the goldens of the unmodified reference with
     this rank count, both known answers -- through the copy-engine and fused-store transports (gpu_dist_worker.py:
-    shared_gpu).  Needs one GPU, so the single-GPU driver run covers slab P > 1, pencil and line too."""
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "gpu_dist_worker.py"), "--share-gpu"]
-    rc, text = run_group(cmd, 300)
-    assert rc is not None, "timed out:\n" + text[-6000:]
-    assert rc == 0, text[-6000:]
-    assert text.count("GPU_WORKER_OK") == nproc, text[-6000:]
+    shared_gpu).  Needs one GPU, so the single-GPU driver run covers slab P > 1, pencil and line too.  Both passed on a
+    B200 (profiles/r02_shared_gpu/); the 8-rank run (4x2 and 2x4 pencil grids) is tests/test_zz_shared_gpu_8.py."""
+    shared_gpu_run(nproc)
