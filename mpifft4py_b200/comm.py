@@ -85,9 +85,12 @@ class TorchComm(object):
         if isinstance(arr, torch.Tensor):
             self._dist.broadcast(arr, src=self._ranks[root], group=self.group)
             return
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self._device())
+        flat = np.ascontiguousarray(arr)
+        if np.iscomplexobj(flat):  # as pairs of reals: not every backend broadcasts complex tensors
+            flat = flat.view(flat.real.dtype)
+        t = torch.from_numpy(flat).to(self._device())
         self._dist.broadcast(t, src=self._ranks[root], group=self.group)
-        arr[...] = t.cpu().numpy().reshape(arr.shape)
+        arr[...] = t.cpu().numpy().view(arr.dtype).reshape(arr.shape)
 
     def barrier(self):
         self._dist.barrier(group=self.group)

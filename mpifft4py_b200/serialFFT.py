@@ -193,9 +193,11 @@ def irfftn(a, b=None, axes=(0, 1, 2), overwrite_input=False, threads=1, planner_
 
 
 # ------------------------------------------------------------------------------------------------
-# dct (serialFFT/pyfftw_fft.py:205-244, numpy_fft.py:11-22): types 2 and 3 with scipy.fftpack's
-# unnormalised convention, through ONE complex FFT of the engine along `axis` (Makhoul's reordering);
-# complex input is transformed part by part like upstream (real and imaginary parts share the FFT).
+# dct (serialFFT/pyfftw_fft.py:205-244, numpy_fft.py:11-22): types 1 to 4 with scipy.fftpack's unnormalised
+# convention.  Types 2 and 3: ONE complex FFT of the engine along `axis` (Makhoul's reordering), real and
+# imaginary parts of a complex input sharing it; type 1: the FFT of the even extension (length 2(N-1): the
+# Chebyshev-Gauss-Lobatto sizes N = 2^k + 1 have kernels); type 4: a pre- and post-twiddled FFT of length 2N.
+# Complex input is transformed part by part like upstream.
 # Not on the R2C hot path (no caller in slab / pencil / line); provided because the function table of
 # the reference's serialFFT module has it.
 # ------------------------------------------------------------------------------------------------
@@ -224,8 +226,26 @@ def _dct_core(x, type, axis, fft_inplace):
         y = torch.empty_like(w)
         y[..., 0::2] = w[..., :(N + 1) // 2]
         y[..., 1::2] = w.flip(-1)[..., :N // 2]
+    elif type == 1:
+        # even extension [x0 .. x_{N-1}, x_{N-2} .. x1] of length 2(N-1): its FFT is real for real input, so the
+        # real and the imaginary part of a complex x come out of ONE transform as the real and imaginary part
+        assert N >= 2, "dct type 1 needs at least two points"
+        v = torch.cat([x, x[..., 1:N - 1].flip(-1)], dim=-1).contiguous()
+        y = fft_inplace(v, v.dim() - 1, False)[..., :N]
+    elif type == 4:
+        # y[k] = 2 Re( exp(-i pi (2k+1) / 4N) * FFT_2N(x[n] exp(-i pi n / 2N), zero-padded)[k] ); the pre-twiddled
+        # sequence has no symmetry to separate two real inputs with, so a complex x takes two transforms
+        pre = torch.complex(torch.cos(ang), -torch.sin(ang))                 # exp(-i pi n / 2N)
+        post = torch.complex(torch.cos(ang + torch.pi / (4 * N)), -torch.sin(ang + torch.pi / (4 * N)))
+
+        def part(r):
+            w = torch.cat([r * pre, torch.zeros_like(x)], dim=-1).contiguous()
+            return 2 * (fft_inplace(w, w.dim() - 1, False)[..., :N] * post).real
+
+        yr = part(x.real)
+        y = torch.complex(yr, part(x.imag) if bool((x.imag != 0).any()) else torch.zeros_like(yr))
     else:
-        raise NotImplementedError("dct type %r: types 2 and 3 are implemented" % (type,))
+        raise NotImplementedError("dct type %r: scipy.fftpack has types 1 to 4" % (type,))
     return y.movedim(-1, axis)
 
 

@@ -24,6 +24,12 @@ def main():
     a = np.arange(12, dtype=np.float64).reshape(3, 4) if r == 0 else np.zeros((3, 4))
     comm.Bcast(a, root=0)
     assert np.array_equal(a, np.arange(12).reshape(3, 4))
+    z = (np.arange(6) * (1 - 2j)).reshape(2, 3) if r == 0 else np.zeros((2, 3), dtype=complex)   # complex arrays too
+    comm.Bcast(z, root=0)                                                                          # (tests/test_FFT.py:78)
+    assert np.array_equal(z, (np.arange(6) * (1 - 2j)).reshape(2, 3))
+    z32 = np.full((4,), 1 + 1j, dtype=np.complex64) if r == 0 else np.zeros((4,), dtype=np.complex64)
+    comm.Bcast(z32, root=0)
+    assert z32.dtype == np.complex64 and np.all(z32 == 1 + 1j)
     assert comm.bcast({"id": 7} if r == 0 else None, root=0) == {"id": 7}
     tot = comm.reduce(float(r + 1))
     if r == 0:

@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 
 import mpifft4py_b200 as m  # noqa: E402
 import oracle  # noqa: E402
+import ref_procedures  # noqa: E402
 from mpifft4py_b200.comm import world  # noqa: E402
 
 TOL = {"double": 1e-12, "single": 1e-5}
@@ -259,10 +260,12 @@ def shared_gpu(comm):
             run_3d(comm, "pencil", N, "single", al, None, "Alltoall", transport="p2p", chunks=2)
     note(comm, "goldens")
     run_golden(comm)
-    note(comm, "known answer")
+    # the reference's own test procedures (tests/test_FFT.py) on this communicator: all 16 + 2 + 2 fixture parameters
+    ref_procedures.run_all(comm, lambda msg: note(comm, msg))
     if P < 8:
+        note(comm, "known answer")
         run_known_answer(comm)
-    run_known_answer_kernels(comm)
+        run_known_answer_kernels(comm)
     note(comm, "done")
 
 
@@ -336,13 +339,14 @@ def main():
             run_3d(comm, "pencil", N, "double", al, None, "Alltoallw", transport="nccl")
     note(comm, "goldens")
     run_golden(comm)
+    ref_procedures.run_all(comm, lambda msg: note(comm, msg))
     note(comm, "known answer")
     run_known_answer(comm)
     run_known_answer_kernels(comm)
     note(comm, "done")
     comm.barrier()
     dist.destroy_process_group()
-    print("GPU_WORKER_OK", comm.Get_rank() if False else local)
+    print("GPU_WORKER_OK", local)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,4 @@
-"""serialFFT.dct (types 2 and 3, scipy.fftpack convention; pyfftw_fft.py:205-244): the reordering / rotation
+"""serialFFT.dct (types 1 to 4, scipy.fftpack convention; pyfftw_fft.py:205-244): the reordering / rotation
 around the engine's complex FFT is checked on the CPU with torch.fft standing in for the kernel, the whole
 function on the device."""
 import numpy as np
@@ -13,8 +13,8 @@ def _torch_fft(t, axis, inverse):
     return torch.fft.ifft(t, dim=axis) if inverse else torch.fft.fft(t, dim=axis)
 
 
-@pytest.mark.parametrize("type", [2, 3])
-@pytest.mark.parametrize("N,axis", [(8, 0), (16, 1), (12, 2), (48, 1), (7, 0)])
+@pytest.mark.parametrize("type", [1, 2, 3, 4])
+@pytest.mark.parametrize("N,axis", [(8, 0), (16, 1), (12, 2), (48, 1), (7, 0), (2, 1), (33, 2)])
 def test_dct_reordering_against_scipy(N, axis, type):
     rng = np.random.default_rng(N + type)
     shape = [3, 4, 5]
@@ -28,16 +28,18 @@ def test_dct_reordering_against_scipy(N, axis, type):
 
 def test_dct_type_errors():
     with pytest.raises(NotImplementedError):
-        serialFFT._dct_core(torch.zeros(8, dtype=torch.complex128), 1, 0, _torch_fft)
+        serialFFT._dct_core(torch.zeros(8, dtype=torch.complex128), 5, 0, _torch_fft)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("type", [2, 3])
+@pytest.mark.parametrize("type", [1, 2, 3, 4])
 @pytest.mark.parametrize("prec", ["double", "single"])
 def test_dct_on_device(prec, type):
     rt, ct, tol = (np.float64, np.complex128, 1e-12) if prec == "double" else (np.float32, np.complex64, 2e-5)
     rng = np.random.default_rng(5)
-    for shape, axis in (((64, 6, 5), 0), ((4, 96, 7), 1), ((3, 5, 1024), 2)):
+    # (type 1 runs a complex FFT of length 2(N-1): the Gauss-Lobatto sizes 2^k + 1 and 3*2^k + 1)
+    cases = (((65, 6, 5), 0), ((4, 97, 7), 1), ((3, 5, 1025), 2)) if type == 1 else (((64, 6, 5), 0), ((4, 96, 7), 1), ((3, 5, 1024), 2))
+    for shape, axis in cases:
         x = rng.standard_normal(shape).astype(rt)
         ref = scipy_dct(x.astype(np.float64), type=type, axis=axis)
         got = serialFFT.dct(x, np.zeros(shape, dtype=rt), type=type, axis=axis)

@@ -1,0 +1,134 @@
+"""tests/ref_procedures.py (the reference's own test procedures restated for this engine) checked on the CPU: the
+ORACLE stands in for the device -- ranks are threads, every transform call of the classes is answered by the oracle's
+all-ranks function, the serial functions by numpy.fft.  What this pins down without a GPU: the procedures' data flow,
+slices and tolerances are satisfiable by an implementation that reproduces the reference (the oracle is pinned to the
+unmodified reference's goldens), for every fixture parameter at 1, 2 and 4 ranks.  The device runs are
+tests/test_gpu_reference_procedures.py (P = 1) and tests/gpu_dist_worker.py (P > 1)."""
+import threading
+
+import numpy as np
+import pytest
+
+import mpifft4py_b200 as m
+import oracle
+import ref_procedures as rp
+from mpifft4py_b200 import _engine, line, pencil, slab
+
+
+class ThreadWorld(object):
+    def __init__(self, P):
+        self.P = P
+        self.barrier = threading.Barrier(P)
+        self.slots = [None] * P
+        self.failed = []
+
+
+class ThreadComm(object):
+    """The communicator surface the classes and the procedures use, ranks being threads of one process."""
+
+    def __init__(self, world, rank, members=None):
+        self.world, self.members = world, members or list(range(world.P))
+        self.wrank = rank
+
+    def Get_size(self):
+        return len(self.members)
+
+    def Get_rank(self):
+        return self.members.index(self.wrank)
+
+    def allgather_world(self, obj):
+        w = self.world
+        w.slots[self.wrank] = obj
+        w.barrier.wait(timeout=120)
+        out = list(w.slots)
+        w.barrier.wait(timeout=120)
+        return out
+
+    def Bcast(self, buf, root=0):
+        assert len(self.members) == self.world.P
+        src = self.allgather_world(buf if self.wrank == root else None)[root]
+        if self.wrank != root:
+            buf[...] = src
+        self.world.barrier.wait(timeout=120)  # root keeps its array untouched until everybody has copied
+
+    def Split(self, color=0, key=0):
+        colors = self.allgather_world(int(color))
+        return ThreadComm(self.world, self.wrank, [r for r in range(self.world.P) if colors[r] == int(color)])
+
+
+def oracle_run(self, inverse, src, dst, dealias, src_shape, src_dtype, dst_shape, dst_dtype):
+    """Stand-in for Transform._run: all ranks hand in their block, the oracle transforms them together."""
+    assert tuple(src.shape) == tuple(int(s) for s in src_shape) and tuple(dst.shape) == tuple(int(s) for s in dst_shape)
+    comm = self.comm
+    P = comm.Get_size()
+    prec = "double" if self.float is np.float64 else "single"
+    N = tuple(int(n) for n in self.N)
+    blocks = comm.allgather_world(np.array(src)) if P > 1 else [np.array(src)]
+    kw = dict(dealias=dealias, precision=prec)
+    if isinstance(self, slab.C2C):
+        fn = oracle.slab.c2c_ifftn if inverse else oracle.slab.c2c_fftn
+    elif isinstance(self, slab.R2C):
+        fn = oracle.slab.ifftn if inverse else oracle.slab.fftn
+    elif isinstance(self, line.R2C):
+        fn = oracle.line.ifft2 if inverse else oracle.line.fft2
+        if not inverse:
+            kw["exact"] = True  # the engine transforms the Nyquist column exactly (no pack trick)
+    else:
+        fn = oracle.pencil.ifftn if inverse else oracle.pencil.fftn
+        kw.update(alignment="X" if isinstance(self, pencil.R2CX) else "Y", P1=self.P1, communication=self.communication)
+    dst[...] = fn(blocks, N, P, **kw)[comm.Get_rank() if P > 1 else 0]
+    return dst
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    monkeypatch.setattr(_engine.Transform, "_run", oracle_run)
+
+    def serial(npfn):
+        def f(a, b, axes):
+            b[...] = npfn(a, axes=axes)
+            return b
+        return f
+
+    for name, fn in (("rfftn", np.fft.rfftn), ("irfftn", np.fft.irfftn), ("rfft2", np.fft.rfft2), ("irfft2", np.fft.irfft2),
+                     ("fftn", np.fft.fftn), ("ifftn", np.fft.ifftn)):
+        monkeypatch.setattr(m, name, serial(fn))
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_reference_procedures_hold_for_the_oracle(oracle_backend, P):
+    if P == 1:
+        assert rp.run_all(m.comm.COMM_SELF) == 2 * 6 + 2
+        return
+    world = ThreadWorld(P)
+    counts = [None] * P
+
+    def rank_main(r):
+        try:
+            counts[r] = rp.run_all(ThreadComm(world, r))
+        except BaseException as e:  # noqa: BLE001 - reported below; the barrier is broken so the other ranks stop too
+            world.failed.append((r, repr(e)))
+            world.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    real = [f for f in world.failed if "BrokenBarrierError" not in f[1]]
+    assert not world.failed, real or world.failed
+    expect = 2 * ((16 if P >= 4 else 4) + 2) + 2
+    assert counts == [expect] * P
+
+
+def test_parameter_lists_are_the_reference_fixtures():
+    """tests/test_FFT.py:24-31: 4 slab parameters, 12 pencil ones from four ranks on; :48, :54."""
+    three_d, lines, c2cs = rp.params(4)
+    assert len(three_d) == 16 and len(set(three_d)) == 16 and len(rp.params(2)[0]) == 4
+    assert sorted(three_d) == sorted(["slabas", "slabad", "slabws", "slabwd", "pencilsys", "pencilsyd", "pencilnys", "pencilnyd",
+                                      "pencilsxd", "pencilsxs", "pencilnxd", "pencilnxs", "pencilaxd", "pencilaxs", "pencilayd",
+                                      "pencilays"])
+    F = rp.make("pencilnyd", type("C", (), {"Get_size": lambda s: 4, "Get_rank": lambda s: 0,
+                                            "Split": lambda s, c=0, k=0: type("S", (), {"Get_size": lambda t: 2, "Get_rank": lambda t: 0})()})())
+    assert F.communication == "AlltoallN" and type(F).__name__ == "R2CY" and F.float is np.float64
+    assert lines == ["lines", "lined"] and c2cs == ["c2cd", "c2cs"]
