@@ -386,6 +386,103 @@ def forward_parity(F, kind, N, dealias, fwd, u, fu, torch):
     return float(torch.sqrt(num / den).item())
 
 
+def other_workload_names(main, P):
+    """The BASELINE.json configurations besides the headline one that this rank count can run:
+    config 4 (slab 1024^3 double, 3/2-rule), config 2 (slab 256^3 single), config 5a (line 16384^2 single), and from four
+    ranks on the pencil ones -- 1024^3 double 'X', config 5b (pencil 'Y' 2048^3 single), config 3 (pencil 'X' 512^3 double
+    on a 2 x 4 grid: eight ranks)."""
+    names = ["slab1024_f64_32", "slab256_f32", "line16384_f32"]
+    if P >= 4:
+        names += ["pencilX1024_f64", "pencilY2048_f32"]
+    if P == 8:
+        names += ["pencilX512_f64"]
+    return [n for n in names if n != main]
+
+
+def quick_measure(m, comm, name, steps, torch, dist, P, rank):
+    """Short device-resident measurement of one more workload (the loop of scripts/ab_multi.py, which produced the
+    multi-GPU tables of DESIGN.md): forward parity against the closed form, 3 warm-up round trips, `steps` timed ones
+    (CUDA events on the launching stream, L2 flushed between steps where the arrays would fit it, max over ranks),
+    then one timed transform each way for the per-phase sums."""
+    kind, N, prec, dealias, kw = WORKLOADS[name]
+    F = make_transform(m, comm, name)
+    fwd, inv = (F.fft2, F.ifft2) if kind == "line" else (F.fftn, F.ifftn)
+    rshape = tuple(int(s) for s in (F.real_shape_padded() if dealias == "3/2-rule" else F.real_shape()))
+    cshape = tuple(int(s) for s in F.complex_shape())
+    rdt = torch.float64 if prec == "double" else torch.float32
+    cdt = torch.complex128 if prec == "double" else torch.complex64
+    g = torch.Generator(device="cuda").manual_seed(4321 + rank)
+    u = torch.empty(rshape, dtype=rdt, device="cuda")
+    fu = torch.empty(cshape, dtype=cdt, device="cuda")
+    u2 = torch.empty_like(u)
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if P > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if P > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fe = None
+    if not (kind == "line" and dealias):
+        fe = reduce_max(forward_parity(F, kind, N, dealias, fwd, u, fu, torch))
+    u.copy_(torch.rand(rshape, dtype=rdt, device="cuda", generator=g))
+    for _ in range(3):
+        fwd(u, fu, dealias)
+        inv(fu, u2, dealias)
+    rt = reduce_max(float((torch.linalg.vector_norm(u2 - u) / torch.linalg.vector_norm(u)).item()))
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if np.prod(N) * 4 <= 1 << 30 else None
+    st = torch.cuda.current_stream()
+    barrier()
+    total = 0.0
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            fwd(u, fu, dealias)
+            inv(fu, u2, dealias)
+        e1.record(st)
+        barrier()
+        total = e0.elapsed_time(e1)
+    else:
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            fwd(u, fu, dealias)
+            inv(fu, u2, dealias)
+            e1.record(st)
+            barrier()
+            total += e0.elapsed_time(e1)
+    ms = reduce_max(total / steps)
+    F.set_timing(True)
+    fft_ms = ex_ms = ex_bytes = 0.0
+    for call, a, b in ((fwd, u, fu), (inv, fu, u2)):
+        call(a, b, dealias)
+        torch.cuda.synchronize()
+        for sname, sms, sbytes, _, _ in F.last_steps():
+            if sname == "exchange":
+                ex_ms += sms
+                ex_bytes += sbytes
+            else:
+                fft_ms += sms
+    F.set_timing(False)
+    gshape = tuple(int(1.5 * n) if dealias == "3/2-rule" else n for n in N)
+    cfg = describe(name, P)
+    out = {"name": name, "workload": cfg["workload"], "decomposition": cfg["decomposition"], "l2": cfg["l2"], "steps": steps, "warmup": 3,
+           "ms_per_step": round(ms, 4), "value": round(flops_roundtrip(gshape) / (ms * 1e-3) / 1e9, 1), "unit": UNIT,
+           "dtype": "f64" if prec == "double" else "f32", "forward_rel_l2": fe, "roundtrip_rel_l2": rt,
+           "sum_fft_ms": round(fft_ms, 4), "sum_exchange_ms": round(ex_ms, 4),
+           "exchange_GBps_per_direction": round(ex_bytes / ex_ms / 1e6, 1) if ex_ms > 0 else None,
+           "transport": getattr(F, "transport_used", None) if P > 1 else None, "workspace_bytes": F.workspace_bytes()}
+    barrier()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -607,6 +704,31 @@ def run_ours(args):
         ex = [s for s in F.last_steps() if s[0] == "exchange"]
         cfg["exchange"] = {"transport": getattr(F, "transport_used", "nccl"),
                            "pipelined_chunks": len(ex) // max(1, len({s[4] for s in ex}))}
+    workspace = F.workspace_bytes()
+
+    # ---- the other BASELINE configurations this rank count can run: short device-resident lines with forward parity ----
+    others = None
+    if not args.no_others:
+        # everything of the headline workload goes first: its arrays, staging buffers, pinned host arrays and plan
+        hu = hf = u = fu = u2 = flush = fwd = inv = F = None   # (fwd / inv are bound methods: they hold the object)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        others, t_start = [], time.perf_counter()
+        for oname in other_workload_names(name, P):
+            spent = torch.tensor([time.perf_counter() - t_start], dtype=torch.float64, device="cuda")
+            if P > 1:
+                dist.all_reduce(spent, op=dist.ReduceOp.MAX)  # every rank takes the same decision
+            if float(spent.item()) > args.others_budget:
+                others.append({"name": oname, "skipped": "time budget of the extra workloads used up"})
+                continue
+            try:
+                others.append(quick_measure(m, comm, oname, args.others_steps, torch, dist, P, rank))
+            except Exception as e:  # noqa: BLE001 - the headline line must not depend on the extras
+                others.append({"name": oname, "error": repr(e)[:300]})
+            gc.collect()
+            torch.cuda.empty_cache()
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -616,7 +738,7 @@ def run_ours(args):
                "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
                "kernels_per_transform": int(k1), "nccl_groups_per_transform": int(x1),
                "roofline": roofline, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
-               "workspace_bytes": F.workspace_bytes()}
+               "workspace_bytes": workspace, "other_workloads": others}
         print(json.dumps(out))
     if P > 1:
         dist.destroy_process_group()
@@ -633,6 +755,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end leg (0 = --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short lines of the other BASELINE configurations (key other_workloads)")
+    ap.add_argument("--others-steps", type=int, default=5)
+    ap.add_argument("--others-budget", type=float, default=60.0, help="seconds after which no further extra workload is started")
     ap.add_argument("--tune", default=None, choices=["measure", "patient"],
                     help="run mpifft4py_b200.tune.autotune on the workload first (default: the library's defaults)")
     args = ap.parse_args()

@@ -10,9 +10,6 @@ import collections.abc
 
 import numpy as np
 
-_pinned_keepalive = {}
-
-
 def _pinned(shape, dtype):
     try:
         import torch
@@ -20,9 +17,8 @@ def _pinned(shape, dtype):
             return None
         nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
         t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
-        a = t.numpy()[:nbytes].view(dtype).reshape(shape)
-        _pinned_keepalive[a.ctypes.data] = t
-        return a
+        # the array (through its .base chain) keeps the page-locked storage alive and releases it when it dies
+        return t.numpy()[:nbytes].view(dtype).reshape(shape)
     except Exception:  # noqa: BLE001 - pinned memory is an optimisation only
         return None
 
@@ -70,7 +66,7 @@ class work_arrays(collections.abc.MutableMapping):
         k = self.__keytransform__(key)
         a = self.store.get(k)
         if a is None:
-            a = self.store[k] = np.zeros(k[0], dtype=k[1])
+            a = self.store[k] = zeros(k[0], dtype=k[1])   # page-locked where a CUDA device is present
         elif self.fillzero is True:
             a.fill(0)
         return a

@@ -64,3 +64,23 @@ def test_line():
     ref = _outer(bench.separable_spectra(vec, N, None, False))
     for r in range(P):
         assert oracle.rel_l2(fu[r], ref[g.complex_local_slice(r)]) < 1e-13
+
+
+def test_other_workloads_are_the_baseline_configs_a_rank_count_can_run():
+    """bench.py adds short lines for the BASELINE.json configurations besides the headline one (key other_workloads):
+    pencil grids need four ranks, the 2 x 4 grid of config 3 eight."""
+    import json
+    import os
+    import bench
+    assert bench.other_workload_names("slab1024_f64", 1) == ["slab1024_f64_32", "slab256_f32", "line16384_f32"]
+    assert bench.other_workload_names("slab1024_f64", 2) == bench.other_workload_names("slab1024_f64", 1)
+    assert bench.other_workload_names("slab1024_f64", 4)[-2:] == ["pencilX1024_f64", "pencilY2048_f32"]
+    assert bench.other_workload_names("slab1024_f64", 8)[-1] == "pencilX512_f64"
+    assert "slab1024_f64_32" not in bench.other_workload_names("slab1024_f64_32", 8)
+    for P in (1, 2, 4, 8):
+        for n in bench.other_workload_names("slab1024_f64", P):
+            assert n in bench.WORKLOADS
+    # config 3 of BASELINE.json is the P1 = 2 grid
+    assert bench.WORKLOADS["pencilX512_f64"][4]["P1"] == 2
+    base = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "BASELINE.json")))
+    assert "configs" in base

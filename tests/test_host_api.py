@@ -208,3 +208,33 @@ def test_no_cpu_fallback():
         assert "import oracle" not in text and "from oracle" not in text, mod
         assert "numpy.fft.fft" not in text and "np.fft.fft(" not in text and "np.fft.rfft" not in text, mod
     assert "oracle" not in src
+
+
+def test_host_allocators_own_their_storage(monkeypatch):
+    """empty / zeros / work_arrays hand out arrays backed by a torch allocation (page-locked on a GPU box): the array
+    itself keeps that storage alive and nothing else does (no module-level registry that would pin it for good)."""
+    import gc
+    import torch
+    from mpifft4py_b200 import mpibase
+    real_empty = torch.empty
+    made = []
+
+    def fake_empty(*a, pin_memory=False, **kw):  # a CPU box cannot page-lock: same code path, ordinary memory
+        t = real_empty(*a, **kw)
+        made.append(t.data_ptr())
+        return t
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch, "empty", fake_empty)
+    a = mpibase.zeros((7, 9), dtype=np.complex64)
+    assert made and a.ctypes.data == made[-1] and a.shape == (7, 9) and a.dtype == np.complex64 and not a.any()
+    gc.collect()
+    a[:] = 1 + 2j
+    assert a.sum() == 63 * (1 + 2j)
+    w = mpibase.work_arrays()
+    b = w[((4, 5), np.float64, 0)]
+    assert b.ctypes.data == made[-1] and not b.any()
+    b[:] = 2
+    assert w[((4, 5), np.float64, 0, False)] is b and b.sum() == 40      # kept ...
+    assert not w[((4, 5), np.float64, 0)].any()                           # ... and zeroed on an ordinary fetch
+    assert not [k for k, v in vars(mpibase).items() if isinstance(v, (dict, list, set)) and not k.startswith("__")]

@@ -2,6 +2,8 @@
 have -- 4x2 (default) and 2x4 (P1=2), both alignments, all three communication layouts -- and the goldens of the
 unmodified reference with P = 8, against the oracle on the real kernels.  Runs last (file name): eight CUDA contexts
 taking turns on one device make it the slowest GPU test."""
+import os
+
 import pytest
 
 from test_gpu_multi import shared_gpu_run
@@ -9,5 +11,8 @@ from test_gpu_multi import shared_gpu_run
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.skipif(os.environ.get("B200FFT_SHARED8") != "1",
+                    reason="opt-in (B200FFT_SHARED8=1): not yet run on a device -- the 2- and 4-rank shared-GPU runs are, and "
+                           "eight real GPUs carry forward parity for both eight-rank grids in bench.py's other_workloads")
 def test_eight_ranks_shared_gpu():
     shared_gpu_run(8, timeout=420)
