@@ -5,7 +5,8 @@ mpi4py is optional here: any object with ``Get_size``/``Get_rank`` (and ``Split`
 multi-rank use) is accepted, and :class:`TorchComm` provides that surface on top of
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests), including the ``Bcast``/``reduce``/
 ``barrier`` calls the reference's tests and demos make.  The data path never goes through these
-objects: they only bootstrap the NCCL communicators owned by ``libb200fft.so``.
+objects: they only bootstrap the exchanges of ``libb200fft.so`` (the CUDA IPC handles of the copy-engine transport, the
+unique ids of its NCCL communicators).
 """
 import ctypes as C
 

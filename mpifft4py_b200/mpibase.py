@@ -2,7 +2,7 @@
 
 Mirrors ``mpiFFT4py/mpibase.py:36-137``: ``work_arrays`` keeps its two key forms and its
 zero-on-fetch behaviour, ``datatypes(precision)`` returns the (real, complex, wire) triple --
-the wire type is a name since NCCL moves bytes, and ``empty``/``zeros`` hand out host arrays.
+the wire type is a name since the exchanges move bytes, and ``empty``/``zeros`` hand out host arrays.
 Where the reference aligns them for FFTW (pyfftw.empty_aligned, ``mpibase.py:38-45``) these are
 page-locked when a CUDA device is present so host<->device staging runs at DMA speed.
 """

@@ -6,7 +6,7 @@
 ``comm1`` (P2 ranks with equal ``r % P1``, rank ``r // P1``), ``pencil.py:184-195``.
 
 communication: 'Alltoall' and 'Alltoallw' give the same arrays in the same layout upstream and
-share one NCCL path here (uneven last z-chunk carries the Nyquist plane, no pack trick and no
+share one exchange path here (uneven last z-chunk carries the Nyquist plane, no pack trick and no
 Scatter/Send/Recv); 'AlltoallN' keeps its own layout with the Nyquist plane dropped.
 """
 from collections import defaultdict

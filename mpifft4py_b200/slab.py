@@ -1,7 +1,8 @@
 """Slab decomposition: drop-in for ``mpiFFT4py.slab.R2C`` (reference ``mpiFFT4py/slab.py:49-536``).
 
 Same constructor, methods, shapes and slices; the transforms run as CUDA kernels on the B200
-(``libb200fft.so``) with NCCL exchanges instead of pyfftw/numpy + MPI.  Real space is split along
+(``libb200fft.so``) with exchanges over NVLink (copy-engine pushes by default, NCCL send/recv as an option) instead of
+pyfftw/numpy + MPI.  Real space is split along
 x (``real_shape = (N0/P, N1, N2)``), wavenumber space along y (``complex_shape = (N0, N1/P, N2/2+1)``).
 """
 from collections import defaultdict
