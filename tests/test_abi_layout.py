@@ -31,3 +31,22 @@ def test_struct_layouts_match_the_header():
         subprocess.run(["g++", "-I", ROOT, src, "-o", exe], check=True)
         out = subprocess.run([exe], check=True, stdout=subprocess.PIPE).stdout.decode().split("\n")
     assert [ln for ln in out if ln] == expected
+
+
+def test_integration_md_stub_has_the_same_structs():
+    """The ctypes stub INTEGRATION.md shows a maintainer (section B.1) declares the structs field for field like
+    _cdefs.py: a stale stub would hand the library a mis-sized descriptor."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    ns = {"C": C, "MAXP": D.MAXP}
+    found = {}
+    for m in re.finditer(r"^class (\w+)\(C\.Structure\):[^\n]*\n((?:[ \t]+[^\n]*\n)+)", text, re.M):
+        exec("class %s(C.Structure):\n%s" % (m.group(1), m.group(2)), ns)
+        found[m.group(1)] = ns[m.group(1)]
+    assert set(found) >= {"Side", "Mask", "StridedDesc"}
+    for name, ct in found.items():
+        mine = getattr(D, name)
+        assert [f[0] for f in ct._fields_] == [f[0] for f in mine._fields_], name
+        assert C.sizeof(ct) == C.sizeof(mine), name
+        for f in ct._fields_:
+            assert getattr(ct, f[0]).offset == getattr(mine, f[0]).offset, (name, f[0])
