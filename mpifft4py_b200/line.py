@@ -61,6 +61,17 @@ class R2C(Transform):
     def real_shape_padded(self):
         return G.padded(self.real_shape(), self.padsize)
 
+    # shapes of the 3/2-rule intermediates (line.py:146-156; public methods upstream): the padded half spectrum of the
+    # local rows, the local rows before the y pad, and this rank's spectral columns padded in x
+    def complex_padded_xy(self):
+        return (int(self.padsize * self.Np[0]), int(self.padsize * self.N[1] / 2 + 1))
+
+    def complex_shape_padded_01(self):
+        return (int(self.padsize * self.Np[0]), self.Nf)
+
+    def complex_padded_x(self):
+        return (int(self.padsize * self.N[0]), self.Npf)
+
     def work_shape(self, dealias):
         return self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
 

@@ -74,6 +74,31 @@ class R2C(Transform):
         """Real-space shape a transform with this dealias mode works on."""
         return self.real_shape_padded() if dealias == '3/2-rule' else self.real_shape()
 
+    # ---- shapes of the 3/2-rule intermediates (slab.py:491-514).  Upstream allocates work arrays of these shapes; here
+    # they describe the stages of the plan's fused passes (kept because they are public methods of the class):
+    # after the z pass (_3: everything padded), after the y truncation (_2 -> _1), as per-peer blocks around the
+    # exchange (_I, _0_I) and in front of the x pass (_0).
+    def _pad(self, n):
+        return int(self.padsize * n)
+
+    def complex_shape_padded_0(self):
+        return (self._pad(self.N[0]), self.Np[1], self.Nf)
+
+    def complex_shape_padded_0_I(self):
+        return (self.num_processes, self._pad(self.Np[0]), self.Np[1], self.Nf)
+
+    def complex_shape_padded_1(self):
+        return (self._pad(self.Np[0]), self.N[1], self.Nf)
+
+    def complex_shape_padded_2(self):
+        return (self._pad(self.Np[0]), self._pad(self.N[1]), self.Nf)
+
+    def complex_shape_padded_3(self):
+        return (self._pad(self.Np[0]), self._pad(self.N[1]), self.Nfp)
+
+    def complex_shape_padded_I(self):
+        return (self._pad(self.Np[0]), self.num_processes, self.Np[1], self.Nf)
+
     # ---- slices into the global arrays (slab.py:129-144): every step is 1
     def real_local_slice(self, padsize=1):
         return (G.block(self.Np[0], self.rank, padsize), G.whole(self.N[1], padsize), G.whole(self.N[2], padsize))
@@ -136,9 +161,8 @@ class R2C(Transform):
             ushape = self.real_shape()
         return self._run(0, u, fu, dealias, ushape, self.float, self.complex_shape(), self.complex)
 
-    # The reference's intermediate shapes (complex_shape_padded_0 ... _I) and its copy_to_padded /
-    # copy_from_padded helpers (slab.py:491-536) have no counterpart here: the pad / truncate copies are index
-    # maps inside the FFT passes and the intermediates live in the plan's work buffers.
+    # The reference's copy_to_padded / copy_from_padded helpers (slab.py:516-536) have no counterpart here: the pad /
+    # truncate copies are index maps inside the FFT passes and the intermediates live in the plan's work buffers.
 
 
 class C2C(R2C):

@@ -129,6 +129,15 @@ def test_mesh_helpers_equal_reference(kind, P, alignment, P1, prec):
             assert F.global_complex_shape(1.5) == R.global_complex_shape(1.5)
         assert F.float is R.float and F.complex is R.complex
         assert np.array_equal(F.L, R.L) and F.L.dtype == R.L.dtype
+        # every public shape method of the reference class that takes no argument (the 3/2-rule intermediates included)
+        names = [n for n in dir(R) if ("shape" in n or n.startswith("complex_padded")) and callable(getattr(R, n))]
+        for n in names:
+            try:
+                want = getattr(R, n)()
+            except (TypeError, AttributeError):  # needs an argument / refers to attributes the class never sets upstream
+                continue
+            got = getattr(F, n)()
+            assert tuple(int(x) for x in got) == tuple(int(x) for x in want), (n, got, want)
         return True
 
     assert all(FAKE.run_ranks(P, body))
