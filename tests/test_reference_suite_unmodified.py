@@ -1,0 +1,147 @@
+"""The reference's OWN test functions -- /root/reference/tests/test_FFT.py, loaded unmodified from where it lies --
+executed on mpifft4py_b200's classes: ``mpiFFT4py`` / ``mpiFFT4py.slab`` / ``.pencil`` / ``.line`` resolve to this
+package's modules and ``mpi4py.MPI`` to its communicators while that file is imported, then every test function is
+called with objects built the way its fixtures build them (``:36-56``), for every fixture parameter, on 1 rank and on
+4 ranks (threads).  What this proves is the drop-in claim at the level of a caller's source code: names, signatures,
+return conventions, attributes (``FFT.N``, ``.float``, ``.comm``, ``.communication`` ...), shapes and slices are what
+upstream's own tests expect.  There is no GPU here, so the ORACLE answers the transform calls (as in
+test_ref_procedures_oracle.py) and numpy.fft the serial functions; the kernels' parity is the business of the `-m gpu`
+tests, where tests/ref_procedures.py restates these same procedures (the reference tree does not exist on the GPU
+box).  Skipped where /root/reference is absent."""
+import importlib.util
+import os
+import sys
+import threading
+import types
+
+import numpy as np
+import pytest
+
+import mpifft4py_b200 as m
+import ref_procedures as rp
+from mpifft4py_b200 import _engine
+from test_ref_procedures_oracle import ThreadComm, ThreadWorld, oracle_run
+
+REF_TEST = "/root/reference/tests/test_FFT.py"
+pytestmark = pytest.mark.skipif(not os.path.isfile(REF_TEST), reason="reference tree not present")
+
+SERIAL = {"rfftn": np.fft.rfftn, "irfftn": np.fft.irfftn, "rfft2": np.fft.rfft2, "irfft2": np.fft.irfft2, "fftn": np.fft.fftn,
+          "ifftn": np.fft.ifftn, "irfft": np.fft.irfft, "ifft": np.fft.ifft}
+
+
+def _serial(npfn):
+    def f(a, b, axes=None, axis=None, **kw):
+        b[...] = npfn(a, axes=axes) if axis is None else npfn(a, axis=axis)
+        return b
+    return f
+
+
+class WorldProxy(object):
+    """``MPI.COMM_WORLD`` of the loaded test module: each thread-rank sees its own communicator."""
+
+    def __init__(self, size):
+        self.size = size
+        self.local = threading.local()
+
+    def _c(self):
+        return getattr(self.local, "comm", None)
+
+    def Get_size(self):
+        return self.size
+
+    def Get_rank(self):
+        return self._c().Get_rank() if self._c() is not None else 0
+
+    def __getattr__(self, name):
+        return getattr(self._c(), name)
+
+
+def load_reference_tests(world):
+    """Import the reference's test file with this package standing where mpiFFT4py is imported from."""
+    pkg = types.ModuleType("mpiFFT4py")
+    pkg.__path__ = []
+    for name, fn in SERIAL.items():
+        setattr(pkg, name, _serial(fn))
+    mpi = types.ModuleType("mpi4py")
+    mpi.MPI = types.SimpleNamespace(COMM_WORLD=world, COMM_SELF=m.comm.COMM_SELF, MIN="MIN", SUM="SUM")
+    alias = {"mpiFFT4py": pkg, "mpiFFT4py.slab": m.slab, "mpiFFT4py.pencil": m.pencil, "mpiFFT4py.line": m.line, "mpi4py": mpi}
+    saved = {k: sys.modules.get(k) for k in alias}
+    gone = [n for n in ("int", "float") if not hasattr(np, n)]  # `from numpy import ... int ...` (:5), removed in numpy 1.24
+    try:
+        sys.modules.update(alias)
+        for n in gone:
+            setattr(np, n, {"int": int, "float": float}[n])
+        spec = importlib.util.spec_from_file_location("reference_test_FFT_%d" % world.Get_size(), REF_TEST)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for n in gone:
+            delattr(np, n)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def run_module(mod, comm):
+    """What pytest would run for this communicator: each test function x each parameter of its fixture."""
+    P = comm.Get_size()
+    three_d, lines, c2cs = rp.params(P)
+    assert sorted(mod.params) == sorted(three_d)  # the module's own parameter list for this rank count (:24-31)
+    ran = 0
+    for p in three_d:
+        F = rp.make(p, comm)
+        mod.test_FFT(F)
+        mod.test_FFT_padded(F)
+        ran += 2
+    for p in lines:
+        F = rp.make(p, comm)
+        mod.test_FFT2(F)
+        mod.test_FFT2_padded(F)
+        ran += 2
+    for p in c2cs:
+        mod.test_FFT_C2C(rp.make(p, comm))
+        ran += 1
+    return ran
+
+
+@pytest.fixture
+def oracle_device(monkeypatch):
+    monkeypatch.setattr(_engine.Transform, "_run", oracle_run)
+
+
+def test_reference_tests_pass_on_one_rank(oracle_device):
+    world = WorldProxy(1)
+    world.local.comm = m.comm.COMM_SELF
+    mod = load_reference_tests(world)
+    assert {"test_FFT", "test_FFT2", "test_FFT2_padded", "test_FFT_padded", "test_FFT_C2C"} <= set(dir(mod))
+    assert run_module(mod, m.comm.COMM_SELF) == 2 * 4 + 2 * 2 + 2
+
+
+def test_reference_tests_pass_on_four_ranks(oracle_device):
+    P = 4
+    tw = ThreadWorld(P)
+    world = WorldProxy(P)
+    mod = load_reference_tests(world)
+    assert len(mod.params) == 16
+    counts = [None] * P
+
+    def rank_main(r):
+        comm = ThreadComm(tw, r)
+        world.local.comm = comm
+        try:
+            counts[r] = run_module(mod, comm)
+        except BaseException as e:  # noqa: BLE001
+            tw.failed.append((r, repr(e)[:400]))
+            tw.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=900)
+    real = [f for f in tw.failed if "BrokenBarrierError" not in f[1]]
+    assert not tw.failed, real or tw.failed
+    assert counts == [2 * 16 + 2 * 2 + 2] * P
