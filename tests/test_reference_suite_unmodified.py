@@ -1,6 +1,7 @@
 """The reference's OWN test functions -- /root/reference/tests/test_FFT.py, loaded unmodified from where it lies --
-executed on mpifft4py_b200's classes: ``mpiFFT4py`` / ``mpiFFT4py.slab`` / ``.pencil`` / ``.line`` resolve to this
-package's modules and ``mpi4py.MPI`` to its communicators while that file is imported, then every test function is
+executed on mpifft4py_b200's classes: ``mpifft4py_b200.compat.install()`` makes ``mpiFFT4py`` / ``mpiFFT4py.slab`` /
+``.pencil`` / ``.line`` resolve to this package's modules and ``mpi4py.MPI`` to its communicators while that file is
+imported, then every test function is
 called with objects built the way its fixtures build them (``:36-56``), for every fixture parameter, on 1 rank and on
 4 ranks (threads).  What this proves is the drop-in claim at the level of a caller's source code: names, signatures,
 return conventions, attributes (``FFT.N``, ``.float``, ``.comm``, ``.communication`` ...), shapes and slices are what
@@ -12,7 +13,6 @@ import importlib.util
 import os
 import sys
 import threading
-import types
 
 import numpy as np
 import pytest
@@ -57,18 +57,17 @@ class WorldProxy(object):
 
 
 def load_reference_tests(world):
-    """Import the reference's test file with this package standing where mpiFFT4py is imported from."""
-    pkg = types.ModuleType("mpiFFT4py")
-    pkg.__path__ = []
-    for name, fn in SERIAL.items():
-        setattr(pkg, name, _serial(fn))
-    mpi = types.ModuleType("mpi4py")
-    mpi.MPI = types.SimpleNamespace(COMM_WORLD=world, COMM_SELF=m.comm.COMM_SELF, MIN="MIN", SUM="SUM")
-    alias = {"mpiFFT4py": pkg, "mpiFFT4py.slab": m.slab, "mpiFFT4py.pencil": m.pencil, "mpiFFT4py.line": m.line, "mpi4py": mpi}
-    saved = {k: sys.modules.get(k) for k in alias}
+    """Import the reference's test file after mpifft4py_b200.compat.install() -- the product's own way of running a
+    program written for mpiFFT4py unedited -- with this test's communicator as COMM_WORLD and, there being no GPU,
+    numpy.fft behind the serial function names."""
+    from mpifft4py_b200 import compat
+    saved = {k: sys.modules.get(k) for k in compat._NAMES + ("mpi4py", "mpi4py.MPI")}
     gone = [n for n in ("int", "float") if not hasattr(np, n)]  # `from numpy import ... int ...` (:5), removed in numpy 1.24
     try:
-        sys.modules.update(alias)
+        pkg = compat.install(mpi4py=True)
+        sys.modules["mpi4py.MPI"].COMM_WORLD = world
+        for name, fn in SERIAL.items():
+            setattr(pkg, name, _serial(fn))
         for n in gone:
             setattr(np, n, {"int": int, "float": float}[n])
         spec = importlib.util.spec_from_file_location("reference_test_FFT_%d" % world.Get_size(), REF_TEST)
@@ -77,10 +76,9 @@ def load_reference_tests(world):
     finally:
         for n in gone:
             delattr(np, n)
+        compat.uninstall()
         for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
+            if v is not None:
                 sys.modules[k] = v
     return mod
 
