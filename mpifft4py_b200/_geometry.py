@@ -55,6 +55,22 @@ def dense_physical_mesh(slices, N, L, dtype):
     return X
 
 
+class Vectors(list):
+    """The list of per-axis arrays the mesh methods return, usable as ONE operand of ``*`` as well: ``a * K`` is the
+    stack ``[a * K[0], a * K[1], ...]``.  The reference's callers write exactly that (``P_hat*K`` with the sparse
+    wavenumber list, ``demo/spectral_dns_solver.py:75``); numpy used to build it from the ragged list on its own and
+    refuses to since 1.24, which is why the upstream demo no longer runs on a current numpy -- with this class it
+    does, unedited.  Everything else (indexing, iteration, ``len``, ``isinstance(K, list)``) is a plain list."""
+
+    __array_ufunc__ = None  # ndarray.__mul__(K) then defers to K.__rmul__ instead of trying np.asarray(K)
+
+    def __mul__(self, other):
+        return np.array([k * other for k in self])
+
+    def __rmul__(self, other):
+        return np.array([other * k for k in self])
+
+
 def sparse_spectral_mesh(ks, shape=None):
     """Outer (sparse) mesh of the per-axis wavenumber vectors; broadcast to ``shape`` when given."""
     K = list(np.meshgrid(*ks, indexing='ij', sparse=True))

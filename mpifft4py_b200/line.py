@@ -99,7 +99,7 @@ class R2C(Transform):
         if scaled is True:
             for k, f in zip(K, 2 * np.pi / self.L):
                 k *= f
-        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
+        return G.Vectors([np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K)
 
     def get_dealias_filter(self):
         """``line.py:131-136``: the mask tests the default (scaled) wavenumbers, i.e. assumes the 2 pi-periodic box; the

@@ -124,7 +124,7 @@ class R2CY(Transform):
         K = G.sparse_spectral_mesh((ks[0][s[0]], ks[1], ks[2][s[2]]))
         if scaled is True:
             K = [(k * f).astype(self.float) for k, f in zip(K, 2 * np.pi / self.L)]
-        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
+        return G.Vectors([np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K)
 
     def get_dealias_filter(self):
         """2/3-rule mask on the local spectral block (applied by the transforms inside their first inverse pass)."""

@@ -130,7 +130,7 @@ class R2C(Transform):
         if scaled:
             for k, f in zip(K, 2 * np.pi / self.L):
                 k *= f
-        return [np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K
+        return G.Vectors([np.broadcast_to(k, self.complex_shape()) for k in K] if broadcast is True else K)
 
     def get_dealias_filter(self):
         """2/3-rule mask on the local spectral block.  The transforms apply it inside the first inverse FFT
