@@ -164,8 +164,10 @@ class Transform(object):
         a = np.ascontiguousarray(src, dtype=src_dtype)
         out = dst if (isinstance(dst, np.ndarray) and dst.dtype == np.dtype(dst_dtype) and dst.flags["C_CONTIGUOUS"]
                       and dst.flags["WRITEABLE"]) else np.empty(dst_shape, dtype=dst_dtype)
-        dsrc = self._dev("in%d" % inverse, src_shape, src_dtype)
-        ddst = self._dev("out%d" % inverse, dst_shape, dst_dtype)
+        # two staging buffers serve both directions: what fftn stages its result in is what ifftn stages its input in
+        # (same shape and type), and the other way round -- half the device memory of a buffer pair per direction
+        dsrc = self._dev("ab"[inverse], src_shape, src_dtype)
+        ddst = self._dev("ba"[inverse], dst_shape, dst_dtype)
         _lib.check(L.b200fft_copy(C.c_void_p(dsrc.data_ptr()), C.c_void_p(a.ctypes.data), a.nbytes, st))
         _lib.check(fn(self._plan, C.c_void_p(dsrc.data_ptr()), C.c_void_p(ddst.data_ptr()), mode, st))
         _lib.check(L.b200fft_copy(C.c_void_p(out.ctypes.data), C.c_void_p(ddst.data_ptr()), out.nbytes, st))

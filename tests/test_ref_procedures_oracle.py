@@ -1,18 +1,17 @@
 """tests/ref_procedures.py (the reference's own test procedures restated for this engine) checked on the CPU: the
-ORACLE stands in for the device -- ranks are threads, every transform call of the classes is answered by the oracle's
-all-ranks function, the serial functions by numpy.fft.  What this pins down without a GPU: the procedures' data flow,
-slices and tolerances are satisfiable by an implementation that reproduces the reference (the oracle is pinned to the
-unmodified reference's goldens), for every fixture parameter at 1, 2 and 4 ranks.  The device runs are
-tests/test_gpu_reference_procedures.py (P = 1) and tests/gpu_dist_worker.py (P > 1)."""
+ORACLE stands in for the device -- ranks are threads, the C-ABI calls under every transform call of the classes are
+answered by the oracle's all-ranks function (tests/fake_device.py), the serial functions by numpy.fft.  What this pins
+down without a GPU: the procedures' data flow, slices and tolerances are satisfiable by an implementation that
+reproduces the reference (the oracle is pinned to the unmodified reference's goldens), for every fixture parameter at 1,
+2 and 4 ranks.  The device runs are tests/test_gpu_reference_procedures.py (P = 1) and tests/gpu_dist_worker.py (P > 1)."""
 import threading
 
 import numpy as np
 import pytest
 
+import fake_device
 import mpifft4py_b200 as m
-import oracle
 import ref_procedures as rp
-from mpifft4py_b200 import _engine, line, pencil, slab
 
 
 class ThreadWorld(object):
@@ -56,33 +55,9 @@ class ThreadComm(object):
         return ThreadComm(self.world, self.wrank, [r for r in range(self.world.P) if colors[r] == int(color)])
 
 
-def oracle_run(self, inverse, src, dst, dealias, src_shape, src_dtype, dst_shape, dst_dtype):
-    """Stand-in for Transform._run: all ranks hand in their block, the oracle transforms them together."""
-    assert tuple(src.shape) == tuple(int(s) for s in src_shape) and tuple(dst.shape) == tuple(int(s) for s in dst_shape)
-    comm = self.comm
-    P = comm.Get_size()
-    prec = "double" if self.float is np.float64 else "single"
-    N = tuple(int(n) for n in self.N)
-    blocks = comm.allgather_world(np.array(src)) if P > 1 else [np.array(src)]
-    kw = dict(dealias=dealias, precision=prec)
-    if isinstance(self, slab.C2C):
-        fn = oracle.slab.c2c_ifftn if inverse else oracle.slab.c2c_fftn
-    elif isinstance(self, slab.R2C):
-        fn = oracle.slab.ifftn if inverse else oracle.slab.fftn
-    elif isinstance(self, line.R2C):
-        fn = oracle.line.ifft2 if inverse else oracle.line.fft2
-        if not inverse:
-            kw["exact"] = True  # the engine transforms the Nyquist column exactly (no pack trick)
-    else:
-        fn = oracle.pencil.ifftn if inverse else oracle.pencil.fftn
-        kw.update(alignment="X" if isinstance(self, pencil.R2CX) else "Y", P1=self.P1, communication=self.communication)
-    dst[...] = fn(blocks, N, P, **kw)[comm.Get_rank() if P > 1 else 0]
-    return dst
-
-
 @pytest.fixture
 def oracle_backend(monkeypatch):
-    monkeypatch.setattr(_engine.Transform, "_run", oracle_run)
+    fake_device.install(monkeypatch)   # the oracle behind the C-ABI calls of Transform._run
 
     def serial(npfn):
         def f(a, b, axes):

@@ -5,8 +5,8 @@ imported, then every test function is
 called with objects built the way its fixtures build them (``:36-56``), for every fixture parameter, on 1 rank and on
 4 ranks (threads).  What this proves is the drop-in claim at the level of a caller's source code: names, signatures,
 return conventions, attributes (``FFT.N``, ``.float``, ``.comm``, ``.communication`` ...), shapes and slices are what
-upstream's own tests expect.  There is no GPU here, so the ORACLE answers the transform calls (as in
-test_ref_procedures_oracle.py) and numpy.fft the serial functions; the kernels' parity is the business of the `-m gpu`
+upstream's own tests expect.  There is no GPU here, so the ORACLE answers the C-ABI calls under the transform methods
+(tests/fake_device.py) and numpy.fft the serial functions; the kernels' parity is the business of the `-m gpu`
 tests, where tests/ref_procedures.py restates these same procedures (the reference tree does not exist on the GPU
 box).  Skipped where /root/reference is absent."""
 import importlib.util
@@ -17,10 +17,10 @@ import threading
 import numpy as np
 import pytest
 
+import fake_device
 import mpifft4py_b200 as m
 import ref_procedures as rp
-from mpifft4py_b200 import _engine
-from test_ref_procedures_oracle import ThreadComm, ThreadWorld, oracle_run
+from test_ref_procedures_oracle import ThreadComm, ThreadWorld
 
 REF_TEST = "/root/reference/tests/test_FFT.py"
 pytestmark = pytest.mark.skipif(not os.path.isfile(REF_TEST), reason="reference tree not present")
@@ -107,7 +107,7 @@ def run_module(mod, comm):
 
 @pytest.fixture
 def oracle_device(monkeypatch):
-    monkeypatch.setattr(_engine.Transform, "_run", oracle_run)
+    fake_device.install(monkeypatch)
 
 
 def test_reference_tests_pass_on_one_rank(oracle_device):
