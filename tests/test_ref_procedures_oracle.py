@@ -9,6 +9,7 @@ import threading
 import numpy as np
 import pytest
 
+import cpu_engine
 import fake_device
 import mpifft4py_b200 as m
 import ref_procedures as rp
@@ -35,6 +36,9 @@ class ThreadComm(object):
     def Get_rank(self):
         return self.members.index(self.wrank)
 
+    def allgather(self, obj):  # (of the whole world: sub-communicators only report size and rank in these tests)
+        return self.allgather_world(obj)
+
     def allgather_world(self, obj):
         w = self.world
         w.slots[self.wrank] = obj
@@ -55,25 +59,39 @@ class ThreadComm(object):
         return ThreadComm(self.world, self.wrank, [r for r in range(self.world.P) if colors[r] == int(color)])
 
 
-@pytest.fixture
-def oracle_backend(monkeypatch):
-    fake_device.install(monkeypatch)   # the oracle behind the C-ABI calls of Transform._run
+SERIAL = {"rfftn": np.fft.rfftn, "irfftn": np.fft.irfftn, "rfft2": np.fft.rfft2, "irfft2": np.fft.irfft2, "fftn": np.fft.fftn,
+          "ifftn": np.fft.ifftn, "irfft": np.fft.irfft, "ifft": np.fft.ifft}
 
-    def serial(npfn):
-        def f(a, b, axes):
-            b[...] = npfn(a, axes=axes)
-            return b
-        return f
 
-    for name, fn in (("rfftn", np.fft.rfftn), ("irfftn", np.fft.irfftn), ("rfft2", np.fft.rfft2), ("irfft2", np.fft.irfft2),
-                     ("fftn", np.fft.fftn), ("ifftn", np.fft.ifftn)):
-        monkeypatch.setattr(m, name, serial(fn))
+def numpy_serial(npfn):
+    def f(a, b, axes=None, axis=None, **kw):
+        b[...] = npfn(a, axes=axes) if axis is None else npfn(a, axis=axis)
+        return b
+    return f
+
+
+@pytest.fixture(params=["oracle", "engine"])
+def backend(request, monkeypatch):
+    """What stands under the classes where there is no GPU.  "oracle": tests/fake_device.py answers the C-ABI calls of
+    Transform._run with the oracle, numpy.fft stands behind the serial function names.  "engine": tests/cpu_engine.py --
+    the product's own C-ABI layer, plan programs and kernel phase bodies built for the host, serial functions included."""
+    if request.param == "oracle":
+        fake_device.install(monkeypatch)
+        for name, fn in SERIAL.items():
+            monkeypatch.setattr(m, name, numpy_serial(fn))
+        yield request.param
+    else:
+        cleanup = cpu_engine.install(monkeypatch)
+        yield cleanup.calls
+        cleanup()
 
 
 @pytest.mark.parametrize("P", [1, 2, 4])
-def test_reference_procedures_hold_for_the_oracle(oracle_backend, P):
+def test_reference_procedures_hold(backend, P):
     if P == 1:
         assert rp.run_all(m.comm.COMM_SELF) == 2 * 6 + 2
+        if backend != "oracle":
+            assert backend["b200fft_exec_forward"] >= 14 and backend["b200fft_exec_strided"] > 0 and backend["b200fft_exec_r2c"] > 0
         return
     world = ThreadWorld(P)
     counts = [None] * P
@@ -94,6 +112,11 @@ def test_reference_procedures_hold_for_the_oracle(oracle_backend, P):
     assert not world.failed, real or world.failed
     expect = 2 * ((16 if P >= 4 else 4) + 2) + 2
     assert counts == [expect] * P
+    if backend != "oracle":  # the engine's own entry points did the work: plans with connected transports, serial passes
+        assert backend["b200fft_exec_forward"] >= expect * P and backend["b200fft_exec_inverse"] >= expect * P
+        assert backend["b200fft_plan_p2p_connect"] >= (20 if P >= 4 else 8) * P
+        assert backend["b200fft_exec_strided"] > 0 and backend["b200fft_exec_r2c"] > 0
+        assert backend["b200fft_exec_c2r"] > 0 or P < 4   # irfftn: only the 'AlltoallN' parameters call it (:66-69)
 
 
 def test_parameter_lists_are_the_reference_fixtures():

@@ -1,14 +1,17 @@
 """The reference's OWN test functions -- /root/reference/tests/test_FFT.py, loaded unmodified from where it lies --
 executed on mpifft4py_b200's classes: ``mpifft4py_b200.compat.install()`` makes ``mpiFFT4py`` / ``mpiFFT4py.slab`` /
 ``.pencil`` / ``.line`` resolve to this package's modules and ``mpi4py.MPI`` to its communicators while that file is
-imported, then every test function is
-called with objects built the way its fixtures build them (``:36-56``), for every fixture parameter, on 1 rank and on
-4 ranks (threads).  What this proves is the drop-in claim at the level of a caller's source code: names, signatures,
-return conventions, attributes (``FFT.N``, ``.float``, ``.comm``, ``.communication`` ...), shapes and slices are what
-upstream's own tests expect.  There is no GPU here, so the ORACLE answers the C-ABI calls under the transform methods
-(tests/fake_device.py) and numpy.fft the serial functions; the kernels' parity is the business of the `-m gpu`
-tests, where tests/ref_procedures.py restates these same procedures (the reference tree does not exist on the GPU
-box).  Skipped where /root/reference is absent."""
+imported, then every test function is called with objects built the way its fixtures build them (``:36-56``), for every
+fixture parameter, on 1 rank and on 4 ranks (threads).  Likewise the reference's demo solver, run as a script to its
+asserted known answer.
+
+There is no GPU here, so each test runs twice (fixture ``device``): with the ORACLE answering the C-ABI calls
+(tests/fake_device.py) -- which pins the drop-in claim at the level of a caller's source code: names, signatures,
+return conventions, attributes, shapes, slices are what upstream's own tests and demo expect -- and with the product's
+own stack built for the host (tests/cpu_engine.py: the real Transform._run / _ensure_plan handshake, the real C-ABI
+layer and plan programs, the kernels' phase bodies in the emulator; only the CUDA runtime is a stand-in) -- so the
+numbers upstream's assertions see there were computed by the engine's code.  On the device the same procedures are
+tests/ref_procedures.py (the reference tree does not exist on the GPU box).  Skipped where /root/reference is absent."""
 import importlib.util
 import os
 import sys
@@ -17,24 +20,14 @@ import threading
 import numpy as np
 import pytest
 
+import cpu_engine
 import fake_device
 import mpifft4py_b200 as m
 import ref_procedures as rp
-from test_ref_procedures_oracle import ThreadComm, ThreadWorld
+from test_ref_procedures_oracle import ThreadComm, ThreadWorld, numpy_serial, SERIAL
 
 REF_TEST = "/root/reference/tests/test_FFT.py"
 pytestmark = pytest.mark.skipif(not os.path.isfile(REF_TEST), reason="reference tree not present")
-
-SERIAL = {"rfftn": np.fft.rfftn, "irfftn": np.fft.irfftn, "rfft2": np.fft.rfft2, "irfft2": np.fft.irfft2, "fftn": np.fft.fftn,
-          "ifftn": np.fft.ifftn, "irfft": np.fft.irfft, "ifft": np.fft.ifft}
-
-
-def _serial(npfn):
-    def f(a, b, axes=None, axis=None, **kw):
-        b[...] = npfn(a, axes=axes) if axis is None else npfn(a, axis=axis)
-        return b
-    return f
-
 
 class WorldProxy(object):
     """``MPI.COMM_WORLD`` of the loaded test module: each thread-rank sees its own communicator."""
@@ -56,7 +49,7 @@ class WorldProxy(object):
         return getattr(self._c(), name)
 
 
-def load_reference_tests(world):
+def load_reference_tests(world, numpy_serial_functions=True):
     """Import the reference's test file after mpifft4py_b200.compat.install() -- the product's own way of running a
     program written for mpiFFT4py unedited -- with this test's communicator as COMM_WORLD and, there being no GPU,
     numpy.fft behind the serial function names."""
@@ -66,8 +59,9 @@ def load_reference_tests(world):
     try:
         pkg = compat.install(mpi4py=True)
         sys.modules["mpi4py.MPI"].COMM_WORLD = world
-        for name, fn in SERIAL.items():
-            setattr(pkg, name, _serial(fn))
+        if numpy_serial_functions:
+            for name, fn in SERIAL.items():
+                setattr(pkg, name, numpy_serial(fn))
         for n in gone:
             setattr(np, n, {"int": int, "float": float}[n])
         spec = importlib.util.spec_from_file_location("reference_test_FFT_%d" % world.Get_size(), REF_TEST)
@@ -105,24 +99,33 @@ def run_module(mod, comm):
     return ran
 
 
-@pytest.fixture
-def oracle_device(monkeypatch):
-    fake_device.install(monkeypatch)
+@pytest.fixture(params=["oracle", "engine"])
+def device(request, monkeypatch):
+    """ "oracle": the oracle answers the C-ABI calls under the transform methods and numpy.fft the serial function names
+    (tests/fake_device.py).  "engine": nothing of the product is replaced but the CUDA runtime -- its C-ABI layer, plan
+    programs and kernel phase bodies run in the host build (tests/cpu_engine.py), serial functions included."""
+    if request.param == "oracle":
+        fake_device.install(monkeypatch)
+        yield request.param
+    else:
+        cleanup = cpu_engine.install(monkeypatch)
+        yield request.param
+        cleanup()
 
 
-def test_reference_tests_pass_on_one_rank(oracle_device):
+def test_reference_tests_pass_on_one_rank(device):
     world = WorldProxy(1)
     world.local.comm = m.comm.COMM_SELF
-    mod = load_reference_tests(world)
+    mod = load_reference_tests(world, device == "oracle")
     assert {"test_FFT", "test_FFT2", "test_FFT2_padded", "test_FFT_padded", "test_FFT_C2C"} <= set(dir(mod))
     assert run_module(mod, m.comm.COMM_SELF) == 2 * 4 + 2 * 2 + 2
 
 
-def test_reference_tests_pass_on_four_ranks(oracle_device):
+def test_reference_tests_pass_on_four_ranks(device):
     P = 4
     tw = ThreadWorld(P)
     world = WorldProxy(P)
-    mod = load_reference_tests(world)
+    mod = load_reference_tests(world, device == "oracle")
     assert len(mod.params) == 16
     counts = [None] * P
 
@@ -145,7 +148,7 @@ def test_reference_tests_pass_on_four_ranks(oracle_device):
     assert counts == [2 * 16 + 2 * 2 + 2] * P
 
 
-def test_reference_demo_runs_unedited_and_reaches_its_known_answer(oracle_device, capsys):
+def test_reference_demo_runs_unedited_and_reaches_its_known_answer(device):
     """/root/reference/demo/spectral_dns_solver.py as it lies there: a Taylor-Green run of ten RK4 steps with the
     3/2-rule (90 inverse + 90 forward padded transforms through ``work_arrays``, ``get_local_mesh``,
     ``get_local_wavenumbermesh(scaled=True)``, ``P_hat*K`` on the sparse wavenumber list) that ends in
