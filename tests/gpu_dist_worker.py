@@ -19,6 +19,7 @@ import ref_procedures  # noqa: E402
 from mpifft4py_b200.comm import world  # noqa: E402
 
 TOL = {"double": 1e-12, "single": 1e-5}
+DEVICE_TENSORS = True  # tests/test_worker_lists_cpu.py runs these checks on the host build of the engine: numpy callers only
 L3 = np.array([2 * np.pi] * 3)
 
 
@@ -89,6 +90,8 @@ def run_3d(comm, kind, N, prec, alignment=None, P1=None, communication=None, tra
     up = [rng.random(g.real_shape_padded()).astype(rt) for _ in range(P)]
     got = F.fftn(up[r], np.zeros(cshape[r], dtype=ct), dealias="3/2-rule")
     check(tag + " fftn 3/2", got, fwd(up, "3/2-rule")[r], tol, r)
+    if not DEVICE_TENSORS:
+        return
     # CUDA tensors in place of numpy arrays
     tu = torch.from_numpy(u[r]).cuda()
     tf = torch.zeros(tuple(int(s) for s in cshape[r]), dtype=torch.complex128 if prec == "double" else torch.complex64,

@@ -47,6 +47,16 @@ class ThreadComm(object):
         w.barrier.wait(timeout=120)
         return out
 
+    def bcast(self, obj, root=0):  # (works for sub-communicators too: every rank of the world is in one such call)
+        return self.allgather_world(obj if self.Get_rank() == root else None)[self.members[root]]
+
+    def barrier(self):
+        self.world.barrier.wait(timeout=120)
+
+    def reduce(self, value, op="SUM", root=0):
+        vals = [v for r, v in enumerate(self.allgather_world(value)) if r in self.members]
+        return None if self.Get_rank() != root else (min(vals) if op == "MIN" else max(vals) if op == "MAX" else sum(vals))
+
     def Bcast(self, buf, root=0):
         assert len(self.members) == self.world.P
         src = self.allgather_world(buf if self.wrank == root else None)[root]
@@ -86,7 +96,7 @@ def backend(request, monkeypatch):
         cleanup()
 
 
-@pytest.mark.parametrize("P", [1, 2, 4])
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
 def test_reference_procedures_hold(backend, P):
     if P == 1:
         assert rp.run_all(m.comm.COMM_SELF) == 2 * 6 + 2
