@@ -3,7 +3,6 @@ for the decompositions and dealias modes the bench lines use.  CPU only."""
 import os
 import sys
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -4,7 +4,6 @@
  * the plan programs + kernels in the CPU emulator against the oracle, every rank count;
  * the host class's shapes / slices against the goldens;
  * (gpu) the class on the device against the oracle and the goldens."""
-import ctypes as C
 import glob
 import json
 import os
@@ -12,7 +11,6 @@ import os
 import numpy as np
 import pytest
 
-import emu_util
 import oracle
 from conftest import ROOT
 from mpifft4py_b200 import _cdefs as D

@@ -2,7 +2,6 @@
 oracle, the reference's golden vectors and size-independent properties.
 
 Tolerances are the north-star's: relative L2 <= 1e-12 (double), <= 1e-5 (single)."""
-import glob
 import json
 import os
 

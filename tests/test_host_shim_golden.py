@@ -2,7 +2,6 @@
 slices included) through the product's C-ABI layer on the CPU -- host build of csrc/b200fft.cu, ranks as
 threads, kernels in the emulator (tests/host_shim_util.py).  Same comparisons as the multi-GPU worker
 (tests/gpu_dist_worker.py: run_golden), for every transport the plan kind supports."""
-import ctypes as C
 import glob
 import json
 import os
