@@ -16,6 +16,14 @@ exchanges up).  Where ``mpi4py`` is not installed, a stand-in ``mpi4py.MPI`` pro
 (its tests and demos: ``COMM_WORLD``, ``COMM_SELF``, ``MIN`` / ``MAX`` / ``SUM``, ``Compute_dims``): ``COMM_WORLD`` is
 the ``torch.distributed`` world once that is initialised (one process per GPU under ``torchrun``), a single-process
 communicator before.  tests/test_reference_suite_unmodified.py runs the reference's own test file through this.
+
+As a launcher -- where upstream has ``mpirun -np P python script.py``:
+
+    python -m mpifft4py_b200.compat script.py [args ...]                                            # one GPU
+    python -m torch.distributed.run --nproc-per-node P -m mpifft4py_b200.compat script.py [args ...]
+
+installs the aliases, binds the process to GPU ``LOCAL_RANK`` and initialises ``torch.distributed`` when launched with
+several ranks, then runs the script as ``__main__``.
 """
 import importlib
 import sys
@@ -92,3 +100,36 @@ def uninstall():
         mod = sys.modules.get(name)
         if mod is not None and "stand-in of mpifft4py_b200.compat" in (getattr(mod, "__doc__", None) or ""):
             del sys.modules[name]
+
+
+def main(argv=None):
+    """``python -m mpifft4py_b200.compat script.py [args ...]`` (see the module docstring)."""
+    import os
+    import runpy
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] in ("-h", "--help"):
+        print(__doc__)
+        return 0 if argv else 2
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if not dist.is_initialized():
+            dist.init_process_group(os.environ.get("B200FFT_DIST_BACKEND", "nccl" if cuda else "gloo"))
+    install()
+    sys.argv = argv
+    try:
+        runpy.run_path(argv[0], run_name="__main__")
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,3 +63,55 @@ def test_stand_in_leaves_a_real_mpi4py_alone(monkeypatch):
     finally:
         compat.uninstall()
     assert sys.modules["mpi4py"] is real  # uninstall only removes its own stand-in
+
+
+SCRIPT = r'''
+import sys
+import numpy as np
+from mpi4py import MPI
+from mpiFFT4py.slab import R2C
+from mpiFFT4py import Line_R2C
+comm = MPI.COMM_WORLD
+N = np.array([8, 16, 32]); L = np.array([2 * np.pi] * 3)
+F = R2C(N, L, comm, "double")
+P, r = comm.Get_size(), comm.Get_rank()
+assert F.real_shape() == (8 // P, 16, 32) and F.complex_local_slice()[1] == slice(r * 16 // P, (r + 1) * 16 // P, 1)
+tot = comm.reduce(r + 1.0)
+if r == 0:
+    assert tot == P * (P + 1) / 2
+print("SCRIPT_OK", r, P, sys.argv[1:], __name__)
+'''
+
+
+def _launch(tmp_path, nproc):
+    import os
+    import socket
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "user_program.py"
+    script.write_text(SCRIPT)
+    if nproc == 1:
+        cmd = [sys.executable, "-m", "mpifft4py_b200.compat", str(script), "--flag", "7"]
+    else:
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+               "--master-port", str(port), "-m", "mpifft4py_b200.compat", str(script), "--flag", "7"]
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    return out.returncode, out.stdout.decode("utf-8", "replace")
+
+
+def test_launcher_runs_a_script_as_main(tmp_path):
+    rc, text = _launch(tmp_path, 1)
+    assert rc == 0 and "SCRIPT_OK 0 1 ['--flag', '7'] __main__" in text, text[-2000:]
+
+
+def test_launcher_under_torchrun(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("CPU check of the launcher (gloo); on a GPU box the ranks would want one GPU each")
+    rc, text = _launch(tmp_path, 2)
+    assert rc == 0 and text.count("SCRIPT_OK") == 2 and "SCRIPT_OK 1 2" in text, text[-2000:]
