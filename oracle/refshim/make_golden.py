@@ -232,27 +232,36 @@ for al in "XY":
 CONFIGS.append(("pencilX_P8p1_2_Alltoallw_d", ("pencil", N3, 8, "double", "Alltoallw", "X", 2)))
 CONFIGS.append(("pencilY_P8_Alltoall_d", ("pencil", N3, 8, "double", "Alltoall", "Y", None)))
 CONFIGS.append(("pencilX_P4_Alltoall_s", ("pencil", N3, 4, "single", "Alltoall", "X", None)))
+# eight ranks: the other grid of each alignment, and a slab whose first axis allows the 3/2-rule there (P <= N[0] // 2)
+N8 = (16, 16, 32)
+CONFIGS.append(("slab_P8_Alltoallw_d", ("slab", N8, 8, "double", "Alltoallw", None, None)))
+CONFIGS.append(("pencilX_P8_Alltoall_s", ("pencil", N3, 8, "single", "Alltoall", "X", None)))
+CONFIGS.append(("pencilY_P8p1_2_AlltoallN_d", ("pencil", N3, 8, "double", "AlltoallN", "Y", 2)))
 LINES = [("line_P%d_%s" % (P, prec[0]), ((16, 32), P, prec))
-         for P, prec in [(1, "double"), (2, "double"), (4, "double"), (2, "single")]]
+         for P, prec in [(1, "double"), (2, "double"), (4, "double"), (2, "single"), (8, "double")]]
 
 
 def main():
+    """``--missing``: write only the files that do not exist yet (npz archives carry timestamps, so rewriting the
+    others would change their bytes without changing their content)."""
+    missing_only = "--missing" in sys.argv[1:]
     os.makedirs(OUT, exist_ok=True)
     load_reference.load()
+
+    def write(path, make):
+        if missing_only and os.path.exists(path):
+            return
+        np.savez_compressed(path, **make())
+        print("wrote", os.path.basename(path))
+
     for name, args in CONFIGS:
-        d = slab_or_pencil(*args)
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
-        print("wrote", name)
+        write(os.path.join(OUT, name + ".npz"), lambda: slab_or_pencil(*args))
     for name, args in LINES:
-        d = line(*args)
-        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
-        print("wrote", name)
+        write(os.path.join(OUT, name + ".npz"), lambda: line(*args))
     out_c2c = os.path.join(os.path.dirname(OUT), "golden_c2c")
     os.makedirs(out_c2c, exist_ok=True)
-    for P, prec in [(1, "double"), (2, "double"), (4, "double"), (2, "single")]:
-        name = "c2c_P%d_%s" % (P, prec[0])
-        np.savez_compressed(os.path.join(out_c2c, name + ".npz"), **slab_c2c(N3, P, prec))
-        print("wrote", name)
+    for P, prec, N in [(1, "double", N3), (2, "double", N3), (4, "double", N3), (2, "single", N3), (8, "double", N8)]:
+        write(os.path.join(out_c2c, "c2c_P%d_%s.npz" % (P, prec[0])), lambda: slab_c2c(N, P, prec))
 
 
 if __name__ == "__main__":
