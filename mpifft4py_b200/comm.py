@@ -86,7 +86,7 @@ class TorchComm(object):
         if isinstance(arr, torch.Tensor):
             self._dist.broadcast(arr, src=self._ranks[root], group=self.group)
             return
-        flat = np.ascontiguousarray(arr)
+        flat = np.ascontiguousarray(arr).reshape(-1)
         if np.iscomplexobj(flat):  # as pairs of reals: not every backend broadcasts complex tensors
             flat = flat.view(flat.real.dtype)
         t = torch.from_numpy(flat).to(self._device())

@@ -27,6 +27,9 @@ def main():
     z = (np.arange(6) * (1 - 2j)).reshape(2, 3) if r == 0 else np.zeros((2, 3), dtype=complex)   # complex arrays too
     comm.Bcast(z, root=0)                                                                          # (tests/test_FFT.py:78)
     assert np.array_equal(z, (np.arange(6) * (1 - 2j)).reshape(2, 3))
+    z0 = np.array(3 - 4j) if r == 0 else np.array(0j)            # 0-d
+    comm.Bcast(z0, root=0)
+    assert z0 == 3 - 4j
     z32 = np.full((4,), 1 + 1j, dtype=np.complex64) if r == 0 else np.zeros((4,), dtype=np.complex64)
     comm.Bcast(z32, root=0)
     assert z32.dtype == np.complex64 and np.all(z32 == 1 + 1j)
