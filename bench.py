@@ -485,6 +485,61 @@ def quick_measure(m, comm, name, steps, torch, dist, P, rank):
     return out
 
 
+def golden_check(m, comm, reduce_max):
+    """Every golden file of the UNMODIFIED reference (tests/golden/*.npz, written by oracle/refshim/make_golden.py in the
+    build container) whose rank count is this run's, through the classes with numpy arrays: ``fftn``, ``ifftn``, the
+    3/2-rule both ways and the 2/3-rule, each rank comparing its block -- rel. L2, max over checks, files and ranks
+    (``reduce_max``).  Tiny meshes: a few milliseconds per file; on N GPUs this is parity against the reference's own
+    outputs over the real exchange.  No data-dependent control flow: every rank makes the same calls."""
+    import glob
+    P, r = comm.Get_size(), comm.Get_rank()
+    L3 = np.array([2 * np.pi] * 3)
+    worst = {"double": 0.0, "single": 0.0, "double_forward_3_2": 0.0, "single_forward_3_2": 0.0}
+    names = []
+
+    def err(got, ref):
+        return float(np.linalg.norm((got - ref).ravel()) / max(np.linalg.norm(ref.ravel()), 1e-300))
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
+        z = np.load(path)
+        meta = json.loads(str(z["meta"]))
+        if meta["P"] != P:
+            continue
+        prec, N = meta["precision"], meta["N"]
+        if meta["kind"] == "slab":
+            F = m.Slab_R2C(np.array(N), L3, comm, prec, communication=meta["communication"])
+            fwd, inv = F.fftn, F.ifftn
+        elif meta["kind"] == "pencil":
+            F = m.Pencil_R2C(np.array(N), L3, comm, prec, P1=meta["P1"], communication=meta["communication"],
+                             alignment=meta["alignment"])
+            fwd, inv = F.fftn, F.ifftn
+        else:
+            F = m.Line_R2C(np.array(N), L3[:2], comm, prec)
+            fwd, inv = F.fft2, F.ifft2
+        info = meta["ranks"][r]
+        rs = tuple(slice(*x) for x in info["real_local_slice"])
+        rps = tuple(slice(*x) for x in info["real_local_slice_padded"])
+        cs = tuple(slice(*x) for x in info["complex_local_slice"])
+        A, Cg, Ap = z["A"], z["C"], z["Ap"]
+        e = [err(fwd(np.ascontiguousarray(A[rs]), np.zeros(Cg[cs].shape, dtype=Cg.dtype)), Cg[cs]),
+             err(inv(np.ascontiguousarray(Cg[cs]), np.zeros(A[rs].shape, dtype=A.dtype)), z["A2"][rs])]
+        Cin = Cg.copy()
+        if meta["kind"] == "line":
+            Cin[-N[0] // 2] = 0  # (tests/test_FFT.py:128: the line goldens' padded pair starts from this spectrum)
+        e.append(err(inv(np.ascontiguousarray(Cin[cs]), np.zeros(Ap[rps].shape, dtype=Ap.dtype), dealias="3/2-rule"), Ap[rps]))
+        if meta["has23"]:
+            e.append(err(inv(np.ascontiguousarray(Cg[cs]), np.zeros(A[rs].shape, dtype=A.dtype), dealias="2/3-rule"), z["A23"][rs]))
+        worst[prec] = max([worst[prec]] + e)
+        e32 = err(fwd(np.ascontiguousarray(Ap[rps]), np.zeros(Cg[cs].shape, dtype=Cg.dtype), dealias="3/2-rule"), z["Cp"][cs])
+        worst[prec + "_forward_3_2"] = max(worst[prec + "_forward_3_2"], e32)
+        names.append(os.path.basename(path)[:-4])
+        F = fwd = inv = None
+    out = {k: reduce_max(v) for k, v in sorted(worst.items())}
+    return {"files": names, "max_rel_l2": out,
+            "what": "goldens of the unmodified reference with this rank count: fftn, ifftn, 3/2-rule inverse, 2/3-rule inverse "
+                    "(max_rel_l2.double / .single) and the truncating 3/2-rule forward (…_forward_3_2), max over ranks"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -731,6 +786,21 @@ def run_ours(args):
             gc.collect()
             torch.cuda.empty_cache()
 
+    # ---- parity against the reference's own outputs at THIS rank count (stored goldens; milliseconds) --------------------
+    golden = None
+    if not args.no_golden:
+        def rmax(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            if P > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        try:
+            golden = golden_check(m, comm, rmax)
+        except Exception as e:  # noqa: BLE001
+            golden = {"error": repr(e)[:300]}
+        import gc
+        gc.collect()
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": P, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -740,7 +810,7 @@ def run_ours(args):
                "gpu_launches": int(k1) * 2 * args.steps if kind else 0,
                "kernels_per_transform": int(k1), "nccl_groups_per_transform": int(x1),
                "roofline": roofline, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
-               "workspace_bytes": workspace, "other_workloads": others}
+               "workspace_bytes": workspace, "other_workloads": others, "reference_goldens": golden}
         print(json.dumps(out))
     if P > 1:
         dist.destroy_process_group()
@@ -759,6 +829,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true",
                     help="skip the short lines of the other BASELINE configurations (key other_workloads)")
+    ap.add_argument("--no-golden", action="store_true", help="skip the check against the stored outputs of the unmodified reference")
     ap.add_argument("--others-steps", type=int, default=5)
     ap.add_argument("--others-budget", type=float, default=60.0, help="seconds after which no further extra workload is started")
     ap.add_argument("--tune", default=None, choices=["measure", "patient"],

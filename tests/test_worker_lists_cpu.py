@@ -78,3 +78,28 @@ def test_nccl_bootstrap_lists(engine, P):
                 W.run_3d(comm, "pencil", N, "double", al, None, "Alltoallw", transport="nccl")
     run_ranks(P, body)
     assert engine["b200fft_plan_p2p_connect"] == 0
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+def test_bench_golden_check(engine, P):
+    """bench.py's `reference_goldens` key (the stored outputs of the unmodified reference at the run's rank count,
+    through the classes) on the host build: files found for every rank count the driver benches, errors at rounding."""
+    import bench
+    import mpifft4py_b200 as m
+    results = [None] * P
+
+    def body(comm):
+        def reduce_max(x):
+            return max((getattr(comm, "allgather_world", None) or (lambda v: [v]))(x))
+        results[comm.Get_rank()] = bench.golden_check(m, comm, reduce_max)
+
+    if P == 1:
+        body(m.comm.COMM_SELF)
+    else:
+        run_ranks(P, body)
+    g = results[0]
+    assert all(r == g for r in results)
+    assert len(g["files"]) == {1: 2, 2: 3, 4: 10, 8: 6}[P], g["files"]
+    e = g["max_rel_l2"]
+    assert e["double"] < 1e-13 and e["double_forward_3_2"] < 1e-12
+    assert e["single"] < 2e-6 and e["single_forward_3_2"] < 1e-5
