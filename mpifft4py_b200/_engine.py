@@ -154,7 +154,9 @@ class Transform(object):
         if _is_tensor(src) or _is_tensor(dst):
             torch = _torch()
             assert _is_tensor(src) and _is_tensor(dst), "pass either numpy arrays or CUDA tensors, not a mix"
-            assert src.is_cuda and dst.is_cuda and src.is_contiguous() and dst.is_contiguous()
+            assert src.device == self.device and dst.device == self.device, \
+                "tensors must live on the transform's device (%s), not %s / %s" % (self.device, src.device, dst.device)
+            assert src.is_contiguous() and dst.is_contiguous(), "tensors must be contiguous"
             want = {np.float32: torch.float32, np.float64: torch.float64, np.complex64: torch.complex64,
                     np.complex128: torch.complex128}
             assert src.dtype == want[src_dtype] and dst.dtype == want[dst_dtype], "wrong dtype for this precision"

@@ -76,9 +76,28 @@ def test_argument_errors(fake):
     import torch
     with pytest.raises(AssertionError):
         F.fftn(torch.zeros(N, dtype=torch.float64), fu)      # numpy arrays or CUDA tensors, not a mix
-    with pytest.raises(AssertionError):
-        F.fftn(torch.zeros(N, dtype=torch.float64), torch.zeros(tuple(fu.shape), dtype=torch.complex128))  # host tensors
+    with pytest.raises(AssertionError):   # tensors of another device than the transform's
+        F.fftn(torch.zeros(N, dtype=torch.float64, device="meta"), torch.zeros(tuple(fu.shape), dtype=torch.complex128, device="meta"))
+    with pytest.raises(AssertionError):   # ... of the wrong precision
+        F.fftn(torch.zeros(N, dtype=torch.float32), torch.zeros(tuple(fu.shape), dtype=torch.complex64))
+    with pytest.raises(AssertionError):   # ... not contiguous
+        F.fftn(torch.zeros((8, 16, 64), dtype=torch.float64)[:, :, ::2], torch.zeros(tuple(fu.shape), dtype=torch.complex128))
     assert fake.execs == 0
+
+
+def test_device_tensors_are_used_in_place(fake):
+    """Tensors on the transform's device (here: the host tensors the fake device works on) go to the C ABI by pointer:
+    no staging buffer, no copy, the output tensor itself is filled and returned."""
+    import torch
+    F = m.Slab_R2C(np.array(N), L3, COMM_SELF, "double")
+    u = torch.rand(N, dtype=torch.float64)
+    keep = u.clone()
+    fu = torch.zeros(tuple(int(s) for s in F.complex_shape()), dtype=torch.complex128)
+    assert F.fftn(u, fu) is fu and fake.copies == 0 and not F._stage
+    assert torch.equal(u, keep)
+    assert oracle.rel_l2(fu.numpy(), oracle.slab.fftn([keep.numpy()], N, 1)[0]) < 1e-14
+    back = F.ifftn(fu, torch.empty_like(u))
+    assert oracle.rel_l2(back.numpy(), keep.numpy()) < 1e-14 and fake.copies == 0
 
 
 @pytest.mark.parametrize("prec", ["double", "single"])
