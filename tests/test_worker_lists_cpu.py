@@ -103,3 +103,23 @@ def test_bench_golden_check(engine, P):
     e = g["max_rel_l2"]
     assert e["double"] < 1e-13 and e["double_forward_3_2"] < 1e-12
     assert e["single"] < 2e-6 and e["single_forward_3_2"] < 1e-5
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_the_shared_gpu_list_itself(monkeypatch, P):
+    """gpu_dist_worker.shared_gpu -- exactly what tests/test_gpu_multi.py::test_multi_rank_shared_gpu and
+    tests/test_zz_shared_gpu_8.py run on GPU 0 -- with tensors in place of numpy arrays, the back-to-back round trips
+    and the known answers included, on thread-ranks of the host build (host tensors where the device has CUDA ones)."""
+    import torch
+    import mpifft4py_b200 as m
+    from test_bench_cpu_smoke import host_cuda
+    monkeypatch.setattr(W, "note", lambda comm, msg: None)
+    cleanup = cpu_engine.install(monkeypatch)
+    host_cuda(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(m.ns.Solver, "_device", lambda self: torch.device("cpu"))
+    try:
+        run_ranks(P, W.shared_gpu)
+    finally:
+        cleanup()
+    assert cleanup.calls["b200fft_plan_p2p_connect"] >= 20 * P

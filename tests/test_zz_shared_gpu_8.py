@@ -12,7 +12,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(os.environ.get("B200FFT_SHARED8") != "1",
-                    reason="opt-in (B200FFT_SHARED8=1): not yet run on a device -- the 2- and 4-rank shared-GPU runs are, and "
-                           "eight real GPUs carry forward parity for both eight-rank grids in bench.py's other_workloads")
+                    reason="opt-in (B200FFT_SHARED8=1): eight contexts on one device have not been timed yet -- the same list "
+                           "passes on eight thread-ranks of the host build (test_worker_lists_cpu.py), the 2- and 4-rank "
+                           "shared-GPU runs pass on a B200, and eight real GPUs carry the reference goldens and forward "
+                           "parity of both eight-rank grids in bench.py (reference_goldens, other_workloads)")
 def test_eight_ranks_shared_gpu():
     shared_gpu_run(8, timeout=420)
